@@ -1,0 +1,952 @@
+"""NumPy fp64 restatement of ODINN.jl's SIA2D hot path -- TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED BY STORED NUMBERS (see ``oracle/__init__.py``).  Every function
+cites the reference file:line it follows (paths relative to the ODINN.jl tree,
+v1.1.0 / commit 31dfbf2).  The code is deliberately written array-at-a-time,
+with the same temporaries as the Julia source, so that it can be read side by
+side with it.  It is slow on purpose; the timed CPU baseline is the C oracle.
+
+Array convention: ``H[i, j]`` with ``i`` in ``0..nx-1`` the fast ("x") axis of
+the Julia column-major ``Matrix`` and ``j`` in ``0..ny-1``; shapes are
+``(nx, ny)`` exactly like ``size(H)`` in Julia, only 0-based.
+
+Assumptions that cannot be resolved from the tree (Huginn/Sleipnir are not
+vendored) are marked ``ASSUMPTION`` and listed in DESIGN.md.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# F2 -- grid primitives.  Huginn.diff_x/diff_y/avg/avg_x/avg_y/inn/inn1 are NOT
+# IN TREE; their semantics are fixed by the explicit transposes in
+# src/inverse/SIA2D/inversion_utils.jl:3-66 and the identity tests in
+# test/SIA2D_adjoint_utils.jl:8-126 (re-run in tests/test_oracle_identities.py).
+# Call sites: src/inverse/SIA2D/adjoint.jl:58-67,87-88,96-97.
+# --------------------------------------------------------------------------
+
+
+def diff_x(A):
+    """Huginn.diff_x(A) = A[2:end,:] - A[1:end-1,:]  (adjoint.jl:58)."""
+    return A[1:, :] - A[:-1, :]
+
+
+def diff_y(A):
+    """Huginn.diff_y(A) = A[:,2:end] - A[:,1:end-1]  (adjoint.jl:59)."""
+    return A[:, 1:] - A[:, :-1]
+
+
+def diff_x_inplace(O, I, d):
+    """Huginn.diff_x!(O, I, Δ): divides by Δ (test/SIA2D_adjoint_utils.jl:18)."""
+    O[...] = diff_x(I) / d
+
+
+def diff_y_inplace(O, I, d):
+    """Huginn.diff_y!(O, I, Δ) (test/SIA2D_adjoint_utils.jl:30)."""
+    O[...] = diff_y(I) / d
+
+
+def avg(A):
+    """Huginn.avg: 4-point mean onto the dual grid (adjoint.jl:67)."""
+    return 0.25 * (A[:-1, :-1] + A[1:, :-1] + A[:-1, 1:] + A[1:, 1:])
+
+
+def avg_x(A):
+    """Huginn.avg_x: 2-point mean along x (adjoint.jl:61,97)."""
+    return 0.5 * (A[:-1, :] + A[1:, :])
+
+
+def avg_y(A):
+    """Huginn.avg_y: 2-point mean along y (adjoint.jl:60,96)."""
+    return 0.5 * (A[:, :-1] + A[:, 1:])
+
+
+def inn(A):
+    """Huginn.inn(A) = A[2:end-1, 2:end-1] (adjoint.jl:553)."""
+    return A[1:-1, 1:-1]
+
+
+def inn1(A):
+    """Huginn.inn1(A) = A[1:end-1, 1:end-1] (adjoint.jl:329)."""
+    return A[:-1, :-1]
+
+
+# --- transposes, verbatim from src/inverse/SIA2D/inversion_utils.jl ----------
+
+
+def diff_x_adjoint(I, dx):
+    """inversion_utils.jl:3-8."""
+    O = np.zeros((I.shape[0] + 1, I.shape[1]))
+    O[1:, :] += I
+    O[:-1, :] -= I
+    return O / dx
+
+
+def diff_y_adjoint(I, dy):
+    """inversion_utils.jl:10-15."""
+    O = np.zeros((I.shape[0], I.shape[1] + 1))
+    O[:, 1:] += I
+    O[:, :-1] -= I
+    return O / dy
+
+
+def clamp_borders_dx(dS, H, eta0, dx):
+    """inversion_utils.jl:17-20."""
+    return np.maximum(np.minimum(dS, eta0 * H[1:, 1:-1] / dx), -eta0 * H[:-1, 1:-1] / dx)
+
+
+def clamp_borders_dx_adjoint(ddS, dH, dC, eta0, dx, H, dS):
+    """inversion_utils.jl:22-29 (in-place on ddS, dH; strict inequalities)."""
+    ddS[...] = dC * ((dS < eta0 * H[1:, 1:-1] / dx) & (dS > -eta0 * H[:-1, 1:-1] / dx))
+    dH[:-1, 1:-1] = -(eta0 * dC / dx) * (dS < -eta0 * H[:-1, 1:-1] / dx)
+    dH[1:, 1:-1] += (eta0 * dC / dx) * (dS > eta0 * H[1:, 1:-1] / dx)
+
+
+def clamp_borders_dy(dS, H, eta0, dy):
+    """inversion_utils.jl:31-34."""
+    return np.maximum(np.minimum(dS, eta0 * H[1:-1, 1:] / dy), -eta0 * H[1:-1, :-1] / dy)
+
+
+def clamp_borders_dy_adjoint(ddS, dH, dC, eta0, dy, H, dS):
+    """inversion_utils.jl:36-43."""
+    ddS[...] = dC * ((dS < eta0 * H[1:-1, 1:] / dy) & (dS > -eta0 * H[1:-1, :-1] / dy))
+    dH[1:-1, :-1] = -(eta0 * dC / dy) * (dS < -eta0 * H[1:-1, :-1] / dy)
+    dH[1:-1, 1:] += (eta0 * dC / dy) * (dS > eta0 * H[1:-1, 1:] / dy)
+
+
+def avg_adjoint(I):
+    """inversion_utils.jl:45-52."""
+    O = np.zeros((I.shape[0] + 1, I.shape[1] + 1))
+    O[:-1, :-1] += I
+    O[1:, :-1] += I
+    O[:-1, 1:] += I
+    O[1:, 1:] += I
+    return 0.25 * O
+
+
+def avg_x_adjoint(I):
+    """inversion_utils.jl:54-59."""
+    O = np.zeros((I.shape[0] + 1, I.shape[1]))
+    O[:-1, :] += I
+    O[1:, :] += I
+    return 0.5 * O
+
+
+def avg_y_adjoint(I):
+    """inversion_utils.jl:61-66."""
+    O = np.zeros((I.shape[0], I.shape[1] + 1))
+    O[:, :-1] += I
+    O[:, 1:] += I
+    return 0.5 * O
+
+
+# --------------------------------------------------------------------------
+# M1/T1 -- the Lux MLP.  Architecture: src/models/trainable_components/
+# ML_utils.jl:23-39; flat parameter layout T1: ComponentVector of Lux Dense
+# params, (weight[out x in] column-major, bias[out]) per layer in chain order
+# [Lux 1.x convention, NOT IN TREE] => theta = [vec(W1); b1; vec(W2); b2; ...].
+# --------------------------------------------------------------------------
+
+
+def softplus(x):
+    """NNlib.softplus(x) = log1p(exp(x)) in its overflow-safe form."""
+    return np.log1p(np.exp(-np.abs(x))) + np.maximum(x, 0.0)
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+_ACT = {
+    "softplus": (softplus, lambda z, a: sigmoid(z)),
+    "sigmoid": (sigmoid, lambda z, a: a * (1.0 - a)),
+    "identity": (lambda z: z, lambda z, a: np.ones_like(z)),
+}
+
+
+@dataclass
+class MLP:
+    """Chain of Dense layers.  ``widths = [n_in, h1, ..., n_out]``."""
+
+    widths: Sequence[int]
+    acts: Sequence[str]
+
+    @staticmethod
+    def default(n_input=1, light=False):
+        """build_default_NN (ML_utils.jl:23-39)."""
+        if light:
+            return MLP([n_input, 3, 1], ["softplus", "sigmoid"])
+        return MLP([n_input, 3, 10, 3, 1], ["softplus", "softplus", "softplus", "sigmoid"])
+
+    @property
+    def n_params(self):
+        return sum(o * i + o for i, o in zip(self.widths[:-1], self.widths[1:]))
+
+    def unpack(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        assert theta.size == self.n_params
+        out, k = [], 0
+        for i, o in zip(self.widths[:-1], self.widths[1:]):
+            W = theta[k : k + o * i].reshape((o, i), order="F")  # vec(W) column-major
+            k += o * i
+            b = theta[k : k + o]
+            k += o
+            out.append((W, b))
+        return out
+
+    def init(self, seed=666, scale=None):
+        """Deterministic Glorot-uniform init (Lux default is glorot_uniform /
+        zeros bias; the MersenneTwister(666) stream itself is not reproducible
+        here, so parity tests always pass theta explicitly)."""
+        rng = np.random.default_rng(seed)
+        parts = []
+        for i, o in zip(self.widths[:-1], self.widths[1:]):
+            lim = np.sqrt(6.0 / (i + o)) if scale is None else scale
+            parts.append(rng.uniform(-lim, lim, size=o * i))
+            parts.append(np.zeros(o))
+        return np.concatenate(parts)
+
+    def forward(self, theta, X, keep=False):
+        """X: (N, n_in) -> (N, n_out).  Dense: act.(W*x .+ b)."""
+        a = np.asarray(X, dtype=np.float64)
+        tape = []
+        for (W, b), act in zip(self.unpack(theta), self.acts):
+            z = a @ W.T + b
+            a_new = _ACT[act][0](z)
+            if keep:
+                tape.append((a, z, a_new))
+            a = a_new
+        return (a, tape) if keep else a
+
+    def backward(self, theta, X, gout):
+        """Pullback of forward: given gout (N, n_out) returns
+        (dtheta_per_sample (N, n_params), dX (N, n_in))."""
+        y, tape = self.forward(theta, X, keep=True)
+        layers = self.unpack(theta)
+        N = y.shape[0]
+        g = np.asarray(gout, dtype=np.float64)
+        grads = [None] * len(layers)
+        for li in reversed(range(len(layers))):
+            W, b = layers[li]
+            a_in, z, a_out = tape[li]
+            dz = g * _ACT[self.acts[li]][1](z, a_out)  # (N, o)
+            dW = dz[:, :, None] * a_in[:, None, :]  # (N, o, i)
+            grads[li] = (dW, dz)
+            g = dz @ W
+        flat = []
+        for dW, db in grads:
+            flat.append(dW.transpose(0, 2, 1).reshape(N, -1))  # column-major vec(W)
+            flat.append(db)
+        return np.concatenate(flat, axis=1), g
+
+
+# --- pre / post scaling, src/models/target/target_utils.jl --------------------
+
+
+def normalize(X, lims):
+    """target_utils.jl:131-141, method=:shift."""
+    return (X - lims[0]) / (lims[1] - lims[0]) - 0.5
+
+
+def ml_model_postscale(Y, max_NN):
+    """_ml_model_postscale, target_utils.jl:86-93."""
+    return max_NN * np.exp((Y - 1.0) / Y)
+
+
+def scale(X, lims):
+    """target_utils.jl:109-113."""
+    return lims[0] + (lims[1] - lims[0]) * X
+
+
+# --------------------------------------------------------------------------
+# Physical parameters + laws
+# --------------------------------------------------------------------------
+
+
+@dataclass
+class Phys:
+    """params.physical / iceflow cache scalars (test/params_construction.jl:24-34).
+
+    ASSUMPTION: Weertman exponents default p=3, q=0 (Huginn defaults NOT IN
+    TREE; irrelevant while C=0, which every functional-inversion test uses)."""
+
+    rho: float = 900.0
+    g: float = 9.81
+    eta0: float = 1.0
+    n: float = 3.0
+    p: float = 3.0
+    q: float = 0.0
+    C: float = 0.0
+    minA: float = 8.5e-20
+    maxA: float = 8e-17
+
+
+def Gamma(ph: Phys, A=None):
+    """Γ, target_utils.jl:3-13 (include_A=False when A is None)."""
+    G = 2.0 * (ph.rho * ph.g) ** ph.n / (ph.n + 2)
+    return G if A is None else A * G
+
+
+def S_slide(ph: Phys):
+    """S, target_utils.jl:15-19."""
+    return ph.C * (ph.rho * ph.g) ** (ph.p - ph.q)
+
+
+def Gamma_up(ph: Phys, A=None):
+    """Γꜛ, target_utils.jl:21-30."""
+    G = 2.0 * (ph.rho * ph.g) ** ph.n / (ph.n + 1)
+    return G if A is None else A * G
+
+
+class TargetA:
+    """SIA2D_A_target (src/models/target/target_A.jl) with the A laws of
+    src/laws/Laws.jl.
+
+    kind:
+      "const"   A given (scalar or dual-grid matrix); no trainable theta
+      "nn"      LawA(nn, params): A = minA + (maxA-minA) * NN([T]; theta)   (Laws.jl:348-358)
+      "scalar"  LawA(params; scalar=true): A = minA+(maxA-minA)*(tanh(theta)+1)/2, one theta (Laws.jl:404-412)
+      "gridded" LawA(params; scalar=false): same per dual-grid node, theta is (nx-1)x(ny-1) (Laws.jl:430-454)
+    """
+
+    def __init__(self, ph: Phys, kind="const", A=None, mlp: Optional[MLP] = None, T=None):
+        self.ph, self.kind, self.A_const, self.mlp, self.T = ph, kind, A, mlp, T
+        self.A = None
+        self.vjp_theta = None
+
+    # -- law forward (M1) ------------------------------------------------
+    def apply_laws(self, Hb, gS, theta):
+        ph = self.ph
+        if self.kind == "const":
+            self.A = self.A_const
+        elif self.kind == "nn":
+            y = self.mlp.forward(theta, np.array([[self.T]]))[0, 0]
+            self.A = scale(y, (ph.minA, ph.maxA))
+        elif self.kind in ("scalar", "gridded"):
+            th = np.asarray(theta, dtype=np.float64)
+            self.A = ph.minA + (ph.maxA - ph.minA) * (np.tanh(th) + 1.0) / 2.0
+            if self.kind == "scalar":
+                self.A = float(self.A.reshape(-1)[0])
+        else:
+            raise ValueError(self.kind)
+
+    # -- law pullback (M2), precompute_all_VJPs_laws! (inversion_utils.jl:647-686)
+    def precompute_vjp(self, theta):
+        ph = self.ph
+        if self.kind == "nn":
+            dth, _ = self.mlp.backward(theta, np.array([[self.T]]), np.ones((1, 1)))
+            self.vjp_theta = (ph.maxA - ph.minA) * dth[0]
+        elif self.kind in ("scalar", "gridded"):
+            th = np.asarray(theta, dtype=np.float64)
+            self.vjp_theta = (ph.maxA - ph.minA) * 0.5 * (1.0 - np.tanh(th) ** 2)
+        else:
+            self.vjp_theta = np.zeros(0)
+
+    # -- target_A.jl:16-30
+    def Diffusivity(self, Hb, gS):
+        ph = self.ph
+        G = Gamma(ph)
+        return S_slide(ph) * Hb ** (ph.p - ph.q + 1) * gS ** (ph.p - 1) + self.A * G * Hb ** (ph.n + 2) * gS ** (
+            ph.n - 1
+        )
+
+    # -- target_A.jl:32-46
+    def dD_dH(self, Hb, gS, theta=None):
+        ph = self.ph
+        return (ph.p - ph.q + 1) * S_slide(ph) * Hb ** (ph.p - ph.q) * gS ** (ph.p - 1) + self.A * Gamma(ph) * (
+            ph.n + 2
+        ) * Hb ** (ph.n + 1) * gS ** (ph.n - 1)
+
+    # -- target_A.jl:48-62   (this is (1/|∇S|) ∂D/∂|∇S|)
+    def dD_dgradH(self, Hb, gS, theta=None):
+        ph = self.ph
+        return S_slide(ph) * (ph.p - 1) * Hb ** (ph.p - ph.q + 1) * gS ** (ph.p - 3) + self.A * Gamma(ph) * (
+            ph.n - 1
+        ) * Hb ** (ph.n + 2) * gS ** (ph.n - 3)
+
+    # -- target_A.jl:64-92 contracted with D_adjoint (adjoint.jl:250).
+    def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
+        ph = self.ph
+        dA_spatial = Gamma(ph) * Hb ** (ph.n + 2) * gS ** (ph.n - 1)
+        if self.vjp_theta is None:
+            self.precompute_vjp(theta)
+        if self.kind in ("nn", "scalar"):
+            v = np.atleast_1d(self.vjp_theta).reshape(-1)
+            if dense:  # cartesian_tensor (target_utils.jl:156-162) then Tullio
+                T3 = dA_spatial[:, :, None] * v[None, None, :]
+                return np.einsum("ijk,ij->k", T3, D_adjoint)
+            return v * np.sum(dA_spatial * D_adjoint)
+        if self.kind == "gridded":  # sparse_cartesian_tensor (target_utils.jl:163-173)
+            return (dA_spatial * self.vjp_theta.reshape(dA_spatial.shape) * D_adjoint).reshape(-1, order="F")
+        return np.zeros(0)
+
+    # -- surface velocity pieces, target_A.jl:94-141 -----------------------
+    def Velocity_up(self, Hb, gS):
+        ph = self.ph
+        return S_slide(ph) * (ph.p - ph.q + 2) * Hb ** (ph.p - ph.q + 1) * gS ** (ph.n - 1) + self.A * Gamma_up(
+            ph
+        ) * Hb ** (ph.n + 1) * gS ** (ph.n - 1)
+
+    def dV_dH(self, Hb, gS):
+        ph = self.ph
+        return S_slide(ph) * (ph.p - ph.q + 2) * Hb ** (ph.p - ph.q) * gS ** (ph.n - 1) + self.A * Gamma_up(ph) * (
+            ph.n + 1
+        ) * Hb**ph.n * gS ** (ph.n - 1)
+
+    def dV_dgradH(self, Hb, gS):
+        ph = self.ph
+        return S_slide(ph) * (ph.p - ph.q + 2) * (ph.p - 1) * Hb ** (ph.p - ph.q + 1) * gS ** (
+            ph.n - 3
+        ) + self.A * Gamma_up(ph) * (ph.n - 1) * Hb ** (ph.n + 1) * gS ** (ph.n - 3)
+
+
+class TargetD:
+    """SIA2D_D_target (src/models/target/target_D_pure.jl): D = H̄ * U,
+    U = post(NN(pre([H̄, ∇S]); theta))  (LawU, src/laws/Laws.jl:97-123).
+
+    The H̄- and ∇S-partials are central finite differences of the network
+    exactly as in the reference (target_D_pure.jl:105-137): δH=1e-4, δ∇S=1e-6.
+    Note that the reference's ∂Diffusivity∂∇H returns ∂D/∂|∇S| (not divided by
+    |∇S|); we follow the reference."""
+
+    def __init__(self, ph: Phys, mlp: MLP, prescale_bounds=None, max_NN=None):
+        self.ph, self.mlp, self.bounds, self.max_NN = ph, mlp, prescale_bounds, max_NN
+        self.U = None
+
+    def _pre(self, Hb, gS):
+        a, b = Hb, gS
+        if self.bounds is not None:
+            a = normalize(Hb, self.bounds[0])
+            b = normalize(gS, self.bounds[1])
+        return np.stack([a.reshape(-1), b.reshape(-1)], axis=1)
+
+    def eval_U(self, Hb, gS, theta):
+        y = self.mlp.forward(theta, self._pre(Hb, gS))[:, 0]
+        if self.max_NN is not None:
+            y = ml_model_postscale(y, self.max_NN)
+        return y.reshape(Hb.shape)
+
+    def apply_laws(self, Hb, gS, theta):
+        self.U = self.eval_U(Hb, gS, theta)
+        self._theta = theta
+
+    def precompute_vjp(self, theta):
+        pass
+
+    def Diffusivity(self, Hb, gS):
+        return Hb * self.U  # target_D_pure.jl:78-96
+
+    def dD_dH(self, Hb, gS, theta):
+        dHdH = np.where(Hb > 0.0, 1.0, 0.0)
+        d = 1e-4 * np.ones_like(Hb)
+        Dp = self.eval_U(Hb + d, gS, theta) * (Hb + d)
+        Dm = self.eval_U(Hb - d, gS, theta) * (Hb - d)
+        return dHdH * (Dp - Dm) / (2.0 * d)
+
+    def dD_dgradH(self, Hb, gS, theta):
+        d = 1e-6 * np.ones_like(gS)
+        Dp = self.eval_U(Hb, gS + d, theta) * Hb
+        Dm = self.eval_U(Hb, gS - d, theta) * Hb
+        return (Dp - Dm) / (2.0 * d)
+
+    def dU_dtheta(self, Hb, gS, theta):
+        """Exact per-cell gradient (interpolation=:None, target_D_pure.jl:165-178)."""
+        X = self._pre(Hb, gS)
+        y = self.mlp.forward(theta, X)[:, 0]
+        if self.max_NN is not None:
+            gout = (ml_model_postscale(y, self.max_NN) / (y * y))[:, None]  # d/dy max*exp((y-1)/y)
+        else:
+            gout = np.ones((X.shape[0], 1))
+        dth, _ = self.mlp.backward(theta, X, gout)
+        dth = dth.reshape(Hb.shape + (-1,))
+        dth[Hb == 0.0] = 0.0  # `continue` at target_D_pure.jl:169-171
+        return dth
+
+    def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
+        dspatial = np.where(Hb > 0.0, 1.0, 0.0)
+        T3 = dspatial[:, :, None] * self.dU_dtheta(Hb, gS, theta) * Hb[:, :, None]
+        return np.einsum("ijk,ij->k", T3, D_adjoint)
+
+
+class TargetDHybrid:
+    """SIA2D_D_hybrid_target (src/models/target/target_D_hybrid.jl):
+    D = S H̄^{p-q+1} ∇S^{p-1} + Y Γ H̄^{n_H+2} ∇S^{n_∇S-1},
+    Y = post(NN(pre([T, H̄]); theta))  (LawY, src/laws/Laws.jl:240-273).
+    Exact per-cell θ-gradient (interpolation=:None, target_D_hybrid.jl:122-132);
+    the H̄-partial of the network is the reference's one-sided difference with
+    δH = 1e-4 (target_D_hybrid.jl:58-73)."""
+
+    def __init__(self, ph: Phys, mlp: MLP, T: float, prescale_bounds=((-25.0, 0.0), (0.0, 500.0)), max_NN=None,
+                 n_H=None, n_gS=None):
+        self.ph, self.mlp, self.T, self.bounds = ph, mlp, T, prescale_bounds
+        self.max_NN = ph.maxA if max_NN is None else max_NN
+        self.n_H = ph.n if n_H is None else n_H
+        self.n_gS = ph.n if n_gS is None else n_gS
+        self.Y = None
+
+    def eval_Y(self, Hb, theta):
+        X = np.stack([np.full(Hb.size, normalize(self.T, self.bounds[0])), normalize(Hb.reshape(-1), self.bounds[1])],
+                     axis=1)
+        y = self.mlp.forward(theta, X)[:, 0]
+        return ml_model_postscale(y, self.max_NN).reshape(Hb.shape)
+
+    def apply_laws(self, Hb, gS, theta):
+        self.Y = self.eval_Y(Hb, theta)
+
+    def precompute_vjp(self, theta):
+        pass
+
+    def compute_D(self, Y, Hb, gS):
+        ph = self.ph
+        return S_slide(ph) * Hb ** (ph.p - ph.q + 1) * gS ** (ph.p - 1) + Y * Gamma(ph) * Hb ** (self.n_H + 2) * gS ** (
+            self.n_gS - 1
+        )
+
+    def Diffusivity(self, Hb, gS):
+        return self.compute_D(self.Y, Hb, gS)
+
+    def dD_dH(self, Hb, gS, theta):
+        ph = self.ph
+        no_NN = (ph.p - ph.q + 1) * S_slide(ph) * Hb ** (ph.p - ph.q) * gS ** (ph.p - 1) + (
+            self.n_H + 2
+        ) * self.Y * Gamma(ph) * Hb ** (self.n_H + 1) * gS ** (self.n_gS - 1)
+        d = 1e-4 * np.ones_like(Hb)
+        a = self.compute_D(self.eval_Y(Hb + d, theta), Hb, gS)
+        b = self.compute_D(self.eval_Y(Hb, theta), Hb, gS)
+        return no_NN + (a - b) / d
+
+    def dD_dgradH(self, Hb, gS, theta):
+        ph = self.ph
+        return S_slide(ph) * (ph.p - 1) * Hb ** (ph.p - ph.q + 1) * gS ** (ph.p - 3) + Gamma(ph) * self.Y * (
+            self.n_gS - 1
+        ) * Hb ** (self.n_H + 2) * gS ** (self.n_gS - 3)
+
+    def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
+        ph = self.ph
+        dA_spatial = Gamma(ph) * Hb ** (self.n_H + 2) * gS ** (self.n_gS - 1)
+        X = np.stack([np.full(Hb.size, normalize(self.T, self.bounds[0])), normalize(Hb.reshape(-1), self.bounds[1])],
+                     axis=1)
+        y = self.mlp.forward(theta, X)[:, 0]
+        gout = (ml_model_postscale(y, self.max_NN) / (y * y))[:, None]
+        dth, _ = self.mlp.backward(theta, X, gout)
+        T3 = dA_spatial[:, :, None] * dth.reshape(Hb.shape + (-1,))
+        return np.einsum("ijk,ij->k", T3, D_adjoint)
+
+
+# --------------------------------------------------------------------------
+# Glacier container (Sleipnir.Glacier2D fields used on the path: adjoint.jl:47-49)
+# --------------------------------------------------------------------------
+
+
+@dataclass
+class Glacier:
+    B: np.ndarray
+    dx: float
+    dy: float
+    H0: Optional[np.ndarray] = None
+
+    @property
+    def shape(self):
+        return self.B.shape
+
+
+def _recompute_forward(H, glacier, target, theta):
+    """The forward intermediates, in the order of adjoint.jl:52-97."""
+    B, dx, dy = glacier.B, glacier.dx, glacier.dy
+    eta0 = target.ph.eta0
+    H = np.where(H > 0.0, H, 0.0)  # adjoint.jl:52
+    S = B + H  # :54
+    dSdx = diff_x(S) / dx  # :58
+    dSdy = diff_y(S) / dy  # :59
+    gSx = avg_y(dSdx)  # :60
+    gSy = avg_x(dSdy)  # :61
+    gS = (gSx**2 + gSy**2) ** 0.5  # :64
+    Hb = avg(H)  # :67
+    target.apply_laws(Hb, gS, theta)  # :75-76
+    D = target.Diffusivity(Hb, gS)  # :79-84
+    dSdx_edges = diff_x(S[:, 1:-1]) / dx  # :87
+    dSdy_edges = diff_y(S[1:-1, :]) / dy  # :88
+    dSdx_edges_clamp = clamp_borders_dx(dSdx_edges, H, eta0, dx)  # :93
+    dSdy_edges_clamp = clamp_borders_dy(dSdy_edges, H, eta0, dy)  # :94
+    Dx = avg_y(D)  # :96
+    Dy = avg_x(D)  # :97
+    return dict(H=H, S=S, gSx=gSx, gSy=gSy, gS=gS, Hb=Hb, D=D, dSdx_edges=dSdx_edges, dSdy_edges=dSdy_edges,
+                cx=dSdx_edges_clamp, cy=dSdy_edges_clamp, Dx=Dx, Dy=Dy)
+
+
+# --------------------------------------------------------------------------
+# F1 -- Huginn.SIA2D!(dH, H, simulation, t, θ)  [NOT IN TREE]
+# Restated from adjoint.jl:47-104 (every intermediate, in order) plus the
+# divergence / sign / zero border of the forward-form twin at :522-533,552-553.
+# --------------------------------------------------------------------------
+
+
+def SIA2D(H, glacier, target, theta=None):
+    f = _recompute_forward(H, glacier, target, theta)
+    Fx = -f["Dx"] * f["cx"]
+    Fy = -f["Dy"] * f["cy"]
+    Fxx = diff_x(Fx) / glacier.dx
+    Fyy = diff_y(Fy) / glacier.dy
+    dH = np.zeros_like(f["H"])
+    inn(dH)[...] = -(Fxx + Fyy)
+    return dH
+
+
+# --------------------------------------------------------------------------
+# A1 -- VJP_λ_∂SIA∂H_discrete, adjoint.jl:31-151
+# --------------------------------------------------------------------------
+
+
+def _D_adjoint(lam, f, dx, dy):
+    """adjoint.jl:99-104."""
+    lam_inn = lam[1:-1, 1:-1]
+    Fx_adjoint = diff_x_adjoint(-lam_inn, dx)
+    Fy_adjoint = diff_y_adjoint(-lam_inn, dy)
+    Dx_adjoint = avg_y_adjoint(-Fx_adjoint * f["cx"])
+    Dy_adjoint = avg_x_adjoint(-Fy_adjoint * f["cy"])
+    return Fx_adjoint, Fy_adjoint, Dx_adjoint + Dy_adjoint
+
+
+def VJP_dSIA_dH_discrete(lam, H, glacier, target, theta=None):
+    dx, dy, eta0 = glacier.dx, glacier.dy, target.ph.eta0
+    f = _recompute_forward(H, glacier, target, theta)
+    Hc, Hb, gS = f["H"], f["Hb"], f["gS"]
+    Fx_adjoint, Fy_adjoint, D_adjoint = _D_adjoint(lam, f, dx, dy)
+
+    # First term (adjoint.jl:106-127)
+    alpha = target.dD_dH(Hb, gS, theta)
+    beta = target.dD_dgradH(Hb, gS, theta)
+    bx = beta * f["gSx"]
+    by = beta * f["gSy"]
+    dDdH_adj = (
+        avg_adjoint(alpha * D_adjoint)
+        + diff_x_adjoint(avg_y_adjoint(bx * D_adjoint), dx)
+        + diff_y_adjoint(avg_x_adjoint(by * D_adjoint), dy)
+    )
+
+    # Second term (adjoint.jl:129-144)
+    dCx = -Fx_adjoint * f["Dx"]
+    dCy = -Fy_adjoint * f["Dy"]
+    ddSx = np.zeros_like(f["dSdx_edges"])
+    ddSy = np.zeros_like(f["dSdy_edges"])
+    dHlocx = np.zeros_like(Hc)
+    dHlocy = np.zeros_like(Hc)
+    clamp_borders_dx_adjoint(ddSx, dHlocx, dCx, eta0, dx, Hc, f["dSdx_edges"])
+    clamp_borders_dy_adjoint(ddSy, dHlocy, dCy, eta0, dy, Hc, f["dSdy_edges"])
+    gx = np.zeros_like(Hc)
+    gx[:, 1:-1] = diff_x_adjoint(ddSx, dx)
+    gy = np.zeros_like(Hc)
+    gy[1:-1, :] = diff_y_adjoint(ddSy, dy)
+    dCdH_adj = (gx + dHlocx) + (gy + dHlocy)
+
+    dlam = dDdH_adj + dCdH_adj  # :147
+    dlam = dlam * (Hc > 0)  # :148
+    return dlam
+
+
+# --------------------------------------------------------------------------
+# A2 -- VJP_λ_∂SIA∂θ_discrete, adjoint.jl:178-255
+# --------------------------------------------------------------------------
+
+
+def VJP_dSIA_dtheta_discrete(lam, H, glacier, target, theta=None, dense=False):
+    f = _recompute_forward(H, glacier, target, theta)
+    _, _, D_adjoint = _D_adjoint(lam, f, glacier.dx, glacier.dy)
+    return target.dD_dtheta_contract(f["Hb"], f["gS"], theta, D_adjoint, dense=dense)
+
+
+def node_reduction_S(lam, H, glacier, target, theta=None):
+    """Σ_ij (Γ_noA H̄^{n+2} ∇S^{n-1})·D† -- the scalar the GPU A2 kernel reduces
+    (target_A.jl:71-72 contracted at adjoint.jl:250)."""
+    f = _recompute_forward(H, glacier, target, theta)
+    _, _, D_adjoint = _D_adjoint(lam, f, glacier.dx, glacier.dy)
+    ph = target.ph
+    return float(np.sum(Gamma(ph) * f["Hb"] ** (ph.n + 2) * f["gS"] ** (ph.n - 1) * D_adjoint))
+
+
+# --------------------------------------------------------------------------
+# A1c / A2c -- continuous VJPs, adjoint.jl:442-662
+# --------------------------------------------------------------------------
+
+
+def VJP_dSIA_dH_continuous(lam, H, glacier, target, theta=None):
+    dx, dy = glacier.dx, glacier.dy
+    f = _recompute_forward(H, glacier, target, theta)
+    Hb, gS, D, S = f["Hb"], f["gS"], f["D"], f["S"]
+    dSdx = diff_x(S) / dx
+    dSdy = diff_y(S) / dy
+    dDdH = avg(target.dD_dH(Hb, gS, theta))  # :500-506
+    beta = target.dD_dgradH(Hb, gS, theta)
+    dDdgx = beta * f["gSx"]
+    dDdgy = beta * f["gSy"]
+    dldx_e = diff_x(lam[:, 1:-1]) / dx  # :522
+    dldy_e = diff_y(lam[1:-1, :]) / dy
+    Fx = -avg_y(D) * dldx_e
+    Fy = -avg_x(D) * dldy_e
+    div = -(diff_x(Fx) / dx + diff_y(Fy) / dy)  # :528-532
+    lsx = avg_y(dSdx * diff_x(lam) / dx)  # :535-538
+    lsy = avg_x(dSdy * diff_y(lam) / dy)
+    ls = lsx + lsy
+    t2 = dDdH * avg(ls)  # :541
+    t3 = avg_y(diff_x(ls * dDdgx) / dx) + avg_x(diff_y(ls * dDdgy) / dy)  # :544-549
+    out = np.zeros_like(lam)
+    inn(out)[...] = div - t2 + t3  # :552-553
+    return out
+
+
+def VJP_dSIA_dtheta_continuous(lam, H, glacier, target, theta=None):
+    """adjoint.jl:582-662 for glacier-wide A (the dense tensor factorises as
+    ∂A_spatial ⊗ vjp_θ, so the Tullio chain acts on ∂A_spatial alone)."""
+    dx, dy = glacier.dx, glacier.dy
+    f = _recompute_forward(H, glacier, target, theta)
+    ph = target.ph
+    assert isinstance(target, TargetA) and target.kind in ("nn", "scalar")
+    if target.vjp_theta is None:
+        target.precompute_vjp(theta)
+    dA = Gamma(ph) * f["Hb"] ** (ph.n + 2) * f["gS"] ** (ph.n - 1)
+    Fx = avg_y(dA) * f["cx"]  # :646
+    Fy = avg_x(dA) * f["cy"]  # :647
+    Fxx = diff_x(Fx) / dx
+    Fyy = diff_y(Fy) / dy
+    pad = np.zeros_like(lam)
+    inn(pad)[...] = Fxx + Fyy  # :653-654
+    return np.atleast_1d(target.vjp_theta).reshape(-1) * np.sum(pad * lam)  # :657
+
+
+# --------------------------------------------------------------------------
+# Surface velocity (Huginn.V_from_H / surface_V, NOT IN TREE; shape fixed by
+# adjoint.jl:268-350: V lives on inn1 cells, Vx = -D^ * ∇Sx) and its VJPs.
+# --------------------------------------------------------------------------
+
+
+def surface_V(H, glacier, target, theta=None):
+    f = _recompute_forward(H, glacier, target, theta)
+    Dup = target.Velocity_up(f["Hb"], f["gS"])
+    nx, ny = f["H"].shape
+    Vx = np.zeros((nx, ny))
+    Vy = np.zeros((nx, ny))
+    inn1(Vx)[...] = -Dup * f["gSx"]
+    inn1(Vy)[...] = -Dup * f["gSy"]
+    return Vx, Vy
+
+
+def VJP_dsurfaceV_dH_discrete(dVx, dVy, H, glacier, target, theta=None):
+    """adjoint.jl:268-350."""
+    dx, dy = glacier.dx, glacier.dy
+    f = _recompute_forward(H, glacier, target, theta)
+    Hb, gS, gSx, gSy = f["Hb"], f["gS"], f["gSx"], f["gSy"]
+    alpha = target.dV_dH(Hb, gS)
+    beta = target.dV_dgradH(Hb, gS)
+    a, b = inn1(dVx), inn1(dVy)
+    sv = gSx * a + gSy * b
+    dDdH = (
+        avg_adjoint(alpha * sv)
+        + diff_x_adjoint(avg_y_adjoint(beta * gSx * sv), dx)
+        + diff_y_adjoint(avg_x_adjoint(beta * gSy * sv), dy)
+    )
+    Dup = target.Velocity_up(Hb, gS)
+    dgS = diff_x_adjoint(avg_y_adjoint(Dup * a), dx) + diff_y_adjoint(avg_x_adjoint(Dup * b), dy)
+    return -(dDdH + dgS)
+
+
+# --------------------------------------------------------------------------
+# L1 -- losses.  L2Sum: src/losses/Losses.jl:116-152; LossH: :250-291.
+# --------------------------------------------------------------------------
+
+
+def is_in_glacier(A, distance):
+    """Sleipnir.is_in_glacier [NOT IN TREE].  ASSUMPTION: a cell is "in" when
+    it and every cell within `distance` 4-neighbour steps (circular shifts) are
+    non-zero, i.e. `distance` erosions of the mask A != 0."""
+    Bm = (A != 0).astype(np.float64)
+    for _ in range(int(distance)):
+        Bm = np.minimum.reduce(
+            [Bm, np.roll(Bm, 1, 0), np.roll(Bm, -1, 0), np.roll(Bm, 1, 1), np.roll(Bm, -1, 1)]
+        )
+    return Bm > 0.001
+
+
+def loss_L2Sum(a, b, mask, normalization):
+    """Losses.jl:133-141."""
+    return np.sum(((a - b)[mask]) ** 2) / normalization
+
+
+def backward_loss_L2Sum(a, b, mask, normalization):
+    """Losses.jl:142-152."""
+    d = np.zeros_like(a)
+    d[mask] = a[mask] - b[mask]
+    return 2.0 * d / normalization
+
+
+# --------------------------------------------------------------------------
+# Time integration.  The reference delegates to OrdinaryDiffEq (RDPK3Sp35 by
+# default, src/inverse/AdjointTypes.jl:60) [NOT IN TREE]; the solver is a user
+# parameter (params.solver.solver).  The B200 on-device loop and this oracle
+# implement the same explicitly stated schemes so they can be compared:
+#   "euler"  explicit Euler, fixed substeps
+#   "ssprk3" Shu-Osher SSPRK(3,3), fixed substeps
+#   "bs3"    Bogacki-Shampine 3(2) FSAL pair with an I-controller, adaptive,
+#            landing exactly on every tstop (inversion_utils.jl:487-495).
+# --------------------------------------------------------------------------
+
+
+def define_callback_steps(tspan, step):
+    """Huginn.define_callback_steps [NOT IN TREE]; call site gradient.jl:96."""
+    n = int(round((tspan[1] - tspan[0]) / step))
+    return tspan[0] + step * np.arange(n + 1)
+
+
+def solve_forward(H0, glacier, target, theta, tstops, method="ssprk3", nsub=8, reltol=1e-6, abstol=1e-6, dt0=None,
+                  max_steps=10_000_000, stats=None):
+    """Returns the list of snapshots H(t) at every tstop (incl. the first)."""
+    f = lambda H: SIA2D(H, glacier, target, theta)
+    H = np.array(H0, dtype=np.float64, copy=True)
+    out = [H.copy()]
+    nrhs = 0
+    dt = dt0
+    k1 = None
+    for a, b in zip(tstops[:-1], tstops[1:]):
+        if method in ("euler", "ssprk3"):
+            h = (b - a) / nsub
+            for _ in range(nsub):
+                if method == "euler":
+                    H = H + h * f(H)
+                    nrhs += 1
+                else:
+                    u1 = H + h * f(H)
+                    u2 = 0.75 * H + 0.25 * (u1 + h * f(u1))
+                    H = H / 3.0 + (2.0 / 3.0) * (u2 + h * f(u2))
+                    nrhs += 3
+        elif method == "bs3":
+            t = a
+            if dt is None:
+                dt = (b - a) / 16.0
+            if k1 is None:
+                k1 = f(H)
+                nrhs += 1
+            steps = 0
+            while t < b:
+                last = dt >= (b - t)
+                h = (b - t) if last else dt
+                truncated = h < dt
+                k2 = f(H + 0.5 * h * k1)
+                k3 = f(H + 0.75 * h * k2)
+                Hn = H + h * (2.0 / 9.0 * k1 + 1.0 / 3.0 * k2 + 4.0 / 9.0 * k3)
+                k4 = f(Hn)
+                nrhs += 3
+                err = h * (-5.0 / 72.0 * k1 + 1.0 / 12.0 * k2 + 1.0 / 9.0 * k3 - 1.0 / 8.0 * k4)
+                sc = abstol + reltol * np.maximum(np.abs(H), np.abs(Hn))
+                en = np.sqrt(np.mean((err / sc) ** 2))
+                fac = 0.9 * (1.0 / max(en, 1e-10)) ** (1.0 / 3.0)
+                fac = min(5.0, max(0.2, fac))
+                if en <= 1.0:
+                    t = b if last else t + h
+                    H, k1 = Hn, k4
+                    # a step shortened only to land on the tstop must not shrink the proposal
+                    dt = max(h * fac, dt) if (truncated and fac >= 1.0) else h * fac
+                else:
+                    dt = h * fac
+                steps += 1
+                if steps > max_steps:
+                    raise RuntimeError("bs3: too many steps")
+        else:
+            raise ValueError(method)
+        out.append(H.copy())
+    if stats is not None:
+        stats["nrhs"] = nrhs
+    return out
+
+
+# --------------------------------------------------------------------------
+# R1 -- discrete-adjoint gradient of the transient LossH(L2Sum) loss.
+# gradient.jl:45-274 (DiscreteAdjoint branch, no MB, no velocity term).
+# --------------------------------------------------------------------------
+
+
+def loss_and_grad_discrete(theta, glacier, target, t, Hs, H_ref, distance=3):
+    """Hs: forward snapshots at times t (len k).  H_ref: reference thickness at
+    the same times (tH_ref == t).  Returns (loss, dLdθ, λ[0])."""
+    k = len(Hs)
+    Dt = np.diff(t)
+    N = glacier.shape
+    normalization = float(N[0] * N[1]) * 1.0  # prod(N) * normalization, gradient.jl:161
+    target.precompute_vjp(theta)  # gradient.jl:126
+    lam = [np.zeros(N) for _ in range(k)]
+    # Δt_HV.H[ind-1] with safe_slice -> 0 for the first data point (gradient.jl:146-149)
+    DtH = [0.0] + list(np.diff(t))
+    dLdH = []
+    for j in range(k):
+        mask = is_in_glacier(H_ref[j], distance)
+        dLdH.append(backward_loss_L2Sum(Hs[j], H_ref[j], mask, normalization) * DtH[j])  # Losses.jl:270-291
+    ell = 0.0
+    dLdtheta = None
+    for j in reversed(range(k)):
+        mask = is_in_glacier(H_ref[j], distance)
+        ell += loss_L2Sum(Hs[j], H_ref[j], mask, normalization) * DtH[j]  # gradient.jl:218-232
+        l_dfdH = VJP_dSIA_dH_discrete(lam[j], Hs[j], glacier, target, theta)  # :235-237
+        if j > 0:
+            lam[j - 1] = lam[j] + Dt[j - 1] * l_dfdH + dLdH[j]  # :242
+            l_dfdth = VJP_dSIA_dtheta_discrete(lam[j - 1], Hs[j], glacier, target, theta)  # :245-246
+            dLdtheta = Dt[j - 1] * l_dfdth if dLdtheta is None else dLdtheta + Dt[j - 1] * l_dfdth  # :249
+    return ell, dLdtheta, lam[0]
+
+
+def loss_forward(Hs, H_ref, t, shape, distance=3):
+    """loss_iceflow_transient for LossH(L2Sum) (inversion_utils.jl:383-461)."""
+    normalization = float(shape[0] * shape[1])
+    DtH = [0.0] + list(np.diff(t))
+    return sum(
+        loss_L2Sum(Hs[j], H_ref[j], is_in_glacier(H_ref[j], distance), normalization) * DtH[j] for j in range(len(Hs))
+    )
+
+
+# --------------------------------------------------------------------------
+# Known answer: Halfar (1983) similarity solution, n = 3, flat bed.
+# Reference setup: scripts/MWEs/inversion_diffusivity/inversion_setup.jl:44-71
+# (Huginn.Halfar itself is NOT IN TREE; this is the published closed form).
+# --------------------------------------------------------------------------
+
+
+def halfar_t0(R0, H0, A, rho=900.0, g=9.81):
+    Gam = 2.0 * A * (rho * g) ** 3 / 5.0
+    return (1.0 / (18.0 * Gam)) * (7.0 / 4.0) ** 3 * R0**4 / H0**7
+
+
+def halfar(x, y, t, R0, H0, A, rho=900.0, g=9.81):
+    t0 = halfar_t0(R0, H0, A, rho, g)
+    r = np.sqrt(x * x + y * y)
+    s = (t0 / t) ** (1.0 / 18.0) * r / R0
+    inside = np.maximum(0.0, 1.0 - s ** (4.0 / 3.0))
+    return H0 * (t0 / t) ** (1.0 / 9.0) * inside ** (3.0 / 7.0)
+
+
+# --------------------------------------------------------------------------
+# Synthetic inputs of SURVEY §8(d) (shared by tests, smoke and bench)
+# --------------------------------------------------------------------------
+
+
+def dome_glacier(nx, ny, dx=50.0, H0=400.0, A=2.21e-18):
+    """Halfar dome at t0 on a flat bed, R0 = 0.4*nx*dx (config 1, case 1)."""
+    R0 = 0.4 * nx * dx
+    xs = (np.arange(nx) - nx / 2) * dx
+    ys = (np.arange(ny) - ny / 2) * dx
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    t0 = halfar_t0(R0, H0, A)
+    H = halfar(X, Y, t0, R0, H0, A)
+    return Glacier(B=np.zeros((nx, ny)), dx=dx, dy=dx, H0=H)
+
+
+def rough_bed_glacier(nx, ny, dx=50.0):
+    """Sloped rough bed + parabolic cap (config 1, case 2): exercises the
+    flux clamp and the H>0 mask."""
+    xs = np.arange(nx) * dx
+    ys = np.arange(ny) * dx
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    B = 2000.0 + 0.15 * X + 30.0 * np.sin(2 * np.pi * X / 1500.0) * np.cos(2 * np.pi * Y / 1100.0)
+    L = min(nx, ny) * dx
+    r = np.sqrt((X - 0.5 * nx * dx) ** 2 + (Y - 0.5 * ny * dx) ** 2)
+    H = np.maximum(0.0, 250.0 * (1.0 - (r / (0.35 * L)) ** 2))
+    return Glacier(B=B, dx=dx, dy=dx, H0=H)
