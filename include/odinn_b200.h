@@ -1,0 +1,142 @@
+/*
+ * odinn_b200.h -- C ABI of libodinn_b200.so: the B200 (sm_100a) SIA2D hot path of ODINN.jl.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference (ODINN.jl v1.1.0,
+ * commit 31dfbf2) interface it replaces as  file:line  relative to the reference tree.
+ * Plain pointers and sizes only; no C++/torch types.  All matrices are Julia `Matrix`
+ * layout: column-major, element (i,j) at  ptr[i + j*ld],  i = 0..nx-1 the fast ("x") axis,
+ * ld >= nx in ELEMENTS.  Element type is the ensemble's dtype (Sleipnir.Float: Float64 by
+ * default, Float32 build -- test/SIA2D_adjoint_utils.jl:22).
+ *
+ * Ownership: the caller owns host buffers for the duration of a call only; the library owns
+ * every device buffer behind the handle.  A handle is bound to ONE CUDA device and ONE stream;
+ * calls on one handle must not overlap; different handles are independent (one handle per
+ * worker process = the reference's pmap worker, src/inverse/SIA2D/gradient.jl:9-10).
+ *
+ * Errors: every function returns 0 on success and a negative odinn_status otherwise; the
+ * message is available from odinn_last_error().  The library never calls exit/abort.
+ */
+#ifndef ODINN_B200_H
+#define ODINN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct odinn_ensemble odinn_ensemble;
+
+enum odinn_dtype { ODINN_F32 = 0, ODINN_F64 = 1 };
+
+enum odinn_status {
+    ODINN_OK = 0,
+    ODINN_EARG = -1,   /* bad argument (null pointer, size mismatch, index out of range) */
+    ODINN_ECUDA = -2,  /* a CUDA runtime call or kernel launch failed                    */
+    ODINN_ESTATE = -3, /* call sequence error (e.g. gradient before forward solve)       */
+    ODINN_ENOMEM = -4
+};
+
+/* Device-resident per-glacier planes that can be uploaded / downloaded. */
+enum odinn_field {
+    ODINN_FIELD_B = 0,       /* bedrock glacier.B                       (adjoint.jl:47)            */
+    ODINN_FIELD_H = 1,       /* state / ice thickness                                              */
+    ODINN_FIELD_DH = 2,      /* last RHS output                                                    */
+    ODINN_FIELD_LAMBDA = 3,  /* adjoint variable lambda                                            */
+    ODINN_FIELD_VJP_H = 4,   /* last dH-VJP output                                                 */
+    ODINN_FIELD_A = 5,       /* gridded creep coefficient on the dual grid, (nx-1) x (ny-1)        */
+    ODINN_FIELD_VJP_A = 6,   /* dual-grid integrand  (Gamma_noA Hbar^{n+2} gradS^{n-1}) * D_adj    */
+    ODINN_FIELD_H0 = 7,      /* initial condition of the forward solve                             */
+    ODINN_FIELD_COUNT_ = 8
+};
+
+/* params.physical + the scalar iceflow-cache entries read on the path
+ * (src/models/target/target_utils.jl:3-29, src/models/target/target_A.jl:22,
+ *  test/params_construction.jl:24-34). */
+typedef struct odinn_phys {
+    double rho;   /* ice density                    */
+    double g;     /* gravity                        */
+    double eta0;  /* flux-clamp factor  (adjoint.jl:92) */
+    double n;     /* Glen exponent                  */
+    double p;     /* Weertman exponents             */
+    double q;
+    double C;     /* sliding coefficient            */
+    double minA;  /* law output bounds (Laws.jl:337-338, target_utils.jl:109-113) */
+    double maxA;
+} odinn_phys;
+
+/* ---------------------------------------------------------------------------------------- */
+/* Lifetime / state behind the boundary                                                      */
+/* ---------------------------------------------------------------------------------------- */
+
+/* Build an ensemble of n_glaciers independent glaciers on CUDA device `device`.
+ * Replaces: the per-glacier state captured by `simulation` -- glacier.B, dx, dy, nx, ny
+ * (src/inverse/SIA2D/adjoint.jl:39-49) and init_cache (src/simulations/inversions/
+ * inversion_utils.jl:482-483).  One glacier == one pmap task of the reference. */
+int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, const int* ny,
+                          const double* dx, const double* dy, const odinn_phys* phys,
+                          odinn_ensemble** out);
+void odinn_ensemble_destroy(odinn_ensemble* e);
+
+/* Last error message of `e` (or of the calling thread's last failed create when e == NULL). */
+const char* odinn_last_error(const odinn_ensemble* e);
+
+int odinn_n_glaciers(const odinn_ensemble* e);
+int odinn_dtype_of(const odinn_ensemble* e);
+/* Count of CUDA kernels launched by this handle so far (bench.py's gpu_launches). */
+long long odinn_launch_count(const odinn_ensemble* e);
+int odinn_synchronize(odinn_ensemble* e);
+
+/* Copy one glacier's plane host <-> device.  Dual-grid fields are (nx-1) x (ny-1). */
+int odinn_upload(odinn_ensemble* e, int glacier, int field, const void* host, int ld);
+int odinn_download(odinn_ensemble* e, int glacier, int field, void* host, int ld);
+
+/* cache.iceflow.A.value as a glacier-wide scalar (ScalarCache, src/laws/Cache.jl:23-97). */
+int odinn_set_A_scalar(odinn_ensemble* e, int glacier, double A);
+/* Switch the ensemble between scalar A (0) and the gridded A field ODINN_FIELD_A (1)
+ * (MatrixCache; LawA(params; scalar=false), src/laws/Laws.jl:430-454). */
+int odinn_set_A_mode(odinn_ensemble* e, int gridded);
+int odinn_set_phys(odinn_ensemble* e, const odinn_phys* phys);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Reference-facing per-call operators (host buffers in, host buffers out)                   */
+/* ---------------------------------------------------------------------------------------- */
+
+/* dH <- SIA2D(H).  Replaces SIA2D_UDE!(dH, H, container, t) -> Huginn.SIA2D!
+ * (src/simulations/inversions/inversion_utils.jl:691-699).  Writes all nx*ny entries of dH
+ * (border = 0); never writes H. */
+int odinn_sia2d_rhs(odinn_ensemble* e, int glacier, const void* H, int ldH, void* dH, int lddH, double t);
+
+/* out <- (dSIA/dH)^T lambda.  Replaces VJP_lambda_dSIAdH(::DiscreteVJP, lambda, H, theta, simulation, t)
+ * (src/inverse/SIA2D/VJPs.jl:2-5 -> src/inverse/SIA2D/adjoint.jl:31-151). */
+int odinn_sia2d_vjp_H(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                      void* out, int ldo, double t);
+
+/* *out_S <- sum_ij (Gamma_noA Hbar^{n+2} gradS^{n-1})[i,j] * D_adj[i,j]  -- the glacier-wide
+ * contraction of VJP_lambda_dSIAdtheta(::DiscreteVJP, ...) (VJPs.jl:30-33 -> adjoint.jl:178-255,
+ * target_A.jl:64-92): d_theta = (dA/dtheta) * S.  With the gridded A mode the per-node integrand is
+ * left in ODINN_FIELD_VJP_A instead and *out_S is its sum. */
+int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                          double* out_S, double t);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Ensemble (batched) operators on device-resident planes                                    */
+/* ---------------------------------------------------------------------------------------- */
+
+/* FIELD_DH <- SIA2D(FIELD_H) for every glacier in one launch. */
+int odinn_rhs_resident(odinn_ensemble* e);
+/* flags bit0: FIELD_VJP_H <- (dSIA/dH)^T FIELD_LAMBDA ; bit1: per-glacier S (and FIELD_VJP_A).
+ * S_out may be NULL; otherwise n_glaciers doubles (device->host read inside the call). */
+int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
+
+/* One pmap batch through host buffers: for every glacier g upload H[g] (and lambda[g]), run
+ * F1 + A1 + A2, download dH[g], vjpH[g], S[g].  Any of dH / vjpH / S may be NULL to skip that
+ * output; lambda may be NULL when only dH is requested.  All matrices use ld = nx. */
+int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void* const* lambda,
+                             void* const* dH, void* const* vjpH, double* S);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODINN_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of ``libodinn_b200.so`` (the C ABI declared in ``include/odinn_b200.h``).
+
+The product path has NO CPU fallback: if the CUDA library is missing or no device is present,
+loading / creating an ensemble raises.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libodinn_b200.so")
+
+F32, F64 = 0, 1
+
+FIELD_B, FIELD_H, FIELD_DH, FIELD_LAMBDA, FIELD_VJP_H, FIELD_A, FIELD_VJP_A, FIELD_H0 = range(8)
+
+
+class Phys(C.Structure):
+    """``odinn_phys``: params.physical + iceflow-cache scalars (test/params_construction.jl:24-34)."""
+
+    _fields_ = [(k, C.c_double) for k in ("rho", "g", "eta0", "n", "p", "q", "C", "minA", "maxA")]
+
+    def __init__(self, rho=900.0, g=9.81, eta0=1.0, n=3.0, p=3.0, q=0.0, C=0.0, minA=8.5e-20, maxA=8e-17):
+        super().__init__(rho, g, eta0, n, p, q, C, minA, maxA)
+
+
+class OdinnError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); must list every symbol of include/odinn_b200.h
+SIGNATURES = {
+    "odinn_ensemble_create": (_i, [_i, _i, _i, _ip, _ip, _dp, _dp, C.POINTER(Phys), C.POINTER(_vp)]),
+    "odinn_ensemble_destroy": (None, [_vp]),
+    "odinn_last_error": (C.c_char_p, [_vp]),
+    "odinn_n_glaciers": (_i, [_vp]),
+    "odinn_dtype_of": (_i, [_vp]),
+    "odinn_launch_count": (C.c_longlong, [_vp]),
+    "odinn_synchronize": (_i, [_vp]),
+    "odinn_upload": (_i, [_vp, _i, _i, _vp, _i]),
+    "odinn_download": (_i, [_vp, _i, _i, _vp, _i]),
+    "odinn_set_A_scalar": (_i, [_vp, _i, _d]),
+    "odinn_set_A_mode": (_i, [_vp, _i]),
+    "odinn_set_phys": (_i, [_vp, C.POINTER(Phys)]),
+    "odinn_sia2d_rhs": (_i, [_vp, _i, _vp, _i, _vp, _i, _d]),
+    "odinn_sia2d_vjp_H": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _d]),
+    "odinn_sia2d_vjp_theta": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
+    "odinn_rhs_resident": (_i, [_vp]),
+    "odinn_vjp_resident": (_i, [_vp, _i, _dp]),
+    "odinn_fwd_adj_batch_host": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _dp]),
+}
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OdinnError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(handle, rc):
+    if rc != 0:
+        msg = load().odinn_last_error(handle)
+        raise OdinnError(f"libodinn_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,93 @@
+// Host-side state behind an odinn_ensemble handle: glacier descriptors, device planes, tile table.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/odinn_b200.h"
+#include "common.cuh"
+
+struct GlacierHost {
+    int nx, ny, ld;
+    long long off;
+    double dx, dy;
+    double A;
+    double temp;
+    int tile0, ntx, nty;
+};
+
+struct odinn_ensemble {
+    int device = 0;
+    int dtype = ODINN_F64;
+    int G = 0;
+    size_t esize = 8;
+    std::vector<GlacierHost> gl;
+    long long total = 0;  // elements per plane (padded)
+    long long cells = 0;  // Σ nx*ny
+    odinn_phys phys{};
+    bool cubic = false;   // n == 3 && C == 0
+    int a_gridded = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    void* plane[ODINN_FIELD_COUNT_] = {nullptr};
+    void* d_descs = nullptr;
+    bool descs_dirty = true;
+    int2* d_tiles = nullptr;
+    int* d_tile_start = nullptr;
+    int n_tiles = 0;
+    double* d_partial = nullptr;
+    double* d_S = nullptr;
+    double* h_S = nullptr;  // pinned
+    long long launches = 0;
+    std::string err;
+
+    // pinned staging for the batched host path (two slots per direction)
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+};
+
+namespace odinn {
+
+extern thread_local std::string g_create_error;
+
+inline int fail(odinn_ensemble* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define ODINN_CUDA(e, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _st = (call);                                                                        \
+        if (_st != cudaSuccess)                                                                          \
+            return odinn::fail((e), ODINN_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_st));   \
+    } while (0)
+
+#define ODINN_CHECK_LAUNCH(e)                                                                            \
+    do {                                                                                                 \
+        cudaError_t _st = cudaGetLastError();                                                            \
+        if (_st != cudaSuccess)                                                                          \
+            return odinn::fail((e), ODINN_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_st)); \
+        (e)->launches++;                                                                                 \
+    } while (0)
+
+template <typename T>
+inline PhysDev<T> make_phys(const odinn_phys& p) {
+    PhysDev<T> d;
+    d.n = (T)p.n;
+    d.p = (T)p.p;
+    d.q = (T)p.q;
+    d.Gam = (T)(2.0 * std::pow(p.rho * p.g, p.n) / (p.n + 2.0));  // target_utils.jl:3-13
+    d.Sl = (T)(p.C * std::pow(p.rho * p.g, p.p - p.q));           // target_utils.jl:15-19
+    d.eta0 = (T)p.eta0;
+    return d;
+}
+
+int ensure_plane(odinn_ensemble* e, int field);
+int sync_descs(odinn_ensemble* e);
+
+}  // namespace odinn

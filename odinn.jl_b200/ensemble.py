@@ -1,0 +1,132 @@
+"""Thin object wrapper over the C ABI: one ``Ensemble`` == one ``odinn_ensemble*`` handle.
+
+An ensemble is the batch of independent glaciers one worker owns -- the unit the reference maps
+with ``pmap`` (src/inverse/SIA2D/gradient.jl:9-10, src/models/trainable_components/ML_utils.jl:135-144).
+Matrices cross the boundary exactly as Julia stores them: column-major ``(nx, ny)``, ``i`` fastest.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import Phys
+
+
+def _np_dtype(dtype):
+    return np.float32 if dtype == _capi.F32 else np.float64
+
+
+def _as_f(a, npdt):
+    """Column-major contiguous view/copy (what a Julia ``Matrix`` pointer is)."""
+    return np.asfortranarray(a, dtype=npdt)
+
+
+class Ensemble:
+    def __init__(self, nx: Sequence[int], ny: Sequence[int], dx: Sequence[float], dy: Sequence[float],
+                 phys: Optional[Phys] = None, dtype: str = "f64", device: int = 0):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        self.dtype_code = {"f32": _capi.F32, "f64": _capi.F64}[dtype]
+        self.np_dtype = _np_dtype(self.dtype_code)
+        self.G = len(nx)
+        self.nx, self.ny = [int(v) for v in nx], [int(v) for v in ny]
+        self.phys = phys if phys is not None else Phys()
+        ia = (C.c_int * self.G)(*self.nx)
+        ja = (C.c_int * self.G)(*self.ny)
+        da = (C.c_double * self.G)(*[float(v) for v in dx])
+        db = (C.c_double * self.G)(*[float(v) for v in dy])
+        rc = self._lib.odinn_ensemble_create(int(device), self.dtype_code, self.G, ia, ja, da, db, C.byref(self.phys),
+                                             C.byref(self._h))
+        _capi.check(None, rc)
+
+    # -- lifetime --------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.odinn_ensemble_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _capi.check(self._h, rc)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.odinn_launch_count(self._h))
+
+    def synchronize(self):
+        self._ck(self._lib.odinn_synchronize(self._h))
+
+    # -- state -----------------------------------------------------------------------------
+    def upload(self, g: int, field: int, a):
+        a = _as_f(a, self.np_dtype)
+        self._ck(self._lib.odinn_upload(self._h, g, field, a.ctypes.data, a.shape[0]))
+
+    def download(self, g: int, field: int):
+        dual = field in (_capi.FIELD_A, _capi.FIELD_VJP_A)
+        shape = (self.nx[g] - 1, self.ny[g] - 1) if dual else (self.nx[g], self.ny[g])
+        out = np.empty(shape, dtype=self.np_dtype, order="F")
+        self._ck(self._lib.odinn_download(self._h, g, field, out.ctypes.data, shape[0]))
+        return out
+
+    def set_A_scalar(self, g: int, A: float):
+        self._ck(self._lib.odinn_set_A_scalar(self._h, g, float(A)))
+
+    def set_A_field(self, g: int, A):
+        self._ck(self._lib.odinn_set_A_mode(self._h, 1))
+        self.upload(g, _capi.FIELD_A, A)
+
+    def set_A_mode(self, gridded: bool):
+        self._ck(self._lib.odinn_set_A_mode(self._h, int(bool(gridded))))
+
+    def set_phys(self, phys: Phys):
+        self.phys = phys
+        self._ck(self._lib.odinn_set_phys(self._h, C.byref(self.phys)))
+
+    # -- reference-facing per-call operators (host in, host out) ----------------------------------
+    def sia2d_rhs(self, g: int, H, t: float = 0.0, out=None):
+        H = _as_f(H, self.np_dtype)
+        dH = np.empty_like(H, order="F") if out is None else out
+        self._ck(self._lib.odinn_sia2d_rhs(self._h, g, H.ctypes.data, H.shape[0], dH.ctypes.data, dH.shape[0], float(t)))
+        return dH
+
+    def sia2d_vjp_H(self, g: int, lam, H, t: float = 0.0):
+        H = _as_f(H, self.np_dtype)
+        lam = _as_f(lam, self.np_dtype)
+        out = np.empty_like(H, order="F")
+        self._ck(self._lib.odinn_sia2d_vjp_H(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
+                                             out.ctypes.data, out.shape[0], float(t)))
+        return out
+
+    def sia2d_vjp_theta(self, g: int, lam, H, t: float = 0.0) -> float:
+        H = _as_f(H, self.np_dtype)
+        lam = _as_f(lam, self.np_dtype)
+        S = C.c_double(0.0)
+        self._ck(self._lib.odinn_sia2d_vjp_theta(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
+                                                 C.byref(S), float(t)))
+        return S.value
+
+    # -- device-resident ensemble operators ---------------------------------------------------
+    def rhs_resident(self):
+        self._ck(self._lib.odinn_rhs_resident(self._h))
+
+    def vjp_resident(self, want_H=True, want_S=True, read_S=True):
+        flags = (1 if want_H else 0) | (2 if want_S else 0)
+        if want_S and read_S:
+            S = np.empty(self.G, dtype=np.float64)
+            self._ck(self._lib.odinn_vjp_resident(self._h, flags, S.ctypes.data_as(C.POINTER(C.c_double))))
+            return S
+        self._ck(self._lib.odinn_vjp_resident(self._h, flags, None))
+        return None
+
+    def fwd_adj_batch_host(self, H_ptrs, lam_ptrs, dH_ptrs, vjpH_ptrs, S):
+        """Raw-pointer batched call (bench e2e path).  Each ``*_ptrs`` is a ctypes ``c_void_p`` array or None."""
+        sp = S.ctypes.data_as(C.POINTER(C.c_double)) if S is not None else None
+        self._ck(self._lib.odinn_fwd_adj_batch_host(self._h, H_ptrs, lam_ptrs, dH_ptrs, vjpH_ptrs, sp))

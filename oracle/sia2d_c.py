@@ -1,0 +1,77 @@
+"""ctypes binding of the C oracle (oracle/sia2d_c.c) -- TEST INFRASTRUCTURE / CPU BASELINE ONLY."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_build", "libsia2d_oracle.so")
+
+
+class _Par64(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("dx", "dy", "eta0", "n", "p", "q", "rho", "g", "C", "A")] + [("Afield", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            import sys
+
+            sys.path.insert(0, os.path.dirname(_HERE))
+            import __graft_entry__ as ge
+
+            ge.build_oracle()
+        _lib = C.CDLL(SO)
+        _lib.sia2d_oracle_threads.restype = C.c_int
+    return _lib
+
+
+def threads():
+    return int(lib().sia2d_oracle_threads())
+
+
+def _par(dx, dy, ph, A, npdt):
+    p = _Par64(dx, dy, ph.eta0, ph.n, ph.p, ph.q, ph.rho, ph.g, ph.C, 0.0, None)
+    keep = None
+    if np.ndim(A) == 2:
+        keep = np.asfortranarray(A, dtype=npdt)
+        p.Afield = keep.ctypes.data
+    else:
+        p.A = float(A)
+    return p, keep
+
+
+def rhs(H, B, dx, dy, ph, A, dtype=np.float64):
+    """F1 on one glacier; arrays are (nx, ny), returned column-major."""
+    H = np.asfortranarray(H, dtype=dtype)
+    B = np.asfortranarray(B, dtype=dtype)
+    nx, ny = H.shape
+    out = np.empty((nx, ny), dtype=dtype, order="F")
+    work = np.empty((nx - 1) * (ny - 1), dtype=dtype)
+    p, keep = _par(dx, dy, ph, A, dtype)
+    fn = lib().sia2d_rhs_f64 if dtype == np.float64 else lib().sia2d_rhs_f32
+    fn(C.c_int(nx), C.c_int(ny), C.c_void_p(H.ctypes.data), C.c_void_p(B.ctypes.data), C.c_void_p(out.ctypes.data),
+       C.c_void_p(work.ctypes.data), C.byref(p))
+    return out
+
+
+def vjp(lam, H, B, dx, dy, ph, A, dtype=np.float64, want_H=True, want_field=False):
+    """A1 + A2 on one glacier: returns (vjp_H or None, S, vjpA field or None)."""
+    H = np.asfortranarray(H, dtype=dtype)
+    B = np.asfortranarray(B, dtype=dtype)
+    lam = np.asfortranarray(lam, dtype=dtype)
+    nx, ny = H.shape
+    out = np.empty((nx, ny), dtype=dtype, order="F") if want_H else None
+    fld = np.empty((nx - 1, ny - 1), dtype=dtype, order="F") if want_field else None
+    work = np.empty(4 * (nx - 1) * (ny - 1), dtype=dtype)
+    S = C.c_double(0.0)
+    p, keep = _par(dx, dy, ph, A, dtype)
+    fn = lib().sia2d_vjp_f64 if dtype == np.float64 else lib().sia2d_vjp_f32
+    fn(C.c_int(nx), C.c_int(ny), C.c_void_p(lam.ctypes.data), C.c_void_p(H.ctypes.data), C.c_void_p(B.ctypes.data),
+       C.c_void_p(out.ctypes.data if want_H else None), C.byref(S), C.c_void_p(fld.ctypes.data if want_field else None),
+       C.c_void_p(work.ctypes.data), C.byref(p))
+    return out, S.value, fld

@@ -1,0 +1,219 @@
+"""GPU parity: the CUDA path (through the C ABI) against the NumPy oracle on the same inputs.
+
+Tolerances: fp64 kernel vs fp64 oracle rel-L2 <= 1e-12 per call
+(the reference's operator tests use rtol 1e-11, test/SIA2D_adjoint_utils.jl:22); fp32 kernel vs
+fp64 oracle evaluated on the SAME fp32-rounded inputs rel-L2 <= 1e-5 (the reference's fp32 rtol).
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import sia2d_numpy as o
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-12, "f32": 1e-5}
+A0 = 2.21e-18  # test/test_grad_loss.jl:157
+
+
+def _tilted_dome(nx, ny):
+    g = o.dome_glacier(nx, ny)
+    X = np.arange(nx)[:, None] * g.dx
+    Y = np.arange(ny)[None, :] * g.dy
+    g.B = 0.03 * X + 0.011 * Y
+    return g
+
+
+def _noisy(nx, ny):
+    """Rough bed + noisy thickness with holes: many clamp-active edges and H = 0 cells inside the ice."""
+    g = o.rough_bed_glacier(nx, ny)
+    rng = np.random.default_rng(7)
+    H = g.H0 * (1.0 + 0.3 * rng.standard_normal(g.H0.shape))
+    H[rng.random(H.shape) < 0.05] = 0.0
+    H[rng.random(H.shape) < 0.02] = -3.0  # negative input must be clipped, not propagated (adjoint.jl:52)
+    g.H0 = H
+    return g
+
+
+MAKERS = {"rough": o.rough_bed_glacier, "dome": o.dome_glacier, "tilted": _tilted_dome, "noisy": _noisy}
+
+
+def _round_inputs(g, H, lam, dtype):
+    """Inputs as the kernel sees them (fp32 rounding applied before the fp64 oracle runs)."""
+    npdt = np.float32 if dtype == "f32" else np.float64
+    g2 = o.Glacier(B=g.B.astype(npdt).astype(np.float64), dx=g.dx, dy=g.dy)
+    return g2, H.astype(npdt).astype(np.float64), lam.astype(npdt).astype(np.float64)
+
+
+def _sim(ob, g, phys_kw, A, dtype):
+    return ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy)], ob.Phys(**phys_kw), A=A, dtype=dtype)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import odinn_b200
+
+    return odinn_b200
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("maker", list(MAKERS))
+@pytest.mark.parametrize("shape", [(14, 17), (3, 3), (3, 41), (40, 3), (33, 47), (128, 128), (97, 64)])
+def test_forward_and_vjps_match_oracle(ob, dtype, maker, shape):
+    nx, ny = shape
+    g = MAKERS[maker](nx, ny)
+    lam = np.random.default_rng(1234).standard_normal((nx, ny))
+    g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+    tg = o.TargetA(o.Phys(), "const", A=A0)
+    sim = _sim(ob, g, {}, A0, dtype)
+    try:
+        dH = np.full((nx, ny), np.nan, order="F")
+        Hin = H.copy()
+        ob.SIA2D_(dH, Hin, sim, 0.0)
+        assert np.array_equal(Hin, H)  # the RHS must not mutate H (docs/src/sensitivity.md:83)
+        ref = o.SIA2D(H, g, tg)
+        assert rel_l2(dH, ref) <= TOL[dtype], ("rhs", rel_l2(dH, ref))
+        # border rows/columns are exactly zero
+        assert np.all(dH[0, :] == 0) and np.all(dH[-1, :] == 0) and np.all(dH[:, 0] == 0) and np.all(dH[:, -1] == 0)
+
+        vH, none = ob.VJP_λ_dSIAdH(ob.B200VJP(), lam, H, None, sim, 0.0)
+        assert none is None
+        refv = o.VJP_dSIA_dH_discrete(lam, H, g, tg)
+        assert rel_l2(vH, refv) <= TOL[dtype], ("vjp_H", rel_l2(vH, refv))
+        assert np.all(vH[np.maximum(H, 0) <= 0] == 0)  # adjoint.jl:148
+
+        S = ob.VJP_λ_dSIAdθ(ob.B200VJP(), lam, H, None, None, sim, 0.0)
+        refS = o.node_reduction_S(lam, H, g, tg)
+        assert abs(S - refS) <= max(TOL[dtype] * 10, 0) * max(abs(refS), 1e-300) or abs(refS) == 0.0, ("vjp_theta", S, refS)
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("phys_kw", [dict(C=7e-8), dict(n=3.5), dict(n=4.0, C=3e-9, p=2.5, q=0.5), dict(eta0=0.3)])
+def test_generic_exponents_and_sliding(ob, dtype, phys_kw):
+    """The pow() path: sliding term C != 0 (test/runtests.jl:94,99) and non-cubic Glen exponents."""
+    nx, ny = 37, 29
+    g = o.rough_bed_glacier(nx, ny)
+    lam = np.random.default_rng(1234).standard_normal((nx, ny))
+    g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+    tg = o.TargetA(o.Phys(**phys_kw), "const", A=A0)
+    sim = _sim(ob, g, phys_kw, A0, dtype)
+    tol = TOL[dtype] * (4 if dtype == "f32" else 1)
+    try:
+        dH = np.zeros((nx, ny), order="F")
+        ob.SIA2D_(dH, H, sim, 0.0)
+        assert rel_l2(dH, o.SIA2D(H, g, tg)) <= tol
+        vH, _ = ob.VJP_λ_dSIAdH(ob.B200VJP(), lam, H, None, sim, 0.0)
+        assert rel_l2(vH, o.VJP_dSIA_dH_discrete(lam, H, g, tg)) <= tol
+        S = ob.VJP_λ_dSIAdθ(ob.B200VJP(), lam, H, None, None, sim, 0.0)
+        refS = o.node_reduction_S(lam, H, g, tg)
+        assert abs(S - refS) <= 10 * tol * abs(refS)
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_gridded_A(ob, dtype):
+    """Spatially varying A on the dual grid (MatrixCache; LawA(params; scalar=false), Laws.jl:430-454)."""
+    nx, ny = 45, 38
+    g = o.rough_bed_glacier(nx, ny)
+    rng = np.random.default_rng(5)
+    Afield = A0 * np.exp(rng.uniform(-1, 1, size=(nx - 1, ny - 1)))
+    lam = rng.standard_normal((nx, ny))
+    g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+    if dtype == "f32":
+        Afield = Afield.astype(np.float32).astype(np.float64)
+    tg = o.TargetA(o.Phys(), "const", A=Afield)
+    sim = _sim(ob, g, {}, [Afield], dtype)
+    try:
+        dH = np.zeros((nx, ny), order="F")
+        ob.SIA2D_(dH, H, sim, 0.0)
+        assert rel_l2(dH, o.SIA2D(H, g, tg)) <= TOL[dtype]
+        vH, _ = ob.VJP_λ_dSIAdH(ob.B200VJP(), lam, H, None, sim, 0.0)
+        assert rel_l2(vH, o.VJP_dSIA_dH_discrete(lam, H, g, tg)) <= TOL[dtype]
+        # per-node integrand ∂A_spatial ∘ D† (sparse_cartesian_tensor path, target_utils.jl:163-173)
+        f = o._recompute_forward(H, g, tg, None)
+        _, _, Dadj = o._D_adjoint(lam, f, g.dx, g.dy)
+        ref_field = o.Gamma(tg.ph) * f["Hb"] ** 5 * f["gS"] ** 2 * Dadj
+        S = ob.VJP_λ_dSIAdθ(ob.B200VJP(), lam, H, None, None, sim, 0.0)
+        from odinn_b200 import _capi
+
+        got = sim.ensemble.download(0, _capi.FIELD_VJP_A)
+        assert rel_l2(got, ref_field) <= TOL[dtype]
+        assert abs(S - ref_field.sum()) <= 10 * TOL[dtype] * abs(ref_field.sum())
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_mixed_size_ensemble_batch(ob, dtype):
+    """One launch over a ragged ensemble (config 3 in miniature) == per-glacier oracle results."""
+    rng = np.random.default_rng(2024)
+    shapes = [(int(rng.integers(20, 90)), int(rng.integers(20, 90))) for _ in range(7)] + [(3, 3), (32, 16), (33, 17)]
+    gl, Hs, lams, As = [], [], [], []
+    for k, (nx, ny) in enumerate(shapes):
+        g = (o.rough_bed_glacier if k % 2 else _tilted_dome)(nx, ny)
+        lam = rng.standard_normal((nx, ny))
+        g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+        gl.append(g), Hs.append(H), lams.append(lam), As.append(A0 * (1 + k))
+    sim = ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy) for g in gl], ob.Phys(), A=As, dtype=dtype)
+    from odinn_b200 import _capi
+
+    try:
+        ens = sim.ensemble
+        for k in range(len(gl)):
+            ens.upload(k, _capi.FIELD_H, Hs[k])
+            ens.upload(k, _capi.FIELD_LAMBDA, lams[k])
+        ens.rhs_resident()
+        S = ens.vjp_resident(True, True)
+        for k, g in enumerate(gl):
+            tg = o.TargetA(o.Phys(), "const", A=As[k])
+            assert rel_l2(ens.download(k, _capi.FIELD_DH), o.SIA2D(Hs[k], g, tg)) <= TOL[dtype], k
+            assert rel_l2(ens.download(k, _capi.FIELD_VJP_H), o.VJP_dSIA_dH_discrete(lams[k], Hs[k], g, tg)) <= TOL[dtype], k
+            refS = o.node_reduction_S(lams[k], Hs[k], g, tg)
+            assert abs(S[k] - refS) <= 10 * TOL[dtype] * abs(refS) or refS == 0.0, k
+        # determinism: the two-stage reduction is bit-stable run to run
+        S2 = ens.vjp_resident(True, True)
+        assert np.array_equal(S, S2)
+    finally:
+        sim.close()
+
+
+def test_vjp_is_transpose_of_jacobian_at_scale(ob):
+    """Size-independent property at BASELINE config-2 size (500x500): <J v, λ> == <v, Jᵀ λ> with the
+    directional derivative taken by central differences of the CUDA forward (fp64)."""
+    nx = ny = 500
+    g = _tilted_dome(nx, ny)
+    rng = np.random.default_rng(1234)
+    lam = rng.standard_normal((nx, ny))
+    v = rng.standard_normal((nx, ny)) * (g.H0 > 5.0)  # stay away from the H = 0 kink
+    sim = _sim(ob, g, {}, A0, "f64")
+    try:
+        eps = 1e-4
+        dp = np.zeros((nx, ny), order="F")
+        dm = np.zeros((nx, ny), order="F")
+        ob.SIA2D_(dp, g.H0 + eps * v, sim, 0.0)
+        ob.SIA2D_(dm, g.H0 - eps * v, sim, 0.0)
+        lhs = np.sum((dp - dm) / (2 * eps) * lam)
+        vH, _ = ob.VJP_λ_dSIAdH(ob.B200VJP(), lam, g.H0, None, sim, 0.0)
+        rhs = np.sum(vH * v)
+        assert abs(lhs - rhs) <= 1e-6 * abs(rhs), (lhs, rhs)
+        # mass conservation of the forward: Σ dH == 0 up to rounding when no ice touches the border
+        d0 = np.zeros((nx, ny), order="F")
+        ob.SIA2D_(d0, g.H0, sim, 0.0)
+        assert abs(d0.sum()) <= 1e-9 * np.abs(d0).sum()
+    finally:
+        sim.close()
+
+
+def test_error_convention(ob):
+    """Nonzero return code -> exception carrying odinn_last_error (never exit)."""
+    with pytest.raises(ob.OdinnError):
+        ob.Ensemble([2], [5], [50.0], [50.0])  # grid smaller than 3x3
+    sim = _sim(ob, o.rough_bed_glacier(8, 9), {}, A0, "f64")
+    try:
+        with pytest.raises(ob.OdinnError):
+            sim.ensemble.sia2d_rhs(3, np.zeros((8, 9)))  # glacier index out of range
+    finally:
+        sim.close()
