@@ -87,6 +87,9 @@ int odinn_dtype_of(const odinn_ensemble* e);
 /* Count of CUDA kernels launched by this handle so far (bench.py's gpu_launches). */
 long long odinn_launch_count(const odinn_ensemble* e);
 int odinn_synchronize(odinn_ensemble* e);
+/* The handle's cudaStream_t (as void*): every kernel and copy of this handle is issued on it, so device-side
+ * timing (CUDA events) must be recorded on this stream. */
+void* odinn_stream(odinn_ensemble* e);
 
 /* Copy one glacier's plane host <-> device.  Dual-grid fields are (nx-1) x (ny-1). */
 int odinn_upload(odinn_ensemble* e, int glacier, int field, const void* host, int ld);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "odinn_dtype_of": (_i, [_vp]),
     "odinn_launch_count": (C.c_longlong, [_vp]),
     "odinn_synchronize": (_i, [_vp]),
+    "odinn_stream": (_vp, [_vp]),
     "odinn_upload": (_i, [_vp, _i, _i, _vp, _i]),
     "odinn_download": (_i, [_vp, _i, _i, _vp, _i]),
     "odinn_set_A_scalar": (_i, [_vp, _i, _d]),

@@ -28,6 +28,8 @@ static int sync_descs_t(odinn_ensemble* e) {
         d.ny = s.ny;
         d.ld = s.ld;
         d.tile0 = s.tile0;
+        d.dx = (T)s.dx;
+        d.dy = (T)s.dy;
         d.inv_dx = (T)(1.0 / s.dx);
         d.inv_dy = (T)(1.0 / s.dy);
         d.A = (T)s.A;
@@ -280,6 +282,8 @@ const char* odinn_last_error(const odinn_ensemble* e) { return e ? e->err.c_str(
 int odinn_n_glaciers(const odinn_ensemble* e) { return e ? e->G : 0; }
 int odinn_dtype_of(const odinn_ensemble* e) { return e ? e->dtype : -1; }
 long long odinn_launch_count(const odinn_ensemble* e) { return e ? e->launches : 0; }
+
+void* odinn_stream(odinn_ensemble* e) { return e ? (void*)e->stream : nullptr; }
 
 int odinn_synchronize(odinn_ensemble* e) {
     GUARD(e);

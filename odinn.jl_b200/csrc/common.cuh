@@ -16,7 +16,7 @@ template <typename T>
 struct GDesc {
     long long off;
     int nx, ny, ld, tile0;  // tile0: index of this glacier's first tile in the tile table
-    T inv_dx, inv_dy;
+    T dx, dy, inv_dx, inv_dy;
     T A;     // glacier-wide creep coefficient (cache.iceflow.A.value, ScalarCache)
     T temp;  // long-term air temperature fed to the A law (Laws.jl:348-358)
 };

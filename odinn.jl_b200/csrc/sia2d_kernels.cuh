@@ -40,6 +40,18 @@ __device__ __forceinline__ T clamp_raw(T dS, T eta0, T H_lo, T H_up) {
     return tmax(tmin(dS, eta0 * H_up), -(eta0 * H_lo));
 }
 
+// Strict comparisons of the clamp sub-gradient (inversion_utils.jl:24-28, 38-42).  The reference compares the
+// DIVIDED quantities  dS/Δ  and  ±η₀H/Δ ; two raw values one ulp apart can round to the same quotient, which
+// turns a strict inequality into a tie (this happens on structured inputs: a margin edge over a locally flat
+// bed).  The kernels work with raw differences, so fp64 re-checks near-ties with true divisions (rare, divergent
+// slow path) to take the same branch as the reference; fp32 is only ever compared within 1e-5 and skips it.
+__device__ __forceinline__ bool gt_div(double x, double y, double d) {
+    if (!(x > y)) return false;
+    if ((x - y) > 1e-14 * fmax(fabs(x), fabs(y))) return true;
+    return (x / d) > (y / d);
+}
+__device__ __forceinline__ bool gt_div(float x, float y, float) { return x > y; }
+
 // Stage one (TX+2) x (TY+2) tile of max(H,0) and B in shared memory; zero outside the grid.
 template <typename T>
 __device__ __forceinline__ void load_cells(const GDesc<T>& d, int x0, int y0, const T* __restrict__ H,
@@ -243,29 +255,29 @@ sia2d_vjp_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ ti
                         T dS = sdiff<T>(bc, bw, hc, hw);
                         T dC = -((lc - lw) * d.inv_dx) * (T(0.5) * (d00 + d01));
                         T up = ph.eta0 * hc, lo = -(ph.eta0 * hw);
-                        if (dS < up && dS > lo) t2 += dC * d.inv_dx;   // +∂dS[i-1]/Δx
-                        if (dS > up) t2 += e_dx * dC;
+                        if (gt_div(up, dS, d.dx) && gt_div(dS, lo, d.dx)) t2 += dC * d.inv_dx;   // +∂dS[i-1]/Δx
+                        if (gt_div(dS, up, d.dx)) t2 += e_dx * dC;
                     }
                     {   // east x-edge (i,j): this cell is the LOWER cell
                         T dS = sdiff<T>(be, bc, he, hc);
                         T dC = -((le - lc) * d.inv_dx) * (T(0.5) * (d10 + d11));
                         T up = ph.eta0 * he, lo = -(ph.eta0 * hc);
-                        if (dS < up && dS > lo) t2 -= dC * d.inv_dx;   // -∂dS[i]/Δx
-                        if (dS < lo) t2 -= e_dx * dC;
+                        if (gt_div(up, dS, d.dx) && gt_div(dS, lo, d.dx)) t2 -= dC * d.inv_dx;   // -∂dS[i]/Δx
+                        if (gt_div(lo, dS, d.dx)) t2 -= e_dx * dC;
                     }
                     {   // south y-edge (i,j-1): UPPER cell
                         T dS = sdiff<T>(bc, bs, hc, hs);
                         T dC = -((lc - ls) * d.inv_dy) * (T(0.5) * (d00 + d10));
                         T up = ph.eta0 * hc, lo = -(ph.eta0 * hs);
-                        if (dS < up && dS > lo) t2 += dC * d.inv_dy;
-                        if (dS > up) t2 += e_dy * dC;
+                        if (gt_div(up, dS, d.dy) && gt_div(dS, lo, d.dy)) t2 += dC * d.inv_dy;
+                        if (gt_div(dS, up, d.dy)) t2 += e_dy * dC;
                     }
                     {   // north y-edge (i,j): LOWER cell
                         T dS = sdiff<T>(bn, bc, hn, hc);
                         T dC = -((ln - lc) * d.inv_dy) * (T(0.5) * (d01 + d11));
                         T up = ph.eta0 * hn, lo = -(ph.eta0 * hc);
-                        if (dS < up && dS > lo) t2 -= dC * d.inv_dy;
-                        if (dS < lo) t2 -= e_dy * dC;
+                        if (gt_div(up, dS, d.dy) && gt_div(dS, lo, d.dy)) t2 -= dC * d.inv_dy;
+                        if (gt_div(lo, dS, d.dy)) t2 -= e_dy * dC;
                     }
                     res = t1 + t2;
                 }

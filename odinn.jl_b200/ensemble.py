@@ -61,6 +61,11 @@ class Ensemble:
     def launch_count(self) -> int:
         return int(self._lib.odinn_launch_count(self._h))
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this handle (record timing events on it)."""
+        return int(self._lib.odinn_stream(self._h) or 0)
+
     def synchronize(self):
         self._ck(self._lib.odinn_synchronize(self._h))
 
