@@ -1,6 +1,8 @@
 // C ABI of libodinn_b200.so (see include/odinn_b200.h for the reference interfaces replaced).
 #include "ensemble.cuh"
 #include "sia2d_kernels.cuh"
+#include "sia2d_march.cuh"
+#include <cstdlib>
 
 namespace odinn {
 
@@ -52,14 +54,21 @@ static void refresh_phys(odinn_ensemble* e) { e->cubic = (e->phys.n == 3.0 && e-
 // ---- launches -----------------------------------------------------------------------------
 
 template <typename T>
-static int launch_rhs_t(odinn_ensemble* e, const int2* tiles, int n_tiles) {
+static int launch_rhs_t(odinn_ensemble* e, const int2* tiles, int n_tiles, const int4* items, int n_items) {
     PhysDev<T> ph = make_phys<T>(e->phys);
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
     const T* H = (const T*)e->plane[ODINN_FIELD_H];
     const T* B = (const T*)e->plane[ODINN_FIELD_B];
     const T* Af = (const T*)e->plane[ODINN_FIELD_A];
     T* dH = (T*)e->plane[ODINN_FIELD_DH];
-#define L(CUB, AF) sia2d_rhs_kernel<T, CUB, AF><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, H, B, Af, dH, ph)
+#define L(CUB, AF)                                                                                         \
+    do {                                                                                                   \
+        if (e->use_tiled)                                                                                  \
+            sia2d_rhs_kernel<T, CUB, AF><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, H, B, Af, dH, ph);   \
+        else                                                                                               \
+            sia2d_rhs_march<T, CUB, AF><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
+                descs, items, n_items, H, B, Af, dH, ph);                                                  \
+    } while (0)
     if (e->cubic) {
         if (e->a_gridded) L(true, true); else L(true, false);
     } else {
@@ -71,19 +80,26 @@ static int launch_rhs_t(odinn_ensemble* e, const int2* tiles, int n_tiles) {
 }
 
 // tile range [t0, t0+n_tiles): the whole ensemble or one glacier
-static int launch_rhs(odinn_ensemble* e, int t0, int n_tiles) {
+static int launch_rhs(odinn_ensemble* e, int g) {
+    int t0 = 0, n_tiles = e->n_tiles, i0 = 0, n_items = e->n_items;
+    if (g >= 0) {
+        t0 = e->gl[g].tile0;
+        n_tiles = e->gl[g].ntx * e->gl[g].nty;
+        i0 = e->gl[g].item0;
+        n_items = e->gl[g].n_items;
+    }
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_B)) ||
         (rc = ensure_plane(e, ODINN_FIELD_DH)))
         return rc;
     if (e->a_gridded && (rc = ensure_plane(e, ODINN_FIELD_A))) return rc;
     if ((rc = sync_descs(e))) return rc;
-    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, e->d_tiles + t0, n_tiles)
-                                 : launch_rhs_t<double>(e, e->d_tiles + t0, n_tiles);
+    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, e->d_tiles + t0, n_tiles, e->d_items + i0, n_items)
+                                 : launch_rhs_t<double>(e, e->d_tiles + t0, n_tiles, e->d_items + i0, n_items);
 }
 
 template <typename T>
-static int launch_vjp_t(odinn_ensemble* e, int t0, int n_tiles, bool wH, bool wS) {
+static int launch_vjp_t(odinn_ensemble* e, int t0, int n_tiles, int i0, int n_items, bool wH, bool wS) {
     PhysDev<T> ph = make_phys<T>(e->phys);
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
     const int2* tiles = e->d_tiles + t0;
@@ -93,9 +109,17 @@ static int launch_vjp_t(odinn_ensemble* e, int t0, int n_tiles, bool wH, bool wS
     const T* Af = (const T*)e->plane[ODINN_FIELD_A];
     T* out = (T*)e->plane[ODINN_FIELD_VJP_H];
     T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
-    double* partial = e->d_partial + t0;
-#define L(CUB, AF, WH, WS) \
-    sia2d_vjp_kernel<T, CUB, AF, WH, WS><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, lam, H, B, Af, out, vjpA, partial, ph)
+    double* partial = e->d_partial + (e->use_tiled ? t0 : i0);
+    const int4* items = e->d_items + i0;
+#define L(CUB, AF, WH, WS)                                                                                           \
+    do {                                                                                                             \
+        if (e->use_tiled)                                                                                            \
+            sia2d_vjp_kernel<T, CUB, AF, WH, WS><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, lam, H, B, Af, out,    \
+                                                                                vjpA, partial, ph);                  \
+        else                                                                                                         \
+            sia2d_vjp_march<T, CUB, AF, WH, WS><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>(   \
+                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph);                                       \
+    } while (0)
 #define L2(CUB, AF)                        \
     do {                                   \
         if (wH && wS) L(CUB, AF, true, true);   \
@@ -124,18 +148,22 @@ static int launch_vjp(odinn_ensemble* e, int g, bool wH, bool wS) {
     if (e->a_gridded && ((rc = ensure_plane(e, ODINN_FIELD_A)) || (wS && (rc = ensure_plane(e, ODINN_FIELD_VJP_A)))))
         return rc;
     if ((rc = sync_descs(e))) return rc;
-    int t0 = 0, nt = e->n_tiles;
+    int t0 = 0, nt = e->n_tiles, i0 = 0, ni = e->n_items;
     if (g >= 0) {
         t0 = e->gl[g].tile0;
         nt = e->gl[g].ntx * e->gl[g].nty;
+        i0 = e->gl[g].item0;
+        ni = e->gl[g].n_items;
     }
-    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, t0, nt, wH, wS) : launch_vjp_t<double>(e, t0, nt, wH, wS);
+    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, t0, nt, i0, ni, wH, wS)
+                               : launch_vjp_t<double>(e, t0, nt, i0, ni, wH, wS);
     if (rc) return rc;
     if (wS) {
+        const int* starts = e->use_tiled ? e->d_tile_start : e->d_item_start;
         if (g >= 0)
-            reduce_tiles_kernel<<<1, NT, 0, e->stream>>>(e->d_tile_start + g, e->d_partial, e->d_S + g);
+            reduce_items_kernel<<<1, NT, 0, e->stream>>>(starts + g, e->d_partial, e->d_S + g);
         else
-            reduce_tiles_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, e->d_S);
+            reduce_items_kernel<<<e->G, NT, 0, e->stream>>>(starts, e->d_partial, e->d_S);
         ODINN_CHECK_LAUNCH(e);
     }
     return ODINN_OK;
@@ -222,6 +250,31 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     }
     e->total = off;
     e->n_tiles = tile;
+    {
+        const char* k = std::getenv("ODINN_KERNEL");
+        e->use_tiled = (k && std::string(k) == "tiled") ? 1 : 0;
+    }
+    // Marching work items: strips of STRIP output columns x chunks of rows.  Shorter chunks for small
+    // ensembles so that the grid still fills 148 SMs.
+    std::vector<int4> items;
+    std::vector<int> istart(n_glaciers + 1);
+    for (int rows = 32; rows >= 8; rows /= 2) {
+        long long n = 0;
+        for (int g = 0; g < n_glaciers; ++g) n += (long long)div_up(e->gl[g].nx, STRIP) * div_up(e->gl[g].ny, rows);
+        e->chunk_rows = rows;
+        if (n >= 148LL * 48) break;
+    }
+    for (int g = 0; g < n_glaciers; ++g) {
+        GlacierHost& s = e->gl[g];
+        s.item0 = (int)items.size();
+        istart[g] = s.item0;
+        for (int r0 = 0; r0 < s.ny; r0 += e->chunk_rows)
+            for (int st = 0; st < div_up(s.nx, STRIP); ++st)
+                items.push_back(make_int4(g, st * STRIP - 1, r0, std::min(r0 + e->chunk_rows, s.ny)));
+        s.n_items = (int)items.size() - s.item0;
+    }
+    istart[n_glaciers] = (int)items.size();
+    e->n_items = (int)items.size();
 
     std::vector<int2> tiles(tile);
     std::vector<int> tstart(n_glaciers + 1);
@@ -249,7 +302,11 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     CREATE_CUDA(cudaMalloc(&e->d_descs, dsz * n_glaciers));
     CREATE_CUDA(cudaMalloc(&e->d_tiles, sizeof(int2) * tile));
     CREATE_CUDA(cudaMalloc(&e->d_tile_start, sizeof(int) * (n_glaciers + 1)));
-    CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * tile));
+    CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * std::max(tile, e->n_items)));
+    CREATE_CUDA(cudaMalloc(&e->d_items, sizeof(int4) * e->n_items));
+    CREATE_CUDA(cudaMalloc(&e->d_item_start, sizeof(int) * (n_glaciers + 1)));
+    CREATE_CUDA(cudaMemcpy(e->d_items, items.data(), sizeof(int4) * e->n_items, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(e->d_item_start, istart.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMalloc(&e->d_S, sizeof(double) * n_glaciers));
     CREATE_CUDA(cudaMallocHost(&e->h_S, sizeof(double) * n_glaciers));
     CREATE_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(int2) * tile, cudaMemcpyHostToDevice));
@@ -269,6 +326,8 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
     if (e->d_tiles) cudaFree(e->d_tiles);
     if (e->d_tile_start) cudaFree(e->d_tile_start);
     if (e->d_partial) cudaFree(e->d_partial);
+    if (e->d_items) cudaFree(e->d_items);
+    if (e->d_item_start) cudaFree(e->d_item_start);
     if (e->d_S) cudaFree(e->d_S);
     if (e->h_S) cudaFreeHost(e->h_S);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -334,7 +393,7 @@ int odinn_sia2d_rhs(odinn_ensemble* e, int glacier, const void* H, int ldH, void
     (void)t;  // autonomous RHS: laws with callback_freq = 0 do not depend on t (Laws.jl:346)
     int rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
-    if ((rc = launch_rhs(e, e->gl[glacier].tile0, e->gl[glacier].ntx * e->gl[glacier].nty))) return rc;
+    if ((rc = launch_rhs(e, glacier))) return rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_DH, dH, lddH, false, e->stream))) return rc;
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     return ODINN_OK;
@@ -370,7 +429,7 @@ int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, in
 
 int odinn_rhs_resident(odinn_ensemble* e) {
     GUARD(e);
-    return launch_rhs(e, 0, e->n_tiles);
+    return launch_rhs(e, -1);
 }
 
 int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out) {
@@ -397,7 +456,7 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
         if (adj && (rc = copy2d(e, g, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda[g]), e->gl[g].nx, true, e->stream)))
             return rc;
     }
-    if (dH && (rc = launch_rhs(e, 0, e->n_tiles))) return rc;
+    if (dH && (rc = launch_rhs(e, -1))) return rc;
     if (adj && (rc = launch_vjp(e, -1, vjpH != nullptr, S != nullptr))) return rc;
     for (int g = 0; g < e->G; ++g) {
         if (dH && (rc = copy2d(e, g, ODINN_FIELD_DH, dH[g], e->gl[g].nx, false, e->stream))) return rc;

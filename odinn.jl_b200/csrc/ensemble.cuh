@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +19,7 @@ struct GlacierHost {
     double A;
     double temp;
     int tile0, ntx, nty;
+    int item0, n_items;
 };
 
 struct odinn_ensemble {
@@ -39,6 +41,11 @@ struct odinn_ensemble {
     int2* d_tiles = nullptr;
     int* d_tile_start = nullptr;
     int n_tiles = 0;
+    int4* d_items = nullptr;      // marching work items {glacier, first column, row0, row1}
+    int* d_item_start = nullptr;
+    int n_items = 0;
+    int chunk_rows = 32;
+    int use_tiled = 0;            // dev switch: ODINN_KERNEL=tiled selects the v1 shared-memory kernels
     double* d_partial = nullptr;
     double* d_S = nullptr;
     double* h_S = nullptr;  // pinned
