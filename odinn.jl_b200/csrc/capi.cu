@@ -61,12 +61,16 @@ static int launch_rhs_t(odinn_ensemble* e, const int2* tiles, int n_tiles, const
     const T* B = (const T*)e->plane[ODINN_FIELD_B];
     const T* Af = (const T*)e->plane[ODINN_FIELD_A];
     T* dH = (T*)e->plane[ODINN_FIELD_DH];
+    const bool eta1 = (e->phys.eta0 == 1.0);
 #define L(CUB, AF)                                                                                         \
     do {                                                                                                   \
         if (e->use_tiled)                                                                                  \
             sia2d_rhs_kernel<T, CUB, AF><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, H, B, Af, dH, ph);   \
+        else if (eta1)                                                                                     \
+            sia2d_rhs_march<T, CUB, AF, true><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
+                descs, items, n_items, H, B, Af, dH, ph);                                                  \
         else                                                                                               \
-            sia2d_rhs_march<T, CUB, AF><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
+            sia2d_rhs_march<T, CUB, AF, false><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
                 descs, items, n_items, H, B, Af, dH, ph);                                                  \
     } while (0)
     if (e->cubic) {
@@ -111,13 +115,17 @@ static int launch_vjp_t(odinn_ensemble* e, int t0, int n_tiles, int i0, int n_it
     T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
     double* partial = e->d_partial + (e->use_tiled ? t0 : i0);
     const int4* items = e->d_items + i0;
+    const bool eta1 = (e->phys.eta0 == 1.0);
 #define L(CUB, AF, WH, WS)                                                                                           \
     do {                                                                                                             \
         if (e->use_tiled)                                                                                            \
             sia2d_vjp_kernel<T, CUB, AF, WH, WS><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, lam, H, B, Af, out,    \
                                                                                 vjpA, partial, ph);                  \
+        else if (eta1)                                                                                               \
+            sia2d_vjp_march<T, CUB, AF, WH, WS, true><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
+                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph);                                       \
         else                                                                                                         \
-            sia2d_vjp_march<T, CUB, AF, WH, WS><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>(   \
+            sia2d_vjp_march<T, CUB, AF, WH, WS, false><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
                 descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph);                                       \
     } while (0)
 #define L2(CUB, AF)                        \

@@ -1,12 +1,15 @@
-// Register-marching F1 / A1+A2 kernels (v2).
+// Register-marching F1 / A1+A2 kernels.
 //
-// The tiled v1 kernels were instruction-issue bound (ncu: 254 / 427 thread-instructions per cell, 84 % / 70 %
-// issue-slot utilisation, 15 % / 11 % DRAM).  Here every dual node and every edge is evaluated exactly once:
+// The first (shared-memory tiled) kernels were instruction-issue bound (ncu, profiles/r01_v1_*: 254 / 427
+// thread-instructions per cell, 84 % / 70 % issue-slot utilisation, 15 % / 11 % DRAM).  Here every dual node
+// and every edge is evaluated exactly once:
 //   * one warp owns a strip of 32 consecutive columns (lane = column, the contiguous axis, so every row access
-//     is one coalesced 128 B / 256 B line) and marches over a chunk of rows;
+//     is one coalesced line) and marches over a chunk of rows;
 //   * the 3x3 neighbourhood lives in registers: the previous row is carried, x-neighbours come from
 //     warp shuffles (halo exchange), so there is no shared memory and no block barrier at all;
-//   * lanes 0 and 31 are halo lanes: a strip produces 30 output columns.
+//   * lanes 0 and 31 are halo lanes: a strip produces 30 output columns;
+//   * all 1/Δ, 1/2 and 1/4 factors are folded into per-warp constants ("raw" quantities below are sums of
+//     differences that have not been scaled yet).
 // Work items (glacier, first column, row range) come from a table built at ensemble creation, so ragged
 // ensembles are one launch.  Reference semantics and citations: see sia2d_kernels.cuh.
 #pragma once
@@ -23,10 +26,125 @@ __device__ __forceinline__ T shfl_dn(T v) { return __shfl_down_sync(FULL, v, 1);
 template <typename T>
 __device__ __forceinline__ T shfl_up(T v) { return __shfl_up_sync(FULL, v, 1); }
 
+__device__ __forceinline__ float fmx(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmx(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float fmn(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fmn(double a, double b) { return fmin(a, b); }
+
+// Node diffusivity from RAW sums: Hs = Σ of the 4 thicknesses (H̄ = Hs/4), g2 = |∇S|².
+// Returns D and, when PARTIALS, α = ∂D/∂H̄, β = (1/∇S)∂D/∂∇S, gA = Γ H̄^{n+2} ∇S^{n-1} (target_A.jl:16-92).
+template <typename T, bool CUBIC, bool PARTIALS>
+__device__ __forceinline__ void node_raw(const PhysDev<T>& ph, T A, T Hs, T g2, T& D, T& alpha, T& beta, T& gA) {
+    if (CUBIC) {
+        const T K = ph.Gam * T(1.0 / 1024.0);  // Γ/4^5
+        T H2 = Hs * Hs;
+        T H4 = H2 * H2;
+        T w = H4 * Hs;
+        if (!PARTIALS) {
+            D = ((A * K) * g2) * w;
+            return;
+        }
+        T tg = K * g2;
+        gA = tg * w;
+        D = A * gA;
+        if (PARTIALS) {
+            alpha = (T(20) * A) * (tg * H4);  // 5 A Γ H̄^4 ∇S^2
+            beta = (T(2) * A * K) * w;        // 2 A Γ H̄^5
+        }
+    } else {
+        node_diffusivity<T, false, PARTIALS>(ph, A, T(0.25) * Hs, g2, D, alpha, beta, gA);
+    }
+}
+
+// Sub-gradient of the flux clamp  c = max(min(e, up), lo)  pushed onto the two cells of an edge
+// (clamp_borders_d{x,y}_adjoint!, inversion_utils.jl:22-29 / 36-43; strict inequalities, ties give zero):
+//   strictly inside      : ∂dS = dC            -> lower cell gets -dC,      upper cell +dC
+//   e < lo (= -η₀H_lo)   : ∂H_lo = -η₀ dC      -> lower cell gets -η₀ dC
+//   e > up (=  η₀H_up)   : ∂H_up = +η₀ dC      -> upper cell gets +η₀ dC
+// dC here already carries the 1/Δ of diff_adjoint.  With η₀ = 1 (ETA1) the cases merge:
+// lower gets -dC unless (e >= up or e == lo), upper gets +dC unless (e <= lo or e == up).
+template <typename T, bool ETA1>
+__device__ __forceinline__ void subgrad(T dC, T e, T lo, T up, T delta, T eta0, T& to_lower, T& to_upper) {
+    if (ETA1) {
+        bool lt_up = gt_div(up, e, delta), gt_lo = gt_div(e, lo, delta);
+        bool lt_lo = gt_div(lo, e, delta), gt_up = gt_div(e, up, delta);
+        to_lower = (lt_up && (gt_lo || lt_lo)) ? -dC : T(0);
+        to_upper = (gt_lo && (lt_up || gt_up)) ? dC : T(0);
+    } else {
+        bool inside = gt_div(up, e, delta) && gt_div(e, lo, delta);
+        T pass = inside ? dC : T(0);
+        T edC = eta0 * dC;
+        to_lower = -pass - (gt_div(lo, e, delta) ? edC : T(0));
+        to_upper = pass + (gt_div(e, up, delta) ? edC : T(0));
+    }
+}
+
 // --------------------------------------------------------------------------------------------
-// F1
+// F1.  One marching step consumes cell row `row+1` and produces dual-node row `row`, the y-edges
+// row→row+1, the x-edges of row `row` and (OUT) the output row `row`.  MASKED steps carry the
+// row-boundary logic (clamped row pointer, zero border rows); the main loop runs unmasked steps only.
 // --------------------------------------------------------------------------------------------
-template <typename T, bool CUBIC, bool AFIELD>
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1>
+struct RhsMarch {
+    // per-warp / per-lane constants
+    const T *hp, *bp, *ap;
+    T* op;
+    int ld, nym1, ny2;
+    T eta0, hdx, hdy, kx, ky, A;  // kx, ky are zeroed on border columns
+    bool store_lane;
+    PhysDev<T> ph;
+    // carried row state
+    T h, b, eh, ex, hx, ehE, Dp, Fy, h1n, b1n;
+
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void step(int row) {
+        T h1 = h1n, b1 = b1n;
+        if (MASKED) {
+            int stp = (row + 2 <= nym1) ? ld : 0;
+            hp += stp;
+            bp += stp;
+        } else {
+            hp += ld;
+            bp += ld;
+        }
+        h1n = __ldg(hp);
+        b1n = __ldg(bp);
+        h1 = fmx(h1, T(0));                // adjoint.jl:52
+        b1 = surf_store<T>(b1, h1);
+        T eh1 = ETA1 ? h1 : eta0 * h1;
+        T hE1 = shfl_dn(h1), bE1 = shfl_dn(b1);
+        T ex1 = sdiff<T>(bE1, b1, hE1, h1);  // raw x-edge difference S[i+1]-S[i], row+1
+        T hx1 = h1 + hE1;
+        T ehE1 = ETA1 ? hE1 : eta0 * hE1;
+        T ey = sdiff<T>(b1, b, h1, h);       // raw y-edge difference S[j+1]-S[j]
+        T eyE = shfl_dn(ey);
+        // node (i, row): ∇Sx = ½(ex+ex1)/Δx, ∇Sy = ½(ey+eyE)/Δy, H̄ = ¼(hx+hx1)   (adjoint.jl:58-67)
+        T u = (ex + ex1) * hdx, v = (ey + eyE) * hdy;
+        T g2 = u * u + v * v;
+        T Anode = A;
+        if (AFIELD) {
+            Anode = __ldg(ap);
+            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+        }
+        T D1, al, be, gA;
+        node_raw<T, CUBIC, false>(ph, Anode, hx + hx1, g2, D1, al, be, gA);
+        T D1W = shfl_up(D1);
+        // raw fluxes: y-edge (i, row→row+1) and x-edge (i→i+1, row)          (adjoint.jl:93-97)
+        T Fy1 = (D1W + D1) * fmx(fmn(ey, eh1), -eh);
+        T Fx = (Dp + D1) * fmx(fmn(ex, ehE), -eh);
+        T FxW = shfl_up(Fx);
+        if (OUT) {
+            // dH = -(∂x Fx + ∂y Fy), F = -½(D+D)·clamp/Δ  ⇒  dH = ½/Δx² ΔFx_raw + ½/Δy² ΔFy_raw
+            T outv = kx * (Fx - FxW) + ky * (Fy1 - Fy);
+            if (MASKED) { if (row < 1 || row >= nym1) outv = T(0); }
+            if (store_lane) *op = outv;
+        }
+        op += ld;
+        h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; Dp = D1; Fy = Fy1;
+    }
+};
+
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af, T* __restrict__ dH,
@@ -38,68 +156,157 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const GDesc<T> d = descs[it.x];
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
-    const T* Hp = H + d.off + ic;
-    const T* Bp = B + d.off + ic;
-    const T* Ap = AFIELD ? Af + d.off + min(ic, d.nx - 2) : nullptr;
-    T* Op = dH + d.off + ic;
-    const bool store_lane = (lane >= 1 && lane <= STRIP && i < d.nx);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    const T eta0 = ph.eta0;
+    RhsMarch<T, CUBIC, AFIELD, ETA1> m;
+    m.ph = ph;
+    m.ld = d.ld;
+    m.nym1 = d.ny - 1;
+    m.ny2 = d.ny - 2;
+    m.eta0 = ph.eta0;
+    m.hdx = T(0.5) * d.inv_dx;
+    m.hdy = T(0.5) * d.inv_dy;
+    m.kx = col_inner ? m.hdx * d.inv_dx : T(0);  // ½/Δx²
+    m.ky = col_inner ? m.hdy * d.inv_dy : T(0);
+    m.A = d.A;
+    m.store_lane = (lane >= 1 && lane <= STRIP && i < d.nx);
+    const int rc = max(r0 - 1, 0);
+    m.hp = H + d.off + ic + (long long)rc * d.ld;
+    m.bp = B + d.off + ic + (long long)rc * d.ld;
+    m.ap = AFIELD ? Af + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
+    m.op = dH + d.off + ic + (long long)(r0 - 1) * d.ld;  // dereferenced for rows >= r0 only
 
-    // cell row r0-1
-    int rc = max(r0 - 1, 0);
-    T h = __ldg(Hp + (long long)rc * d.ld), b = __ldg(Bp + (long long)rc * d.ld);
-    h = h > T(0) ? h : T(0);
-    b = surf_store<T>(b, h);
-    T hE = shfl_dn(h), bE = shfl_dn(b);
-    T ex = sdiff<T>(bE, b, hE, h);
-    T hx = h + hE;
-    T Dp = T(0), Fy = T(0);
-
-    int rn = min(r0, d.ny - 1);
-    T h1n = __ldg(Hp + (long long)rn * d.ld), b1n = __ldg(Bp + (long long)rn * d.ld);
-
-    for (int row = r0 - 1; row < r1; ++row) {
-        // cell row row+1 (prefetched), then issue the prefetch of row+2
-        T h1 = h1n, b1 = b1n;
-        {
-            int r2 = min(row + 2, d.ny - 1);
-            h1n = __ldg(Hp + (long long)r2 * d.ld);
-            b1n = __ldg(Bp + (long long)r2 * d.ld);
-        }
-        h1 = h1 > T(0) ? h1 : T(0);
-        b1 = surf_store<T>(b1, h1);
-        T hE1 = shfl_dn(h1), bE1 = shfl_dn(b1);
-        T ex1 = sdiff<T>(bE1, b1, hE1, h1);
-        T hx1 = h1 + hE1;
-        T ey = sdiff<T>(b1, b, h1, h);
-        T eyE = shfl_dn(ey);
-        // node (i, row)
-        T gx = T(0.5) * (ex + ex1) * d.inv_dx;
-        T gy = T(0.5) * (ey + eyE) * d.inv_dy;
-        T Hb = T(0.25) * (hx + hx1);
-        T A = d.A;
-        if (AFIELD) A = __ldg(Ap + (long long)min(max(row, 0), d.ny - 2) * d.ld);
-        T D1, al, be, gA;
-        node_diffusivity<T, CUBIC, false>(ph, A, Hb, gx * gx + gy * gy, D1, al, be, gA);
-        T D1W = shfl_up(D1);
-        // y-edge (i, row -> row+1)
-        T Fy1 = -(T(0.5) * (D1W + D1)) * (clamp_raw<T>(ey, eta0, h, h1) * d.inv_dy);
-        if (row >= r0) {  // warp-uniform
-            T Fx = -(T(0.5) * (Dp + D1)) * (clamp_raw<T>(ex, eta0, h, hE) * d.inv_dx);
-            T FxW = shfl_up(Fx);
-            T out = -((Fx - FxW) * d.inv_dx + (Fy1 - Fy) * d.inv_dy);
-            if (!(col_inner && row >= 1 && row <= d.ny - 2)) out = T(0);
-            if (store_lane) Op[(long long)row * d.ld] = out;
-        }
-        h = h1; b = b1; hE = hE1; ex = ex1; hx = hx1; Dp = D1; Fy = Fy1;
+    // ---- cell row r0-1 (rows outside the grid are clamped: they only feed masked quantities) ----
+    m.h = fmx(__ldg(m.hp), T(0));
+    m.b = surf_store<T>(__ldg(m.bp), m.h);
+    m.eh = ETA1 ? m.h : m.eta0 * m.h;
+    {
+        T hE = shfl_dn(m.h), bE = shfl_dn(m.b);
+        m.ex = sdiff<T>(bE, m.b, hE, m.h);
+        m.hx = m.h + hE;
+        m.ehE = ETA1 ? hE : m.eta0 * hE;
     }
+    m.Dp = T(0);
+    m.Fy = T(0);
+    if (r0 >= 1) { m.hp += d.ld; m.bp += d.ld; }
+    m.h1n = __ldg(m.hp);
+    m.b1n = __ldg(m.bp);
+
+    int row = r0 - 1;
+    m.template step<false, true>(row);  // warm-up: node row r0-1, no output
+    ++row;
+    const int main_end = min(r1, d.ny - 2);
+    for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
+#pragma unroll 4
+    for (; row < main_end; ++row) m.template step<true, false>(row);
+    for (; row < r1; ++row) m.template step<true, true>(row);
 }
 
 // --------------------------------------------------------------------------------------------
-// A1 + A2 (see sia2d_vjp_kernel for the math; this is the same arithmetic, marched)
+// A1 + A2 (math: see sia2d_vjp_kernel; same arithmetic, marched, constants folded)
 // --------------------------------------------------------------------------------------------
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S>
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+struct VjpMarch {
+    const T *hp, *bp, *lp, *ap;
+    T *op, *vp;  // output row pointer; gridded-A integrand pointer (or null)
+    int ld, nym1, ny2, r0;
+    T eta0, hdx, hdy, nhx2, nhy2, qx, qy, A, dx, dy;
+    T lmask;     // 1 on inner columns, 0 on border columns (λ_inn zero-extension)
+    bool store_lane, node_col_ok, own_lane;
+    PhysDev<T> ph;
+    // carried row state
+    T h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc, h1n, b1n, l1n;
+
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void step(int row) {
+        T h1 = h1n, b1 = b1n, l1 = l1n * lmask;
+        if (MASKED) {
+            int stp = (row + 2 <= nym1) ? ld : 0;
+            hp += stp;
+            bp += stp;
+            lp += stp;
+            if (!(row >= 0 && row + 1 < nym1)) l1 = T(0);  // λ_inn zero-extended on border rows
+        } else {
+            hp += ld;
+            bp += ld;
+            lp += ld;
+        }
+        h1n = __ldg(hp);
+        b1n = __ldg(bp);
+        l1n = __ldg(lp);
+        h1 = fmx(h1, T(0));
+        b1 = surf_store<T>(b1, h1);
+        T eh1 = ETA1 ? h1 : eta0 * h1;
+        T hE1 = shfl_dn(h1), bE1 = shfl_dn(b1), lE1 = shfl_dn(l1);
+        // x-edge (i→i+1, row+1)
+        T ex1 = sdiff<T>(bE1, b1, hE1, h1);
+        T hx1 = h1 + hE1;
+        T ehE1 = ETA1 ? hE1 : eta0 * hE1;
+        T fxr1 = lE1 - l1;                                   // raw Fx† = λ̃[i+1]-λ̃[i]   (adjoint.jl:100)
+        T px1 = fxr1 * fmx(fmn(ex1, ehE1), -eh1);            // raw Fx†·clamp(dSdx)       (adjoint.jl:102)
+        // y-edge (i, row→row+1)
+        T ey = sdiff<T>(b1, b, h1, h);
+        T fyr = l1 - l;
+        T py = fyr * fmx(fmn(ey, eh1), -eh);
+        T eyE = shfl_dn(ey), pyE = shfl_dn(py);
+        // node (i, row)
+        T gxr = ex + ex1, gyr = ey + eyE;  // raw: ∇Sx = hdx·gxr, ∇Sy = hdy·gyr
+        T u = gxr * hdx, v = gyr * hdy;
+        T Anode = A;
+        if (AFIELD) {
+            Anode = __ldg(ap);
+            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+        }
+        T D1, al, be, gA;
+        node_raw<T, CUBIC, true>(ph, Anode, hx + hx1, u * u + v * v, D1, al, be, gA);
+        T Dadj = (px + px1) * nhx2 + (py + pyE) * nhy2;  // D† (adjoint.jl:102-104)
+        bool node_ok = node_col_ok;
+        if (MASKED) node_ok = node_ok && row >= 0 && row < nym1;
+        if (!node_ok) Dadj = T(0);            // nodes outside the dual grid: zero-extension of the transposes
+        T bD = be * Dadj;
+        T aD1 = al * Dadj;                    // α D†
+        T P1 = bD * gxr;                      // β D† ∇Sx / hdx
+        T Q1 = bD * gyr;                      // β D† ∇Sy / hdy
+        if (WRITE_S) {
+            if (OUT) {                        // node rows r0..r1-1 belong to this item, columns i0..i0+29
+                T vS = gA * Dadj;             // ∂A_spatial ∘ D† (adjoint.jl:250)
+                if (own_lane) acc += vS;
+                if (AFIELD) { if (own_lane && node_ok) *vp = vS; }
+            }
+            if (AFIELD) vp += ld;
+        }
+        if (WRITE_H) {
+            T D1W = shfl_up(D1), Q1W = shfl_up(Q1);
+            T Qrow1 = Q1W + Q1;
+            // y-edge sub-gradient (inversion_utils.jl:36-43): lower cell = row, upper cell = row+1
+            T yl, yu1;
+            {
+                T dC = (fyr * nhy2) * (D1W + D1);  // ∂Cy/Δy = -Fy†·Dy/Δy
+                subgrad<T, ETA1>(dC, ey, -eh, eh1, dy, eta0, yl, yu1);
+            }
+            // x-edge sub-gradient (inversion_utils.jl:22-29): lower cell = i, upper cell = i+1
+            T xl, xu;
+            {
+                T dC = (fxr * nhx2) * (Dp + D1);
+                subgrad<T, ETA1>(dC, ex, -eh, ehE, dx, eta0, xl, xu);
+            }
+            T aDc = T(0.25) * (aDp + aD1);
+            T Pc = qx * (Pp + P1);
+            T ZW = shfl_up(aDc + Pc + xu);  // everything column i-1 sends to cell (i, row)
+            if (OUT) {
+                T res = ZW + (aDc - Pc + xl) + qy * (Qrow_p - Qrow1) + (yl + yu_p);
+                if (!(h > T(0))) res = T(0);  // adjoint.jl:148
+                if (store_lane) *op = res;
+            }
+            op += ld;
+            Qrow_p = Qrow1;
+            yu_p = yu1;
+        }
+        h = h1; b = b1; l = l1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; fxr = fxr1; px = px1;
+        Dp = D1; aDp = aD1; Pp = P1;
+    }
+};
+
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ lam, const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af,
@@ -111,117 +318,69 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const GDesc<T> d = descs[it.x];
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
-    const T* Hp = H + d.off + ic;
-    const T* Bp = B + d.off + ic;
-    const T* Lp = lam + d.off + ic;
-    const T* Ap = AFIELD ? Af + d.off + min(ic, d.nx - 2) : nullptr;
-    T* Op = WRITE_H ? out + d.off + ic : nullptr;
-    const bool store_lane = (lane >= 1 && lane <= STRIP && i < d.nx);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    const bool node_col_ok = (i >= 0 && i <= d.nx - 2);
-    const bool own_lane = (lane < STRIP);  // nodes i0 .. i0+29 are owned by this strip
-    const T eta0 = ph.eta0;
-    const T idx2 = d.inv_dx * d.inv_dx, idy2 = d.inv_dy * d.inv_dy;
-    const T e_dx = eta0 * d.inv_dx, e_dy = eta0 * d.inv_dy;
+    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1> m;
+    m.ph = ph;
+    m.ld = d.ld;
+    m.nym1 = d.ny - 1;
+    m.ny2 = d.ny - 2;
+    m.r0 = r0;
+    m.eta0 = ph.eta0;
+    m.dx = d.dx;
+    m.dy = d.dy;
+    m.hdx = T(0.5) * d.inv_dx;
+    m.hdy = T(0.5) * d.inv_dy;
+    m.nhx2 = -m.hdx * d.inv_dx;  // -½/Δx²
+    m.nhy2 = -m.hdy * d.inv_dy;
+    m.qx = m.hdx * m.hdx;        // ¼/Δx²
+    m.qy = m.hdy * m.hdy;
+    m.A = d.A;
+    m.lmask = col_inner ? T(1) : T(0);
+    m.store_lane = (lane >= 1 && lane <= STRIP && i < d.nx);
+    m.node_col_ok = (i >= 0 && i <= d.nx - 2);
+    m.own_lane = (lane < STRIP);  // nodes i0 .. i0+29 are owned by this strip
+    const int rc = max(r0 - 1, 0);
+    m.hp = H + d.off + ic + (long long)rc * d.ld;
+    m.bp = B + d.off + ic + (long long)rc * d.ld;
+    m.lp = lam + d.off + ic + (long long)rc * d.ld;
+    m.ap = AFIELD ? Af + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
+    m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
 
-    // cell row r0-1
-    int rc = max(r0 - 1, 0);
-    T h = __ldg(Hp + (long long)rc * d.ld), b = __ldg(Bp + (long long)rc * d.ld), l = __ldg(Lp + (long long)rc * d.ld);
-    h = h > T(0) ? h : T(0);
-    b = surf_store<T>(b, h);
-    if (!(col_inner && (r0 - 1) >= 1 && (r0 - 1) <= d.ny - 2)) l = T(0);
-    T hE = shfl_dn(h), bE = shfl_dn(b), lE = shfl_dn(l);
-    T ex = sdiff<T>(bE, b, hE, h);
-    T hx = h + hE;
-    T fxr = lE - l;
-    T px = fxr * clamp_raw<T>(ex, eta0, h, hE);
-    T Dp = T(0), aDp = T(0), Pp = T(0), Qrow_p = T(0), yu_p = T(0);
-    double acc = 0.0;
-
-    int rn = min(r0, d.ny - 1);
-    T h1n = __ldg(Hp + (long long)rn * d.ld), b1n = __ldg(Bp + (long long)rn * d.ld), l1n = __ldg(Lp + (long long)rn * d.ld);
-
-    for (int row = r0 - 1; row < r1; ++row) {
-        T h1 = h1n, b1 = b1n, l1 = l1n;
-        {
-            int r2 = min(row + 2, d.ny - 1);
-            h1n = __ldg(Hp + (long long)r2 * d.ld);
-            b1n = __ldg(Bp + (long long)r2 * d.ld);
-            l1n = __ldg(Lp + (long long)r2 * d.ld);
-        }
-        h1 = h1 > T(0) ? h1 : T(0);
-        b1 = surf_store<T>(b1, h1);
-        if (!(col_inner && (row + 1) >= 1 && (row + 1) <= d.ny - 2)) l1 = T(0);  // λ_inn zero-extended
-        T hE1 = shfl_dn(h1), bE1 = shfl_dn(b1), lE1 = shfl_dn(l1);
-        // x-edge (i, row+1)
-        T ex1 = sdiff<T>(bE1, b1, hE1, h1);
-        T hx1 = h1 + hE1;
-        T fxr1 = lE1 - l1;
-        T px1 = fxr1 * clamp_raw<T>(ex1, eta0, h1, hE1);
-        // y-edge (i, row -> row+1)
-        T ey = sdiff<T>(b1, b, h1, h);
-        T fyr = l1 - l;
-        T py = fyr * clamp_raw<T>(ey, eta0, h, h1);
-        T eyE = shfl_dn(ey), pyE = shfl_dn(py);
-        // node (i, row)
-        T gSx = T(0.5) * (ex + ex1) * d.inv_dx;
-        T gSy = T(0.5) * (ey + eyE) * d.inv_dy;
-        T Hb = T(0.25) * (hx + hx1);
-        T A = d.A;
-        if (AFIELD) A = __ldg(Ap + (long long)min(max(row, 0), d.ny - 2) * d.ld);
-        T D1, al, be, gA;
-        node_diffusivity<T, CUBIC, true>(ph, A, Hb, gSx * gSx + gSy * gSy, D1, al, be, gA);
-        T Dadj = -T(0.5) * ((px + px1) * idx2 + (py + pyE) * idy2);
-        const bool node_ok = node_col_ok && row >= 0 && row <= d.ny - 2;
-        T bD = be * Dadj;
-        T aD1 = node_ok ? al * Dadj : T(0);
-        T P1 = node_ok ? bD * gSx : T(0);
-        T Q1 = node_ok ? bD * gSy : T(0);
-        if (WRITE_S) {
-            if (node_ok && own_lane && row >= r0) {
-                T v = gA * Dadj;
-                acc += (double)v;
-                if (vjpA != nullptr) vjpA[d.off + (long long)row * d.ld + i] = v;
-            }
-        }
-        if (WRITE_H) {
-            T D1W = shfl_up(D1), Q1W = shfl_up(Q1);
-            T Qrow1 = Q1W + Q1;
-            // y-edge sub-gradient (inversion_utils.jl:36-43): lower cell = row, upper cell = row+1
-            T yl, yu1;
-            {
-                T dC = -(fyr * d.inv_dy) * (T(0.5) * (D1W + D1));
-                T up = eta0 * h1, lo = -(eta0 * h);
-                bool inside = gt_div(up, ey, d.dy) && gt_div(ey, lo, d.dy);
-                T pass = inside ? dC * d.inv_dy : T(0);
-                yl = -pass - (gt_div(lo, ey, d.dy) ? e_dy * dC : T(0));
-                yu1 = pass + (gt_div(ey, up, d.dy) ? e_dy * dC : T(0));
-            }
-            if (row >= r0) {  // warp-uniform: output row `row`
-                // x-edge sub-gradient (inversion_utils.jl:22-29): lower cell = i, upper cell = i+1
-                T dC = -(fxr * d.inv_dx) * (T(0.5) * (Dp + D1));
-                T up = eta0 * hE, lo = -(eta0 * h);
-                bool inside = gt_div(up, ex, d.dx) && gt_div(ex, lo, d.dx);
-                T pass = inside ? dC * d.inv_dx : T(0);
-                T xl = -pass - (gt_div(lo, ex, d.dx) ? e_dx * dC : T(0));
-                T xu = pass + (gt_div(ex, up, d.dx) ? e_dx * dC : T(0));
-                T aDc = T(0.25) * (aDp + aD1);
-                T Pc = (T(0.5) * d.inv_dx) * (Pp + P1);
-                T ZW = shfl_up(aDc + Pc + xu);  // everything column i-1 sends to cell (i, row)
-                T res = ZW + (aDc - Pc + xl) + (T(0.5) * d.inv_dy) * (Qrow_p - Qrow1) + (yl + yu_p);
-                if (!(h > T(0))) res = T(0);  // adjoint.jl:148
-                if (store_lane) Op[(long long)row * d.ld] = res;
-            }
-            Qrow_p = Qrow1;
-            yu_p = yu1;
-        }
-        h = h1; b = b1; l = l1; hE = hE1; ex = ex1; hx = hx1; fxr = fxr1; px = px1;
-        Dp = D1; aDp = aD1; Pp = P1;
+    // ---- cell row r0-1 ----
+    m.h = fmx(__ldg(m.hp), T(0));
+    m.b = surf_store<T>(__ldg(m.bp), m.h);
+    m.l = __ldg(m.lp) * m.lmask;
+    if (!(r0 >= 2 && r0 <= m.nym1)) m.l = T(0);  // row r0-1 must be an inner row
+    m.eh = ETA1 ? m.h : m.eta0 * m.h;
+    {
+        T hE = shfl_dn(m.h), bE = shfl_dn(m.b), lE = shfl_dn(m.l);
+        m.ex = sdiff<T>(bE, m.b, hE, m.h);
+        m.hx = m.h + hE;
+        m.ehE = ETA1 ? hE : m.eta0 * hE;
+        m.fxr = lE - m.l;
+        m.px = m.fxr * fmx(fmn(m.ex, m.ehE), -m.eh);
     }
+    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = T(0);
+    if (r0 >= 1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
+    m.h1n = __ldg(m.hp);
+    m.b1n = __ldg(m.bp);
+    m.l1n = __ldg(m.lp);
+
+    int row = r0 - 1;
+    m.template step<false, true>(row);  // warm-up
+    ++row;
+    const int main_end = min(r1, d.ny - 2);
+    for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
+#pragma unroll 4
+    for (; row < main_end; ++row) m.template step<true, false>(row);
+    for (; row < r1; ++row) m.template step<true, true>(row);
+
     if (WRITE_S) {
+        double a = (double)m.acc;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
-        if (lane == 0) partial[item] = acc;
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+        if (lane == 0) partial[item] = a;
     }
 }
 
