@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libodinn_b200.so")
+LIB_PATH = os.environ.get("ODINN_B200_LIB") or os.path.join(_HERE, "lib", "libodinn_b200.so")  # env: dev override
 
 F32, F64 = 0, 1
 

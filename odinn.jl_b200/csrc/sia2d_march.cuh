@@ -20,6 +20,19 @@ namespace odinn {
 constexpr int STRIP = 30;        // output columns per warp
 constexpr int MARCH_WARPS = 8;   // warps per CTA
 constexpr unsigned FULL = 0xffffffffu;
+// Rows of register prefetch (ncu: the 1-row version stalled on long_scoreboard).  Deeper queues cost
+// registers, i.e. resident warps: F1 is light (4 rows), the VJP kernel is not.
+#ifndef ODINN_PF_RHS
+#define ODINN_PF_RHS 4
+#endif
+#ifndef ODINN_PF_VJP32
+#define ODINN_PF_VJP32 2
+#endif
+#ifndef ODINN_PF_VJP64
+#define ODINN_PF_VJP64 2
+#endif
+template <typename T> struct PfVjp { static constexpr int value = ODINN_PF_VJP32; };
+template <> struct PfVjp<double> { static constexpr int value = ODINN_PF_VJP64; };
 
 template <typename T>
 __device__ __forceinline__ T shfl_dn(T v) { return __shfl_down_sync(FULL, v, 1); }
@@ -86,6 +99,7 @@ __device__ __forceinline__ void subgrad(T dC, T e, T lo, T up, T delta, T eta0, 
 // --------------------------------------------------------------------------------------------
 template <typename T, bool CUBIC, bool AFIELD, bool ETA1>
 struct RhsMarch {
+    static constexpr int PF = ODINN_PF_RHS;
     // per-warp / per-lane constants
     const T *hp, *bp, *ap;
     T* op;
@@ -94,21 +108,24 @@ struct RhsMarch {
     bool store_lane;
     PhysDev<T> ph;
     // carried row state
-    T h, b, eh, ex, hx, ehE, Dp, Fy, h1n, b1n;
+    T h, b, eh, ex, hx, ehE, Dp, Fy;
+    T hq[PF], bq[PF];  // prefetched cell rows row+1 .. row+PF
 
     template <bool OUT, bool MASKED>
     __device__ __forceinline__ void step(int row) {
-        T h1 = h1n, b1 = b1n;
+        T h1 = hq[0], b1 = bq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; }
         if (MASKED) {
-            int stp = (row + 2 <= nym1) ? ld : 0;
+            int stp = (row + 1 + PF <= nym1) ? ld : 0;
             hp += stp;
             bp += stp;
         } else {
             hp += ld;
             bp += ld;
         }
-        h1n = __ldg(hp);
-        b1n = __ldg(bp);
+        hq[PF - 1] = __ldg(hp);
+        bq[PF - 1] = __ldg(bp);
         h1 = fmx(h1, T(0));                // adjoint.jl:52
         b1 = surf_store<T>(b1, h1);
         T eh1 = ETA1 ? h1 : eta0 * h1;
@@ -158,6 +175,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
     RhsMarch<T, CUBIC, AFIELD, ETA1> m;
+    constexpr int PF = ODINN_PF_RHS;
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
@@ -187,14 +205,17 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     }
     m.Dp = T(0);
     m.Fy = T(0);
-    if (r0 >= 1) { m.hp += d.ld; m.bp += d.ld; }
-    m.h1n = __ldg(m.hp);
-    m.b1n = __ldg(m.bp);
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {  // rows r0 .. r0+PF-1 (clamped)
+        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; }
+        m.hq[k] = __ldg(m.hp);
+        m.bq[k] = __ldg(m.bp);
+    }
 
     int row = r0 - 1;
     m.template step<false, true>(row);  // warm-up: node row r0-1, no output
     ++row;
-    const int main_end = min(r1, d.ny - 2);
+    const int main_end = min(r1, d.ny - 1 - PF);
     for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
 #pragma unroll 4
     for (; row < main_end; ++row) m.template step<true, false>(row);
@@ -206,6 +227,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 // --------------------------------------------------------------------------------------------
 template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
 struct VjpMarch {
+    static constexpr int PF = PfVjp<T>::value;
     const T *hp, *bp, *lp, *ap;
     T *op, *vp;  // output row pointer; gridded-A integrand pointer (or null)
     int ld, nym1, ny2, r0;
@@ -214,13 +236,16 @@ struct VjpMarch {
     bool store_lane, node_col_ok, own_lane;
     PhysDev<T> ph;
     // carried row state
-    T h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc, h1n, b1n, l1n;
+    T h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc;
+    T hq[PF], bq[PF], lq[PF];
 
     template <bool OUT, bool MASKED>
     __device__ __forceinline__ void step(int row) {
-        T h1 = h1n, b1 = b1n, l1 = l1n * lmask;
+        T h1 = hq[0], b1 = bq[0], l1 = lq[0] * lmask;
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
         if (MASKED) {
-            int stp = (row + 2 <= nym1) ? ld : 0;
+            int stp = (row + 1 + PF <= nym1) ? ld : 0;
             hp += stp;
             bp += stp;
             lp += stp;
@@ -230,9 +255,9 @@ struct VjpMarch {
             bp += ld;
             lp += ld;
         }
-        h1n = __ldg(hp);
-        b1n = __ldg(bp);
-        l1n = __ldg(lp);
+        hq[PF - 1] = __ldg(hp);
+        bq[PF - 1] = __ldg(bp);
+        lq[PF - 1] = __ldg(lp);
         h1 = fmx(h1, T(0));
         b1 = surf_store<T>(b1, h1);
         T eh1 = ETA1 ? h1 : eta0 * h1;
@@ -320,6 +345,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
     VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1> m;
+    constexpr int PF = PfVjp<T>::value;
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
@@ -362,15 +388,18 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
         m.px = m.fxr * fmx(fmn(m.ex, m.ehE), -m.eh);
     }
     m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = T(0);
-    if (r0 >= 1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
-    m.h1n = __ldg(m.hp);
-    m.b1n = __ldg(m.bp);
-    m.l1n = __ldg(m.lp);
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {  // rows r0 .. r0+PF-1 (clamped)
+        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
+        m.hq[k] = __ldg(m.hp);
+        m.bq[k] = __ldg(m.bp);
+        m.lq[k] = __ldg(m.lp);
+    }
 
     int row = r0 - 1;
     m.template step<false, true>(row);  // warm-up
     ++row;
-    const int main_end = min(r1, d.ny - 2);
+    const int main_end = min(r1, d.ny - 1 - PF);
     for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
 #pragma unroll 4
     for (; row < main_end; ++row) m.template step<true, false>(row);
