@@ -30,6 +30,10 @@ typedef struct odinn_ensemble odinn_ensemble;
 
 enum odinn_dtype { ODINN_F32 = 0, ODINN_F64 = 1 };
 
+enum odinn_method { ODINN_EULER = 0, ODINN_SSPRK3 = 1 };
+
+enum odinn_activation { ODINN_ACT_IDENTITY = 0, ODINN_ACT_SOFTPLUS = 1, ODINN_ACT_SIGMOID = 2, ODINN_ACT_TANH = 3, ODINN_ACT_RELU = 4 };
+
 enum odinn_status {
     ODINN_OK = 0,
     ODINN_EARG = -1,   /* bad argument (null pointer, size mismatch, index out of range) */
@@ -97,6 +101,8 @@ int odinn_download(odinn_ensemble* e, int glacier, int field, void* host, int ld
 
 /* cache.iceflow.A.value as a glacier-wide scalar (ScalarCache, src/laws/Cache.jl:23-97). */
 int odinn_set_A_scalar(odinn_ensemble* e, int glacier, double A);
+/* Long-term air temperature of the glacier, the input of LawA(nn, params) (iAvgScalarTemp, Laws.jl:326). */
+int odinn_set_temperature(odinn_ensemble* e, int glacier, double T);
 /* Switch the ensemble between scalar A (0) and the gridded A field ODINN_FIELD_A (1)
  * (MatrixCache; LawA(params; scalar=false), src/laws/Laws.jl:430-454). */
 int odinn_set_A_mode(odinn_ensemble* e, int gridded);
@@ -138,6 +144,47 @@ int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
  * output; lambda may be NULL when only dH is requested.  All matrices use ld = nx. */
 int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void* const* lambda,
                              void* const* dH, void* const* vjpH, double* S);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Device-resident time loop and gradient (H, lambda and the snapshots never leave HBM)      */
+/* ---------------------------------------------------------------------------------------- */
+
+/* Forward solve of every glacier from ODINN_FIELD_H0 over the common time grid t[0..n_snap-1] with `nsub`
+ * fixed sub-steps per interval; the state at every t[j] is kept as snapshot j.  Replaces
+ * simulate_iceflow_UDE! -> solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops)) with saveat = tstops
+ * (src/simulations/inversions/inversion_utils.jl:551-572, 584-610, tstops :487-495).  The integrator is a
+ * user parameter in the reference (params.solver.solver); offered here: explicit Euler and SSPRK(3,3), each
+ * stage fused into the RHS kernel. */
+int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double* t, int nsub);
+int odinn_get_snapshot(odinn_ensemble* e, int glacier, int j, void* host, int ld);
+/* Provide snapshot j from the host instead (e.g. a solution saved by OrdinaryDiffEq). */
+int odinn_set_snapshot(odinn_ensemble* e, int glacier, int j, int n_snap, const void* host, int ld);
+/* Reference thickness H_ref(t_j) and loss weights W = is_in_glacier(H_ref, distance) / (nx*ny)
+ * (src/losses/Losses.jl:270-291 with normalization = prod(N), src/inverse/SIA2D/gradient.jl:161). */
+int odinn_set_reference(odinn_ensemble* e, int glacier, int j, int n_snap, const void* Href, const void* W, int ld);
+
+/* loss_out[g] = sum_j (t_j - t_{j-1}) * sum_cells W (H_j - H_ref,j)^2 : LossH(L2Sum) of
+ * loss_iceflow_transient (src/simulations/inversions/inversion_utils.jl:383-461). */
+int odinn_loss(odinn_ensemble* e, const double* t, int n_t, double* loss_out);
+
+/* The DiscreteAdjoint reverse loop of SIA2D_grad_batch! (src/inverse/SIA2D/gradient.jl:191-253) for
+ * LossH(L2Sum), glacier-wide A:  loss_out[g] as above and
+ * Ssum_out[g] = sum_j dt_{j-1} * S_{g,j},  so that  dL/dtheta = sum_g (dA_g/dtheta) * Ssum_out[g]. */
+int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* loss_out, double* Ssum_out);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Laws                                                                                      */
+/* ---------------------------------------------------------------------------------------- */
+
+/* LawA(nn, params) f! (src/laws/Laws.jl:348-358): for every glacier A_g = minA + (maxA-minA)*NN([T_g]; theta)
+ * with a Lux Dense chain (widths[0..n_layers], acts[0..n_layers-1]; theta = [vec(W1); b1; vec(W2); b2; ...],
+ * W out x in column-major).  Also evaluates the pullback dA_g/dtheta (p_VJP!, Laws.jl:359-362 /
+ * precompute_all_VJPs_laws!, inversion_utils.jl:647-686) and keeps it on the device.  A_out (G doubles) optional. */
+int odinn_law_A_nn_apply(odinn_ensemble* e, int n_layers, const int* widths, const int* acts, const double* theta,
+                         int n_theta, double* A_out);
+/* dtheta[k] = sum_g dA_g/dtheta_k * S[g]  (aggregate of the per-glacier gradients, Model.jl:208-224).
+ * S == NULL uses the sums left on the device by odinn_grad_discrete. */
+int odinn_law_A_nn_pullback(odinn_ensemble* e, const double* S, double* dtheta, int n_theta);
 
 #ifdef __cplusplus
 }

@@ -1,22 +1,30 @@
 // C ABI of libodinn_b200.so (see include/odinn_b200.h for the reference interfaces replaced).
-#include "ensemble.cuh"
-#include "sia2d_kernels.cuh"
-#include "sia2d_march.cuh"
 #include <cstdlib>
+
+#include "ensemble.cuh"
+#include "sia2d_march.cuh"
+#include "timeloop.cuh"
 
 namespace odinn {
 
 thread_local std::string g_create_error;
 
+static int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1) {
+    if (*p) return ODINN_OK;
+    size_t bytes = (size_t)e->total * e->esize * n_planes;
+    cudaError_t st = cudaMalloc(p, bytes);
+    if (st != cudaSuccess) {
+        *p = nullptr;
+        return fail(e, st == cudaErrorMemoryAllocation ? ODINN_ENOMEM : ODINN_ECUDA,
+                    std::string("cudaMalloc of a device plane: ") + cudaGetErrorString(st));
+    }
+    ODINN_CUDA(e, cudaMemsetAsync(*p, 0, bytes, e->stream));
+    return ODINN_OK;
+}
+
 int ensure_plane(odinn_ensemble* e, int field) {
     if (field < 0 || field >= ODINN_FIELD_COUNT_) return fail(e, ODINN_EARG, "bad field id");
-    if (e->plane[field]) return ODINN_OK;
-    void* p = nullptr;
-    size_t bytes = (size_t)e->total * e->esize;
-    ODINN_CUDA(e, cudaMalloc(&p, bytes));
-    ODINN_CUDA(e, cudaMemsetAsync(p, 0, bytes, e->stream));
-    e->plane[field] = p;
-    return ODINN_OK;
+    return alloc_plane(e, &e->plane[field]);
 }
 
 template <typename T>
@@ -51,148 +59,174 @@ int sync_descs(odinn_ensemble* e) {
 
 static void refresh_phys(odinn_ensemble* e) { e->cubic = (e->phys.n == 3.0 && e->phys.C == 0.0); }
 
-// ---- launches -----------------------------------------------------------------------------
-
-template <typename T>
-static int launch_rhs_t(odinn_ensemble* e, const int2* tiles, int n_tiles, const int4* items, int n_items) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const T* H = (const T*)e->plane[ODINN_FIELD_H];
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
-    T* dH = (T*)e->plane[ODINN_FIELD_DH];
-    const bool eta1 = (e->phys.eta0 == 1.0);
-#define L(CUB, AF)                                                                                         \
-    do {                                                                                                   \
-        if (e->use_tiled)                                                                                  \
-            sia2d_rhs_kernel<T, CUB, AF><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, H, B, Af, dH, ph);   \
-        else if (eta1)                                                                                     \
-            sia2d_rhs_march<T, CUB, AF, true><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
-                descs, items, n_items, H, B, Af, dH, ph);                                                  \
-        else                                                                                               \
-            sia2d_rhs_march<T, CUB, AF, false><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
-                descs, items, n_items, H, B, Af, dH, ph);                                                  \
-    } while (0)
-    if (e->cubic) {
-        if (e->a_gridded) L(true, true); else L(true, false);
-    } else {
-        if (e->a_gridded) L(false, true); else L(false, false);
-    }
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
+static inline char* plane_ptr(odinn_ensemble* e, void* base, long long plane_index = 0) {
+    return (char*)base + (size_t)plane_index * (size_t)e->total * e->esize;
 }
 
-// tile range [t0, t0+n_tiles): the whole ensemble or one glacier
-static int launch_rhs(odinn_ensemble* e, int g) {
-    int t0 = 0, n_tiles = e->n_tiles, i0 = 0, n_items = e->n_items;
-    if (g >= 0) {
-        t0 = e->gl[g].tile0;
-        n_tiles = e->gl[g].ntx * e->gl[g].nty;
-        i0 = e->gl[g].item0;
-        n_items = e->gl[g].n_items;
-    }
-    int rc;
-    if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_B)) ||
-        (rc = ensure_plane(e, ODINN_FIELD_DH)))
-        return rc;
-    if (e->a_gridded && (rc = ensure_plane(e, ODINN_FIELD_A))) return rc;
-    if ((rc = sync_descs(e))) return rc;
-    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, e->d_tiles + t0, n_tiles, e->d_items + i0, n_items)
-                                 : launch_rhs_t<double>(e, e->d_tiles + t0, n_tiles, e->d_items + i0, n_items);
-}
+// ---- F1 launch: out = SIA2D(Hin)   or, with a stage,  out = sa·U0 + sb·(Hin + sdt·SIA2D(Hin)) ----------------
+
+struct Stage {
+    const void* U0;
+    double sa, sb, sdt;
+};
 
 template <typename T>
-static int launch_vjp_t(odinn_ensemble* e, int t0, int n_tiles, int i0, int n_items, bool wH, bool wS) {
+static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st) {
     PhysDev<T> ph = make_phys<T>(e->phys);
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const int2* tiles = e->d_tiles + t0;
-    const T* lam = (const T*)e->plane[ODINN_FIELD_LAMBDA];
-    const T* H = (const T*)e->plane[ODINN_FIELD_H];
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
-    T* out = (T*)e->plane[ODINN_FIELD_VJP_H];
-    T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
-    double* partial = e->d_partial + (e->use_tiled ? t0 : i0);
     const int4* items = e->d_items + i0;
+    const T* H = (const T*)Hin;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
+    T* dH = (T*)out;
     const bool eta1 = (e->phys.eta0 == 1.0);
-#define L(CUB, AF, WH, WS)                                                                                           \
-    do {                                                                                                             \
-        if (e->use_tiled)                                                                                            \
-            sia2d_vjp_kernel<T, CUB, AF, WH, WS><<<n_tiles, NT, 0, e->stream>>>(descs, tiles, lam, H, B, Af, out,    \
-                                                                                vjpA, partial, ph);                  \
-        else if (eta1)                                                                                               \
-            sia2d_vjp_march<T, CUB, AF, WH, WS, true><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
-                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph);                                       \
-        else                                                                                                         \
-            sia2d_vjp_march<T, CUB, AF, WH, WS, false><<<div_up(n_items, MARCH_WARPS), MARCH_WARPS * 32, 0, e->stream>>>( \
-                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph);                                       \
-    } while (0)
-#define L2(CUB, AF)                        \
-    do {                                   \
-        if (wH && wS) L(CUB, AF, true, true);   \
-        else if (wH) L(CUB, AF, true, false);   \
-        else L(CUB, AF, false, true);           \
-    } while (0)
+    const T* U0 = st ? (const T*)st->U0 : nullptr;
+    const T sa = st ? (T)st->sa : T(0), sb = st ? (T)st->sb : T(0), sdt = st ? (T)st->sdt : T(0);
+    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define L(CUB, AF, E1, STG) \
+    sia2d_rhs_march<T, CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt)
+#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
+#define L2(CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
     if (e->cubic) {
         if (e->a_gridded) L2(true, true); else L2(true, false);
     } else {
         if (e->a_gridded) L2(false, true); else L2(false, false);
     }
 #undef L2
+#undef L3
 #undef L
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
 
 // g < 0: whole ensemble
-static int launch_vjp(odinn_ensemble* e, int g, bool wH, bool wS) {
-    if (!wH && !wS) return ODINN_OK;
+static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, const Stage* st = nullptr) {
     int rc;
-    if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_B)) ||
-        (rc = ensure_plane(e, ODINN_FIELD_LAMBDA)))
-        return rc;
-    if (wH && (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
-    if (e->a_gridded && ((rc = ensure_plane(e, ODINN_FIELD_A)) || (wS && (rc = ensure_plane(e, ODINN_FIELD_VJP_A)))))
-        return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+    if (e->a_gridded && (rc = ensure_plane(e, ODINN_FIELD_A))) return rc;
     if ((rc = sync_descs(e))) return rc;
-    int t0 = 0, nt = e->n_tiles, i0 = 0, ni = e->n_items;
+    int i0 = 0, ni = e->n_items;
     if (g >= 0) {
-        t0 = e->gl[g].tile0;
-        nt = e->gl[g].ntx * e->gl[g].nty;
         i0 = e->gl[g].item0;
         ni = e->gl[g].n_items;
     }
-    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, t0, nt, i0, ni, wH, wS)
-                               : launch_vjp_t<double>(e, t0, nt, i0, ni, wH, wS);
+    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, i0, ni, Hin, out, st)
+                                 : launch_rhs_t<double>(e, i0, ni, Hin, out, st);
+}
+
+// ---- A1 / A2 launch --------------------------------------------------------------------------------------------
+
+template <typename T>
+static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const void* H_, void* out_, bool wH,
+                        bool wS) {
+    PhysDev<T> ph = make_phys<T>(e->phys);
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const T* lam = (const T*)lam_;
+    const T* H = (const T*)H_;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
+    T* out = (T*)out_;
+    T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
+    double* partial = e->d_partial + i0;
+    const int4* items = e->d_items + i0;
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define L(CUB, AF, WH, WS, E1) \
+    sia2d_vjp_march<T, CUB, AF, WH, WS, E1><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph)
+#define L3(CUB, AF, E1)                         \
+    do {                                        \
+        if (wH && wS) L(CUB, AF, true, true, E1);   \
+        else if (wH) L(CUB, AF, true, false, E1);   \
+        else L(CUB, AF, false, true, E1);           \
+    } while (0)
+#define L2(CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
+    if (e->cubic) {
+        if (e->a_gridded) L2(true, true); else L2(true, false);
+    } else {
+        if (e->a_gridded) L2(false, true); else L2(false, false);
+    }
+#undef L2
+#undef L3
+#undef L
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+// g < 0: whole ensemble.  S_dst: where the per-glacier sums go (d_S or an accumulator), scaled by `scale`.
+static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, void* out, bool wH, bool wS,
+                      double* S_dst = nullptr, double scale = 1.0, int accumulate = 0) {
+    if (!wH && !wS) return ODINN_OK;
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+    if (e->a_gridded && ((rc = ensure_plane(e, ODINN_FIELD_A)) || (wS && (rc = ensure_plane(e, ODINN_FIELD_VJP_A)))))
+        return rc;
+    if ((rc = sync_descs(e))) return rc;
+    int i0 = 0, ni = e->n_items;
+    if (g >= 0) {
+        i0 = e->gl[g].item0;
+        ni = e->gl[g].n_items;
+    }
+    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS)
+                               : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS);
     if (rc) return rc;
     if (wS) {
-        const int* starts = e->use_tiled ? e->d_tile_start : e->d_item_start;
+        double* dst = S_dst ? S_dst : e->d_S;
         if (g >= 0)
-            reduce_items_kernel<<<1, NT, 0, e->stream>>>(starts + g, e->d_partial, e->d_S + g);
+            reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_item_start + g, e->d_partial, dst + g, scale, accumulate);
         else
-            reduce_items_kernel<<<e->G, NT, 0, e->stream>>>(starts, e->d_partial, e->d_S);
+            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_item_start, e->d_partial, dst, scale, accumulate);
         ODINN_CHECK_LAUNCH(e);
     }
     return ODINN_OK;
 }
 
-static int copy2d(odinn_ensemble* e, int g, int field, void* host, int ld, bool up, cudaStream_t st) {
+static int copy2d_ptr(odinn_ensemble* e, int g, char* plane_base, bool dual, void* host, int ld, bool up,
+                      cudaStream_t st) {
     if (g < 0 || g >= e->G) return fail(e, ODINN_EARG, "glacier index out of range");
     if (!host) return fail(e, ODINN_EARG, "null host pointer");
     const GlacierHost& s = e->gl[g];
-    bool dual = (field == ODINN_FIELD_A || field == ODINN_FIELD_VJP_A);
     int w = dual ? s.nx - 1 : s.nx, h = dual ? s.ny - 1 : s.ny;
     if (ld < w) return fail(e, ODINN_EARG, "ld smaller than the number of rows");
-    int rc = ensure_plane(e, field);
-    if (rc) return rc;
-    char* dev = (char*)e->plane[field] + (size_t)s.off * e->esize;
+    char* dev = plane_base + (size_t)s.off * e->esize;
     if (up)
         ODINN_CUDA(e, cudaMemcpy2DAsync(dev, (size_t)s.ld * e->esize, host, (size_t)ld * e->esize, (size_t)w * e->esize,
                                         h, cudaMemcpyHostToDevice, st));
     else
         ODINN_CUDA(e, cudaMemcpy2DAsync(host, (size_t)ld * e->esize, dev, (size_t)s.ld * e->esize, (size_t)w * e->esize,
                                         h, cudaMemcpyDeviceToHost, st));
+    return ODINN_OK;
+}
+
+static int copy2d(odinn_ensemble* e, int g, int field, void* host, int ld, bool up, cudaStream_t st) {
+    int rc = ensure_plane(e, field);
+    if (rc) return rc;
+    bool dual = (field == ODINN_FIELD_A || field == ODINN_FIELD_VJP_A);
+    return copy2d_ptr(e, g, (char*)e->plane[field], dual, host, ld, up, st);
+}
+
+// ---- loss / seed ---------------------------------------------------------------------------------------------
+
+template <typename T>
+static int launch_loss_seed_t(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in,
+                              const void* v, void* lam_out, double dt, double cseed) {
+    loss_seed_kernel<T><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<T>*)e->d_descs, e->d_tiles, (const T*)H,
+                                                          (const T*)Href, (const T*)W, (const T*)lam_in, (const T*)v,
+                                                          (T*)lam_out, e->d_partial, (T)dt, (T)cseed);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+// loss_dst[g] (+)= wloss · Σ W (H - Href)² ; optionally λ_out = λ_in + dt·v + cseed·W·(H - Href)
+static int launch_loss_seed(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in,
+                            const void* v, void* lam_out, double dt, double cseed, double* loss_dst, double wloss,
+                            int accumulate) {
+    int rc = sync_descs(e);
+    if (rc) return rc;
+    rc = e->dtype == ODINN_F32 ? launch_loss_seed_t<float>(e, H, Href, W, lam_in, v, lam_out, dt, cseed)
+                               : launch_loss_seed_t<double>(e, H, Href, W, lam_in, v, lam_out, dt, cseed);
+    if (rc) return rc;
+    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, loss_dst, wloss, accumulate);
+    ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
 
@@ -258,10 +292,17 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     }
     e->total = off;
     e->n_tiles = tile;
-    {
-        const char* k = std::getenv("ODINN_KERNEL");
-        e->use_tiled = (k && std::string(k) == "tiled") ? 1 : 0;
+
+    std::vector<int2> tiles(tile);
+    std::vector<int> tstart(n_glaciers + 1);
+    for (int g = 0; g < n_glaciers; ++g) {
+        const GlacierHost& s = e->gl[g];
+        tstart[g] = s.tile0;
+        for (int ty = 0; ty < s.nty; ++ty)
+            for (int tx = 0; tx < s.ntx; ++tx) tiles[s.tile0 + ty * s.ntx + tx] = make_int2(g, (ty << 16) | tx);
     }
+    tstart[n_glaciers] = tile;
+
     // Marching work items: strips of STRIP output columns x chunks of rows.  Shorter chunks for small
     // ensembles so that the grid still fills 148 SMs.
     std::vector<int4> items;
@@ -277,22 +318,12 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         s.item0 = (int)items.size();
         istart[g] = s.item0;
         for (int r0 = 0; r0 < s.ny; r0 += e->chunk_rows)
-            for (int st = 0; st < div_up(s.nx, STRIP); ++st)
-                items.push_back(make_int4(g, st * STRIP - 1, r0, std::min(r0 + e->chunk_rows, s.ny)));
+            for (int st_ = 0; st_ < div_up(s.nx, STRIP); ++st_)
+                items.push_back(make_int4(g, st_ * STRIP - 1, r0, std::min(r0 + e->chunk_rows, s.ny)));
         s.n_items = (int)items.size() - s.item0;
     }
     istart[n_glaciers] = (int)items.size();
     e->n_items = (int)items.size();
-
-    std::vector<int2> tiles(tile);
-    std::vector<int> tstart(n_glaciers + 1);
-    for (int g = 0; g < n_glaciers; ++g) {
-        const GlacierHost& s = e->gl[g];
-        tstart[g] = s.tile0;
-        for (int ty = 0; ty < s.nty; ++ty)
-            for (int tx = 0; tx < s.ntx; ++tx) tiles[s.tile0 + ty * s.ntx + tx] = make_int2(g, (ty << 16) | tx);
-    }
-    tstart[n_glaciers] = tile;
 
 #define CREATE_CUDA(call)                                                                     \
     do {                                                                                      \
@@ -313,13 +344,17 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * std::max(tile, e->n_items)));
     CREATE_CUDA(cudaMalloc(&e->d_items, sizeof(int4) * e->n_items));
     CREATE_CUDA(cudaMalloc(&e->d_item_start, sizeof(int) * (n_glaciers + 1)));
-    CREATE_CUDA(cudaMemcpy(e->d_items, items.data(), sizeof(int4) * e->n_items, cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMemcpy(e->d_item_start, istart.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
-    CREATE_CUDA(cudaMalloc(&e->d_S, sizeof(double) * n_glaciers));
-    CREATE_CUDA(cudaMallocHost(&e->h_S, sizeof(double) * n_glaciers));
+    CREATE_CUDA(cudaMalloc(&e->d_S, sizeof(double) * n_glaciers * 4));  // S, Ssum, loss, A
+    CREATE_CUDA(cudaMemset(e->d_S, 0, sizeof(double) * n_glaciers * 4));
+    CREATE_CUDA(cudaMallocHost(&e->h_S, sizeof(double) * n_glaciers * 4));
     CREATE_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(int2) * tile, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(e->d_tile_start, tstart.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(e->d_items, items.data(), sizeof(int4) * e->n_items, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(e->d_item_start, istart.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
 #undef CREATE_CUDA
+    e->d_Ssum = e->d_S + n_glaciers;
+    e->d_loss = e->d_S + 2 * n_glaciers;
+    e->d_A = e->d_S + 3 * n_glaciers;
     *out = e;
     return ODINN_OK;
 }
@@ -330,13 +365,10 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int f = 0; f < ODINN_FIELD_COUNT_; ++f)
         if (e->plane[f]) cudaFree(e->plane[f]);
-    if (e->d_descs) cudaFree(e->d_descs);
-    if (e->d_tiles) cudaFree(e->d_tiles);
-    if (e->d_tile_start) cudaFree(e->d_tile_start);
-    if (e->d_partial) cudaFree(e->d_partial);
-    if (e->d_items) cudaFree(e->d_items);
-    if (e->d_item_start) cudaFree(e->d_item_start);
-    if (e->d_S) cudaFree(e->d_S);
+    void* ptrs[] = {e->d_descs, e->d_tiles, e->d_tile_start, e->d_partial, e->d_items, e->d_item_start, e->d_S,
+                    e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
     if (e->h_S) cudaFreeHost(e->h_S);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     for (int k = 0; k < 2; ++k)
@@ -349,7 +381,6 @@ const char* odinn_last_error(const odinn_ensemble* e) { return e ? e->err.c_str(
 int odinn_n_glaciers(const odinn_ensemble* e) { return e ? e->G : 0; }
 int odinn_dtype_of(const odinn_ensemble* e) { return e ? e->dtype : -1; }
 long long odinn_launch_count(const odinn_ensemble* e) { return e ? e->launches : 0; }
-
 void* odinn_stream(odinn_ensemble* e) { return e ? (void*)e->stream : nullptr; }
 
 int odinn_synchronize(odinn_ensemble* e) {
@@ -382,6 +413,14 @@ int odinn_set_A_scalar(odinn_ensemble* e, int glacier, double A) {
     return ODINN_OK;
 }
 
+int odinn_set_temperature(odinn_ensemble* e, int glacier, double T) {
+    GUARD(e);
+    if (glacier < 0 || glacier >= e->G) return fail(e, ODINN_EARG, "glacier index out of range");
+    e->gl[glacier].temp = T;
+    e->descs_dirty = true;
+    return ODINN_OK;
+}
+
 int odinn_set_A_mode(odinn_ensemble* e, int gridded) {
     GUARD(e);
     e->a_gridded = gridded ? 1 : 0;
@@ -396,12 +435,15 @@ int odinn_set_phys(odinn_ensemble* e, const odinn_phys* phys) {
     return ODINN_OK;
 }
 
+// ---- per-call operators (host buffers) -----------------------------------------------------------------------
+
 int odinn_sia2d_rhs(odinn_ensemble* e, int glacier, const void* H, int ldH, void* dH, int lddH, double t) {
     GUARD(e);
     (void)t;  // autonomous RHS: laws with callback_freq = 0 do not depend on t (Laws.jl:346)
     int rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
-    if ((rc = launch_rhs(e, glacier))) return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_DH))) return rc;
+    if ((rc = launch_rhs(e, glacier, e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_DH]))) return rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_DH, dH, lddH, false, e->stream))) return rc;
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     return ODINN_OK;
@@ -414,7 +456,10 @@ int odinn_sia2d_vjp_H(odinn_ensemble* e, int glacier, const void* lambda, int ld
     int rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda), ldl, true, e->stream))) return rc;
-    if ((rc = launch_vjp(e, glacier, true, false))) return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
+    if ((rc = launch_vjp(e, glacier, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
+                         true, false)))
+        return rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_VJP_H, out, ldo, false, e->stream))) return rc;
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     return ODINN_OK;
@@ -428,21 +473,30 @@ int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, in
     int rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
     if ((rc = copy2d(e, glacier, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda), ldl, true, e->stream))) return rc;
-    if ((rc = launch_vjp(e, glacier, false, true))) return rc;
+    if ((rc = launch_vjp(e, glacier, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], nullptr, false, true)))
+        return rc;
     ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + glacier, e->d_S + glacier, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     *out_S = e->h_S[glacier];
     return ODINN_OK;
 }
 
+// ---- ensemble operators on resident planes ---------------------------------------------------------------------
+
 int odinn_rhs_resident(odinn_ensemble* e) {
     GUARD(e);
-    return launch_rhs(e, -1);
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_DH))) return rc;
+    return launch_rhs(e, -1, e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_DH]);
 }
 
 int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out) {
     GUARD(e);
-    int rc = launch_vjp(e, -1, (flags & 1) != 0, (flags & 2) != 0);
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_LAMBDA))) return rc;
+    if ((flags & 1) && (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
+    rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
+                    (flags & 1) != 0, (flags & 2) != 0);
     if (rc) return rc;
     if ((flags & 2) && S_out) {
         ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_S, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
@@ -464,8 +518,16 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
         if (adj && (rc = copy2d(e, g, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda[g]), e->gl[g].nx, true, e->stream)))
             return rc;
     }
-    if (dH && (rc = launch_rhs(e, -1))) return rc;
-    if (adj && (rc = launch_vjp(e, -1, vjpH != nullptr, S != nullptr))) return rc;
+    if (dH) {
+        if ((rc = ensure_plane(e, ODINN_FIELD_DH))) return rc;
+        if ((rc = launch_rhs(e, -1, e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_DH]))) return rc;
+    }
+    if (adj) {
+        if (vjpH && (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
+        if ((rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
+                             vjpH != nullptr, S != nullptr)))
+            return rc;
+    }
     for (int g = 0; g < e->G; ++g) {
         if (dH && (rc = copy2d(e, g, ODINN_FIELD_DH, dH[g], e->gl[g].nx, false, e->stream))) return rc;
         if (vjpH && (rc = copy2d(e, g, ODINN_FIELD_VJP_H, vjpH[g], e->gl[g].nx, false, e->stream))) return rc;
@@ -473,6 +535,234 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
     if (S) ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_S, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     if (S) memcpy(S, e->h_S, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+// ---- on-device time loop ---------------------------------------------------------------------------------------
+
+int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double* t, int nsub) {
+    GUARD(e);
+    if (n_snap < 1 || !t || nsub < 1) return fail(e, ODINN_EARG, "bad time grid");
+    if (method != ODINN_EULER && method != ODINN_SSPRK3) return fail(e, ODINN_EARG, "unknown integration method");
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_H0)) || (rc = ensure_plane(e, ODINN_FIELD_H))) return rc;
+    if ((rc = alloc_plane(e, &e->work[0])) || (rc = alloc_plane(e, &e->work[1]))) return rc;
+    if (e->n_snap != n_snap) {
+        if (e->snap) cudaFree(e->snap);
+        e->snap = nullptr;
+        e->n_snap = 0;
+    }
+    if ((rc = alloc_plane(e, &e->snap, n_snap))) return rc;
+    e->n_snap = n_snap;
+    const size_t pbytes = (size_t)e->total * e->esize;
+    void* Hs = e->plane[ODINN_FIELD_H];  // current state; H and the work planes rotate by pointer
+    void* U1 = e->work[0];
+    void* U2 = e->work[1];
+    ODINN_CUDA(e, cudaMemcpyAsync(Hs, e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, 0), Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    for (int j = 1; j < n_snap; ++j) {
+        const double h = (t[j] - t[j - 1]) / nsub;
+        for (int s = 0; s < nsub; ++s) {
+            if (method == ODINN_EULER) {
+                Stage s1{Hs, 0.0, 1.0, h};  // U1 = H + h f(H)
+                if ((rc = launch_rhs(e, -1, Hs, U1, &s1))) return rc;
+                std::swap(Hs, U1);
+            } else {  // Shu-Osher SSPRK(3,3)
+                Stage s1{Hs, 0.0, 1.0, h};              // u1 = H + h f(H)
+                Stage s2{Hs, 0.75, 0.25, h};            // u2 = 3/4 H + 1/4 (u1 + h f(u1))
+                Stage s3{Hs, 1.0 / 3.0, 2.0 / 3.0, h};  // H  = 1/3 H + 2/3 (u2 + h f(u2))   (in place over U0)
+                if ((rc = launch_rhs(e, -1, Hs, U1, &s1))) return rc;
+                if ((rc = launch_rhs(e, -1, U1, U2, &s2))) return rc;
+                if ((rc = launch_rhs(e, -1, U2, Hs, &s3))) return rc;
+            }
+        }
+        ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, j), Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    if (Hs != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H
+        ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    return ODINN_OK;
+}
+
+int odinn_get_snapshot(odinn_ensemble* e, int glacier, int j, void* host, int ld) {
+    GUARD(e);
+    if (!e->snap || j < 0 || j >= e->n_snap) return fail(e, ODINN_ESTATE, "no such snapshot (run odinn_solve_forward first)");
+    int rc = copy2d_ptr(e, glacier, plane_ptr(e, e->snap, j), false, host, ld, false, e->stream);
+    if (rc) return rc;
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ODINN_OK;
+}
+
+int odinn_set_snapshot(odinn_ensemble* e, int glacier, int j, int n_snap, const void* host, int ld) {
+    GUARD(e);
+    if (n_snap < 1 || j < 0 || j >= n_snap) return fail(e, ODINN_EARG, "bad snapshot index");
+    if (e->n_snap != n_snap) {
+        if (e->snap) cudaFree(e->snap);
+        e->snap = nullptr;
+        e->n_snap = 0;
+    }
+    int rc;
+    if ((rc = alloc_plane(e, &e->snap, n_snap))) return rc;
+    e->n_snap = n_snap;
+    if ((rc = copy2d_ptr(e, glacier, plane_ptr(e, e->snap, j), false, const_cast<void*>(host), ld, true, e->stream)))
+        return rc;
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ODINN_OK;
+}
+
+int odinn_set_reference(odinn_ensemble* e, int glacier, int j, int n_snap, const void* Href, const void* W, int ld) {
+    GUARD(e);
+    if (n_snap < 1 || j < 0 || j >= n_snap) return fail(e, ODINN_EARG, "bad snapshot index");
+    if (e->n_ref != n_snap) {
+        if (e->href) cudaFree(e->href);
+        if (e->wmask) cudaFree(e->wmask);
+        e->href = e->wmask = nullptr;
+        e->n_ref = 0;
+    }
+    int rc;
+    if ((rc = alloc_plane(e, &e->href, n_snap)) || (rc = alloc_plane(e, &e->wmask, n_snap))) return rc;
+    e->n_ref = n_snap;
+    if ((rc = copy2d_ptr(e, glacier, plane_ptr(e, e->href, j), false, const_cast<void*>(Href), ld, true, e->stream)))
+        return rc;
+    if ((rc = copy2d_ptr(e, glacier, plane_ptr(e, e->wmask, j), false, const_cast<void*>(W), ld, true, e->stream)))
+        return rc;
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ODINN_OK;
+}
+
+static int check_grad_state(odinn_ensemble* e, const double* t, int n_t) {
+    if (!e->snap || !e->href) return fail(e, ODINN_ESTATE, "snapshots and reference data must be set first");
+    if (e->n_snap != e->n_ref || n_t != e->n_snap)
+        return fail(e, ODINN_ESTATE, "snapshot / reference / time counts differ");
+    if (!t) return fail(e, ODINN_EARG, "t is null");
+    return ODINN_OK;
+}
+
+int odinn_loss(odinn_ensemble* e, const double* t, int n_t, double* loss_out) {
+    GUARD(e);
+    int rc = check_grad_state(e, t, n_t);
+    if (rc) return rc;
+    if (!loss_out) return fail(e, ODINN_EARG, "loss_out is null");
+    ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
+    for (int j = 1; j < n_t; ++j) {  // Δt_H of the first data point is 0 (safe_slice, gradient.jl:146-149)
+        if ((rc = launch_loss_seed(e, plane_ptr(e, e->snap, j), plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j),
+                                   nullptr, nullptr, nullptr, 0.0, 0.0, e->d_loss, t[j] - t[j - 1], 1)))
+            return rc;
+    }
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(loss_out, e->h_S, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* loss_out, double* Ssum_out) {
+    GUARD(e);
+    int rc = check_grad_state(e, t, n_t);
+    if (rc) return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_LAMBDA)) || (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
+    if (e->a_gridded)
+        return fail(e, ODINN_ESTATE, "odinn_grad_discrete supports glacier-wide A (use the per-call VJPs for gridded A)");
+    const size_t pbytes = (size_t)e->total * e->esize;
+    void* lam = e->plane[ODINN_FIELD_LAMBDA];
+    void* vH = e->plane[ODINN_FIELD_VJP_H];
+    ODINN_CUDA(e, cudaMemsetAsync(lam, 0, pbytes, e->stream));  // λ_k = 0 (gradient.jl:140)
+    ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
+    ODINN_CUDA(e, cudaMemsetAsync(e->d_Ssum, 0, sizeof(double) * e->G, e->stream));
+    for (int j = n_t - 1; j >= 1; --j) {  // gradient.jl:191-253 (the j = 1 pass of the reference updates nothing)
+        const double dt = t[j] - t[j - 1];
+        void* Hj = plane_ptr(e, e->snap, j);
+        // λ_∂f∂H = VJP_H(λ_j, H_j)                                                     (gradient.jl:235-237)
+        if (j < n_t - 1) {
+            if ((rc = launch_vjp(e, -1, lam, Hj, vH, true, false))) return rc;
+        } else {
+            ODINN_CUDA(e, cudaMemsetAsync(vH, 0, pbytes, e->stream));  // λ_k = 0 ⇒ VJP = 0
+        }
+        // ℓ += ℓ_j ;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H,  ∂ℓ_j/∂H = 2 Δt_j W (H_j - H_ref,j)   (:218-242)
+        if ((rc = launch_loss_seed(e, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), lam, vH, lam, dt, 2.0 * dt,
+                                   e->d_loss, dt, 1)))
+            return rc;
+        // dLdθ += Δt_{j-1} · VJP_θ(λ_{j-1}, H_j)                                        (:245-249)
+        if ((rc = launch_vjp(e, -1, lam, Hj, nullptr, false, true, e->d_Ssum, dt, 1))) return rc;
+    }
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + e->G, e->d_Ssum, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (loss_out) memcpy(loss_out, e->h_S, sizeof(double) * e->G);
+    if (Ssum_out) memcpy(Ssum_out, e->h_S + e->G, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+// ---- laws ------------------------------------------------------------------------------------------------------
+
+int odinn_law_A_nn_apply(odinn_ensemble* e, int n_layers, const int* widths, const int* acts, const double* theta,
+                         int n_theta, double* A_out) {
+    GUARD(e);
+    if (n_layers < 1 || n_layers > MLP_MAX_LAYERS || !widths || !acts || !theta)
+        return fail(e, ODINN_EARG, "bad MLP description");
+    MlpArch arch{};
+    arch.n_layers = n_layers;
+    int np = 0;
+    for (int L = 0; L <= n_layers; ++L) {
+        if (widths[L] < 1 || widths[L] > MLP_MAX_WIDTH) return fail(e, ODINN_EARG, "MLP width out of range (1..64)");
+        arch.widths[L] = widths[L];
+    }
+    for (int L = 0; L < n_layers; ++L) {
+        if (acts[L] < ACT_IDENTITY || acts[L] > ACT_RELU) return fail(e, ODINN_EARG, "unknown activation code");
+        arch.acts[L] = acts[L];
+        np += widths[L] * widths[L + 1] + widths[L + 1];
+    }
+    if (widths[0] != 1 || widths[n_layers] != 1) return fail(e, ODINN_EARG, "the A law maps one temperature to one A");
+    if (np != n_theta) return fail(e, ODINN_EARG, "theta length does not match the architecture");
+    arch.n_params = np;
+    if (e->n_theta != np) {
+        if (e->d_theta) cudaFree(e->d_theta);
+        if (e->d_J) cudaFree(e->d_J);
+        if (e->d_dtheta) cudaFree(e->d_dtheta);
+        e->d_theta = e->d_J = e->d_dtheta = nullptr;
+        e->n_theta = 0;
+        ODINN_CUDA(e, cudaMalloc(&e->d_theta, sizeof(double) * np));
+        ODINN_CUDA(e, cudaMalloc(&e->d_J, sizeof(double) * np * e->G));
+        ODINN_CUDA(e, cudaMalloc(&e->d_dtheta, sizeof(double) * np));
+        e->n_theta = np;
+    }
+    if (!e->d_temps) ODINN_CUDA(e, cudaMalloc(&e->d_temps, sizeof(double) * e->G));
+    int rc = sync_descs(e);
+    if (rc) return rc;
+    std::vector<double> temps(e->G);
+    for (int g = 0; g < e->G; ++g) temps[g] = e->gl[g].temp;
+    ODINN_CUDA(e, cudaMemcpyAsync(e->d_temps, temps.data(), sizeof(double) * e->G, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(e->d_theta, theta, sizeof(double) * np, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));  // temps / theta are caller- or stack-owned
+    law_A_nn_kernel<<<div_up(e->G, 64), 64, 0, e->stream>>>(arch, (const double*)e->d_theta, (const double*)e->d_temps,
+                                                           e->G, e->phys.minA, e->phys.maxA, e->d_A, (double*)e->d_J);
+    ODINN_CHECK_LAUNCH(e);
+    if (e->dtype == ODINN_F32)
+        set_A_kernel<float><<<div_up(e->G, 128), 128, 0, e->stream>>>((GDesc<float>*)e->d_descs, e->d_A, e->G);
+    else
+        set_A_kernel<double><<<div_up(e->G, 128), 128, 0, e->stream>>>((GDesc<double>*)e->d_descs, e->d_A, e->G);
+    ODINN_CHECK_LAUNCH(e);
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_A, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int g = 0; g < e->G; ++g) e->gl[g].A = e->h_S[g];  // keep the host mirror in step (descs stay clean)
+    if (A_out) memcpy(A_out, e->h_S, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+int odinn_law_A_nn_pullback(odinn_ensemble* e, const double* S, double* dtheta, int n_theta) {
+    GUARD(e);
+    if (!e->d_J || e->n_theta != n_theta) return fail(e, ODINN_ESTATE, "call odinn_law_A_nn_apply first");
+    if (!dtheta) return fail(e, ODINN_EARG, "dtheta is null");
+    const double* dS = e->d_Ssum;  // default: the sums left by odinn_grad_discrete
+    if (S) {
+        ODINN_CUDA(e, cudaMemcpyAsync(e->d_S, S, sizeof(double) * e->G, cudaMemcpyHostToDevice, e->stream));
+        dS = e->d_S;
+    }
+    law_pullback_kernel<<<div_up(n_theta, 128), 128, 0, e->stream>>>((const double*)e->d_J, dS, e->G, n_theta,
+                                                                     (double*)e->d_dtheta);
+    ODINN_CHECK_LAUNCH(e);
+    std::vector<double> tmp(n_theta);
+    ODINN_CUDA(e, cudaMemcpyAsync(tmp.data(), e->d_dtheta, sizeof(double) * n_theta, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(dtheta, tmp.data(), sizeof(double) * n_theta);
     return ODINN_OK;
 }
 

@@ -45,10 +45,24 @@ struct odinn_ensemble {
     int* d_item_start = nullptr;
     int n_items = 0;
     int chunk_rows = 32;
-    int use_tiled = 0;            // dev switch: ODINN_KERNEL=tiled selects the v1 shared-memory kernels
-    double* d_partial = nullptr;
-    double* d_S = nullptr;
-    double* h_S = nullptr;  // pinned
+    double* d_partial = nullptr;  // per-item / per-tile partial sums (two-stage, fixed-order reductions)
+    double* d_S = nullptr;        // [4 x G]: S | Ssum | loss | A
+    double* d_Ssum = nullptr;
+    double* d_loss = nullptr;
+    double* d_A = nullptr;
+    double* h_S = nullptr;        // pinned mirror of d_S
+    // on-device time loop / gradient state
+    void* snap = nullptr;         // n_snap planes: forward snapshots H(t_j)        (gradient.jl:73,140)
+    void* href = nullptr;         // n_ref planes: reference thickness H_ref(t_j)
+    void* wmask = nullptr;        // n_ref planes: is_in_glacier mask / (nx ny)
+    void* work[2] = {nullptr, nullptr};
+    int n_snap = 0, n_ref = 0;
+    // law state (LawA(nn, params))
+    void* d_theta = nullptr;
+    void* d_J = nullptr;          // [G x n_theta] dA_g/dθ
+    void* d_dtheta = nullptr;
+    double* d_temps = nullptr;
+    int n_theta = 0;
     long long launches = 0;
     std::string err;
 

@@ -135,3 +135,67 @@ class Ensemble:
         """Raw-pointer batched call (bench e2e path).  Each ``*_ptrs`` is a ctypes ``c_void_p`` array or None."""
         sp = S.ctypes.data_as(C.POINTER(C.c_double)) if S is not None else None
         self._ck(self._lib.odinn_fwd_adj_batch_host(self._h, H_ptrs, lam_ptrs, dH_ptrs, vjpH_ptrs, sp))
+
+    # -- laws ------------------------------------------------------------------------------------
+    def set_temperature(self, g: int, T: float):
+        self._ck(self._lib.odinn_set_temperature(self._h, g, float(T)))
+
+    def law_A_nn_apply(self, widths, acts, theta):
+        """A_g = minA + (maxA-minA)·NN([T_g]; θ) for every glacier (LawA f!, Laws.jl:348-358); returns A (G,)."""
+        widths = [int(w) for w in widths]
+        codes = [_capi.ACT[a] if isinstance(a, str) else int(a) for a in acts]
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        A = np.empty(self.G, dtype=np.float64)
+        self._ck(self._lib.odinn_law_A_nn_apply(self._h, len(codes), (C.c_int * len(widths))(*widths),
+                                                (C.c_int * len(codes))(*codes),
+                                                theta.ctypes.data_as(C.POINTER(C.c_double)), theta.size,
+                                                A.ctypes.data_as(C.POINTER(C.c_double))))
+        return A
+
+    def law_A_nn_pullback(self, n_theta: int, S=None):
+        """dθ = Σ_g (∂A_g/∂θ)·S_g ; S=None uses the sums left on the device by grad_discrete."""
+        out = np.empty(n_theta, dtype=np.float64)
+        sp = None
+        if S is not None:
+            S = np.ascontiguousarray(S, dtype=np.float64)
+            sp = S.ctypes.data_as(C.POINTER(C.c_double))
+        self._ck(self._lib.odinn_law_A_nn_pullback(self._h, sp, out.ctypes.data_as(C.POINTER(C.c_double)), n_theta))
+        return out
+
+    # -- device-resident time loop and gradient -----------------------------------------------------
+    def solve_forward(self, t, method: str = "ssprk3", nsub: int = 8):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        m = {"euler": _capi.EULER, "ssprk3": _capi.SSPRK3}[method]
+        self._ck(self._lib.odinn_solve_forward(self._h, m, t.size, t.ctypes.data_as(C.POINTER(C.c_double)), int(nsub)))
+
+    def get_snapshot(self, g: int, j: int):
+        out = np.empty((self.nx[g], self.ny[g]), dtype=self.np_dtype, order="F")
+        self._ck(self._lib.odinn_get_snapshot(self._h, g, j, out.ctypes.data, out.shape[0]))
+        return out
+
+    def set_snapshot(self, g: int, j: int, n_snap: int, H):
+        H = _as_f(H, self.np_dtype)
+        self._ck(self._lib.odinn_set_snapshot(self._h, g, j, n_snap, H.ctypes.data, H.shape[0]))
+
+    def set_reference(self, g: int, j: int, n_snap: int, Href, mask):
+        """mask: boolean is_in_glacier(H_ref, distance); stored as W = mask / (nx·ny) (gradient.jl:161)."""
+        Href = _as_f(Href, self.np_dtype)
+        W = _as_f(np.asarray(mask, dtype=np.float64) / float(self.nx[g] * self.ny[g]), self.np_dtype)
+        self._ck(self._lib.odinn_set_reference(self._h, g, j, n_snap, Href.ctypes.data, W.ctypes.data, Href.shape[0]))
+
+    def loss(self, t):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.empty(self.G, dtype=np.float64)
+        self._ck(self._lib.odinn_loss(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), t.size,
+                                      out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def grad_discrete(self, t):
+        """Returns (loss per glacier, Ssum per glacier) of the DiscreteAdjoint reverse loop."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        loss = np.empty(self.G, dtype=np.float64)
+        Ssum = np.empty(self.G, dtype=np.float64)
+        self._ck(self._lib.odinn_grad_discrete(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), t.size,
+                                               loss.ctypes.data_as(C.POINTER(C.c_double)),
+                                               Ssum.ctypes.data_as(C.POINTER(C.c_double))))
+        return loss, Ssum

@@ -164,6 +164,8 @@ _ACT = {
     "softplus": (softplus, lambda z, a: sigmoid(z)),
     "sigmoid": (sigmoid, lambda z, a: a * (1.0 - a)),
     "identity": (lambda z: z, lambda z, a: np.ones_like(z)),
+    "tanh": (np.tanh, lambda z, a: 1.0 - a * a),
+    "relu": (lambda z: np.maximum(z, 0.0), lambda z, a: (z > 0).astype(np.float64)),
 }
 
 
