@@ -211,7 +211,10 @@ def run_b200(args, rank, local_rank, world):
     ptr = lambda t: (C.c_void_p * G)(*[t.data_ptr() + k * esz for k in range(G)])
     pH, pL, pdH, pV = ptr(hH), ptr(hL), ptr(hdH), ptr(hV)
     S = np.zeros(G)
-    # make the planes resident (also the first e2e pass)
+    # resident planes for the device-timed arm (the host-batch call works on its own staging planes)
+    for k in range(G):
+        ens.upload(k, _capi.FIELD_H, hH[k].numpy().T)
+        ens.upload(k, _capi.FIELD_LAMBDA, hL[k].numpy().T)
     ens.fwd_adj_batch_host(pH, pL, pdH, pV, S)
 
     stream = torch.cuda.ExternalStream(ens.stream_ptr, device=local_rank)

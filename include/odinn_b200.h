@@ -139,11 +139,21 @@ int odinn_rhs_resident(odinn_ensemble* e);
  * S_out may be NULL; otherwise n_glaciers doubles (device->host read inside the call). */
 int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
 
-/* One pmap batch through host buffers: for every glacier g upload H[g] (and lambda[g]), run
+/* One pmap batch through host buffers (the reference maps SIA2D_grad_batch! over glacier batches,
+ * src/inverse/SIA2D/gradient.jl:9-10, 235-246): for every glacier g upload H[g] (and lambda[g]), run
  * F1 + A1 + A2, download dH[g], vjpH[g], S[g].  Any of dH / vjpH / S may be NULL to skip that
- * output; lambda may be NULL when only dH is requested.  All matrices use ld = nx. */
+ * output; lambda may be NULL when only dH is requested.  All matrices use ld = nx.
+ * Glaciers are processed in chunks: the host->device copies of chunk c+1, the kernels of chunk c and the
+ * device->host copies of chunk c-1 overlap on three streams.  The transfers are asynchronous only for pinned
+ * (page-locked) host memory; see odinn_host_register.  The resident planes are not touched. */
 int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void* const* lambda,
                              void* const* dH, void* const* vjpH, double* S);
+/* Cells per pipeline chunk of odinn_fwd_adj_batch_host (default 2 Mi cells). */
+int odinn_set_batch_chunk(odinn_ensemble* e, long long cells);
+/* Page-lock / release a caller-owned host range (a Julia Array's memory) so that transfers from it are true
+ * asynchronous DMA.  Thin wrappers of cudaHostRegister / cudaHostUnregister. */
+int odinn_host_register(odinn_ensemble* e, void* host, size_t bytes);
+int odinn_host_unregister(odinn_ensemble* e, void* host);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Device-resident time loop and gradient (H, lambda and the snapshots never leave HBM)      */

@@ -29,14 +29,17 @@ int ensure_plane(odinn_ensemble* e, int field) {
 
 template <typename T>
 static int sync_descs_t(odinn_ensemble* e) {
-    std::vector<GDesc<T>> h(e->G);
-    for (int g = 0; g < e->G; ++g) {
-        const GlacierHost& s = e->gl[g];
+    // two tables: [0, G) the padded device layout, [G, 2G) the packed layout of the host-batch path
+    // (ld = nx, glaciers back to back: exactly the bytes of the caller's matrices, so every copy is linear)
+    std::vector<GDesc<T>> h(2 * e->G);
+    for (int g = 0; g < 2 * e->G; ++g) {
+        const bool packed = g >= e->G;
+        const GlacierHost& s = e->gl[g % e->G];
         GDesc<T>& d = h[g];
-        d.off = s.off;
+        d.off = packed ? s.off_packed : s.off;
         d.nx = s.nx;
         d.ny = s.ny;
-        d.ld = s.ld;
+        d.ld = packed ? s.nx : s.ld;
         d.tile0 = s.tile0;
         d.dx = (T)s.dx;
         d.dy = (T)s.dy;
@@ -45,7 +48,7 @@ static int sync_descs_t(odinn_ensemble* e) {
         d.A = (T)s.A;
         d.temp = (T)s.temp;
     }
-    ODINN_CUDA(e, cudaMemcpyAsync(e->d_descs, h.data(), sizeof(GDesc<T>) * e->G, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(e->d_descs, h.data(), sizeof(GDesc<T>) * 2 * e->G, cudaMemcpyHostToDevice, e->stream));
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));  // h goes out of scope
     return ODINN_OK;
 }
@@ -71,12 +74,12 @@ struct Stage {
 };
 
 template <typename T>
-static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st) {
+static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed) {
     PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs + (packed ? e->G : 0);
     const int4* items = e->d_items + i0;
     const T* H = (const T*)Hin;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* B = (const T*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
     const T* Af = (const T*)e->plane[ODINN_FIELD_A];
     T* dH = (T*)out;
     const bool eta1 = (e->phys.eta0 == 1.0);
@@ -99,31 +102,34 @@ static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin,
     return ODINN_OK;
 }
 
-// g < 0: whole ensemble
-static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, const Stage* st = nullptr) {
+// Glaciers [g0, g1); g0 < 0: whole ensemble.  `packed` selects the packed descriptor table (host-batch path).
+static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
     if (e->a_gridded && (rc = ensure_plane(e, ODINN_FIELD_A))) return rc;
     if ((rc = sync_descs(e))) return rc;
     int i0 = 0, ni = e->n_items;
-    if (g >= 0) {
-        i0 = e->gl[g].item0;
-        ni = e->gl[g].n_items;
+    if (g0 >= 0) {
+        i0 = e->gl[g0].item0;
+        ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
     }
-    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, i0, ni, Hin, out, st)
-                                 : launch_rhs_t<double>(e, i0, ni, Hin, out, st);
+    return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, i0, ni, Hin, out, st, packed)
+                                 : launch_rhs_t<double>(e, i0, ni, Hin, out, st, packed);
+}
+static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, const Stage* st = nullptr) {
+    return launch_rhs_range(e, g, g + 1, Hin, out, st, false);
 }
 
 // ---- A1 / A2 launch --------------------------------------------------------------------------------------------
 
 template <typename T>
 static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const void* H_, void* out_, bool wH,
-                        bool wS) {
+                        bool wS, bool packed) {
     PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs + (packed ? e->G : 0);
     const T* lam = (const T*)lam_;
     const T* H = (const T*)H_;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* B = (const T*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
     const T* Af = (const T*)e->plane[ODINN_FIELD_A];
     T* out = (T*)out_;
     T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
@@ -152,9 +158,9 @@ static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_
     return ODINN_OK;
 }
 
-// g < 0: whole ensemble.  S_dst: where the per-glacier sums go (d_S or an accumulator), scaled by `scale`.
-static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, void* out, bool wH, bool wS,
-                      double* S_dst = nullptr, double scale = 1.0, int accumulate = 0) {
+// Glaciers [g0, g1); g0 < 0: whole ensemble.  S_dst: where the per-glacier sums go (d_S or an accumulator), scaled by `scale`.
+static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS,
+                            double* S_dst, double scale, int accumulate, bool packed) {
     if (!wH && !wS) return ODINN_OK;
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
@@ -162,22 +168,26 @@ static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, 
         return rc;
     if ((rc = sync_descs(e))) return rc;
     int i0 = 0, ni = e->n_items;
-    if (g >= 0) {
-        i0 = e->gl[g].item0;
-        ni = e->gl[g].n_items;
+    if (g0 >= 0) {
+        i0 = e->gl[g0].item0;
+        ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
     }
-    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS)
-                               : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS);
+    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
+                               : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed);
     if (rc) return rc;
     if (wS) {
         double* dst = S_dst ? S_dst : e->d_S;
-        if (g >= 0)
-            reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_item_start + g, e->d_partial, dst + g, scale, accumulate);
+        if (g0 >= 0)
+            reduce_scaled_kernel<<<g1 - g0, NT, 0, e->stream>>>(e->d_item_start + g0, e->d_partial, dst + g0, scale, accumulate);
         else
             reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_item_start, e->d_partial, dst, scale, accumulate);
         ODINN_CHECK_LAUNCH(e);
     }
     return ODINN_OK;
+}
+static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, void* out, bool wH, bool wS,
+                      double* S_dst = nullptr, double scale = 1.0, int accumulate = 0) {
+    return launch_vjp_range(e, g, g + 1, lam, H, out, wH, wS, S_dst, scale, accumulate, false);
 }
 
 static int copy2d_ptr(odinn_ensemble* e, int g, char* plane_base, bool dual, void* host, int ld, bool up,
@@ -267,7 +277,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     e->phys = *phys;
     refresh_phys(e);
     e->gl.resize(n_glaciers);
-    long long off = 0;
+    long long off = 0, offp = 0;
     int tile = 0;
     for (int g = 0; g < n_glaciers; ++g) {
         if (nx[g] < 3 || ny[g] < 3 || nx[g] > 65535 * TX || !(dx[g] > 0) || !(dy[g] > 0)) {
@@ -279,6 +289,8 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         s.ny = ny[g];
         s.ld = div_up(nx[g], 32) * 32;
         s.off = off;
+        s.off_packed = offp;
+        offp += (long long)nx[g] * ny[g];
         s.dx = dx[g];
         s.dy = dy[g];
         s.A = 0.0;
@@ -338,7 +350,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     CREATE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream[0], cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream[1], cudaStreamNonBlocking));
     size_t dsz = dtype == ODINN_F32 ? sizeof(GDesc<float>) : sizeof(GDesc<double>);
-    CREATE_CUDA(cudaMalloc(&e->d_descs, dsz * n_glaciers));
+    CREATE_CUDA(cudaMalloc(&e->d_descs, dsz * n_glaciers * 2));
     CREATE_CUDA(cudaMalloc(&e->d_tiles, sizeof(int2) * tile));
     CREATE_CUDA(cudaMalloc(&e->d_tile_start, sizeof(int) * (n_glaciers + 1)));
     CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * std::max(tile, e->n_items)));
@@ -366,11 +378,14 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
     for (int f = 0; f < ODINN_FIELD_COUNT_; ++f)
         if (e->plane[f]) cudaFree(e->plane[f]);
     void* ptrs[] = {e->d_descs, e->d_tiles, e->d_tile_start, e->d_partial, e->d_items, e->d_item_start, e->d_S,
-                    e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps};
+                    e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps,
+                    e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (e->h_S) cudaFreeHost(e->h_S);
     if (e->h_stage) cudaFreeHost(e->h_stage);
+    for (cudaEvent_t ev : e->ev_up) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
     for (int k = 0; k < 2; ++k)
         if (e->copy_stream[k]) cudaStreamDestroy(e->copy_stream[k]);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -393,6 +408,7 @@ int odinn_upload(odinn_ensemble* e, int glacier, int field, const void* host, in
     GUARD(e);
     int rc = copy2d(e, glacier, field, const_cast<void*>(host), ld, true, e->stream);
     if (rc) return rc;
+    if (field == ODINN_FIELD_B) e->bpack_dirty = true;
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     return ODINN_OK;
 }
@@ -510,31 +526,109 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
                              void* const* vjpH, double* S) {
     GUARD(e);
     if (!H) return fail(e, ODINN_EARG, "H is null");
-    bool adj = (vjpH != nullptr) || (S != nullptr);
+    const bool adj = (vjpH != nullptr) || (S != nullptr);
     if (adj && !lambda) return fail(e, ODINN_EARG, "lambda is required for the VJP outputs");
     int rc;
-    for (int g = 0; g < e->G; ++g) {
-        if ((rc = copy2d(e, g, ODINN_FIELD_H, const_cast<void*>(H[g]), e->gl[g].nx, true, e->stream))) return rc;
-        if (adj && (rc = copy2d(e, g, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda[g]), e->gl[g].nx, true, e->stream)))
+    if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+    // The call works on its own staging planes, so the resident planes (FIELD_H, ...) keep their contents.
+    if ((rc = alloc_plane(e, &e->stage[0]))) return rc;
+    if (adj && (rc = alloc_plane(e, &e->stage[1]))) return rc;
+    if (dH && (rc = alloc_plane(e, &e->stage[2]))) return rc;
+    if (vjpH && (rc = alloc_plane(e, &e->stage[3]))) return rc;
+    if ((rc = sync_descs(e))) return rc;
+    // Packed layout (ld = nx): the device planes hold exactly the caller's bytes, so every transfer is one linear
+    // DMA instead of ny row copies.  The gridded-A field lives in the padded layout only -> padded (2-D copy) path.
+    const bool packed = !e->a_gridded;
+    if (packed && e->bpack_dirty) {
+        if ((rc = alloc_plane(e, &e->bpack))) return rc;
+        for (int g = 0; g < e->G; ++g) {
+            const GlacierHost& s = e->gl[g];
+            ODINN_CUDA(e, cudaMemcpy2DAsync((char*)e->bpack + (size_t)s.off_packed * e->esize, (size_t)s.nx * e->esize,
+                                            (char*)e->plane[ODINN_FIELD_B] + (size_t)s.off * e->esize,
+                                            (size_t)s.ld * e->esize, (size_t)s.nx * e->esize, s.ny,
+                                            cudaMemcpyDeviceToDevice, e->stream));
+        }
+        e->bpack_dirty = false;
+    }
+    // chunks of ~2 M cells: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap
+    const long long chunk_cells = e->batch_chunk_cells;
+    std::vector<int> cstart{0};
+    {
+        long long acc = 0;
+        for (int g = 0; g < e->G; ++g) {
+            acc += (long long)e->gl[g].nx * e->gl[g].ny;
+            if (acc >= chunk_cells && g + 1 < e->G) { cstart.push_back(g + 1); acc = 0; }
+        }
+        cstart.push_back(e->G);
+    }
+    const int nchunk = (int)cstart.size() - 1;
+    while ((int)e->ev_up.size() < nchunk + 1) {
+        cudaEvent_t a, b;
+        ODINN_CUDA(e, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ODINN_CUDA(e, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->ev_up.push_back(a);
+        e->ev_done.push_back(b);
+    }
+    cudaStream_t up = e->copy_stream[0], dn = e->copy_stream[1];
+    // the copy streams start after everything already queued on the compute stream (bpack, earlier calls)
+    ODINN_CUDA(e, cudaEventRecord(e->ev_done[nchunk], e->stream));
+    ODINN_CUDA(e, cudaStreamWaitEvent(up, e->ev_done[nchunk], 0));
+    ODINN_CUDA(e, cudaStreamWaitEvent(dn, e->ev_done[nchunk], 0));
+    auto xfer = [&](int g, int slot, void* host, bool to_dev, cudaStream_t st) -> int {
+        if (!host) return fail(e, ODINN_EARG, "null host pointer in a batch array");
+        const GlacierHost& s = e->gl[g];
+        if (!packed) return copy2d_ptr(e, g, (char*)e->stage[slot], false, host, s.nx, to_dev, st);
+        char* dev = (char*)e->stage[slot] + (size_t)s.off_packed * e->esize;
+        size_t bytes = (size_t)s.nx * s.ny * e->esize;
+        ODINN_CUDA(e, to_dev ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st)
+                             : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+        return ODINN_OK;
+    };
+    for (int c = 0; c < nchunk; ++c) {
+        const int g0 = cstart[c], g1 = cstart[c + 1];
+        for (int g = g0; g < g1; ++g) {
+            if ((rc = xfer(g, 0, const_cast<void*>(H[g]), true, up))) return rc;
+            if (adj && (rc = xfer(g, 1, const_cast<void*>(lambda[g]), true, up))) return rc;
+        }
+        ODINN_CUDA(e, cudaEventRecord(e->ev_up[c], up));
+        ODINN_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_up[c], 0));
+        if (dH && (rc = launch_rhs_range(e, g0, g1, e->stage[0], e->stage[2], nullptr, packed))) return rc;
+        if (adj && (rc = launch_vjp_range(e, g0, g1, e->stage[1], e->stage[0], e->stage[3], vjpH != nullptr, S != nullptr,
+                                          nullptr, 1.0, 0, packed)))
             return rc;
-    }
-    if (dH) {
-        if ((rc = ensure_plane(e, ODINN_FIELD_DH))) return rc;
-        if ((rc = launch_rhs(e, -1, e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_DH]))) return rc;
-    }
-    if (adj) {
-        if (vjpH && (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
-        if ((rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
-                             vjpH != nullptr, S != nullptr)))
-            return rc;
-    }
-    for (int g = 0; g < e->G; ++g) {
-        if (dH && (rc = copy2d(e, g, ODINN_FIELD_DH, dH[g], e->gl[g].nx, false, e->stream))) return rc;
-        if (vjpH && (rc = copy2d(e, g, ODINN_FIELD_VJP_H, vjpH[g], e->gl[g].nx, false, e->stream))) return rc;
+        ODINN_CUDA(e, cudaEventRecord(e->ev_done[c], e->stream));
+        ODINN_CUDA(e, cudaStreamWaitEvent(dn, e->ev_done[c], 0));
+        for (int g = g0; g < g1; ++g) {
+            if (dH && (rc = xfer(g, 2, dH[g], false, dn))) return rc;
+            if (vjpH && (rc = xfer(g, 3, vjpH[g], false, dn))) return rc;
+        }
     }
     if (S) ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_S, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    // join: the compute stream (the one callers time / synchronise) waits for both copy streams
+    ODINN_CUDA(e, cudaEventRecord(e->ev_up[nchunk], dn));
+    ODINN_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_up[nchunk], 0));
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     if (S) memcpy(S, e->h_S, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+int odinn_set_batch_chunk(odinn_ensemble* e, long long cells) {
+    GUARD(e);
+    if (cells < 1) return fail(e, ODINN_EARG, "chunk size must be positive");
+    e->batch_chunk_cells = cells;
+    return ODINN_OK;
+}
+
+int odinn_host_register(odinn_ensemble* e, void* host, size_t bytes) {
+    GUARD(e);
+    if (!host || !bytes) return fail(e, ODINN_EARG, "null host range");
+    ODINN_CUDA(e, cudaHostRegister(host, bytes, cudaHostRegisterPortable));
+    return ODINN_OK;
+}
+
+int odinn_host_unregister(odinn_ensemble* e, void* host) {
+    GUARD(e);
+    ODINN_CUDA(e, cudaHostUnregister(host));
     return ODINN_OK;
 }
 

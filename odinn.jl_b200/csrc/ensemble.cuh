@@ -15,6 +15,7 @@
 struct GlacierHost {
     int nx, ny, ld;
     long long off;
+    long long off_packed;  // element offset in the packed (ld = nx) layout of the host-batch path
     double dx, dy;
     double A;
     double temp;
@@ -66,7 +67,13 @@ struct odinn_ensemble {
     long long launches = 0;
     std::string err;
 
-    // pinned staging for the batched host path (two slots per direction)
+    // host-batch path (odinn_fwd_adj_batch_host): packed copy of B, chunk events for the
+    // H2D -> compute -> D2H pipeline over copy_stream[0] / stream / copy_stream[1]
+    long long batch_chunk_cells = 2LL << 20;
+    void* bpack = nullptr;
+    bool bpack_dirty = true;
+    void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // H, lambda, dH, vjp_H of the host-batch call
+    std::vector<cudaEvent_t> ev_up, ev_done;
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
 };

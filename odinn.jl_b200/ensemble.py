@@ -136,6 +136,21 @@ class Ensemble:
         sp = S.ctypes.data_as(C.POINTER(C.c_double)) if S is not None else None
         self._ck(self._lib.odinn_fwd_adj_batch_host(self._h, H_ptrs, lam_ptrs, dH_ptrs, vjpH_ptrs, sp))
 
+    def set_batch_chunk(self, cells: int):
+        self._ck(self._lib.odinn_set_batch_chunk(self._h, int(cells)))
+
+    def fwd_adj_batch(self, Hs, lams=None, want_dH=True, want_vjpH=True, want_S=True):
+        """NumPy front end of ``odinn_fwd_adj_batch_host``: lists of (nx, ny) matrices in, (dH list, vjpH list, S) out."""
+        Hs = [_as_f(h, self.np_dtype) for h in Hs]
+        mk = lambda arrs: (C.c_void_p * self.G)(*[a.ctypes.data for a in arrs])
+        adj = want_vjpH or want_S
+        ls = [_as_f(l, self.np_dtype) for l in lams] if adj else None
+        dH = [np.empty_like(h, order="F") for h in Hs] if want_dH else None
+        vH = [np.empty_like(h, order="F") for h in Hs] if want_vjpH else None
+        S = np.empty(self.G, dtype=np.float64) if want_S else None
+        self.fwd_adj_batch_host(mk(Hs), mk(ls) if adj else None, mk(dH) if want_dH else None, mk(vH) if want_vjpH else None, S)
+        return dH, vH, S
+
     # -- laws ------------------------------------------------------------------------------------
     def set_temperature(self, g: int, T: float):
         self._ck(self._lib.odinn_set_temperature(self._h, g, float(T)))

@@ -217,3 +217,45 @@ def test_error_convention(ob):
             sim.ensemble.sia2d_rhs(3, np.zeros((8, 9)))  # glacier index out of range
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("gridded", [False, True])
+def test_host_batch_pipeline(ob, dtype, gridded):
+    """odinn_fwd_adj_batch_host (chunked H2D -> kernels -> D2H pipeline; packed layout for scalar A, padded layout
+    for gridded A) == per-glacier oracle, with several chunks and the resident planes left untouched."""
+    from odinn_b200 import _capi
+
+    rng = np.random.default_rng(99)
+    shapes = [(int(rng.integers(8, 70)), int(rng.integers(8, 70))) for _ in range(9)] + [(3, 3), (64, 5)]
+    gl, Hs, lams, As = [], [], [], []
+    for k, (nx, ny) in enumerate(shapes):
+        g = (o.rough_bed_glacier if k % 2 else _tilted_dome)(nx, ny)
+        lam = rng.standard_normal((nx, ny))
+        g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+        A = A0 * (1 + k)
+        if gridded:
+            A = A0 * np.exp(rng.uniform(-1, 1, size=(nx - 1, ny - 1)))
+            if dtype == "f32":
+                A = A.astype(np.float32).astype(np.float64)
+        gl.append(g), Hs.append(H), lams.append(lam), As.append(A)
+    sim = ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy) for g in gl], ob.Phys(), A=As, dtype=dtype)
+    try:
+        ens = sim.ensemble
+        ens.set_batch_chunk(3000)  # several chunks
+        marker = np.full(shapes[0], 7.0)
+        ens.upload(0, _capi.FIELD_H, marker)
+        for rep in range(2):  # second call reuses the staging planes / events
+            dH, vH, S = ens.fwd_adj_batch(Hs, lams)
+            for k, g in enumerate(gl):
+                tg = o.TargetA(o.Phys(), "const", A=As[k])
+                assert rel_l2(dH[k], o.SIA2D(Hs[k], g, tg)) <= TOL[dtype], k
+                assert rel_l2(vH[k], o.VJP_dSIA_dH_discrete(lams[k], Hs[k], g, tg)) <= TOL[dtype], k
+                refS = o.node_reduction_S(lams[k], Hs[k], g, tg)
+                assert abs(S[k] - refS) <= 10 * TOL[dtype] * abs(refS) or refS == 0.0, k
+        assert np.array_equal(ens.download(0, _capi.FIELD_H), marker.astype(ens.np_dtype))
+        only_dH, none_v, none_S = ens.fwd_adj_batch(Hs, None, want_vjpH=False, want_S=False)
+        assert none_v is None and none_S is None
+        assert all(np.array_equal(a, b) for a, b in zip(only_dH, dH))
+    finally:
+        sim.close()
