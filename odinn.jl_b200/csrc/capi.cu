@@ -3,7 +3,36 @@
 
 #include "ensemble.cuh"
 #include "sia2d_march.cuh"
+#include "sia2d_march2.cuh"
+#ifndef ODINN_NO_BULK
+#include "sia2d_bulk.cuh"
+#endif
 #include "timeloop.cuh"
+
+// Template dispatch on (n == 3 && C == 0, gridded A, eta0 == 1).  ODINN_BENCH_ONLY (developer builds for kernel
+// tuning) instantiates the benchmark configuration only; every other configuration then fails loudly.
+#ifdef ODINN_BENCH_ONLY
+#define ODINN_DISPATCH(L2)                                                                            \
+    do {                                                                                              \
+        if (e->cubic && !e->a_gridded) L2(true, false);                                               \
+        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (n = 3, C = 0, scalar A only)"); \
+    } while (0)
+#define ODINN_ETA(L3, CUB, AF)                                                                        \
+    do {                                                                                              \
+        if (eta1) L3(CUB, AF, true);                                                                  \
+        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (eta0 = 1 only)");       \
+    } while (0)
+#else
+#define ODINN_DISPATCH(L2)                                                                            \
+    do {                                                                                              \
+        if (e->cubic) {                                                                               \
+            if (e->a_gridded) L2(true, true); else L2(true, false);                                   \
+        } else {                                                                                      \
+            if (e->a_gridded) L2(false, true); else L2(false, false);                                 \
+        }                                                                                             \
+    } while (0)
+#define ODINN_ETA(L3, CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
+#endif
 
 namespace odinn {
 
@@ -73,6 +102,52 @@ struct Stage {
     double sa, sb, sdt;
 };
 
+// fp32, two columns per lane (sia2d_march2.cuh)
+static int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
+    PhysDev<float> ph = make_phys<float>(e->phys);
+    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
+    int i0 = 0, n_items = e->n_items2;
+    if (g0 >= 0) {
+        i0 = e->gl[g0].item20;
+        n_items = e->gl[g1 - 1].item20 + e->gl[g1 - 1].n_items2 - i0;
+    }
+    const int4* items = e->d_items2 + i0;
+    const float* H = (const float*)Hin;
+    const float* B = (const float*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
+    const float* Af = (const float*)e->plane[ODINN_FIELD_A];
+    float* dH = (float*)out;
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    const float* U0 = st ? (const float*)st->U0 : nullptr;
+    const float sa = st ? (float)st->sa : 0.f, sb = st ? (float)st->sb : 0.f, sdt = st ? (float)st->sdt : 0.f;
+    const bool bulk = (e->march == 3) && !packed;  // bulk copies need the padded (16-byte aligned) layout
+    dim3 grid(div_up(n_items, bulk ? BK_WARPS : MARCH2_WARPS)), block((bulk ? BK_WARPS : MARCH2_WARPS) * 32);
+#define L(CUB, AF, E1, STG)                                                                                              \
+    do {                                                                                                                 \
+        if (bulk) {                                                                                                      \
+            constexpr size_t smem = bulk_smem_bytes<2 + (AF ? 1 : 0) + (STG ? 1 : 0)>();                                  \
+            static bool attr_set = false;                                                                                \
+            if (!attr_set) {                                                                                             \
+                ODINN_CUDA(e, cudaFuncSetAttribute(sia2d_rhs_bulk<CUB, AF, E1, STG>,                                      \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+                attr_set = true;                                                                                         \
+            }                                                                                                            \
+            sia2d_rhs_bulk<CUB, AF, E1, STG><<<grid, block, smem, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph,   \
+                                                                               U0, sa, sb, sdt);                         \
+        } else {                                                                                                         \
+            sia2d_rhs_march2<CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph,    \
+                                                                              U0, sa, sb, sdt);                          \
+        }                                                                                                                \
+    } while (0)
+#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
+#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
+    ODINN_DISPATCH(L2);
+#undef L2
+#undef L3
+#undef L
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
 template <typename T>
 static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed) {
     PhysDev<T> ph = make_phys<T>(e->phys);
@@ -89,12 +164,8 @@ static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin,
 #define L(CUB, AF, E1, STG) \
     sia2d_rhs_march<T, CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt)
 #define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
-#define L2(CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
-    if (e->cubic) {
-        if (e->a_gridded) L2(true, true); else L2(true, false);
-    } else {
-        if (e->a_gridded) L2(false, true); else L2(false, false);
-    }
+#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
+    ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
 #undef L
@@ -113,6 +184,7 @@ static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, 
         i0 = e->gl[g0].item0;
         ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
     }
+    if (e->dtype == ODINN_F32 && e->march >= 2) return launch_rhs2(e, g0, g1, Hin, out, st, packed);
     return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, i0, ni, Hin, out, st, packed)
                                  : launch_rhs_t<double>(e, i0, ni, Hin, out, st, packed);
 }
@@ -121,6 +193,59 @@ static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, cons
 }
 
 // ---- A1 / A2 launch --------------------------------------------------------------------------------------------
+
+// fp32, two columns per lane (sia2d_march2.cuh).  Partials are indexed by the two-column work items.
+static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void* H_, void* out_, bool wH, bool wS,
+                       bool packed) {
+    PhysDev<float> ph = make_phys<float>(e->phys);
+    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
+    int i0 = 0, n_items = e->n_items2;
+    if (g0 >= 0) {
+        i0 = e->gl[g0].item20;
+        n_items = e->gl[g1 - 1].item20 + e->gl[g1 - 1].n_items2 - i0;
+    }
+    const float* lam = (const float*)lam_;
+    const float* H = (const float*)H_;
+    const float* B = (const float*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
+    const float* Af = (const float*)e->plane[ODINN_FIELD_A];
+    float* out = (float*)out_;
+    float* vjpA = (wS && e->a_gridded) ? (float*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
+    double* partial = e->d_partial + i0;
+    const int4* items = e->d_items2 + i0;
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    const bool bulk = (e->march == 3) && !packed;
+    dim3 grid(div_up(n_items, bulk ? BK_WARPS : MARCH2_WARPS)), block((bulk ? BK_WARPS : MARCH2_WARPS) * 32);
+#define L(CUB, AF, WH, WS, E1)                                                                                           \
+    do {                                                                                                                 \
+        if (bulk) {                                                                                                      \
+            constexpr size_t smem = bulk_smem_bytes<3 + (AF ? 1 : 0)>();                                                  \
+            static bool attr_set = false;                                                                                \
+            if (!attr_set) {                                                                                             \
+                ODINN_CUDA(e, cudaFuncSetAttribute(sia2d_vjp_bulk<CUB, AF, WH, WS, E1>,                                   \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+                attr_set = true;                                                                                         \
+            }                                                                                                            \
+            sia2d_vjp_bulk<CUB, AF, WH, WS, E1><<<grid, block, smem, e->stream>>>(descs, items, n_items, lam, H, B, Af,   \
+                                                                                  out, vjpA, partial, ph);               \
+        } else {                                                                                                         \
+            sia2d_vjp_march2<CUB, AF, WH, WS, E1><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af,    \
+                                                                                 out, vjpA, partial, ph);                \
+        }                                                                                                                \
+    } while (0)
+#define L3(CUB, AF, E1)                         \
+    do {                                        \
+        if (wH && wS) L(CUB, AF, true, true, E1);   \
+        else if (wH) L(CUB, AF, true, false, E1);   \
+        else L(CUB, AF, false, true, E1);           \
+    } while (0)
+#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
+    ODINN_DISPATCH(L2);
+#undef L2
+#undef L3
+#undef L
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
 
 template <typename T>
 static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const void* H_, void* out_, bool wH,
@@ -145,12 +270,8 @@ static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_
         else if (wH) L(CUB, AF, true, false, E1);   \
         else L(CUB, AF, false, true, E1);           \
     } while (0)
-#define L2(CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
-    if (e->cubic) {
-        if (e->a_gridded) L2(true, true); else L2(true, false);
-    } else {
-        if (e->a_gridded) L2(false, true); else L2(false, false);
-    }
+#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
+    ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
 #undef L
@@ -172,15 +293,19 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
         i0 = e->gl[g0].item0;
         ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
     }
-    rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
-                               : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed);
+    const bool two = (e->dtype == ODINN_F32 && e->march >= 2);
+    if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed);
+    else
+        rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
+                                   : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed);
     if (rc) return rc;
     if (wS) {
         double* dst = S_dst ? S_dst : e->d_S;
+        const int* starts = two ? e->d_item2_start : e->d_item_start;
         if (g0 >= 0)
-            reduce_scaled_kernel<<<g1 - g0, NT, 0, e->stream>>>(e->d_item_start + g0, e->d_partial, dst + g0, scale, accumulate);
+            reduce_scaled_kernel<<<g1 - g0, NT, 0, e->stream>>>(starts + g0, e->d_partial, dst + g0, scale, accumulate);
         else
-            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_item_start, e->d_partial, dst, scale, accumulate);
+            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(starts, e->d_partial, dst, scale, accumulate);
         ODINN_CHECK_LAUNCH(e);
     }
     return ODINN_OK;
@@ -337,6 +462,35 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     istart[n_glaciers] = (int)items.size();
     e->n_items = (int)items.size();
 
+    // two-column strips (fp32): STRIP2 output columns per warp, first loaded column = 60k - 2 (even)
+    std::vector<int4> items2;
+    std::vector<int> istart2(n_glaciers + 1);
+    {
+        const char* env = getenv("ODINN_MARCH");
+        if (env && env[0] >= '1' && env[0] <= '3') e->march = env[0] - '0';
+        const char* envr = getenv("ODINN_CHUNK_ROWS2");
+        int forced = envr ? atoi(envr) : 0;
+        for (int rows = 64; rows >= 8; rows /= 2) {
+            long long n = 0;
+            for (int g = 0; g < n_glaciers; ++g) n += (long long)div_up(e->gl[g].nx, STRIP2) * div_up(e->gl[g].ny, rows);
+            e->chunk_rows2 = rows;
+            if (n >= 148LL * 64) break;
+        }
+        if (forced >= 4) e->chunk_rows2 = forced;
+        for (int g = 0; g < n_glaciers; ++g) {
+            GlacierHost& s = e->gl[g];
+            if (s.nx & 1) e->all_nx_even = false;
+            s.item20 = (int)items2.size();
+            istart2[g] = s.item20;
+            for (int r0 = 0; r0 < s.ny; r0 += e->chunk_rows2)
+                for (int st_ = 0; st_ < div_up(s.nx, STRIP2); ++st_)
+                    items2.push_back(make_int4(g, st_ * STRIP2 - 2, r0, std::min(r0 + e->chunk_rows2, s.ny)));
+            s.n_items2 = (int)items2.size() - s.item20;
+        }
+        istart2[n_glaciers] = (int)items2.size();
+        e->n_items2 = (int)items2.size();
+    }
+
 #define CREATE_CUDA(call)                                                                     \
     do {                                                                                      \
         cudaError_t _st = (call);                                                             \
@@ -353,7 +507,11 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     CREATE_CUDA(cudaMalloc(&e->d_descs, dsz * n_glaciers * 2));
     CREATE_CUDA(cudaMalloc(&e->d_tiles, sizeof(int2) * tile));
     CREATE_CUDA(cudaMalloc(&e->d_tile_start, sizeof(int) * (n_glaciers + 1)));
-    CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * std::max(tile, e->n_items)));
+    CREATE_CUDA(cudaMalloc(&e->d_partial, sizeof(double) * std::max(tile, std::max(e->n_items, e->n_items2))));
+    CREATE_CUDA(cudaMalloc(&e->d_items2, sizeof(int4) * e->n_items2));
+    CREATE_CUDA(cudaMalloc(&e->d_item2_start, sizeof(int) * (n_glaciers + 1)));
+    CREATE_CUDA(cudaMemcpy(e->d_items2, items2.data(), sizeof(int4) * e->n_items2, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaMemcpy(e->d_item2_start, istart2.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMalloc(&e->d_items, sizeof(int4) * e->n_items));
     CREATE_CUDA(cudaMalloc(&e->d_item_start, sizeof(int) * (n_glaciers + 1)));
     CREATE_CUDA(cudaMalloc(&e->d_S, sizeof(double) * n_glaciers * 4));  // S, Ssum, loss, A
@@ -379,7 +537,7 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
         if (e->plane[f]) cudaFree(e->plane[f]);
     void* ptrs[] = {e->d_descs, e->d_tiles, e->d_tile_start, e->d_partial, e->d_items, e->d_item_start, e->d_S,
                     e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps,
-                    e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
+                    e->d_items2, e->d_item2_start, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (e->h_S) cudaFreeHost(e->h_S);
@@ -538,7 +696,7 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
     if ((rc = sync_descs(e))) return rc;
     // Packed layout (ld = nx): the device planes hold exactly the caller's bytes, so every transfer is one linear
     // DMA instead of ny row copies.  The gridded-A field lives in the padded layout only -> padded (2-D copy) path.
-    const bool packed = !e->a_gridded;
+    const bool packed = !e->a_gridded && e->all_nx_even;  // (the fp32 kernels need 8-byte aligned column pairs)
     if (packed && e->bpack_dirty) {
         if ((rc = alloc_plane(e, &e->bpack))) return rc;
         for (int g = 0; g < e->G; ++g) {

@@ -21,6 +21,7 @@ struct GlacierHost {
     double temp;
     int tile0, ntx, nty;
     int item0, n_items;
+    int item20, n_items2;  // work items of the two-column fp32 kernels (sia2d_march2.cuh)
 };
 
 struct odinn_ensemble {
@@ -46,6 +47,12 @@ struct odinn_ensemble {
     int* d_item_start = nullptr;
     int n_items = 0;
     int chunk_rows = 32;
+    int4* d_items2 = nullptr;     // two-column strips {glacier, first column (even), row0, row1}
+    int* d_item2_start = nullptr;
+    int n_items2 = 0;
+    int chunk_rows2 = 32;
+    int march = 2;                // fp32 kernel generation: 1 = one column per lane, 2 = two columns + f32x2
+    bool all_nx_even = true;
     double* d_partial = nullptr;  // per-item / per-tile partial sums (two-stage, fixed-order reductions)
     double* d_S = nullptr;        // [4 x G]: S | Ssum | loss | A
     double* d_Ssum = nullptr;

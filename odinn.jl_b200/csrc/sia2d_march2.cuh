@@ -11,6 +11,9 @@
 // Geometry: a warp owns 64 consecutive columns  base .. base+63  (base even), lane l holds columns base+2l (.x)
 // and base+2l+1 (.y); lanes 0 and 31 are halo lanes, so a strip produces the 60 columns base+2 .. base+61.
 // Every row access of a warp is one 256-byte LDG.64 / STG.64.  Requires even ld and even plane offsets.
+// When nx is odd the last pair straddles the row end and reads one padding element: every plane is allocated
+// zero-filled and no kernel or copy ever writes a padding column (pair stores are suppressed there), so the
+// value read is 0 and only feeds quantities that the column masks (kx, ky, lmask, nodemask) zero out.
 #pragma once
 #include "sia2d_march.cuh"
 
@@ -27,6 +30,11 @@ constexpr int MARCH2_WARPS = ODINN_MARCH2_WARPS;
 #ifndef ODINN_PF2_VJP
 #define ODINN_PF2_VJP 2
 #endif
+
+#ifndef ODINN_L2PF_ROWS
+#define ODINN_L2PF_ROWS 8   // rows of L2 prefetch distance ahead of the register queue (0 = off; sweep: profiles/r01_v4_sweep.txt)
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 typedef float2 f2;
 __device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
@@ -74,6 +82,15 @@ __device__ __forceinline__ void node_raw2(const PhysDev<float>& ph, f2 A, f2 Hs,
     }
 }
 
+// PF unmasked output steps in ring form (compile-time queue slots)
+template <int PF, int K = 0, typename M>
+__device__ __forceinline__ void ring_steps(M& m, int row) {
+    if constexpr (K < PF) {
+        m.template step<true, false, K>(row + K);
+        ring_steps<PF, K + 1>(m, row);
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // F1 (see RhsMarch for the step structure; every quantity is a pair of adjacent columns)
 // --------------------------------------------------------------------------------------------
@@ -86,20 +103,23 @@ struct RhsMarch2 {
     float eta0;
     f2 hdx, hdy, kx, ky, A;  // kx, ky are zeroed on border / out-of-grid columns
     f2 sa, sb, sdt, hraw;
-    bool store_pair, store_x, y_oob;
+    bool store_pair, store_x;
     PhysDev<float> ph;
     f2 h, b, eh, ex, hx, ehE, Dp, Fy;
     f2 hq[PF], bq[PF];
 
-    __device__ __forceinline__ void sanitize(f2& hv, f2& bv) const {
-        if (y_oob) { hv.y = 0.0f; bv.y = bv.x; }  // the pair straddles the last column (odd nx): keep it finite
-    }
 
-    template <bool OUT, bool MASKED>
+    // SLOT < 0: the prefetch queue is shifted (hq[0] is always the next row).  SLOT >= 0: ring form for the
+    // unrolled main loop -- the step consumes hq[SLOT] and refills the same slot, so no register moves.
+    template <bool OUT, bool MASKED, int SLOT = -1>
     __device__ __forceinline__ void step(int row) {
-        f2 h1 = hq[0], b1 = bq[0];
+        constexpr int RS = SLOT < 0 ? 0 : SLOT;        // slot read
+        constexpr int WS = SLOT < 0 ? PF - 1 : SLOT;   // slot refilled
+        f2 h1 = hq[RS], b1 = bq[RS];
+        if (SLOT < 0) {
 #pragma unroll
-        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; }
+            for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; }
+        }
         if (MASKED) {
             int stp = (row + 1 + PF <= nym1) ? ld : 0;
             hp += stp;
@@ -108,11 +128,32 @@ struct RhsMarch2 {
             hp += ld;
             bp += ld;
         }
-        hq[PF - 1] = ldg2(hp);
-        bq[PF - 1] = ldg2(bp);
+        hq[WS] = ldg2(hp);
+        bq[WS] = ldg2(bp);
+        if (ODINN_L2PF_ROWS > 0 && !MASKED) {
+            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) {
+                prefetch_l2(hp + (long long)ODINN_L2PF_ROWS * ld);
+                prefetch_l2(bp + (long long)ODINN_L2PF_ROWS * ld);
+            }
+        }
         f2 u0 = bc2(0.0f);
-        if (STAGE && OUT) { if (store_pair) u0 = ldg2(up); else if (store_x) u0.x = __ldg(up); }
-        sanitize(h1, b1);
+        if (STAGE && OUT) {
+            if (store_pair) u0 = ldg2(up);
+            if (store_x) u0.x = __ldg(up);
+        }
+        f2 Anode = A;
+        if (AFIELD) {
+            Anode = ldg2(ap);
+            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+        }
+        compute<OUT, MASKED>(row, h1, b1, u0, Anode);
+        if (STAGE) up += ld;
+    }
+
+    // One marching step given the cell row `row+1` (h1, b1), the stage operand u0 and the node coefficient A of node
+    // row `row`; produces output row `row` at `op` and advances `op`.
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void compute(int row, f2 h1, f2 b1, f2 u0, f2 Anode) {
         const f2 hraw1 = h1;
         h1 = max2(h1, bc2(0.0f));                 // adjoint.jl:52
         f2 eh1 = ETA1 ? h1 : mul2(bc2(eta0), h1);
@@ -124,11 +165,6 @@ struct RhsMarch2 {
         f2 eyE = east2(ey);
         f2 u = mul2(add2(ex, ex1), hdx), v = mul2(add2(ey, eyE), hdy);
         f2 g2 = fma2(v, v, mul2(u, u));
-        f2 Anode = A;
-        if (AFIELD) {
-            Anode = ldg2(ap);
-            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
-        }
         f2 D1, al, be, gA;
         node_raw2<CUBIC, false>(ph, Anode, add2(hx, hx1), g2, D1, al, be, gA);
         f2 D1W = west2(D1);
@@ -140,10 +176,10 @@ struct RhsMarch2 {
             if (MASKED) { if (row < 1 || row >= nym1) outv = bc2(0.0f); }
             if (STAGE) outv = fma2(sb, fma2(sdt, outv, hraw), mul2(sa, u0));
             if (store_pair) *reinterpret_cast<float2*>(op) = outv;
-            else if (store_x) *op = outv.x;
+            if (store_x) *op = outv.x;  // (exclusive with store_pair: the pair straddling the last column, odd nx)
         }
         op += ld;
-        if (STAGE) { up += ld; hraw = hraw1; }
+        if (STAGE) hraw = hraw1;
         h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; Dp = D1; Fy = Fy1;
     }
 };
@@ -179,7 +215,6 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const bool out_lane = (lane >= 1 && lane <= 30 && c0 >= 0);
     m.store_pair = out_lane && (c0 + 1 < d.nx);
     m.store_x = out_lane && (c0 + 1 == d.nx);
-    m.y_oob = (ic + 1 >= d.nx);
     const int rc = max(r0 - 1, 0);
     m.hp = H + d.off + ic + (long long)rc * d.ld;
     m.bp = B + d.off + ic + (long long)rc * d.ld;
@@ -194,7 +229,6 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     // ---- cell row r0-1 ----
     {
         f2 hv = ldg2(m.hp), bv = ldg2(m.bp);
-        m.sanitize(hv, bv);
         m.h = max2(hv, bc2(0.0f));
         m.b = bv;
     }
@@ -219,9 +253,251 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     ++row;
     const int main_end = min(r1, d.ny - 1 - PF);
     for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
-#pragma unroll 4
+    for (; row + PF <= main_end; row += PF) ring_steps<PF>(m, row);
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
+}
+
+// --------------------------------------------------------------------------------------------
+// A1 + A2 (see VjpMarch; every quantity is a pair of adjacent columns)
+// --------------------------------------------------------------------------------------------
+// Clamp sub-gradient for one column (see subgrad<> in sia2d_march.cuh), fp32 comparisons on raw differences.
+template <bool ETA1>
+__device__ __forceinline__ void subgrad1(float dC, float e, float lo, float up, float eta0, float& to_lower, float& to_upper) {
+    if (ETA1) {
+        bool lt_up = up > e, gt_lo = e > lo;
+        to_lower = (lt_up && e != lo) ? -dC : 0.0f;
+        to_upper = (gt_lo && e != up) ? dC : 0.0f;
+    } else {
+        bool inside = (up > e) && (e > lo);
+        float pass = inside ? dC : 0.0f;
+        float edC = eta0 * dC;
+        to_lower = -pass - ((lo > e) ? edC : 0.0f);
+        to_upper = pass + ((e > up) ? edC : 0.0f);
+    }
+}
+template <bool ETA1>
+__device__ __forceinline__ void subgrad2(f2 dC, f2 e, f2 lo, f2 up, float eta0, f2& to_lower, f2& to_upper) {
+    subgrad1<ETA1>(dC.x, e.x, lo.x, up.x, eta0, to_lower.x, to_upper.x);
+    subgrad1<ETA1>(dC.y, e.y, lo.y, up.y, eta0, to_lower.y, to_upper.y);
+}
+
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+struct VjpMarch2 {
+    static constexpr int PF = ODINN_PF2_VJP;
+    const float *hp, *bp, *lp, *ap;
+    float *op, *vp;
+    int ld, nym1, ny2;
+    float eta0;
+    f2 hdx, hdy, nhx2, nhy2, qx, qy, A;
+    f2 lmask;     // 1 on inner columns, 0 on border / out-of-grid columns (λ_inn zero-extension)
+    f2 nodemask;  // 1 where the column carries a dual node (0 <= c <= nx-2)
+    bool store_pair, store_x, own_lane, vstore_pair, vstore_x;
+    PhysDev<float> ph;
+    f2 h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc;
+    f2 hq[PF], bq[PF], lq[PF];
+
+
+    template <bool OUT, bool MASKED, int SLOT = -1>
+    __device__ __forceinline__ void step(int row) {
+        constexpr int RS = SLOT < 0 ? 0 : SLOT;
+        constexpr int WS = SLOT < 0 ? PF - 1 : SLOT;
+        f2 h1 = hq[RS], b1 = bq[RS], l1 = lq[RS];
+        if (SLOT < 0) {
+#pragma unroll
+            for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
+        }
+        if (MASKED) {
+            int stp = (row + 1 + PF <= nym1) ? ld : 0;
+            hp += stp;
+            bp += stp;
+            lp += stp;
+        } else {
+            hp += ld;
+            bp += ld;
+            lp += ld;
+        }
+        hq[WS] = ldg2(hp);
+        bq[WS] = ldg2(bp);
+        lq[WS] = ldg2(lp);
+        if (ODINN_L2PF_ROWS > 0 && !MASKED) {
+            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) {
+                prefetch_l2(hp + (long long)ODINN_L2PF_ROWS * ld);
+                prefetch_l2(bp + (long long)ODINN_L2PF_ROWS * ld);
+                prefetch_l2(lp + (long long)ODINN_L2PF_ROWS * ld);
+            }
+        }
+        f2 Anode = A;
+        if (AFIELD) {
+            Anode = ldg2(ap);
+            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+        }
+        compute<OUT, MASKED>(row, h1, b1, l1, Anode);
+    }
+
+    // One marching step given the cell row `row+1` (h1, b1, raw λ row l1) and the node coefficient of node row `row`.
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void compute(int row, f2 h1, f2 b1, f2 l1, f2 Anode) {
+        l1 = mul2(l1, lmask);
+        if (MASKED) { if (!(row >= 0 && row + 1 < nym1)) l1 = bc2(0.0f); }  // λ_inn zero-extended on border rows
+        h1 = max2(h1, bc2(0.0f));
+        f2 eh1 = ETA1 ? h1 : mul2(bc2(eta0), h1);
+        f2 hE1 = east2(h1), bE1 = east2(b1), lE1 = east2(l1);
+        // x-edge (i→i+1, row+1)
+        f2 ex1 = sdiff2(bE1, b1, hE1, h1);
+        f2 hx1 = add2(h1, hE1);
+        f2 ehE1 = ETA1 ? hE1 : mul2(bc2(eta0), hE1);
+        f2 fxr1 = sub2(lE1, l1);                          // raw Fx† (adjoint.jl:100)
+        f2 px1 = mul2(fxr1, clamp2(ex1, ehE1, eh1));      // raw Fx†·clamp(dSdx) (adjoint.jl:102)
+        // y-edge (i, row→row+1)
+        f2 ey = sdiff2(b1, b, h1, h);
+        f2 fyr = sub2(l1, l);
+        f2 py = mul2(fyr, clamp2(ey, eh1, eh));
+        f2 eyE = east2(ey), pyE = east2(py);
+        // node (i, row)
+        f2 gxr = add2(ex, ex1), gyr = add2(ey, eyE);
+        f2 u = mul2(gxr, hdx), v = mul2(gyr, hdy);
+        f2 D1, al, be, gA;
+        node_raw2<CUBIC, true>(ph, Anode, add2(hx, hx1), fma2(v, v, mul2(u, u)), D1, al, be, gA);
+        f2 Dadj = fma2(add2(py, pyE), nhy2, mul2(add2(px, px1), nhx2));  // D† (adjoint.jl:102-104)
+        Dadj = mul2(Dadj, nodemask);
+        bool row_ok = true;
+        if (MASKED) { row_ok = (row >= 0 && row < nym1); if (!row_ok) Dadj = bc2(0.0f); }
+        f2 bD = mul2(be, Dadj);
+        f2 aD1 = mul2(al, Dadj);
+        f2 P1 = mul2(bD, gxr);
+        f2 Q1 = mul2(bD, gyr);
+        if (WRITE_S) {
+            if (OUT) {
+                f2 vS = mul2(gA, Dadj);                   // ∂A_spatial ∘ D† (adjoint.jl:250)
+                if (own_lane) acc = add2(acc, vS);
+                if (AFIELD) {
+                    if (row_ok) {
+                        if (vstore_pair) *reinterpret_cast<float2*>(vp) = vS;
+                        if (vstore_x) *vp = vS.x;
+                    }
+                }
+            }
+            if (AFIELD) vp += ld;
+        }
+        if (WRITE_H) {
+            f2 D1W = west2(D1), Q1W = west2(Q1);
+            f2 Qrow1 = add2(Q1W, Q1);
+            f2 yl, yu1, xl, xu;
+            {
+                f2 dC = mul2(mul2(fyr, nhy2), add2(D1W, D1));  // ∂Cy/Δy = -Fy†·Dy/Δy
+                subgrad2<ETA1>(dC, ey, neg2(eh), eh1, eta0, yl, yu1);
+            }
+            {
+                f2 dC = mul2(mul2(fxr, nhx2), add2(Dp, D1));
+                subgrad2<ETA1>(dC, ex, neg2(eh), ehE, eta0, xl, xu);
+            }
+            f2 aDc = mul2(bc2(0.25f), add2(aDp, aD1));
+            f2 Pc = mul2(qx, add2(Pp, P1));
+            f2 ZW = west2(add2(add2(aDc, Pc), xu));  // everything column i-1 sends to cell (i, row)
+            if (OUT) {
+                f2 res = add2(add2(add2(ZW, add2(sub2(aDc, Pc), xl)), mul2(qy, sub2(Qrow_p, Qrow1))), add2(yl, yu_p));
+                if (!(h.x > 0.0f)) res.x = 0.0f;  // adjoint.jl:148
+                if (!(h.y > 0.0f)) res.y = 0.0f;
+                if (store_pair) *reinterpret_cast<float2*>(op) = res;
+                if (store_x) *op = res.x;
+            }
+            op += ld;
+            Qrow_p = Qrow1;
+            yu_p = yu1;
+        }
+        h = h1; b = b1; l = l1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; fxr = fxr1; px = px1;
+        Dp = D1; aDp = aD1; Pp = P1;
+    }
+};
+
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+__global__ void __launch_bounds__(MARCH2_WARPS * 32)
+sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
+                 const float* __restrict__ lam, const float* __restrict__ H, const float* __restrict__ B,
+                 const float* __restrict__ Af, float* __restrict__ out, float* __restrict__ vjpA,
+                 double* __restrict__ partial, PhysDev<float> ph) {
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int4 it = items[item];
+    const GDesc<float> d = descs[it.x];
+    const int c0 = it.y + 2 * lane, r0 = it.z, r1 = it.w;
+    const int cmax = (d.nx - 1) & ~1;
+    const int ic = min(max(c0, 0), cmax);
+    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1> m;
+    constexpr int PF = ODINN_PF2_VJP;
+    m.ph = ph;
+    m.ld = d.ld;
+    m.nym1 = d.ny - 1;
+    m.ny2 = d.ny - 2;
+    m.eta0 = ph.eta0;
+    const float hdx = 0.5f * d.inv_dx, hdy = 0.5f * d.inv_dy;
+    m.hdx = bc2(hdx);
+    m.hdy = bc2(hdy);
+    m.nhx2 = bc2(-hdx * d.inv_dx);  // -½/Δx²
+    m.nhy2 = bc2(-hdy * d.inv_dy);
+    m.qx = bc2(hdx * hdx);          // ¼/Δx²
+    m.qy = bc2(hdy * hdy);
+    m.A = bc2(d.A);
+    const int c1 = c0 + 1;
+    m.lmask = mk2((c0 >= 1 && c0 <= d.nx - 2) ? 1.0f : 0.0f, (c1 >= 1 && c1 <= d.nx - 2) ? 1.0f : 0.0f);
+    m.nodemask = mk2((c0 >= 0 && c0 <= d.nx - 2) ? 1.0f : 0.0f, (c1 >= 0 && c1 <= d.nx - 2) ? 1.0f : 0.0f);
+    const bool out_lane = (lane >= 1 && lane <= 30 && c0 >= 0);
+    m.store_pair = out_lane && (c1 < d.nx);
+    m.store_x = out_lane && (c1 == d.nx);
+    m.own_lane = (lane >= 1 && lane <= 30);
+    m.vstore_pair = out_lane && (c1 <= d.nx - 2);
+    m.vstore_x = out_lane && (c1 == d.nx - 1);
+    const int rc = max(r0 - 1, 0);
+    m.hp = H + d.off + ic + (long long)rc * d.ld;
+    m.bp = B + d.off + ic + (long long)rc * d.ld;
+    m.lp = lam + d.off + ic + (long long)rc * d.ld;
+    m.ap = AFIELD ? Af + d.off + ic + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
+    m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+
+    // ---- cell row r0-1 ----
+    {
+        f2 hv = ldg2(m.hp), bv = ldg2(m.bp), lv = ldg2(m.lp);
+        m.h = max2(hv, bc2(0.0f));
+        m.b = bv;
+        m.l = mul2(lv, m.lmask);
+        if (!(r0 >= 2 && r0 <= m.nym1)) m.l = bc2(0.0f);  // row r0-1 must be an inner row
+    }
+    m.eh = ETA1 ? m.h : mul2(bc2(m.eta0), m.h);
+    {
+        f2 hE = east2(m.h), bE = east2(m.b), lE = east2(m.l);
+        m.ex = sdiff2(bE, m.b, hE, m.h);
+        m.hx = add2(m.h, hE);
+        m.ehE = ETA1 ? hE : mul2(bc2(m.eta0), hE);
+        m.fxr = sub2(lE, m.l);
+        m.px = mul2(m.fxr, clamp2(m.ex, m.ehE, m.eh));
+    }
+    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = bc2(0.0f);
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
+        m.hq[k] = ldg2(m.hp);
+        m.bq[k] = ldg2(m.bp);
+        m.lq[k] = ldg2(m.lp);
+    }
+
+    int row = r0 - 1;
+    m.template step<false, true>(row);
+    ++row;
+    const int main_end = min(r1, d.ny - 1 - PF);
+    for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
+    for (; row + PF <= main_end; row += PF) ring_steps<PF>(m, row);
+    for (; row < main_end; ++row) m.template step<true, false>(row);
+    for (; row < r1; ++row) m.template step<true, true>(row);
+
+    if (WRITE_S) {
+        double a = (double)m.acc.x + (double)m.acc.y;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+        if (lane == 0) partial[item] = a;
+    }
 }
 
 }  // namespace odinn
