@@ -129,13 +129,23 @@ int odinn_sia2d_vjp_H(odinn_ensemble* e, int glacier, const void* lambda, int ld
 int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
                           double* out_S, double t);
 
+/* Continuous-adjoint flavours (differentiate-then-discretise; no flux clamp, no H > 0 mask, border 0).
+ * Replace VJP_lambda_dSIAdH(::ContinuousVJP, ...) (src/inverse/SIA2D/VJPs.jl:7-10 -> adjoint.jl:442-555) and
+ * VJP_lambda_dSIAdtheta(::ContinuousVJP, ...) (VJPs.jl:35-38 -> adjoint.jl:582-662).  As for the discrete flavour the
+ * theta-VJP of a glacier-wide law returns the scalar S with d_theta = (dA/dtheta) * S. */
+int odinn_sia2d_vjp_H_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                                 void* out, int ldo, double t);
+int odinn_sia2d_vjp_theta_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                                     double* out_S, double t);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Ensemble (batched) operators on device-resident planes                                    */
 /* ---------------------------------------------------------------------------------------- */
 
 /* FIELD_DH <- SIA2D(FIELD_H) for every glacier in one launch. */
 int odinn_rhs_resident(odinn_ensemble* e);
-/* flags bit0: FIELD_VJP_H <- (dSIA/dH)^T FIELD_LAMBDA ; bit1: per-glacier S (and FIELD_VJP_A).
+/* flags bit0: FIELD_VJP_H <- (dSIA/dH)^T FIELD_LAMBDA ; bit1: per-glacier S (and FIELD_VJP_A) ;
+ * bit2: use the continuous flavour instead of the discrete one.
  * S_out may be NULL; otherwise n_glaciers doubles (device->host read inside the call). */
 int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
 

@@ -63,6 +63,8 @@ SIGNATURES = {
     "odinn_sia2d_rhs": (_i, [_vp, _i, _vp, _i, _vp, _i, _d]),
     "odinn_sia2d_vjp_H": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _d]),
     "odinn_sia2d_vjp_theta": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
+    "odinn_sia2d_vjp_H_continuous": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _d]),
+    "odinn_sia2d_vjp_theta_continuous": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
     "odinn_rhs_resident": (_i, [_vp]),
     "odinn_vjp_resident": (_i, [_vp, _i, _dp]),
     "odinn_fwd_adj_batch_host": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _dp]),

@@ -7,6 +7,7 @@
 #ifndef ODINN_NO_BULK
 #include "sia2d_bulk.cuh"
 #endif
+#include "sia2d_cont.cuh"
 #include "timeloop.cuh"
 
 // Template dispatch on (n == 3 && C == 0, gridded A, eta0 == 1).  ODINN_BENCH_ONLY (developer builds for kernel
@@ -313,6 +314,73 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
 static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, void* out, bool wH, bool wS,
                       double* S_dst = nullptr, double scale = 1.0, int accumulate = 0) {
     return launch_vjp_range(e, g, g + 1, lam, H, out, wH, wS, S_dst, scale, accumulate, false);
+}
+
+// ---- continuous VJPs (sia2d_cont.cuh) ---------------------------------------------------------------------------
+
+template <typename T>
+static int launch_vjpc_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out) {
+    PhysDev<T> ph = make_phys<T>(e->phys);
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const int4* items = e->d_items + i0;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
+    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define L(CUB, AF) sia2d_vjpc_march<T, CUB, AF><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)lam, (const T*)H, B, Af, (T*)out, ph)
+    ODINN_DISPATCH(L);
+#undef L
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+// out = (dSIA/dH)^T lam, continuous form (adjoint.jl:442-555).  g < 0: whole ensemble.
+static int launch_vjpc(odinn_ensemble* e, int g, const void* lam, const void* H, void* out) {
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+    if (e->a_gridded && (rc = ensure_plane(e, ODINN_FIELD_A))) return rc;
+    if ((rc = sync_descs(e))) return rc;
+    int i0 = 0, ni = e->n_items;
+    if (g >= 0) { i0 = e->gl[g].item0; ni = e->gl[g].n_items; }
+    return e->dtype == ODINN_F32 ? launch_vjpc_t<float>(e, i0, ni, lam, H, out) : launch_vjpc_t<double>(e, i0, ni, lam, H, out);
+}
+
+template <typename T>
+static int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst) {
+    odinn_phys p1 = e->phys;
+    p1.C = 0.0;  // ∂D/∂A carries no sliding term (target_A.jl:71-72)
+    PhysDev<T> ph = make_phys<T>(p1);
+    const bool cubic = (p1.n == 3.0);
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    int i0 = 0, ni = e->n_items, t0 = 0, nt = e->n_tiles;
+    if (g >= 0) {
+        i0 = e->gl[g].item0; ni = e->gl[g].n_items;
+        t0 = e->gl[g].tile0; nt = e->gl[g].ntx * e->gl[g].nty;
+    }
+    const int4* items = e->d_items + i0;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    T* scratch = (T*)e->work[0];
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    dim3 grid(div_up(ni, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define LU(CUB, E1) sia2d_rhs_march<T, CUB, false, E1, false><<<grid, block, 0, e->stream>>>(descs, items, ni, (const T*)H, B, nullptr, scratch, ph, nullptr, T(0), T(0), T(0), T(1), 1)
+    if (cubic) { if (eta1) LU(true, true); else LU(true, false); }
+    else { if (eta1) LU(false, true); else LU(false, false); }
+#undef LU
+    ODINN_CHECK_LAUNCH(e);
+    dot_inner_kernel<T><<<nt, NT, 0, e->stream>>>(descs, e->d_tiles + t0, (const T*)lam, scratch, e->d_partial + t0);
+    ODINN_CHECK_LAUNCH(e);
+    if (g >= 0) reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_tile_start + g, e->d_partial, S_dst + g, 1.0, 0);
+    else reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, S_dst, 1.0, 0);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+// S[g] = Σ λ ⊙ pad(∇·(avg(∂A_spatial)·clamp(∇S)))  (adjoint.jl:582-662, glacier-wide law).  g < 0: whole ensemble.
+static int launch_unitA_dot(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst) {
+    if (e->a_gridded) return fail(e, ODINN_ESTATE, "the continuous theta-VJP is provided for glacier-wide A laws");
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = alloc_plane(e, &e->work[0]))) return rc;
+    if ((rc = sync_descs(e))) return rc;
+    return e->dtype == ODINN_F32 ? launch_unitA_dot_t<float>(e, g, lam, H, S_dst) : launch_unitA_dot_t<double>(e, g, lam, H, S_dst);
 }
 
 static int copy2d_ptr(odinn_ensemble* e, int g, char* plane_base, bool dual, void* host, int ld, bool up,
@@ -655,6 +723,36 @@ int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, in
     return ODINN_OK;
 }
 
+int odinn_sia2d_vjp_H_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                                 void* out, int ldo, double t) {
+    GUARD(e);
+    (void)t;
+    int rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda), ldl, true, e->stream))) return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
+    if ((rc = launch_vjpc(e, glacier, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H])))
+        return rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_VJP_H, out, ldo, false, e->stream))) return rc;
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ODINN_OK;
+}
+
+int odinn_sia2d_vjp_theta_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                                     double* out_S, double t) {
+    GUARD(e);
+    (void)t;
+    if (!out_S) return fail(e, ODINN_EARG, "out_S is null");
+    int rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda), ldl, true, e->stream))) return rc;
+    if ((rc = launch_unitA_dot(e, glacier, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->d_S))) return rc;
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + glacier, e->d_S + glacier, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    *out_S = e->h_S[glacier];
+    return ODINN_OK;
+}
+
 // ---- ensemble operators on resident planes ---------------------------------------------------------------------
 
 int odinn_rhs_resident(odinn_ensemble* e) {
@@ -669,9 +767,16 @@ int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out) {
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_H)) || (rc = ensure_plane(e, ODINN_FIELD_LAMBDA))) return rc;
     if ((flags & 1) && (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
-    rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
-                    (flags & 1) != 0, (flags & 2) != 0);
-    if (rc) return rc;
+    if (flags & 4) {  // continuous flavour
+        if ((flags & 1) && (rc = launch_vjpc(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H])))
+            return rc;
+        if ((flags & 2) && (rc = launch_unitA_dot(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->d_S)))
+            return rc;
+    } else {
+        rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
+                        (flags & 1) != 0, (flags & 2) != 0);
+        if (rc) return rc;
+    }
     if ((flags & 2) && S_out) {
         ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_S, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
         ODINN_CUDA(e, cudaStreamSynchronize(e->stream));

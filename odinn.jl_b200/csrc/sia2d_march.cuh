@@ -20,6 +20,11 @@ namespace odinn {
 constexpr int STRIP = 30;        // output columns per warp
 constexpr int MARCH_WARPS = 8;   // warps per CTA
 constexpr unsigned FULL = 0xffffffffu;
+// L2 prefetch distance in rows ahead of the register prefetch queue (0 = off); see sia2d_march2.cuh / profiles/r01_v4_sweep.txt
+#ifndef ODINN_L2PF_ROWS1
+#define ODINN_L2PF_ROWS1 8
+#endif
+__device__ __forceinline__ void prefetch_l2_row(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Rows of register prefetch (ncu: the 1-row version stalled on long_scoreboard).  Deeper queues cost
 // registers, i.e. resident warps: F1 is light (4 rows), the VJP kernel is not.
 #ifndef ODINN_PF_RHS
@@ -77,19 +82,41 @@ __device__ __forceinline__ void node_raw(const PhysDev<T>& ph, T A, T Hs, T g2, 
 // dC here already carries the 1/Δ of diff_adjoint.  With η₀ = 1 (ETA1) the cases merge:
 // lower gets -dC unless (e >= up or e == lo), upper gets +dC unless (e <= lo or e == up).
 template <typename T, bool ETA1>
-__device__ __forceinline__ void subgrad(T dC, T e, T lo, T up, T delta, T eta0, T& to_lower, T& to_upper) {
+__device__ __forceinline__ void subgrad_cmp(T dC, bool gt_lo, bool lt_lo, bool lt_up, bool gt_up, T eta0, T& to_lower, T& to_upper) {
     if (ETA1) {
-        bool lt_up = gt_div(up, e, delta), gt_lo = gt_div(e, lo, delta);
-        bool lt_lo = gt_div(lo, e, delta), gt_up = gt_div(e, up, delta);
         to_lower = (lt_up && (gt_lo || lt_lo)) ? -dC : T(0);
         to_upper = (gt_lo && (lt_up || gt_up)) ? dC : T(0);
     } else {
-        bool inside = gt_div(up, e, delta) && gt_div(e, lo, delta);
-        T pass = inside ? dC : T(0);
+        T pass = (lt_up && gt_lo) ? dC : T(0);
         T edC = eta0 * dC;
-        to_lower = -pass - (gt_div(lo, e, delta) ? edC : T(0));
-        to_upper = pass + (gt_div(e, up, delta) ? edC : T(0));
+        to_lower = -pass - (lt_lo ? edC : T(0));
+        to_upper = pass + (gt_up ? edC : T(0));
     }
+}
+// fp32: plain comparisons of the raw differences.
+template <typename T, bool ETA1>
+__device__ __forceinline__ void subgrad(float dC, float e, float lo, float up, float delta, float eta0, float& to_lower,
+                                        float& to_upper) {
+    (void)delta;
+    subgrad_cmp<float, ETA1>(dC, e > lo, lo > e, up > e, e > up, eta0, to_lower, to_upper);
+}
+// fp64: the reference compares the DIVIDED quantities dS/Δ and ±η₀H/Δ (inversion_utils.jl:24-28, 38-42); two raw
+// values an ulp apart can round to the same quotient, which turns a strict inequality into a tie (see gt_div).
+// The sign of a floating-point difference is exact, so d1 = e - lo and d2 = up - e classify the edge with two DADDs;
+// the true divisions are needed only when a difference is non-zero yet below 1e-14·|e| -- a rare per-lane slow path.
+// (An exact zero difference is a tie in both forms; ice-free flat regions, e = lo = up = 0, stay on the fast path.)
+template <typename T, bool ETA1>
+__device__ __forceinline__ void subgrad(double dC, double e, double lo, double up, double delta, double eta0,
+                                        double& to_lower, double& to_upper) {
+    const double d1 = e - lo, d2 = up - e;
+    bool gt_lo = d1 > 0.0, lt_lo = d1 < 0.0, lt_up = d2 > 0.0, gt_up = d2 < 0.0;
+    const double tol = 1e-14 * fmax(fabs(e), fmax(fabs(lo), fabs(up)));
+    const bool near = (d1 != 0.0 && fabs(d1) < tol) || (d2 != 0.0 && fabs(d2) < tol);
+    if (near) {
+        const double qe = e / delta, ql = lo / delta, qu = up / delta;
+        gt_lo = qe > ql; lt_lo = ql > qe; lt_up = qu > qe; gt_up = qe > qu;
+    }
+    subgrad_cmp<double, ETA1>(dC, gt_lo, lt_lo, lt_up, gt_up, eta0, to_lower, to_upper);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -129,6 +156,12 @@ struct RhsMarch {
         }
         hq[PF - 1] = __ldg(hp);
         bq[PF - 1] = __ldg(bp);
+        if (ODINN_L2PF_ROWS1 > 0 && !MASKED) {
+            if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) {
+                prefetch_l2_row(hp + (long long)ODINN_L2PF_ROWS1 * ld);
+                prefetch_l2_row(bp + (long long)ODINN_L2PF_ROWS1 * ld);
+            }
+        }
         T u0 = T(0);
         if (STAGE && OUT) { if (store_lane) u0 = __ldg(up); }
         const T hraw1 = h1;
@@ -173,7 +206,7 @@ template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af, T* dH,
-                PhysDev<T> ph, const T* U0, T sa, T sb, T sdt) {
+                PhysDev<T> ph, const T* U0, T sa, T sb, T sdt, T A_ovr = T(0), int use_A_ovr = 0) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -193,7 +226,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.hdy = T(0.5) * d.inv_dy;
     m.kx = col_inner ? m.hdx * d.inv_dx : T(0);  // ½/Δx²
     m.ky = col_inner ? m.hdy * d.inv_dy : T(0);
-    m.A = d.A;
+    m.A = use_A_ovr ? A_ovr : d.A;  // (A ≡ 1: the ∂A_spatial flux of the continuous θ-VJP, sia2d_cont.cuh)
     m.store_lane = (lane >= 1 && lane <= STRIP && i < d.nx);
     const int rc = max(r0 - 1, 0);
     m.hp = H + d.off + ic + (long long)rc * d.ld;
@@ -271,6 +304,13 @@ struct VjpMarch {
         hq[PF - 1] = __ldg(hp);
         bq[PF - 1] = __ldg(bp);
         lq[PF - 1] = __ldg(lp);
+        if (ODINN_L2PF_ROWS1 > 0 && !MASKED) {
+            if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) {
+                prefetch_l2_row(hp + (long long)ODINN_L2PF_ROWS1 * ld);
+                prefetch_l2_row(bp + (long long)ODINN_L2PF_ROWS1 * ld);
+                prefetch_l2_row(lp + (long long)ODINN_L2PF_ROWS1 * ld);
+            }
+        }
         h1 = fmx(h1, T(0));
         b1 = surf_store<T>(b1, h1);
         T eh1 = ETA1 ? h1 : eta0 * h1;
@@ -414,7 +454,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     ++row;
     const int main_end = min(r1, d.ny - 1 - PF);
     for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
-#pragma unroll 4
+#pragma unroll 2
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
 

@@ -36,6 +36,11 @@ constexpr int MARCH2_WARPS = ODINN_MARCH2_WARPS;
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+#ifndef ODINN_VJP_RING_UNROLL
+#define ODINN_VJP_RING_UNROLL 1
+#endif
+constexpr int VJP_RING_UNROLL = ODINN_VJP_RING_UNROLL;  // ring passes per main-loop iteration of the A1+A2 kernel
+
 typedef float2 f2;
 __device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ f2 bc2(float a) { return make_float2(a, a); }
@@ -488,6 +493,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     ++row;
     const int main_end = min(r1, d.ny - 1 - PF);
     for (; row < min(r1, 1); ++row) m.template step<true, true>(row);
+#pragma unroll VJP_RING_UNROLL
     for (; row + PF <= main_end; row += PF) ring_steps<PF>(m, row);
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);

@@ -102,19 +102,21 @@ class Ensemble:
         self._ck(self._lib.odinn_sia2d_rhs(self._h, g, H.ctypes.data, H.shape[0], dH.ctypes.data, dH.shape[0], float(t)))
         return dH
 
-    def sia2d_vjp_H(self, g: int, lam, H, t: float = 0.0):
+    def sia2d_vjp_H(self, g: int, lam, H, t: float = 0.0, continuous: bool = False):
         H = _as_f(H, self.np_dtype)
         lam = _as_f(lam, self.np_dtype)
         out = np.empty_like(H, order="F")
-        self._ck(self._lib.odinn_sia2d_vjp_H(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
+        fn = self._lib.odinn_sia2d_vjp_H_continuous if continuous else self._lib.odinn_sia2d_vjp_H
+        self._ck(fn(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
                                              out.ctypes.data, out.shape[0], float(t)))
         return out
 
-    def sia2d_vjp_theta(self, g: int, lam, H, t: float = 0.0) -> float:
+    def sia2d_vjp_theta(self, g: int, lam, H, t: float = 0.0, continuous: bool = False) -> float:
         H = _as_f(H, self.np_dtype)
         lam = _as_f(lam, self.np_dtype)
         S = C.c_double(0.0)
-        self._ck(self._lib.odinn_sia2d_vjp_theta(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
+        fn = self._lib.odinn_sia2d_vjp_theta_continuous if continuous else self._lib.odinn_sia2d_vjp_theta
+        self._ck(fn(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
                                                  C.byref(S), float(t)))
         return S.value
 
@@ -122,8 +124,8 @@ class Ensemble:
     def rhs_resident(self):
         self._ck(self._lib.odinn_rhs_resident(self._h))
 
-    def vjp_resident(self, want_H=True, want_S=True, read_S=True):
-        flags = (1 if want_H else 0) | (2 if want_S else 0)
+    def vjp_resident(self, want_H=True, want_S=True, read_S=True, continuous=False):
+        flags = (1 if want_H else 0) | (2 if want_S else 0) | (4 if continuous else 0)
         if want_S and read_S:
             S = np.empty(self.G, dtype=np.float64)
             self._ck(self._lib.odinn_vjp_resident(self._h, flags, S.ctypes.data_as(C.POINTER(C.c_double))))

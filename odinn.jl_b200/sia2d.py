@@ -52,7 +52,7 @@ class DiscreteVJP(AbstractVJPMethod):
 
 
 class ContinuousVJP(AbstractVJPMethod):
-    """src/inverse/VJPTypes.jl:57."""
+    """src/inverse/VJPTypes.jl:57 -- the continuous adjoint (adjoint.jl:442-662), here sia2d_cont.cuh."""
 
 
 class B200VJP(DiscreteVJP):
@@ -117,10 +117,10 @@ def SIA2D_(dH, H, simulation: Simulation, t, θ=None):
 
 def VJP_λ_dSIAdH(VJPMode: AbstractVJPMethod, λ, H, θ, simulation: Simulation, t):
     """Mirror of ``VJP_λ_∂SIA∂H`` (src/inverse/SIA2D/VJPs.jl:2-5): returns ``(λ_∂f∂H, nothing)``."""
-    if not isinstance(VJPMode, DiscreteVJP):
+    if not isinstance(VJPMode, (DiscreteVJP, ContinuousVJP)):
         raise NotImplementedError(f"VJP flavour {type(VJPMode).__name__} is not provided by libodinn_b200")
     g = simulation.cache.glacier_idx
-    return simulation.ensemble.sia2d_vjp_H(g, λ, H, t), None
+    return simulation.ensemble.sia2d_vjp_H(g, λ, H, t, continuous=isinstance(VJPMode, ContinuousVJP)), None
 
 
 def VJP_λ_dSIAdθ(VJPMode: AbstractVJPMethod, λ, H, θ, dH_H, simulation: Simulation, t, vjp_θ=None):
@@ -130,10 +130,10 @@ def VJP_λ_dSIAdθ(VJPMode: AbstractVJPMethod, λ, H, θ, dH_H, simulation: Simu
     ``∂A_spatial ⊗ vjp_θ`` (src/models/target/target_A.jl:85-87), so the kernel reduces the scalar
     ``Σ ∂A_spatial ∘ D†`` and the result is ``vjp_θ * scalar``.  ``vjp_θ`` is ``cache.iceflow.A.vjp_θ``
     (the law pullback ∂A/∂θ); when omitted the bare scalar is returned."""
-    if not isinstance(VJPMode, DiscreteVJP):
+    if not isinstance(VJPMode, (DiscreteVJP, ContinuousVJP)):
         raise NotImplementedError(f"VJP flavour {type(VJPMode).__name__} is not provided by libodinn_b200")
     g = simulation.cache.glacier_idx
-    S = simulation.ensemble.sia2d_vjp_theta(g, λ, H, t)
+    S = simulation.ensemble.sia2d_vjp_theta(g, λ, H, t, continuous=isinstance(VJPMode, ContinuousVJP))
     if vjp_θ is None:
         return S
     return np.asarray(vjp_θ, dtype=np.float64) * S

@@ -259,3 +259,98 @@ def test_host_batch_pipeline(ob, dtype, gridded):
         assert all(np.array_equal(a, b) for a, b in zip(only_dH, dH))
     finally:
         sim.close()
+
+
+def _oracle_S_continuous(lam, H, g, ph, A):
+    """Σ λ ⊙ pad(∇·(avg(∂A_spatial)·clamp(∇S))) -- the scalar of adjoint.jl:582-662 for a glacier-wide law: the oracle
+    returns vjp_θ·S, so evaluate it with a per-glacier scalar law and divide by its (known) vjp_θ."""
+    th = np.array([0.3])
+    tg = o.TargetA(ph, "scalar")
+    tg.apply_laws(None, None, th)
+    tg.precompute_vjp(th)
+    out = o.VJP_dSIA_dtheta_continuous(lam, H, g, tg, th)
+    return float(out[0] / np.atleast_1d(tg.vjp_theta)[0])
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("maker", list(MAKERS))
+def test_continuous_vjps(ob, dtype, maker):
+    """A1c / A2c (ContinuousVJP, adjoint.jl:442-662) against the oracle."""
+    nx, ny = 61, 47
+    g = MAKERS[maker](nx, ny)
+    lam = np.random.default_rng(11).standard_normal((nx, ny))
+    g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+    ph = o.Phys()
+    tg = o.TargetA(ph, "const", A=A0)
+    sim = _sim(ob, g, {}, A0, dtype)
+    try:
+        vH, _ = ob.VJP_λ_dSIAdH(ob.ContinuousVJP(), lam, H, None, sim, 0.0)
+        ref = o.VJP_dSIA_dH_continuous(lam, H, g, tg)
+        assert rel_l2(vH, ref) <= TOL[dtype]
+        assert not vH[0, :].any() and not vH[-1, :].any() and not vH[:, 0].any() and not vH[:, -1].any()  # border 0
+        S = ob.VJP_λ_dSIAdθ(ob.ContinuousVJP(), lam, H, None, None, sim, 0.0)
+        refS = _oracle_S_continuous(lam, H, g, ph, A0)
+        assert abs(S - refS) <= 10 * TOL[dtype] * abs(refS)
+    finally:
+        sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_continuous_vjp_generic_physics_and_gridded_A(ob, dtype):
+    nx, ny = 38, 52
+    rng = np.random.default_rng(21)
+    g = o.rough_bed_glacier(nx, ny)
+    lam = rng.standard_normal((nx, ny))
+    g, H, lam = _round_inputs(g, g.H0, lam, dtype)
+    tol = TOL[dtype] * (4 if dtype == "f32" else 1)
+    # sliding + real Glen exponent
+    kw = dict(C=7e-8, n=3.3, eta0=0.6)
+    sim = _sim(ob, g, kw, A0, dtype)
+    try:
+        tg = o.TargetA(o.Phys(**kw), "const", A=A0)
+        vH, _ = ob.VJP_λ_dSIAdH(ob.ContinuousVJP(), lam, H, None, sim, 0.0)
+        assert rel_l2(vH, o.VJP_dSIA_dH_continuous(lam, H, g, tg)) <= tol
+        S = ob.VJP_λ_dSIAdθ(ob.ContinuousVJP(), lam, H, None, None, sim, 0.0)
+        refS = _oracle_S_continuous(lam, H, g, o.Phys(**kw), A0)
+        assert abs(S - refS) <= 10 * tol * abs(refS)
+    finally:
+        sim.close()
+    # gridded A (dual grid)
+    Af = A0 * np.exp(rng.uniform(-1, 1, size=(nx - 1, ny - 1)))
+    if dtype == "f32":
+        Af = Af.astype(np.float32).astype(np.float64)
+    sim = _sim(ob, g, {}, [Af], dtype)
+    try:
+        tg = o.TargetA(o.Phys(), "const", A=Af)
+        vH, _ = ob.VJP_λ_dSIAdH(ob.ContinuousVJP(), lam, H, None, sim, 0.0)
+        assert rel_l2(vH, o.VJP_dSIA_dH_continuous(lam, H, g, tg)) <= TOL[dtype]
+        with pytest.raises(ob.OdinnError):  # the continuous θ-VJP is provided for glacier-wide laws only
+            ob.VJP_λ_dSIAdθ(ob.ContinuousVJP(), lam, H, None, None, sim, 0.0)
+    finally:
+        sim.close()
+
+
+def test_continuous_vjp_resident_ragged(ob):
+    """Whole ragged ensemble in one launch (flags bit2) == per-glacier oracle."""
+    from odinn_b200 import _capi
+
+    rng = np.random.default_rng(31)
+    shapes = [(int(rng.integers(10, 80)), int(rng.integers(10, 80))) for _ in range(6)] + [(3, 3), (33, 4)]
+    gl, Hs, lams = [], [], []
+    for k, (nx, ny) in enumerate(shapes):
+        g = (o.rough_bed_glacier if k % 2 else _tilted_dome)(nx, ny)
+        gl.append(g), Hs.append(g.H0), lams.append(rng.standard_normal((nx, ny)))
+    sim = ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy) for g in gl], ob.Phys(), A=A0, dtype="f64")
+    try:
+        ens = sim.ensemble
+        for k in range(len(gl)):
+            ens.upload(k, _capi.FIELD_H, Hs[k])
+            ens.upload(k, _capi.FIELD_LAMBDA, lams[k])
+        S = ens.vjp_resident(True, True, continuous=True)
+        tg = o.TargetA(o.Phys(), "const", A=A0)
+        for k, g in enumerate(gl):
+            assert rel_l2(ens.download(k, _capi.FIELD_VJP_H), o.VJP_dSIA_dH_continuous(lams[k], Hs[k], g, tg)) <= 1e-12, k
+            refS = _oracle_S_continuous(lams[k], Hs[k], g, o.Phys(), A0)
+            assert abs(S[k] - refS) <= 1e-11 * abs(refS) or refS == 0.0, k
+    finally:
+        sim.close()
