@@ -103,18 +103,23 @@ __device__ __forceinline__ void subgrad(float dC, float e, float lo, float up, f
 // fp64: the reference compares the DIVIDED quantities dS/Δ and ±η₀H/Δ (inversion_utils.jl:24-28, 38-42); two raw
 // values an ulp apart can round to the same quotient, which turns a strict inequality into a tie (see gt_div).
 // The sign of a floating-point difference is exact, so d1 = e - lo and d2 = up - e classify the edge with two DADDs;
-// the true divisions are needed only when a difference is non-zero yet below 1e-14·|e| -- a rare per-lane slow path.
-// (An exact zero difference is a tie in both forms; ice-free flat regions, e = lo = up = 0, stay on the fast path.)
+// the true divisions are needed only when a difference is below 1e-14·|e| -- a rare slow path taken warp-uniformly.
+// (Ice-free flat regions, e = lo = up = 0, stay on the fast path: tol = 0.)
 template <typename T, bool ETA1>
 __device__ __forceinline__ void subgrad(double dC, double e, double lo, double up, double delta, double eta0,
                                         double& to_lower, double& to_upper) {
     const double d1 = e - lo, d2 = up - e;
     bool gt_lo = d1 > 0.0, lt_lo = d1 < 0.0, lt_up = d2 > 0.0, gt_up = d2 < 0.0;
-    const double tol = 1e-14 * fmax(fabs(e), fmax(fabs(lo), fabs(up)));
-    const bool near = (d1 != 0.0 && fabs(d1) < tol) || (d2 != 0.0 && fabs(d2) < tol);
-    if (near) {
-        const double qe = e / delta, ql = lo / delta, qu = up / delta;
-        gt_lo = qe > ql; lt_lo = ql > qe; lt_up = qu > qe; gt_up = qe > qu;
+    // near-tie with a bound implies |bound| ~ |e|, so the test is relative to |e| alone; e == 0 gives tol == 0 (never near)
+    const double tol = 1e-14 * fabs(e);
+    const bool near = (fabs(d1) < tol) || (fabs(d2) < tol);
+    // warp-uniform branch: keeps the six divisions out of the common path (a per-lane `if` gets if-converted and the
+    // divisions then run on every step -- profiles/r01_v5: 48 DFMA + 6 MUFU per step)
+    if (__any_sync(FULL, near)) {
+        if (near) {
+            const double qe = e / delta, ql = lo / delta, qu = up / delta;
+            gt_lo = qe > ql; lt_lo = ql > qe; lt_up = qu > qe; gt_up = qe > qu;
+        }
     }
     subgrad_cmp<double, ETA1>(dC, gt_lo, lt_lo, lt_up, gt_up, eta0, to_lower, to_upper);
 }
