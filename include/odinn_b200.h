@@ -206,6 +206,30 @@ int odinn_law_A_nn_apply(odinn_ensemble* e, int n_layers, const int* widths, con
  * S == NULL uses the sums left on the device by odinn_grad_discrete. */
 int odinn_law_A_nn_pullback(odinn_ensemble* e, const double* S, double* dtheta, int n_theta);
 
+/* Per-cell MLP laws evaluated at every dual-grid node.
+ *   kind 1: LawU  (src/laws/Laws.jl:97-123)   U = post(NN(pre([Hbar, gradS]); theta)),  D = Hbar * U
+ *                 (SIA2D_D_target, src/models/target/target_D_pure.jl:78-199)
+ *   kind 2: LawY  (src/laws/Laws.jl:240-273)  Y = post(NN(pre([T, Hbar]); theta)),
+ *                 D = S Hbar^{p-q+1} gradS^{p-1} + Y Gamma Hbar^{n_H+2} gradS^{n_gS-1}
+ *                 (SIA2D_D_hybrid_target, src/models/target/target_D_hybrid.jl:22-208); T from odinn_set_temperature.
+ * widths[0] must be 2 and widths[n_layers] 1 (width <= 32).  prescale_bounds = {lo0, hi0, lo1, hi1} of pre()
+ * (target_utils.jl:131-141) or NULL for raw inputs; max_NN > 0 enables post() = max_NN exp((y-1)/y)
+ * (target_utils.jl:86-93); n_H, n_gS <= 0 default to the Glen exponent n.
+ * While a per-cell law is set every RHS / VJP entry point of the handle (per-call, resident, time loop, reverse loop)
+ * uses it instead of the A law.  The partials dD/dHbar and dD/dgradS are the reference's finite differences
+ * (target_D_pure.jl:105-137, target_D_hybrid.jl:58-73), evaluated in fp64. */
+int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* widths, const int* acts, const double* theta,
+                          int n_theta, const double* prescale_bounds, double max_NN, double n_H, double n_gS);
+int odinn_law_cell_clear(odinn_ensemble* e);
+/* out_theta[k] = sum_ij (dD/dtheta_k)[i,j] * D_adj[i,j]: VJP_lambda_dSIAdtheta(::DiscreteVJP, ...) for a per-cell law
+ * (adjoint.jl:235-250 with dDiffusivity/dtheta of target_D_pure.jl:139-199 / target_D_hybrid.jl:98-166,
+ * interpolation = :None, i.e. the exact per-node network gradient). */
+int odinn_sia2d_vjp_theta_cell(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                               double* out_theta, int n_theta, double t);
+/* Per-glacier theta-gradients [n_glaciers x n_theta] left on the device by odinn_vjp_resident(flags & 2) (last VJP) or
+ * accumulated by odinn_grad_discrete (sum_j dt_{j-1} VJP_theta). */
+int odinn_law_cell_grad(odinn_ensemble* e, double* out, int n_theta);
+
 #ifdef __cplusplus
 }
 #endif

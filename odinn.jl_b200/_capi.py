@@ -15,6 +15,7 @@ F32, F64 = 0, 1
 
 FIELD_B, FIELD_H, FIELD_DH, FIELD_LAMBDA, FIELD_VJP_H, FIELD_A, FIELD_VJP_A, FIELD_H0 = range(8)
 EULER, SSPRK3 = 0, 1
+LAW_U, LAW_Y = 1, 2
 ACT = {"identity": 0, "softplus": 1, "sigmoid": 2, "tanh": 3, "relu": 4}
 
 
@@ -65,6 +66,10 @@ SIGNATURES = {
     "odinn_sia2d_vjp_theta": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
     "odinn_sia2d_vjp_H_continuous": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _d]),
     "odinn_sia2d_vjp_theta_continuous": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
+    "odinn_law_cell_nn_set": (_i, [_vp, _i, _i, _ip, _ip, _dp, _i, _dp, _d, _d, _d]),
+    "odinn_law_cell_clear": (_i, [_vp]),
+    "odinn_sia2d_vjp_theta_cell": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _i, _d]),
+    "odinn_law_cell_grad": (_i, [_vp, _dp, _i]),
     "odinn_rhs_resident": (_i, [_vp]),
     "odinn_vjp_resident": (_i, [_vp, _i, _dp]),
     "odinn_fwd_adj_batch_host": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _dp]),

@@ -9,6 +9,7 @@
 #endif
 #include "sia2d_cont.cuh"
 #include "timeloop.cuh"
+#include "sia2d_law.cuh"
 
 // Template dispatch on (n == 3 && C == 0, gridded A, eta0 == 1).  ODINN_BENCH_ONLY (developer builds for kernel
 // tuning) instantiates the benchmark configuration only; every other configuration then fails loudly.
@@ -96,6 +97,86 @@ static inline char* plane_ptr(odinn_ensemble* e, void* base, long long plane_ind
     return (char*)base + (size_t)plane_index * (size_t)e->total * e->esize;
 }
 
+__global__ void law_theta_reduce_scaled(const double* __restrict__ block_partial, int n_tiles, int n_params,
+                                        double* __restrict__ out, double scale, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_params) return;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += block_partial[(long long)t * n_params + k];  // tile order: deterministic
+    out[k] = (accumulate ? out[k] : 0.0) + scale * s;
+}
+
+// ---- per-cell laws (sia2d_law.cuh) --------------------------------------------------------------------------------
+
+static inline CellLaw* law_of(odinn_ensemble* e) { return static_cast<CellLaw*>(e->law_cfg); }
+
+static void law_refresh_phys(odinn_ensemble* e) {
+    if (!e->law_cfg) return;
+    CellLaw* lw = law_of(e);
+    lw->Gam = 2.0 * std::pow(e->phys.rho * e->phys.g, e->phys.n) / (e->phys.n + 2.0);
+    lw->Sl = e->phys.C * std::pow(e->phys.rho * e->phys.g, e->phys.p - e->phys.q);
+    lw->p = e->phys.p;
+    lw->q = e->phys.q;
+}
+
+// Pass 1 over the tiles of glaciers [g0, g1) (g0 < 0: all): node planes D (and alpha, beta when partials).
+template <typename T>
+static int launch_law_nodes_t(odinn_ensemble* e, int g0, int g1, const void* H, bool partials) {
+    const CellLaw lw = *law_of(e);
+    int t0 = 0, nt = e->n_tiles;
+    if (g0 >= 0) {
+        t0 = e->gl[g0].tile0;
+        nt = e->gl[g1 - 1].tile0 + e->gl[g1 - 1].ntx * e->gl[g1 - 1].nty - t0;
+    }
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    if (partials) {  // differences of the network: always fp64 (a 1e-6 step is below the fp32 resolution of D)
+        size_t smem = sizeof(double) * lw.arch.n_params;
+        law_nodes_kernel<T, double, true><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                          (T*)e->lawD, (T*)e->lawAl, (T*)e->lawBe);
+    } else {
+        size_t smem = sizeof(T) * lw.arch.n_params;
+        law_nodes_kernel<T, T, false><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                      (T*)e->lawD, nullptr, nullptr);
+    }
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+static int launch_law_nodes(odinn_ensemble* e, int g0, int g1, const void* H, bool partials) {
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = alloc_plane(e, &e->lawD))) return rc;
+    if (partials && ((rc = alloc_plane(e, &e->lawAl)) || (rc = alloc_plane(e, &e->lawBe)))) return rc;
+    if ((rc = sync_descs(e))) return rc;
+    return e->dtype == ODINN_F32 ? launch_law_nodes_t<float>(e, g0, g1, H, partials) : launch_law_nodes_t<double>(e, g0, g1, H, partials);
+}
+
+// Pass 3 for glaciers [g0, g1): d_law_dtheta[g] = (accumulate ? old : 0) + scale * sum_nodes D_adj s dNN/dtheta.
+template <typename T>
+static int launch_law_theta_t(odinn_ensemble* e, int g0, int g1, const void* H, double scale, int accumulate) {
+    const CellLaw lw = *law_of(e);
+    const int np = lw.arch.n_params;
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const size_t smem = sizeof(double) * np * (1 + LAW_NT / 32);
+    for (int g = g0; g < g1; ++g) {  // one glacier at a time: the block partials are [tiles of one glacier x n_theta]
+        const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
+        law_theta_kernel<T><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                            (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
+        ODINN_CHECK_LAUNCH(e);
+        law_theta_reduce_scaled<<<div_up(np, 128), 128, 0, e->stream>>>(e->d_law_partial, nt, np, e->d_law_dtheta + (size_t)g * np,
+                                                                       scale, accumulate);
+        ODINN_CHECK_LAUNCH(e);
+    }
+    return ODINN_OK;
+}
+
+static int launch_law_theta(odinn_ensemble* e, int g0, int g1, const void* H, double scale = 1.0, int accumulate = 0) {
+    if (g0 < 0) { g0 = 0; g1 = e->G; }
+    return e->dtype == ODINN_F32 ? launch_law_theta_t<float>(e, g0, g1, H, scale, accumulate)
+                                 : launch_law_theta_t<double>(e, g0, g1, H, scale, accumulate);
+}
+
 // ---- F1 launch: out = SIA2D(Hin)   or, with a stage,  out = sa·U0 + sb·(Hin + sdt·SIA2D(Hin)) ----------------
 
 struct Stage {
@@ -174,6 +255,43 @@ static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin,
     return ODINN_OK;
 }
 
+template <typename T>
+static int launch_rhs_law_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st) {
+    PhysDev<T> ph = make_phys<T>(e->phys);
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const int4* items = e->d_items + i0;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const T* Dn = (const T*)e->lawD;
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    const T* U0 = st ? (const T*)st->U0 : nullptr;
+    const T sa = st ? (T)st->sa : T(0), sb = st ? (T)st->sb : T(0), sdt = st ? (T)st->sdt : T(0);
+    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define LL(E1, STG) sia2d_rhs_march<T, true, true, E1, STG, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)Hin, B, Dn, (T*)out, ph, U0, sa, sb, sdt)
+    if (eta1) { if (st) LL(true, true); else LL(true, false); }
+    else { if (st) LL(false, true); else LL(false, false); }
+#undef LL
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+template <typename T>
+static int launch_vjp_law_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out, bool wH, bool wS) {
+    PhysDev<T> ph = make_phys<T>(e->phys);
+    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    const int4* items = e->d_items + i0;
+    const T* B = (const T*)e->plane[ODINN_FIELD_B];
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    T* vjpA = wS ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
+    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
+#define LL(WH, WS, E1) sia2d_vjp_march<T, true, true, WH, WS, E1, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)lam, (const T*)H, B, (const T*)e->lawD, (T*)out, vjpA, e->d_partial + i0, ph, (const T*)e->lawAl, (const T*)e->lawBe)
+#define LL2(E1) do { if (wH && wS) LL(true, true, E1); else if (wH) LL(true, false, E1); else LL(false, true, E1); } while (0)
+    if (eta1) LL2(true); else LL2(false);
+#undef LL2
+#undef LL
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
 // Glaciers [g0, g1); g0 < 0: whole ensemble.  `packed` selects the packed descriptor table (host-batch path).
 static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
     int rc;
@@ -184,6 +302,11 @@ static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, 
     if (g0 >= 0) {
         i0 = e->gl[g0].item0;
         ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
+    }
+    if (e->law_kind != LAW_NONE) {  // per-cell law: node pass, then the stencil in D-field mode (generic one-column kernels)
+        if (packed) return fail(e, ODINN_ESTATE, "per-cell laws use the padded plane layout");
+        if ((rc = launch_law_nodes(e, g0, g1, Hin, false))) return rc;
+        return e->dtype == ODINN_F32 ? launch_rhs_law_t<float>(e, i0, ni, Hin, out, st) : launch_rhs_law_t<double>(e, i0, ni, Hin, out, st);
     }
     if (e->dtype == ODINN_F32 && e->march >= 2) return launch_rhs2(e, g0, g1, Hin, out, st, packed);
     return e->dtype == ODINN_F32 ? launch_rhs_t<float>(e, i0, ni, Hin, out, st, packed)
@@ -293,6 +416,17 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
     if (g0 >= 0) {
         i0 = e->gl[g0].item0;
         ni = e->gl[g1 - 1].item0 + e->gl[g1 - 1].n_items - i0;
+    }
+    if (e->law_kind != LAW_NONE) {
+        // node pass with partials -> stencil in D-field mode (D-adjoint plane when the theta-VJP is wanted) -> law pullback
+        if (packed) return fail(e, ODINN_ESTATE, "per-cell laws use the padded plane layout");
+        if (wS && (rc = ensure_plane(e, ODINN_FIELD_VJP_A))) return rc;
+        if ((rc = launch_law_nodes(e, g0, g1, H, true))) return rc;
+        rc = e->dtype == ODINN_F32 ? launch_vjp_law_t<float>(e, i0, ni, lam, H, out, wH, wS)
+                                   : launch_vjp_law_t<double>(e, i0, ni, lam, H, out, wH, wS);
+        if (rc) return rc;
+        if (wS) return launch_law_theta(e, g0, g1, H, scale, accumulate);  // (S_dst is unused: the result is a vector per glacier)
+        return ODINN_OK;
     }
     const bool two = (e->dtype == ODINN_F32 && e->march >= 2);
     if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed);
@@ -492,6 +626,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         s.nty = div_up(s.ny, TY);
         s.tile0 = tile;
         tile += s.ntx * s.nty;
+        e->max_tiles_per_glacier = std::max(e->max_tiles_per_glacier, s.ntx * s.nty);
         off += (long long)s.ld * s.ny;
         e->cells += (long long)s.nx * s.ny;
     }
@@ -605,9 +740,11 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
         if (e->plane[f]) cudaFree(e->plane[f]);
     void* ptrs[] = {e->d_descs, e->d_tiles, e->d_tile_start, e->d_partial, e->d_items, e->d_item_start, e->d_S,
                     e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps,
-                    e->d_items2, e->d_item2_start, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
+                    e->d_items2, e->d_item2_start, e->d_law_theta, e->lawD, e->lawAl, e->lawBe, e->d_law_partial,
+                    e->d_law_dtheta, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    delete law_of(e);
     if (e->h_S) cudaFreeHost(e->h_S);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     for (cudaEvent_t ev : e->ev_up) cudaEventDestroy(ev);
@@ -674,6 +811,7 @@ int odinn_set_phys(odinn_ensemble* e, const odinn_phys* phys) {
     if (!phys) return fail(e, ODINN_EARG, "phys is null");
     e->phys = *phys;
     refresh_phys(e);
+    law_refresh_phys(e);
     return ODINN_OK;
 }
 
@@ -801,7 +939,9 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
     if ((rc = sync_descs(e))) return rc;
     // Packed layout (ld = nx): the device planes hold exactly the caller's bytes, so every transfer is one linear
     // DMA instead of ny row copies.  The gridded-A field lives in the padded layout only -> padded (2-D copy) path.
-    const bool packed = !e->a_gridded && e->all_nx_even;  // (the fp32 kernels need 8-byte aligned column pairs)
+    if (S && e->law_kind != LAW_NONE)
+        return fail(e, ODINN_ESTATE, "with a per-cell law the theta-VJP is a vector per glacier: use odinn_law_cell_grad");
+    const bool packed = !e->a_gridded && e->all_nx_even && e->law_kind == LAW_NONE;  // (the fp32 kernels need 8-byte aligned column pairs)
     if (packed && e->bpack_dirty) {
         if ((rc = alloc_plane(e, &e->bpack))) return rc;
         for (int g = 0; g < e->G; ++g) {
@@ -1018,6 +1158,8 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
     if ((rc = ensure_plane(e, ODINN_FIELD_LAMBDA)) || (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
     if (e->a_gridded)
         return fail(e, ODINN_ESTATE, "odinn_grad_discrete supports glacier-wide A (use the per-call VJPs for gridded A)");
+    if (e->law_kind != LAW_NONE)  // the theta-gradient of a per-cell law accumulates per glacier in d_law_dtheta
+        ODINN_CUDA(e, cudaMemsetAsync(e->d_law_dtheta, 0, sizeof(double) * (size_t)e->G * e->law_n_theta, e->stream));
     const size_t pbytes = (size_t)e->total * e->esize;
     void* lam = e->plane[ODINN_FIELD_LAMBDA];
     void* vH = e->plane[ODINN_FIELD_VJP_H];
@@ -1045,6 +1187,91 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
     if (loss_out) memcpy(loss_out, e->h_S, sizeof(double) * e->G);
     if (Ssum_out) memcpy(Ssum_out, e->h_S + e->G, sizeof(double) * e->G);
+    return ODINN_OK;
+}
+
+// ---- per-cell laws -----------------------------------------------------------------------------------------------
+
+int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* widths, const int* acts, const double* theta,
+                          int n_theta, const double* prescale_bounds, double max_NN, double n_H, double n_gS) {
+    GUARD(e);
+    if (kind != LAW_U && kind != LAW_Y) return fail(e, ODINN_EARG, "law kind must be 1 (LawU) or 2 (LawY)");
+    if (n_layers < 1 || n_layers > MLP_MAX_LAYERS || !widths || !acts || !theta) return fail(e, ODINN_EARG, "bad MLP description");
+    CellLaw lw{};
+    lw.kind = kind;
+    lw.arch.n_layers = n_layers;
+    int np = 0;
+    for (int L = 0; L <= n_layers; ++L) {
+        if (widths[L] < 1 || widths[L] > LAW_MAX_WIDTH) return fail(e, ODINN_EARG, "per-cell law width out of range (1..32)");
+        lw.arch.widths[L] = widths[L];
+    }
+    for (int L = 0; L < n_layers; ++L) {
+        if (acts[L] < ACT_IDENTITY || acts[L] > ACT_RELU) return fail(e, ODINN_EARG, "unknown activation code");
+        lw.arch.acts[L] = acts[L];
+        np += widths[L] * widths[L + 1] + widths[L + 1];
+    }
+    if (widths[0] != 2 || widths[n_layers] != 1) return fail(e, ODINN_EARG, "a per-cell law maps two inputs to one output");
+    if (np != n_theta) return fail(e, ODINN_EARG, "theta length does not match the architecture");
+    lw.arch.n_params = np;
+    lw.prescale = prescale_bounds ? 1 : 0;
+    if (prescale_bounds) { lw.lo0 = prescale_bounds[0]; lw.hi0 = prescale_bounds[1]; lw.lo1 = prescale_bounds[2]; lw.hi1 = prescale_bounds[3]; }
+    lw.postscale = (max_NN > 0.0) ? 1 : 0;
+    lw.max_NN = max_NN;
+    lw.n_H = n_H > 0.0 ? n_H : e->phys.n;
+    lw.n_gS = n_gS > 0.0 ? n_gS : e->phys.n;
+    if (e->law_n_theta != np) {
+        if (e->d_law_theta) cudaFree(e->d_law_theta);
+        if (e->d_law_partial) cudaFree(e->d_law_partial);
+        if (e->d_law_dtheta) cudaFree(e->d_law_dtheta);
+        e->d_law_theta = e->d_law_partial = e->d_law_dtheta = nullptr;
+        e->law_n_theta = 0;
+        ODINN_CUDA(e, cudaMalloc(&e->d_law_theta, sizeof(double) * np));
+        ODINN_CUDA(e, cudaMalloc(&e->d_law_partial, sizeof(double) * (size_t)np * e->max_tiles_per_glacier));
+        ODINN_CUDA(e, cudaMalloc(&e->d_law_dtheta, sizeof(double) * (size_t)np * e->G));
+        ODINN_CUDA(e, cudaMemsetAsync(e->d_law_dtheta, 0, sizeof(double) * (size_t)np * e->G, e->stream));
+        e->law_n_theta = np;
+    }
+    ODINN_CUDA(e, cudaMemcpyAsync(e->d_law_theta, theta, sizeof(double) * np, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));  // theta is caller-owned
+    if (!e->law_cfg) e->law_cfg = new CellLaw();
+    *law_of(e) = lw;
+    law_refresh_phys(e);
+    e->law_kind = kind;
+    return ODINN_OK;
+}
+
+int odinn_law_cell_clear(odinn_ensemble* e) {
+    GUARD(e);
+    e->law_kind = LAW_NONE;
+    return ODINN_OK;
+}
+
+int odinn_sia2d_vjp_theta_cell(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
+                               double* out_theta, int n_theta, double t) {
+    GUARD(e);
+    (void)t;
+    if (e->law_kind == LAW_NONE) return fail(e, ODINN_ESTATE, "no per-cell law is set (odinn_law_cell_nn_set)");
+    if (!out_theta || n_theta != e->law_n_theta) return fail(e, ODINN_EARG, "out_theta / n_theta do not match the law");
+    int rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_H, const_cast<void*>(H), ldH, true, e->stream))) return rc;
+    if ((rc = copy2d(e, glacier, ODINN_FIELD_LAMBDA, const_cast<void*>(lambda), ldl, true, e->stream))) return rc;
+    if ((rc = launch_vjp(e, glacier, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], nullptr, false, true))) return rc;
+    std::vector<double> tmp(n_theta);
+    ODINN_CUDA(e, cudaMemcpyAsync(tmp.data(), e->d_law_dtheta + (size_t)glacier * n_theta, sizeof(double) * n_theta,
+                                  cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out_theta, tmp.data(), sizeof(double) * n_theta);
+    return ODINN_OK;
+}
+
+int odinn_law_cell_grad(odinn_ensemble* e, double* out, int n_theta) {
+    GUARD(e);
+    if (e->law_kind == LAW_NONE) return fail(e, ODINN_ESTATE, "no per-cell law is set (odinn_law_cell_nn_set)");
+    if (!out || n_theta != e->law_n_theta) return fail(e, ODINN_EARG, "out / n_theta do not match the law");
+    std::vector<double> tmp((size_t)n_theta * e->G);
+    ODINN_CUDA(e, cudaMemcpyAsync(tmp.data(), e->d_law_dtheta, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(out, tmp.data(), sizeof(double) * tmp.size());
     return ODINN_OK;
 }
 

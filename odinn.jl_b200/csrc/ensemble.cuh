@@ -71,6 +71,17 @@ struct odinn_ensemble {
     void* d_dtheta = nullptr;
     double* d_temps = nullptr;
     int n_theta = 0;
+    // per-cell law state (LawU / LawY, sia2d_law.cuh)
+    int law_kind = 0;             // LAW_NONE | LAW_U | LAW_Y
+    void* law_cfg = nullptr;      // host copy of the CellLaw struct (opaque here)
+    double* d_law_theta = nullptr;
+    int law_n_theta = 0;
+    void* lawD = nullptr;         // node planes: D, alpha, beta
+    void* lawAl = nullptr;
+    void* lawBe = nullptr;
+    double* d_law_partial = nullptr;   // [max tiles per glacier x n_theta]
+    double* d_law_dtheta = nullptr;    // [G x n_theta] last / accumulated theta-gradient per glacier
+    int max_tiles_per_glacier = 0;
     long long launches = 0;
     std::string err;
 

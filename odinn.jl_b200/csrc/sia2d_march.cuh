@@ -131,7 +131,8 @@ __device__ __forceinline__ void subgrad(double dC, double e, double lo, double u
 // --------------------------------------------------------------------------------------------
 // STAGE fuses a low-storage Runge-Kutta stage into the epilogue:  out = sa·U0 + sb·(H + sdt·SIA2D(H))
 // (removes the separate axpy passes of the time loop: 4 words/cell instead of 3 + 4).
-template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
+// DFIELD (with AFIELD): the node plane holds the diffusivity D itself (per-cell laws, sia2d_law.cuh) instead of A.
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false>
 struct RhsMarch {
     static constexpr int PF = ODINN_PF_RHS;
     // per-warp / per-lane constants
@@ -188,7 +189,8 @@ struct RhsMarch {
             if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
         }
         T D1, al, be, gA;
-        node_raw<T, CUBIC, false>(ph, Anode, hx + hx1, g2, D1, al, be, gA);
+        if (DFIELD) D1 = Anode;
+        else node_raw<T, CUBIC, false>(ph, Anode, hx + hx1, g2, D1, al, be, gA);
         T D1W = shfl_up(D1);
         // raw fluxes: y-edge (i, row→row+1) and x-edge (i→i+1, row)          (adjoint.jl:93-97)
         T Fy1 = (D1W + D1) * fmx(fmn(ey, eh1), -eh);
@@ -207,7 +209,7 @@ struct RhsMarch {
     }
 };
 
-template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af, T* dH,
@@ -220,7 +222,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    RhsMarch<T, CUBIC, AFIELD, ETA1, STAGE> m;
+    RhsMarch<T, CUBIC, AFIELD, ETA1, STAGE, DFIELD> m;
     constexpr int PF = ODINN_PF_RHS;
     m.ph = ph;
     m.ld = d.ld;
@@ -276,10 +278,12 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 // --------------------------------------------------------------------------------------------
 // A1 + A2 (math: see sia2d_vjp_kernel; same arithmetic, marched, constants folded)
 // --------------------------------------------------------------------------------------------
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+// DFIELD (with AFIELD): the node planes hold D, α = ∂D/∂H̄ and β (as the target's ∂Diffusivity∂∇H returns it) of a
+// per-cell law; the θ-integrand plane then receives D† itself (gA ≡ 1) for the law's own pullback (sia2d_law.cuh).
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false>
 struct VjpMarch {
     static constexpr int PF = PfVjp<T>::value;
-    const T *hp, *bp, *lp, *ap;
+    const T *hp, *bp, *lp, *ap, *alp, *bep;
     T *op, *vp;  // output row pointer; gridded-A integrand pointer (or null)
     int ld, nym1, ny2, r0;
     T eta0, hdx, hdy, nhx2, nhy2, qx, qy, A, dx, dy;
@@ -335,12 +339,16 @@ struct VjpMarch {
         T gxr = ex + ex1, gyr = ey + eyE;  // raw: ∇Sx = hdx·gxr, ∇Sy = hdy·gyr
         T u = gxr * hdx, v = gyr * hdy;
         T Anode = A;
+        T D1, al, be, gA;
         if (AFIELD) {
             Anode = __ldg(ap);
-            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+            if (DFIELD) { al = __ldg(alp); be = __ldg(bep); }
+            bool adv = true;
+            if (MASKED) adv = (row >= 0 && row < ny2);
+            if (adv) { ap += ld; if (DFIELD) { alp += ld; bep += ld; } }
         }
-        T D1, al, be, gA;
-        node_raw<T, CUBIC, true>(ph, Anode, hx + hx1, u * u + v * v, D1, al, be, gA);
+        if (DFIELD) { D1 = Anode; gA = T(1); }
+        else node_raw<T, CUBIC, true>(ph, Anode, hx + hx1, u * u + v * v, D1, al, be, gA);
         T Dadj = (px + px1) * nhx2 + (py + pyE) * nhy2;  // D† (adjoint.jl:102-104)
         bool node_ok = node_col_ok;
         if (MASKED) node_ok = node_ok && row >= 0 && row < nym1;
@@ -389,11 +397,12 @@ struct VjpMarch {
     }
 };
 
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ lam, const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af,
-                T* __restrict__ out, T* __restrict__ vjpA, double* __restrict__ partial, PhysDev<T> ph) {
+                T* __restrict__ out, T* __restrict__ vjpA, double* __restrict__ partial, PhysDev<T> ph,
+                const T* __restrict__ alF = nullptr, const T* __restrict__ beF = nullptr) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -402,7 +411,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1> m;
+    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, DFIELD> m;
     constexpr int PF = PfVjp<T>::value;
     m.ph = ph;
     m.ld = d.ld;
@@ -428,6 +437,8 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.bp = B + d.off + ic + (long long)rc * d.ld;
     m.lp = lam + d.off + ic + (long long)rc * d.ld;
     m.ap = AFIELD ? Af + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
+    m.alp = DFIELD ? alF + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
+    m.bep = DFIELD ? beF + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
     m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
     m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
 

@@ -169,6 +169,39 @@ class Ensemble:
                                                 A.ctypes.data_as(C.POINTER(C.c_double))))
         return A
 
+    def law_cell_nn_set(self, kind: str, widths, acts, theta, prescale_bounds=None, max_NN=None, n_H=None, n_gS=None):
+        """Per-cell law: kind "U" (LawU, D = H̄·U(H̄,∇S)) or "Y" (LawY hybrid, Y(T,H̄)).  prescale_bounds = ((lo0,hi0),(lo1,hi1))."""
+        widths = [int(w) for w in widths]
+        codes = [_capi.ACT[a] if isinstance(a, str) else int(a) for a in acts]
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        pb = None
+        if prescale_bounds is not None:
+            pb = (C.c_double * 4)(prescale_bounds[0][0], prescale_bounds[0][1], prescale_bounds[1][0], prescale_bounds[1][1])
+        self._law_n_theta = theta.size
+        self._ck(self._lib.odinn_law_cell_nn_set(self._h, {"U": _capi.LAW_U, "Y": _capi.LAW_Y}[kind], len(codes),
+                                                 (C.c_int * len(widths))(*widths), (C.c_int * len(codes))(*codes),
+                                                 theta.ctypes.data_as(C.POINTER(C.c_double)), theta.size, pb,
+                                                 float(max_NN) if max_NN else 0.0, float(n_H) if n_H else 0.0,
+                                                 float(n_gS) if n_gS else 0.0))
+
+    def law_cell_clear(self):
+        self._ck(self._lib.odinn_law_cell_clear(self._h))
+
+    def sia2d_vjp_theta_cell(self, g: int, lam, H, t: float = 0.0):
+        """∂θ (vector) of the per-cell law for one glacier: Σ (∂D/∂θ_k)·D†."""
+        H = _as_f(H, self.np_dtype)
+        lam = _as_f(lam, self.np_dtype)
+        out = np.empty(self._law_n_theta, dtype=np.float64)
+        self._ck(self._lib.odinn_sia2d_vjp_theta_cell(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
+                                                      out.ctypes.data_as(C.POINTER(C.c_double)), out.size, float(t)))
+        return out
+
+    def law_cell_grad(self):
+        """(G, n_theta) per-glacier θ-gradients left by vjp_resident(want_S=True) or accumulated by grad_discrete."""
+        out = np.empty((self.G, self._law_n_theta), dtype=np.float64)
+        self._ck(self._lib.odinn_law_cell_grad(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), self._law_n_theta))
+        return out
+
     def law_A_nn_pullback(self, n_theta: int, S=None):
         """dθ = Σ_g (∂A_g/∂θ)·S_g ; S=None uses the sums left on the device by grad_discrete."""
         out = np.empty(n_theta, dtype=np.float64)
