@@ -120,6 +120,7 @@ def cpu_fwd_adj(nx, ny, dtype, n_glaciers, min_seconds, reps_max=10**9):
     from oracle import sia2d_c as oc
     from oracle import sia2d_numpy as onp
 
+    oc.use_all_cores()  # all host cores, even when the launcher exported OMP_NUM_THREADS=1 (torchrun does)
     npdt = np.float32 if dtype == "f32" else np.float64
     ph = onp.Phys()
     data = []

@@ -24,6 +24,17 @@
 #undef REAL
 #undef SUF
 
+/* Use n OpenMP threads from now on (n <= 0: leave unchanged).  The timed CPU arm calls this with the number of host
+ * cores available to the process: launchers such as torchrun export OMP_NUM_THREADS=1, which would otherwise cripple
+ * the baseline and inflate every GPU/CPU ratio. */
+void sia2d_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int sia2d_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

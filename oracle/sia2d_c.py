@@ -34,6 +34,17 @@ def threads():
     return int(lib().sia2d_oracle_threads())
 
 
+def use_all_cores():
+    """Run the C oracle on every host core available to this process, whatever OMP_NUM_THREADS says (torchrun sets it
+    to 1).  Returns the thread count now in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().sia2d_oracle_set_threads(C.c_int(n))
+    return threads()
+
+
 def _par(dx, dy, ph, A, npdt):
     p = _Par64(dx, dy, ph.eta0, ph.n, ph.p, ph.q, ph.rho, ph.g, ph.C, 0.0, None)
     keep = None
