@@ -243,8 +243,13 @@ def run_b200(args, rank, local_rank, world):
     vjp_theta = torch.zeros(322, dtype=torch.float64, device="cuda")  # [loss; dθ] of the 1-16-16-1 law (321 params)
 
     def step(i):
-        ens.rhs_resident()
-        ens.vjp_resident(True, True, read_S=False)
+        # F1 + A1 + A2 of every glacier: dH, (dSIA/dH)^T lambda and S.  fp32: ONE fused kernel (the adjoint pass recomputes
+        # every forward intermediate, so dH costs one more store); fp64 / --no-fuse: an F1 launch + an A1+A2 launch.
+        if args.no_fuse:
+            ens.rhs_resident()
+            ens.vjp_resident(True, True, read_S=False)
+        else:
+            ens.vjp_resident(True, True, read_S=False, want_dH=True)
         if dist is not None and (i + 1) % args.allreduce_every == 0:
             ens.synchronize()
             dist.all_reduce(vjp_theta)
@@ -336,6 +341,7 @@ def main():
     ap.add_argument("--ref-glaciers", type=int, default=16, help="glaciers per CPU pass (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="time F1 and A1+A2 as two launches per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

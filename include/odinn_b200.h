@@ -145,7 +145,10 @@ int odinn_sia2d_vjp_theta_continuous(odinn_ensemble* e, int glacier, const void*
 /* FIELD_DH <- SIA2D(FIELD_H) for every glacier in one launch. */
 int odinn_rhs_resident(odinn_ensemble* e);
 /* flags bit0: FIELD_VJP_H <- (dSIA/dH)^T FIELD_LAMBDA ; bit1: per-glacier S (and FIELD_VJP_A) ;
- * bit2: use the continuous flavour instead of the discrete one.
+ * bit2: use the continuous flavour instead of the discrete one ;
+ * bit3 (discrete flavour): also FIELD_DH <- SIA2D(FIELD_H) -- the (lambda_dfdH, dH) pair the reference's VJP returns
+ * (src/inverse/SIA2D/VJPs.jl:12-28); the A1 pass recomputes every forward intermediate, so with bits 0|1|3 the fp32
+ * path is ONE fused F1 + A1 + A2 kernel (5 words/cell instead of 3 + 4).
  * S_out may be NULL; otherwise n_glaciers doubles (device->host read inside the call). */
 int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
 

@@ -319,8 +319,9 @@ static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, cons
 // ---- A1 / A2 launch --------------------------------------------------------------------------------------------
 
 // fp32, two columns per lane (sia2d_march2.cuh).  Partials are indexed by the two-column work items.
+// dH_out != nullptr (with wH && wS, no bulk variant): the fused F1 + A1 + A2 pass.
 static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void* H_, void* out_, bool wH, bool wS,
-                       bool packed) {
+                       bool packed, void* dH_out = nullptr) {
     PhysDev<float> ph = make_phys<float>(e->phys);
     const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
     int i0 = 0, n_items = e->n_items2;
@@ -356,9 +357,13 @@ static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, cons
                                                                                  out, vjpA, partial, ph);                \
         }                                                                                                                \
     } while (0)
+#define LF(CUB, AF, E1)                                                                                                  \
+    sia2d_vjp_march2<CUB, AF, true, true, E1, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af,  \
+                                                                                   out, vjpA, partial, ph, (float*)dH_out)
 #define L3(CUB, AF, E1)                         \
     do {                                        \
-        if (wH && wS) L(CUB, AF, true, true, E1);   \
+        if (dH_out) LF(CUB, AF, E1);                \
+        else if (wH && wS) L(CUB, AF, true, true, E1);   \
         else if (wH) L(CUB, AF, true, false, E1);   \
         else L(CUB, AF, false, true, E1);           \
     } while (0)
@@ -366,6 +371,7 @@ static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, cons
     ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
+#undef LF
 #undef L
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
@@ -404,10 +410,16 @@ static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_
 }
 
 // Glaciers [g0, g1); g0 < 0: whole ensemble.  S_dst: where the per-glacier sums go (d_S or an accumulator), scaled by `scale`.
+// dH_out != nullptr: also dH_out <- SIA2D(H) -- fused into the A1+A2 pass where a fused kernel exists (fp32 two-column
+// kernels, wH && wS), otherwise as a separate F1 launch.
+static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed);
 static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS,
-                            double* S_dst, double scale, int accumulate, bool packed) {
-    if (!wH && !wS) return ODINN_OK;
+                            double* S_dst, double scale, int accumulate, bool packed, void* dH_out = nullptr) {
     int rc;
+    const bool fuse = dH_out && wH && wS && e->law_kind == LAW_NONE && e->dtype == ODINN_F32 && e->march == 2 && !e->no_fuse;
+    if (dH_out && !fuse && (rc = launch_rhs_range(e, g0, g1, H, dH_out, nullptr, packed))) return rc;
+    if (!fuse) dH_out = nullptr;
+    if (!wH && !wS) return ODINN_OK;
     if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
     if (e->a_gridded && ((rc = ensure_plane(e, ODINN_FIELD_A)) || (wS && (rc = ensure_plane(e, ODINN_FIELD_VJP_A)))))
         return rc;
@@ -429,7 +441,7 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
         return ODINN_OK;
     }
     const bool two = (e->dtype == ODINN_F32 && e->march >= 2);
-    if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed);
+    if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed, dH_out);
     else
         rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
                                    : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed);
@@ -632,6 +644,10 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     }
     e->total = off;
     e->n_tiles = tile;
+    if (off + (long long)(ODINN_L2PF_ROWS + 8) * 65536 >= (1LL << 31)) {  // the fp32 A1+A2 kernels index planes with 32-bit element offsets
+        delete e;
+        return fail(nullptr, ODINN_EARG, "ensemble too large for one handle: a plane must stay below 2^31 elements (split the ensemble)");
+    }
 
     std::vector<int2> tiles(tile);
     std::vector<int> tstart(n_glaciers + 1);
@@ -671,6 +687,8 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     {
         const char* env = getenv("ODINN_MARCH");
         if (env && env[0] >= '1' && env[0] <= '3') e->march = env[0] - '0';
+        const char* envf = getenv("ODINN_NO_FUSE");  // developer switch: F1 and A1+A2 as two launches even where a fused kernel exists
+        e->no_fuse = envf && envf[0] == '1';
         const char* envr = getenv("ODINN_CHUNK_ROWS2");
         int forced = envr ? atoi(envr) : 0;
         for (int rows = 64; rows >= 8; rows /= 2) {
@@ -911,8 +929,13 @@ int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out) {
         if ((flags & 2) && (rc = launch_unitA_dot(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->d_S)))
             return rc;
     } else {
-        rc = launch_vjp(e, -1, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
-                        (flags & 1) != 0, (flags & 2) != 0);
+        void* dH_out = nullptr;
+        if (flags & 8) {  // also FIELD_DH <- SIA2D(FIELD_H), in the same pass where a fused kernel exists
+            if ((rc = ensure_plane(e, ODINN_FIELD_DH))) return rc;
+            dH_out = e->plane[ODINN_FIELD_DH];
+        }
+        rc = launch_vjp_range(e, -1, 0, e->plane[ODINN_FIELD_LAMBDA], e->plane[ODINN_FIELD_H], e->plane[ODINN_FIELD_VJP_H],
+                              (flags & 1) != 0, (flags & 2) != 0, nullptr, 1.0, 0, false, dH_out);
         if (rc) return rc;
     }
     if ((flags & 2) && S_out) {
@@ -995,9 +1018,10 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
         }
         ODINN_CUDA(e, cudaEventRecord(e->ev_up[c], up));
         ODINN_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_up[c], 0));
-        if (dH && (rc = launch_rhs_range(e, g0, g1, e->stage[0], e->stage[2], nullptr, packed))) return rc;
-        if (adj && (rc = launch_vjp_range(e, g0, g1, e->stage[1], e->stage[0], e->stage[3], vjpH != nullptr, S != nullptr,
-                                          nullptr, 1.0, 0, packed)))
+        if (!adj) {
+            if (dH && (rc = launch_rhs_range(e, g0, g1, e->stage[0], e->stage[2], nullptr, packed))) return rc;
+        } else if ((rc = launch_vjp_range(e, g0, g1, e->stage[1], e->stage[0], e->stage[3], vjpH != nullptr, S != nullptr,
+                                          nullptr, 1.0, 0, packed, dH ? e->stage[2] : nullptr)))
             return rc;
         ODINN_CUDA(e, cudaEventRecord(e->ev_done[c], e->stream));
         ODINN_CUDA(e, cudaStreamWaitEvent(dn, e->ev_done[c], 0));

@@ -53,6 +53,7 @@ struct odinn_ensemble {
     int chunk_rows2 = 32;
     int march = 2;                // fp32 kernel generation: 1 = one column per lane, 2 = two columns + f32x2
     bool all_nx_even = true;
+    bool no_fuse = false;         // ODINN_NO_FUSE=1: never use the fused F1 + A1 + A2 kernel
     double* d_partial = nullptr;  // per-item / per-tile partial sums (two-stage, fixed-order reductions)
     double* d_S = nullptr;        // [4 x G]: S | Ssum | loss | A
     double* d_Ssum = nullptr;

@@ -277,8 +277,10 @@ sia2d_vjp_bulk(const GDesc<float>* __restrict__ descs, const int4* __restrict__ 
     m.vstore_pair = out_lane && (c1 <= d.nx - 2);
     m.vstore_x = out_lane && (c1 == d.nx - 1);
     const int ic = min(max(c0, 0), (d.nx - 1) & ~1);
-    m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
-    m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    m.Ob = out;
+    m.Vb = vjpA;
+    m.Fb = nullptr;
+    m.oout = (int)d.off + ic + (r0 - 1) * d.ld;
     m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = bc2(0.0f);
 
     const int lo = 2 + 2 * lane;

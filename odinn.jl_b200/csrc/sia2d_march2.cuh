@@ -35,9 +35,23 @@ constexpr int MARCH2_WARPS = ODINN_MARCH2_WARPS;
 #define ODINN_L2PF_ROWS 8   // rows of L2 prefetch distance ahead of the register queue (0 = off; sweep: profiles/r01_v4_sweep.txt)
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// One prefetch instruction per row for ALL input planes of a strip: lane 9p+s (s = 0..8) owns the 32-byte sector s of
+// the 256-byte (possibly misaligned: 9 sectors) row segment of plane p.  Replaces one prefetch + one 64-bit address add
+// per plane and row (3 + 6 issue slots in the A1+A2 kernel) by one of each.
+template <int NPLANES>
+__device__ __forceinline__ const float* prefetch_lane_ptr(int lane, int col0, int cmax, long long off, const float* p0,
+                                                          const float* p1, const float* p2) {
+    const int pl = lane / 9, sec = lane - 9 * pl;
+    if (pl >= NPLANES) return nullptr;
+    const float* base = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
+    return base + off + min(max(col0 + 8 * sec, 0), cmax);
+}
 
 #ifndef ODINN_VJP_RING_UNROLL
 #define ODINN_VJP_RING_UNROLL 1
+#endif
+#ifndef ODINN_VJP2_MIN_CTAS
+#define ODINN_VJP2_MIN_CTAS 4   // 4 CTAs x 4 warps per SM: caps the A1+A2 kernels at 128 registers
 #endif
 constexpr int VJP_RING_UNROLL = ODINN_VJP_RING_UNROLL;  // ring passes per main-loop iteration of the A1+A2 kernel
 
@@ -103,12 +117,13 @@ template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
 struct RhsMarch2 {
     static constexpr int PF = ODINN_PF2_RHS;
     const float *hp, *bp, *ap, *up;
+    const float* pfp;  // this lane's L2-prefetch sector (prefetch_lane_ptr), ODINN_L2PF_ROWS rows ahead of hp
     float* op;
     int ld, nym1, ny2;
     float eta0;
     f2 hdx, hdy, kx, ky, A;  // kx, ky are zeroed on border / out-of-grid columns
     f2 sa, sb, sdt, hraw;
-    bool store_pair, store_x;
+    bool store_pair, store_x, pf_lane;
     PhysDev<float> ph;
     f2 h, b, eh, ex, hx, ehE, Dp, Fy;
     f2 hq[PF], bq[PF];
@@ -135,10 +150,12 @@ struct RhsMarch2 {
         }
         hq[WS] = ldg2(hp);
         bq[WS] = ldg2(bp);
-        if (ODINN_L2PF_ROWS > 0 && !MASKED) {
-            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) {
-                prefetch_l2(hp + (long long)ODINN_L2PF_ROWS * ld);
-                prefetch_l2(bp + (long long)ODINN_L2PF_ROWS * ld);
+        if (ODINN_L2PF_ROWS > 0) {
+            if (MASKED) {
+                pfp += (row + 1 + PF <= nym1) ? ld : 0;
+            } else {
+                pfp += ld;
+                if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1 && pf_lane) prefetch_l2(pfp);
             }
         }
         f2 u0 = bc2(0.0f);
@@ -223,6 +240,11 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const int rc = max(r0 - 1, 0);
     m.hp = H + d.off + ic + (long long)rc * d.ld;
     m.bp = B + d.off + ic + (long long)rc * d.ld;
+    {
+        const float* q = prefetch_lane_ptr<2>(lane, it.y, cmax, d.off, H, B, nullptr);
+        m.pf_lane = q != nullptr;
+        m.pfp = (m.pf_lane ? q : H + d.off) + (long long)rc * d.ld;  // advanced with hp below, then ODINN_L2PF_ROWS rows further
+    }
     m.ap = AFIELD ? Af + d.off + ic + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
     m.op = dH + d.off + ic + (long long)(r0 - 1) * d.ld;  // dereferenced for rows >= r0 only
     m.up = STAGE ? U0 + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
@@ -248,10 +270,11 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.Fy = bc2(0.0f);
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
-        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; }
+        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.pfp += d.ld; }
         m.hq[k] = ldg2(m.hp);
         m.bq[k] = ldg2(m.bp);
     }
+    m.pfp += (long long)ODINN_L2PF_ROWS * d.ld;
 
     int row = r0 - 1;
     m.template step<false, true>(row);
@@ -267,12 +290,54 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
 // A1 + A2 (see VjpMarch; every quantity is a pair of adjacent columns)
 // --------------------------------------------------------------------------------------------
 // Clamp sub-gradient for one column (see subgrad<> in sia2d_march.cuh), fp32 comparisons on raw differences.
+// (a > b && c != d) ? v : 0  as  FSETP, FSETP.AND, FSEL  (the compiler's own choice is FSETP, FSEL, FSETP, FSEL)
+__device__ __forceinline__ float sel_gt_ne(float v, float a, float b, float c, float d) {
+#ifdef ODINN_NO_SELP_ASM
+    return (a > b && c != d) ? v : 0.0f;
+#else
+    float r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.neu.and.f32 q, %3, %4, p;\n\tselp.f32 %0, %5, 0f00000000, q;\n\t}"
+        : "=f"(r) : "f"(a), "f"(b), "f"(c), "f"(d), "f"(v));
+    return r;
+#endif
+}
+// ((a > b) && (c != d)) ? 1.0f : 0.0f  as  FSETP + FSET.BF  (two ALU-pipe instructions; the product with the cotangent
+// then rides on a packed FFMA2 instead of an FSEL per column)
+__device__ __forceinline__ float mask_gt_ne(float a, float b, float c, float d) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\tset.neu.and.f32.f32 %0, %3, %4, p;\n\t}"
+        : "=f"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+    return r;
+}
+__device__ __forceinline__ float mask_gt(float a, float b) {
+    float r;
+    asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+// Clamp sub-gradient (inversion_utils.jl:22-43) as weights: the cotangent dC of the clamped edge slope sends
+// -ml * dC to the lower cell and +mu * dC to the upper cell (strict inequalities: ties send nothing).
+template <bool ETA1>
+__device__ __forceinline__ void submask1(float e, float lo, float up, float eta0, float& ml, float& mu) {
+    if (ETA1) {
+        ml = mask_gt_ne(up, e, e, lo);
+        mu = mask_gt_ne(e, lo, e, up);
+    } else {
+        const float in = (up > e && e > lo) ? 1.0f : 0.0f;
+        ml = in + ((lo > e) ? eta0 : 0.0f);
+        mu = in + ((e > up) ? eta0 : 0.0f);
+    }
+}
+template <bool ETA1>
+__device__ __forceinline__ void submask2(f2 e, f2 lo, f2 up, float eta0, f2& ml, f2& mu) {
+    submask1<ETA1>(e.x, lo.x, up.x, eta0, ml.x, mu.x);
+    submask1<ETA1>(e.y, lo.y, up.y, eta0, ml.y, mu.y);
+}
+
 template <bool ETA1>
 __device__ __forceinline__ void subgrad1(float dC, float e, float lo, float up, float eta0, float& to_lower, float& to_upper) {
     if (ETA1) {
-        bool lt_up = up > e, gt_lo = e > lo;
-        to_lower = (lt_up && e != lo) ? -dC : 0.0f;
-        to_upper = (gt_lo && e != up) ? dC : 0.0f;
+        to_lower = sel_gt_ne(-dC, up, e, e, lo);
+        to_upper = sel_gt_ne(dC, e, lo, e, up);
     } else {
         bool inside = (up > e) && (e > lo);
         float pass = inside ? dC : 0.0f;
@@ -287,11 +352,18 @@ __device__ __forceinline__ void subgrad2(f2 dC, f2 e, f2 lo, f2 up, float eta0, 
     subgrad1<ETA1>(dC.y, e.y, lo.y, up.y, eta0, to_lower.y, to_upper.y);
 }
 
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
+// WRITE_F: the same pass also writes dH = SIA2D(H) (F1): every forward intermediate is recomputed here anyway, so the
+// forward costs one more shuffle, ~8 packed operations and one store per row instead of a second pass over H and B.
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false>
 struct VjpMarch2 {
     static constexpr int PF = ODINN_PF2_VJP;
-    const float *hp, *bp, *lp, *ap;
-    float *op, *vp;
+    // Every plane shares one (offset, pitch) layout, so the kernel keeps 32-bit ELEMENT offsets and adds them to the
+    // (warp-uniform) plane bases at each access -- one IMAD.WIDE per access, as a pointer bump would cost, but 3
+    // registers instead of 14 for the 7 pointers (the kernel sits at the 128-register cap of 4 CTAs/SM).
+    const float *Hb, *Bb, *Lb, *Ab;
+    float *Ob, *Vb, *Fb;
+    const float* pfb;  // per lane: base of the plane this lane prefetches + its sector's column delta + ODINN_L2PF_ROWS rows
+    int oin, oout, oa;  // offsets of the row being loaded / the row being written / the A-field node row
     int ld, nym1, ny2;
     float eta0;
     f2 hdx, hdy, nhx2, nhy2, qx, qy, A;
@@ -300,6 +372,12 @@ struct VjpMarch2 {
     bool store_pair, store_x, own_lane, vstore_pair, vstore_x;
     PhysDev<float> ph;
     f2 h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc;
+    f2 cx, Fyp;  // WRITE_F: clamped x-edge slope of the carried row (replaces the px carry), previous y-edge flux
+    // CUBIC form (compute_cubic): folded constants and its own carried set
+    f2 hdxs, hdys;   // ½/Δx·√K, ½/Δy·√K  with K = Γ/4⁵, so that u² + v² = K |∇S|²
+    f2 lmx, lmy;     // lmask·(-½/Δx²), lmask·(-½/Δy²): λ is scaled once when it is loaded
+    f2 qx2, qy2;     // 2K·¼/Δx², 2K·¼/Δy²
+    f2 ly, fx, Qp;   // scaled λ row (y form), scaled Fx† of the carried row, Q of the previous node row
     f2 hq[PF], bq[PF], lq[PF];
 
 
@@ -312,32 +390,120 @@ struct VjpMarch2 {
 #pragma unroll
             for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
         }
-        if (MASKED) {
-            int stp = (row + 1 + PF <= nym1) ? ld : 0;
-            hp += stp;
-            bp += stp;
-            lp += stp;
-        } else {
-            hp += ld;
-            bp += ld;
-            lp += ld;
-        }
-        hq[WS] = ldg2(hp);
-        bq[WS] = ldg2(bp);
-        lq[WS] = ldg2(lp);
+        if (MASKED) oin += (row + 1 + PF <= nym1) ? ld : 0;
+        else oin += ld;
+        hq[WS] = ldg2(Hb + oin);
+        bq[WS] = ldg2(Bb + oin);
+        lq[WS] = ldg2(Lb + oin);
         if (ODINN_L2PF_ROWS > 0 && !MASKED) {
-            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) {
-                prefetch_l2(hp + (long long)ODINN_L2PF_ROWS * ld);
-                prefetch_l2(bp + (long long)ODINN_L2PF_ROWS * ld);
-                prefetch_l2(lp + (long long)ODINN_L2PF_ROWS * ld);
-            }
+            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) prefetch_l2(pfb + oin);
         }
         f2 Anode = A;
         if (AFIELD) {
-            Anode = ldg2(ap);
-            if (MASKED) { if (row >= 0 && row < ny2) ap += ld; } else ap += ld;
+            Anode = ldg2(Ab + oa);
+            if (MASKED) { if (row >= 0 && row < ny2) oa += ld; } else oa += ld;
         }
-        compute<OUT, MASKED>(row, h1, b1, l1, Anode);
+        if (CUBIC) compute_cubic<OUT, MASKED>(row, h1, b1, l1, Anode);
+        else compute<OUT, MASKED>(row, h1, b1, l1, Anode);
+    }
+
+    // n = 3, C = 0 form of compute(): the same operator with the constants folded and the per-node products shared.
+    //   g2 = K|∇S|² (K folded into the slope scale), m = g2·Hs, z = Hs⁴·D†, zA = A z:
+    //   D = Hs⁴·(A m),  α D† = 5 g2 zA,  β D† ∇S-part = 2K (Hs zA)·(raw slope sums),  ∂A_spatial ∘ D† = m z
+    // λ is scaled by -½/Δ² (and the column mask) when loaded, so D† is a plain sum of four products and the clamp
+    // cotangents need no further scaling; the clamp sub-gradient is applied as 0/1 weights (submask2) through packed FMAs.
+    // Carried: h, b, eh, ex, hx, ehE, cx, fx, ly, px, Dp, aDp, Pp, Qp, yu_p, Fyp, acc.
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void compute_cubic(int row, f2 h1, f2 b1, f2 l1, f2 Anode) {
+        f2 l1x = mul2(l1, lmx), l1y = mul2(l1, lmy);
+        if (MASKED) { if (!(row >= 0 && row + 1 < nym1)) l1x = l1y = bc2(0.0f); }  // λ_inn zero-extended on border rows
+        h1 = max2(h1, bc2(0.0f));
+        f2 eh1 = ETA1 ? h1 : mul2(bc2(eta0), h1);
+        f2 hE1 = east2(h1), bE1 = east2(b1), lE1x = east2(l1x);
+        // x-edge (i→i+1, row+1)
+        f2 ex1 = sdiff2(bE1, b1, hE1, h1);
+        f2 hx1 = add2(h1, hE1);
+        f2 ehE1 = ETA1 ? hE1 : mul2(bc2(eta0), hE1);
+        f2 fx1 = sub2(lE1x, l1x);                         // -½/Δx² · Fx† (adjoint.jl:100)
+        const f2 cx1 = clamp2(ex1, ehE1, eh1);
+        f2 px1 = mul2(fx1, cx1);                          // (adjoint.jl:102)
+        // y-edge (i, row→row+1)
+        f2 ey = sdiff2(b1, b, h1, h);
+        f2 fy = sub2(l1y, ly);
+        const f2 cy = clamp2(ey, eh1, eh);
+        f2 py = mul2(fy, cy);
+        f2 eyE = east2(ey), pyE = east2(py);
+        // node (i, row)
+        f2 gxr = add2(ex, ex1), gyr = add2(ey, eyE);
+        f2 u = mul2(gxr, hdxs), v = mul2(gyr, hdys);
+        f2 g2 = fma2(v, v, mul2(u, u));
+        f2 Hs = add2(hx, hx1);
+        f2 H2 = mul2(Hs, Hs);
+        f2 H4 = mul2(H2, H2);
+        f2 mk = mul2(g2, Hs);
+        f2 D1 = mul2(H4, mul2(mk, Anode));
+        f2 Dadj = add2(add2(py, pyE), add2(px, px1));     // D† (adjoint.jl:102-104)
+        Dadj = mul2(Dadj, nodemask);
+        bool row_ok = true;
+        if (MASKED) { row_ok = (row >= 0 && row < nym1); if (!row_ok) Dadj = bc2(0.0f); }
+        f2 z = mul2(H4, Dadj);
+        f2 zA = mul2(z, Anode);
+        f2 aD1 = mul2(g2, zA);
+        f2 bD = mul2(Hs, zA);
+        f2 P1 = mul2(bD, gxr);
+        f2 Q1 = mul2(bD, gyr);
+        if (WRITE_S) {
+            if (OUT) {
+                if (AFIELD) {
+                    f2 vS = mul2(mk, z);                  // ∂A_spatial ∘ D† (adjoint.jl:250)
+                    acc = add2(acc, vS);                  // (halo lanes are dropped when the strip is reduced)
+                    if (row_ok) {
+                        if (vstore_pair) *reinterpret_cast<float2*>(Vb + oout) = vS;
+                        if (vstore_x) Vb[oout] = vS.x;
+                    }
+                } else {
+                    acc = fma2(mk, z, acc);
+                }
+            }
+        }
+        f2 D1W;
+        if (WRITE_H || WRITE_F) D1W = west2(D1);
+        if (WRITE_F) {
+            // F1 with the operation order of RhsMarch2::compute
+            f2 Fy1 = mul2(add2(D1W, D1), cy);
+            f2 Fx = mul2(add2(Dp, D1), cx);
+            f2 FxW = west2(Fx);
+            if (OUT) {
+                f2 outv = fma2(lmy, sub2(Fyp, Fy1), mul2(lmx, sub2(FxW, Fx)));
+                if (MASKED) { if (row < 1 || row >= nym1) outv = bc2(0.0f); }
+                if (store_pair) *reinterpret_cast<float2*>(Fb + oout) = outv;
+                if (store_x) Fb[oout] = outv.x;
+            }
+            Fyp = Fy1;
+        }
+        if (WRITE_H) {
+            f2 dCy = mul2(fy, add2(D1W, D1));             // ∂Cy/Δy = -Fy†·Dy/Δy
+            f2 dCx = mul2(fx, add2(Dp, D1));
+            f2 myl, myu, mxl, mxu;
+            submask2<ETA1>(ey, neg2(eh), eh1, eta0, myl, myu);
+            submask2<ETA1>(ex, neg2(eh), ehE, eta0, mxl, mxu);
+            f2 SAW = fma2(sub2(Qp, Q1), qy2, mul2(add2(aDp, aD1), bc2(5.0f)));
+            f2 SP = mul2(add2(Pp, P1), qx2);
+            f2 ZW = west2(fma2(mxu, dCx, add2(SAW, SP)));  // everything column i-1 sends to cell (i, row)
+            f2 yu1 = mul2(myu, dCy);
+            if (OUT) {
+                f2 own = fma2(myl, dCy, fma2(mxl, dCx, sub2(SP, SAW)));   // minus the cell's own share
+                f2 res = sub2(ZW, sub2(own, yu_p));
+                res = mul2(res, mk2(mask_gt(h.x, 0.0f), mask_gt(h.y, 0.0f)));  // adjoint.jl:148
+                if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
+                if (store_x) Ob[oout] = res.x;
+            }
+            yu_p = yu1;
+        }
+        oout += ld;
+        h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; cx = cx1;
+        fx = fx1; ly = l1y; px = px1;
+        Dp = D1; aDp = aD1; Pp = P1; Qp = Q1;
     }
 
     // One marching step given the cell row `row+1` (h1, b1, raw λ row l1) and the node coefficient of node row `row`.
@@ -353,11 +519,14 @@ struct VjpMarch2 {
         f2 hx1 = add2(h1, hE1);
         f2 ehE1 = ETA1 ? hE1 : mul2(bc2(eta0), hE1);
         f2 fxr1 = sub2(lE1, l1);                          // raw Fx† (adjoint.jl:100)
-        f2 px1 = mul2(fxr1, clamp2(ex1, ehE1, eh1));      // raw Fx†·clamp(dSdx) (adjoint.jl:102)
+        const f2 cx1 = clamp2(ex1, ehE1, eh1);
+        f2 px1 = mul2(fxr1, cx1);                         // raw Fx†·clamp(dSdx) (adjoint.jl:102)
+        if (WRITE_F) px = mul2(fxr, cx);                  // (same product as the px1 of the previous step)
         // y-edge (i, row→row+1)
         f2 ey = sdiff2(b1, b, h1, h);
         f2 fyr = sub2(l1, l);
-        f2 py = mul2(fyr, clamp2(ey, eh1, eh));
+        const f2 cy = clamp2(ey, eh1, eh);
+        f2 py = mul2(fyr, cy);
         f2 eyE = east2(ey), pyE = east2(py);
         // node (i, row)
         f2 gxr = add2(ex, ex1), gyr = add2(ey, eyE);
@@ -378,15 +547,30 @@ struct VjpMarch2 {
                 if (own_lane) acc = add2(acc, vS);
                 if (AFIELD) {
                     if (row_ok) {
-                        if (vstore_pair) *reinterpret_cast<float2*>(vp) = vS;
-                        if (vstore_x) *vp = vS.x;
+                        if (vstore_pair) *reinterpret_cast<float2*>(Vb + oout) = vS;
+                        if (vstore_x) Vb[oout] = vS.x;
                     }
                 }
             }
-            if (AFIELD) vp += ld;
+        }
+        f2 D1W;
+        if (WRITE_H || WRITE_F) D1W = west2(D1);
+        if (WRITE_F) {
+            // F1 with the operation order of RhsMarch2::compute (nhx2 = -kx, nhy2 = -ky: exact sign flips)
+            f2 Fy1 = mul2(add2(D1W, D1), cy);
+            f2 Fx = mul2(add2(Dp, D1), cx);
+            f2 FxW = west2(Fx);
+            if (OUT) {
+                f2 outv = mul2(fma2(nhy2, sub2(Fyp, Fy1), mul2(nhx2, sub2(FxW, Fx))), lmask);
+                if (MASKED) { if (row < 1 || row >= nym1) outv = bc2(0.0f); }
+                if (store_pair) *reinterpret_cast<float2*>(Fb + oout) = outv;
+                if (store_x) Fb[oout] = outv.x;
+            }
+            Fyp = Fy1;
+            cx = cx1;
         }
         if (WRITE_H) {
-            f2 D1W = west2(D1), Q1W = west2(Q1);
+            f2 Q1W = west2(Q1);
             f2 Qrow1 = add2(Q1W, Q1);
             f2 yl, yu1, xl, xu;
             {
@@ -404,24 +588,25 @@ struct VjpMarch2 {
                 f2 res = add2(add2(add2(ZW, add2(sub2(aDc, Pc), xl)), mul2(qy, sub2(Qrow_p, Qrow1))), add2(yl, yu_p));
                 if (!(h.x > 0.0f)) res.x = 0.0f;  // adjoint.jl:148
                 if (!(h.y > 0.0f)) res.y = 0.0f;
-                if (store_pair) *reinterpret_cast<float2*>(op) = res;
-                if (store_x) *op = res.x;
+                if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
+                if (store_x) Ob[oout] = res.x;
             }
-            op += ld;
             Qrow_p = Qrow1;
             yu_p = yu1;
         }
-        h = h1; b = b1; l = l1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; fxr = fxr1; px = px1;
+        oout += ld;
+        h = h1; b = b1; l = l1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; fxr = fxr1;
+        if (!WRITE_F) px = px1;
         Dp = D1; aDp = aD1; Pp = P1;
     }
 };
 
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1>
-__global__ void __launch_bounds__(MARCH2_WARPS * 32)
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false>
+__global__ void __launch_bounds__(MARCH2_WARPS * 32, ODINN_VJP2_MIN_CTAS)
 sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                  const float* __restrict__ lam, const float* __restrict__ H, const float* __restrict__ B,
                  const float* __restrict__ Af, float* __restrict__ out, float* __restrict__ vjpA,
-                 double* __restrict__ partial, PhysDev<float> ph) {
+                 double* __restrict__ partial, PhysDev<float> ph, float* __restrict__ dH = nullptr) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -430,7 +615,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const int c0 = it.y + 2 * lane, r0 = it.z, r1 = it.w;
     const int cmax = (d.nx - 1) & ~1;
     const int ic = min(max(c0, 0), cmax);
-    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1> m;
+    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, WRITE_F> m;
     constexpr int PF = ODINN_PF2_VJP;
     m.ph = ph;
     m.ld = d.ld;
@@ -455,16 +640,23 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.vstore_pair = out_lane && (c1 <= d.nx - 2);
     m.vstore_x = out_lane && (c1 == d.nx - 1);
     const int rc = max(r0 - 1, 0);
-    m.hp = H + d.off + ic + (long long)rc * d.ld;
-    m.bp = B + d.off + ic + (long long)rc * d.ld;
-    m.lp = lam + d.off + ic + (long long)rc * d.ld;
-    m.ap = AFIELD ? Af + d.off + ic + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
-    m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
-    m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    m.Hb = H; m.Bb = B; m.Lb = lam; m.Ab = Af;
+    m.Ob = out; m.Fb = dH; m.Vb = vjpA;
+    const int o0 = (int)d.off + ic;  // (odinn_ensemble_create refuses planes of 2^31 elements or more)
+    m.oin = o0 + rc * d.ld;
+    m.oa = o0 + min(rc, d.ny - 2) * d.ld;
+    m.oout = o0 + (r0 - 1) * d.ld;   // dereferenced for rows >= r0 only
+    {
+        // one prefetch instruction per row covers the three input planes: 10 lanes per plane, one 32-byte sector each
+        // (the 256-byte row segment of a strip spans up to 9 sectors; lanes 30, 31 touch the next strip's first sectors)
+        const int pl = min(lane / 10, 2), sec = lane - 10 * pl;
+        const float* pb = pl == 0 ? H : (pl == 1 ? B : lam);
+        m.pfb = pb + (min(max(it.y + 8 * sec, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
+    }
 
     // ---- cell row r0-1 ----
     {
-        f2 hv = ldg2(m.hp), bv = ldg2(m.bp), lv = ldg2(m.lp);
+        f2 hv = ldg2(m.Hb + m.oin), bv = ldg2(m.Bb + m.oin), lv = ldg2(m.Lb + m.oin);
         m.h = max2(hv, bc2(0.0f));
         m.b = bv;
         m.l = mul2(lv, m.lmask);
@@ -477,15 +669,30 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
         m.hx = add2(m.h, hE);
         m.ehE = ETA1 ? hE : mul2(bc2(m.eta0), hE);
         m.fxr = sub2(lE, m.l);
-        m.px = mul2(m.fxr, clamp2(m.ex, m.ehE, m.eh));
+        m.cx = clamp2(m.ex, m.ehE, m.eh);
+        m.px = mul2(m.fxr, m.cx);
     }
-    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = bc2(0.0f);
+    if (CUBIC) {
+        const float sK = sqrtf(ph.Gam * (1.0f / 1024.0f)), K2 = 2.0f * (ph.Gam * (1.0f / 1024.0f));
+        m.hdxs = bc2(hdx * sK);
+        m.hdys = bc2(hdy * sK);
+        m.lmx = mul2(m.lmask, m.nhx2);
+        m.lmy = mul2(m.lmask, m.nhy2);
+        m.qx2 = bc2(K2 * (hdx * hdx));
+        m.qy2 = bc2(K2 * (hdy * hdy));
+        const f2 lx = mul2(m.l, m.nhx2);   // m.l is the masked λ row r0-1
+        m.ly = mul2(m.l, m.nhy2);
+        m.fx = sub2(east2(lx), lx);
+        m.px = mul2(m.fx, m.cx);
+        m.Qp = bc2(0.0f);
+    }
+    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = m.Fyp = bc2(0.0f);
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
-        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
-        m.hq[k] = ldg2(m.hp);
-        m.bq[k] = ldg2(m.bp);
-        m.lq[k] = ldg2(m.lp);
+        if (r0 + k >= 1 && r0 + k <= m.nym1) m.oin += d.ld;
+        m.hq[k] = ldg2(m.Hb + m.oin);
+        m.bq[k] = ldg2(m.Bb + m.oin);
+        m.lq[k] = ldg2(m.Lb + m.oin);
     }
 
     int row = r0 - 1;
@@ -499,7 +706,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     for (; row < r1; ++row) m.template step<true, true>(row);
 
     if (WRITE_S) {
-        double a = (double)m.acc.x + (double)m.acc.y;
+        double a = m.own_lane ? (double)m.acc.x + (double)m.acc.y : 0.0;  // (the CUBIC form accumulates in the halo lanes too)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
         if (lane == 0) partial[item] = a;

@@ -124,8 +124,9 @@ class Ensemble:
     def rhs_resident(self):
         self._ck(self._lib.odinn_rhs_resident(self._h))
 
-    def vjp_resident(self, want_H=True, want_S=True, read_S=True, continuous=False):
-        flags = (1 if want_H else 0) | (2 if want_S else 0) | (4 if continuous else 0)
+    def vjp_resident(self, want_H=True, want_S=True, read_S=True, continuous=False, want_dH=False):
+        """want_dH: also FIELD_DH <- SIA2D(FIELD_H) (the (λ_∂f∂H, dH) pair of VJPs.jl:12-28), fused into the same pass."""
+        flags = (1 if want_H else 0) | (2 if want_S else 0) | (4 if continuous else 0) | (8 if want_dH else 0)
         if want_S and read_S:
             S = np.empty(self.G, dtype=np.float64)
             self._ck(self._lib.odinn_vjp_resident(self._h, flags, S.ctypes.data_as(C.POINTER(C.c_double))))

@@ -663,10 +663,17 @@ def VJP_dSIA_dtheta_discrete(lam, H, glacier, target, theta=None, dense=False):
 def node_reduction_S(lam, H, glacier, target, theta=None):
     """Σ_ij (Γ_noA H̄^{n+2} ∇S^{n-1})·D† -- the scalar the GPU A2 kernel reduces
     (target_A.jl:71-72 contracted at adjoint.jl:250)."""
+    return node_reduction_S_terms(lam, H, glacier, target, theta)[0]
+
+
+def node_reduction_S_terms(lam, H, glacier, target, theta=None):
+    """(Σ v, Σ |v|) of the per-node integrand v of node_reduction_S.  With a random λ the sum cancels heavily
+    (Σ|v| / |Σ v| reaches 10^4 on the test grids), so a reduced-precision sum is judged against Σ|v|."""
     f = _recompute_forward(H, glacier, target, theta)
     _, _, D_adjoint = _D_adjoint(lam, f, glacier.dx, glacier.dy)
     ph = target.ph
-    return float(np.sum(Gamma(ph) * f["Hb"] ** (ph.n + 2) * f["gS"] ** (ph.n - 1) * D_adjoint))
+    v = Gamma(ph) * f["Hb"] ** (ph.n + 2) * f["gS"] ** (ph.n - 1) * D_adjoint
+    return float(np.sum(v)), float(np.sum(np.abs(v)))
 
 
 # --------------------------------------------------------------------------

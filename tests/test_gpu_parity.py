@@ -45,6 +45,12 @@ def _round_inputs(g, H, lam, dtype):
     return g2, H.astype(npdt).astype(np.float64), lam.astype(npdt).astype(np.float64)
 
 
+def _S_close(S, lam, H, g, tg, dtype):
+    """|S - ref| <= 10 tol |ref|, or -- when the sum cancels -- a few roundings of the accumulated magnitude Σ|v|."""
+    ref, mag = o.node_reduction_S_terms(lam, H, g, tg)
+    return abs(S - ref) <= 10 * TOL[dtype] * abs(ref) or abs(S - ref) <= (3e-7 if dtype == "f32" else 1e-14) * mag
+
+
 def _sim(ob, g, phys_kw, A, dtype):
     return ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy)], ob.Phys(**phys_kw), A=A, dtype=dtype)
 
@@ -83,8 +89,7 @@ def test_forward_and_vjps_match_oracle(ob, dtype, maker, shape):
         assert np.all(vH[np.maximum(H, 0) <= 0] == 0)  # adjoint.jl:148
 
         S = ob.VJP_λ_dSIAdθ(ob.B200VJP(), lam, H, None, None, sim, 0.0)
-        refS = o.node_reduction_S(lam, H, g, tg)
-        assert abs(S - refS) <= max(TOL[dtype] * 10, 0) * max(abs(refS), 1e-300) or abs(refS) == 0.0, ("vjp_theta", S, refS)
+        assert _S_close(S, lam, H, g, tg, dtype), ("vjp_theta", S, o.node_reduction_S(lam, H, g, tg))
     finally:
         sim.close()
 
@@ -171,8 +176,7 @@ def test_mixed_size_ensemble_batch(ob, dtype):
             tg = o.TargetA(o.Phys(), "const", A=As[k])
             assert rel_l2(ens.download(k, _capi.FIELD_DH), o.SIA2D(Hs[k], g, tg)) <= TOL[dtype], k
             assert rel_l2(ens.download(k, _capi.FIELD_VJP_H), o.VJP_dSIA_dH_discrete(lams[k], Hs[k], g, tg)) <= TOL[dtype], k
-            refS = o.node_reduction_S(lams[k], Hs[k], g, tg)
-            assert abs(S[k] - refS) <= 10 * TOL[dtype] * abs(refS) or refS == 0.0, k
+            assert _S_close(S[k], lams[k], Hs[k], g, tg, dtype), k
         # determinism: the two-stage reduction is bit-stable run to run
         S2 = ens.vjp_resident(True, True)
         assert np.array_equal(S, S2)
@@ -251,12 +255,12 @@ def test_host_batch_pipeline(ob, dtype, gridded):
                 tg = o.TargetA(o.Phys(), "const", A=As[k])
                 assert rel_l2(dH[k], o.SIA2D(Hs[k], g, tg)) <= TOL[dtype], k
                 assert rel_l2(vH[k], o.VJP_dSIA_dH_discrete(lams[k], Hs[k], g, tg)) <= TOL[dtype], k
-                refS = o.node_reduction_S(lams[k], Hs[k], g, tg)
-                assert abs(S[k] - refS) <= 10 * TOL[dtype] * abs(refS) or refS == 0.0, k
+                assert _S_close(S[k], lams[k], Hs[k], g, tg, dtype), k
         assert np.array_equal(ens.download(0, _capi.FIELD_H), marker.astype(ens.np_dtype))
         only_dH, none_v, none_S = ens.fwd_adj_batch(Hs, None, want_vjpH=False, want_S=False)
         assert none_v is None and none_S is None
-        assert all(np.array_equal(a, b) for a, b in zip(only_dH, dH))
+        # (fp32: dH above came out of the fused F1 + A1 + A2 kernel, whose D is rounded in a different order)
+        assert all(rel_l2(a, b) <= (1e-6 if dtype == "f32" else 0.0) for a, b in zip(only_dH, dH))
     finally:
         sim.close()
 
