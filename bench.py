@@ -292,10 +292,19 @@ def run_b200(args, rank, local_rank, world):
     value = world * cells_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * cells_per_step / (ms_e2e * 1e-3) if e2e_steps > 0 else None
     peak, peak_src = load_peaks()
-    # dominant kernel: the fused A1+A2 VJP kernel -- 4 words/cell (read λ, H, B; write ∂H)
+    # Roofline of the dominant kernel.  fp32: the fused F1 + A1 + A2 kernel -- 5 words/cell (read λ, H, B; write dH, ∂H);
+    # fp64 / --no-fuse: the A1+A2 kernel -- 4 words/cell.  The F1 kernel (3 words/cell) is reported beside it.
+    fused = (args.dtype == "f32") and not args.no_fuse and os.environ.get("ODINN_NO_FUSE") != "1" and os.environ.get("ODINN_MARCH", "2") == "2"
     vjp_bytes = 4 * w * cells_per_step
-    achieved = vjp_bytes / (ms_vjp * 1e-3) / 1e9
     rhs_bytes = 3 * w * cells_per_step
+    sub = lambda nbytes, ms_k, words: {"achieved": nbytes / (ms_k * 1e-3) / 1e9, "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak,
+                                       "algorithmic_bytes_per_cell": words * w, "ms_per_launch": ms_k}
+    if fused:
+        dom_name, dom_key, dom_words, dom_ms = "sia2d_vjp_march2<WRITE_F> (F1 + A1 + A2 fused: one launch per step)", "sia2d_fused", 5, ms / args.steps
+    else:
+        dom_name = "sia2d_vjp_march2 (A1+A2 fused)" if args.dtype == "f32" else "sia2d_vjp_march (A1+A2 fused)"
+        dom_key, dom_words, dom_ms = "sia2d_vjp_march2" if args.dtype == "f32" else "sia2d_vjp_march", 4, ms_vjp
+    dom = sub(dom_words * w * cells_per_step, dom_ms, dom_words)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -304,17 +313,12 @@ def run_b200(args, rank, local_rank, world):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * G * esz), "d2h_bytes_per_step": int(2 * G * esz + 8 * G),
                     "api": "odinn_fwd_adj_batch_host (pinned host H, lambda -> dH, vjp_H, S)", "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "kernel": "sia2d_vjp_march2 (A1+A2 fused)" if args.dtype == "f32" else "sia2d_vjp_march (A1+A2 fused)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(args.dtype, "sia2d_vjp_march2", cells_per_step),
-                         "traffic_note": "dram read+write bytes per launch from the committed ncu capture (profiles/r01_traffic.json); algorithmic = 16 B/cell",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell": 4 * w, "ms_per_launch": ms_vjp,
-                         "rhs_kernel": {"achieved": rhs_bytes / (ms_rhs * 1e-3) / 1e9, "frac": rhs_bytes / (ms_rhs * 1e-3) / 1e9 / peak,
-                                        "algorithmic_bytes_per_cell": 3 * w, "ms_per_launch": ms_rhs},
-                         "step": {"achieved": 10 * w * cells_per_step * args.steps / (ms * 1e-3) / 1e9,
-                                  "frac": 10 * w * cells_per_step * args.steps / (ms * 1e-3) / 1e9 / peak,
-                                  "algorithmic_bytes_per_cell": 10 * w}},
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["frac"], "traffic": measured_traffic(args.dtype, dom_key, cells_per_step),
+                         "traffic_note": "dram read+write bytes per launch from the committed ncu capture (profiles/r01_traffic.json)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell": dom_words * w, "ms_per_launch": dom_ms,
+                         "vjp_kernel": sub(vjp_bytes, ms_vjp, 4), "rhs_kernel": sub(rhs_bytes, ms_rhs, 3),
+                         "step_launches": "1 fused kernel (+ the per-glacier S reduction)" if fused else "F1 kernel + A1+A2 kernel (+ the per-glacier S reduction)"},
         }
         if world == 1 and not args.no_cpu:
             rate, el, reps, cores = cpu_fwd_adj(n, n, args.dtype, args.ref_glaciers, args.cpu_seconds)

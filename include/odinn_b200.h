@@ -30,7 +30,7 @@ typedef struct odinn_ensemble odinn_ensemble;
 
 enum odinn_dtype { ODINN_F32 = 0, ODINN_F64 = 1 };
 
-enum odinn_method { ODINN_EULER = 0, ODINN_SSPRK3 = 1 };
+enum odinn_method { ODINN_EULER = 0, ODINN_SSPRK3 = 1, ODINN_BS3 = 2 /* adaptive, odinn_solve_forward_adaptive */ };
 
 enum odinn_activation { ODINN_ACT_IDENTITY = 0, ODINN_ACT_SOFTPLUS = 1, ODINN_ACT_SIGMOID = 2, ODINN_ACT_TANH = 3, ODINN_ACT_RELU = 4 };
 
@@ -179,6 +179,16 @@ int odinn_host_unregister(odinn_ensemble* e, void* host);
  * user parameter in the reference (params.solver.solver); offered here: explicit Euler and SSPRK(3,3), each
  * stage fused into the RHS kernel. */
 int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double* t, int nsub);
+/* Adaptive forward solve with tstops: replaces solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops), solver;
+ * reltol, abstol, maxiters, saveat = tstops) (src/simulations/inversions/inversion_utils.jl:559-568; solver choice
+ * src/parameters ... AdjointTypes.jl:60, test/test_grad_loss.jl:143).  method = ODINN_BS3: Bogacki-Shampine 3(2) with FSAL,
+ * OrdinaryDiffEq's error norm sqrt(mean((err / (abstol + reltol max(|u|, |u_new|)))^2)) and an I controller.  Every glacier
+ * advances with its OWN adaptive step (independent ODEs, one pmap task each in the reference); the controller runs on the
+ * device.  dt0 <= 0: (t[1] - t[0]) / 16.  max_steps bounds the number of ensemble-wide trial steps (maxiters).
+ * steps_out / rejected_out (n_glaciers ints, optional): trial steps and rejected steps per glacier.
+ * Snapshots are kept as by odinn_solve_forward. */
+int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n_snap, const double* t, double reltol, double abstol,
+                                 double dt0, int max_steps, int* steps_out, int* rejected_out);
 int odinn_get_snapshot(odinn_ensemble* e, int glacier, int j, void* host, int ld);
 /* Provide snapshot j from the host instead (e.g. a solution saved by OrdinaryDiffEq). */
 int odinn_set_snapshot(odinn_ensemble* e, int glacier, int j, int n_snap, const void* host, int ld);
@@ -194,6 +204,18 @@ int odinn_loss(odinn_ensemble* e, const double* t, int n_t, double* loss_out);
  * LossH(L2Sum), glacier-wide A:  loss_out[g] as above and
  * Ssum_out[g] = sum_j dt_{j-1} * S_{g,j},  so that  dL/dtheta = sum_g (dA_g/dtheta) * Ssum_out[g]. */
 int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* loss_out, double* Ssum_out);
+
+/* The ContinuousAdjoint branch of SIA2D_grad_batch! (src/inverse/SIA2D/gradient.jl:276-538; the reference's default
+ * gradient, src/parameters/UDEparameters.jl:63) for LossH(L2Sum): linear interpolation H_itp(t) of the snapshots, reverse
+ * ODE d(lambda)/d(tau) = VJP_H(lambda, H_itp(-tau)) with the loss jumps at the tstops t[0..n_t-1], and
+ * Ssum_out[g] = sum_m q_weights[m] * S_g(lambda(q_nodes[m]), H_itp(q_nodes[m])) over the quadrature nodes (GaussQuadrature,
+ * gradient.jl:560-566: Gauss-Legendre nodes / weights mapped to the time span, computed by the caller), so that
+ * dL/dtheta = sum_g (dA_g/dtheta) * Ssum_out[g]; with a per-cell law the gradient accumulates per glacier (odinn_law_cell_grad).
+ * continuous_vjp selects the VJP flavour used inside (gradient.jl:310-314).  The reverse solver (params.UDE.grad.solver in the
+ * reference) is method = ODINN_EULER | ODINN_SSPRK3 with nsub fixed sub-steps between consecutive stops (tstops and nodes). */
+int odinn_grad_continuous(odinn_ensemble* e, const double* t, int n_t, int n_quadrature, const double* q_nodes,
+                          const double* q_weights, int continuous_vjp, int method, int nsub, double* loss_out,
+                          double* Ssum_out);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Laws                                                                                      */

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ODINN_B200_LIB") or os.path.join(_HERE, "lib", "libod
 F32, F64 = 0, 1
 
 FIELD_B, FIELD_H, FIELD_DH, FIELD_LAMBDA, FIELD_VJP_H, FIELD_A, FIELD_VJP_A, FIELD_H0 = range(8)
-EULER, SSPRK3 = 0, 1
+EULER, SSPRK3, BS3 = 0, 1, 2
 LAW_U, LAW_Y = 1, 2
 ACT = {"identity": 0, "softplus": 1, "sigmoid": 2, "tanh": 3, "relu": 4}
 
@@ -53,11 +53,13 @@ SIGNATURES = {
     "odinn_set_A_mode": (_i, [_vp, _i]),
     "odinn_set_temperature": (_i, [_vp, _i, _d]),
     "odinn_solve_forward": (_i, [_vp, _i, _i, _dp, _i]),
+    "odinn_solve_forward_adaptive": (_i, [_vp, _i, _i, _dp, _d, _d, _d, _i, _ip, _ip]),
     "odinn_get_snapshot": (_i, [_vp, _i, _i, _vp, _i]),
     "odinn_set_snapshot": (_i, [_vp, _i, _i, _i, _vp, _i]),
     "odinn_set_reference": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
     "odinn_loss": (_i, [_vp, _dp, _i, _dp]),
     "odinn_grad_discrete": (_i, [_vp, _dp, _i, _dp, _dp]),
+    "odinn_grad_continuous": (_i, [_vp, _dp, _i, _i, _dp, _dp, _i, _i, _i, _dp, _dp]),
     "odinn_law_A_nn_apply": (_i, [_vp, _i, _ip, _ip, _dp, _i, _dp]),
     "odinn_law_A_nn_pullback": (_i, [_vp, _dp, _dp, _i]),
     "odinn_set_phys": (_i, [_vp, C.POINTER(Phys)]),

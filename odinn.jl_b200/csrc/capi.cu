@@ -491,7 +491,7 @@ static int launch_vjpc(odinn_ensemble* e, int g, const void* lam, const void* H,
 }
 
 template <typename T>
-static int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst) {
+static int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst, double scale, int accumulate) {
     odinn_phys p1 = e->phys;
     p1.C = 0.0;  // ∂D/∂A carries no sliding term (target_A.jl:71-72)
     PhysDev<T> ph = make_phys<T>(p1);
@@ -514,19 +514,21 @@ static int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const v
     ODINN_CHECK_LAUNCH(e);
     dot_inner_kernel<T><<<nt, NT, 0, e->stream>>>(descs, e->d_tiles + t0, (const T*)lam, scratch, e->d_partial + t0);
     ODINN_CHECK_LAUNCH(e);
-    if (g >= 0) reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_tile_start + g, e->d_partial, S_dst + g, 1.0, 0);
-    else reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, S_dst, 1.0, 0);
+    if (g >= 0) reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_tile_start + g, e->d_partial, S_dst + g, scale, accumulate);
+    else reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, S_dst, scale, accumulate);
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
 
 // S[g] = Σ λ ⊙ pad(∇·(avg(∂A_spatial)·clamp(∇S)))  (adjoint.jl:582-662, glacier-wide law).  g < 0: whole ensemble.
-static int launch_unitA_dot(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst) {
+static int launch_unitA_dot(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst, double scale = 1.0,
+                            int accumulate = 0) {
     if (e->a_gridded) return fail(e, ODINN_ESTATE, "the continuous theta-VJP is provided for glacier-wide A laws");
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = alloc_plane(e, &e->work[0]))) return rc;
     if ((rc = sync_descs(e))) return rc;
-    return e->dtype == ODINN_F32 ? launch_unitA_dot_t<float>(e, g, lam, H, S_dst) : launch_unitA_dot_t<double>(e, g, lam, H, S_dst);
+    return e->dtype == ODINN_F32 ? launch_unitA_dot_t<float>(e, g, lam, H, S_dst, scale, accumulate)
+                                 : launch_unitA_dot_t<double>(e, g, lam, H, S_dst, scale, accumulate);
 }
 
 static int copy2d_ptr(odinn_ensemble* e, int g, char* plane_base, bool dual, void* host, int ld, bool up,
@@ -578,6 +580,38 @@ static int launch_loss_seed(odinn_ensemble* e, const void* H, const void* Href, 
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
+
+int alloc_work_plane(odinn_ensemble* e, void** p, size_t n_planes) { return alloc_plane(e, p, n_planes); }
+int vjp_planes(odinn_ensemble* e, const void* lam, const void* H, void* out, bool wH, bool wS, double* S_dst, double scale,
+               int accumulate, bool continuous) {
+    if (!continuous) return launch_vjp_range(e, -1, 0, lam, H, out, wH, wS, S_dst, scale, accumulate, false);
+    int rc;
+    if (wH && (rc = launch_vjpc(e, -1, lam, H, out))) return rc;
+    if (wS && (rc = launch_unitA_dot(e, -1, lam, H, S_dst ? S_dst : e->d_S, scale, accumulate))) return rc;
+    return ODINN_OK;
+}
+int loss_seed_planes(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in, const void* v,
+                     void* lam_out, double dt, double cseed, double* loss_dst, double wloss, int accumulate) {
+    return launch_loss_seed(e, H, Href, W, lam_in, v, lam_out, dt, cseed, loss_dst, wloss, accumulate);
+}
+int rhs_planes(odinn_ensemble* e, const void* Hin, void* out) { return launch_rhs(e, -1, Hin, out); }
+int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale, int accumulate) {
+    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, tile_partial, dst, scale, accumulate);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+int prepare_snapshots(odinn_ensemble* e, int n_snap) {
+    if (e->n_snap != n_snap) {
+        if (e->snap) cudaFree(e->snap);
+        e->snap = nullptr;
+        e->n_snap = 0;
+    }
+    int rc = alloc_plane(e, &e->snap, n_snap);
+    if (rc) return rc;
+    e->n_snap = n_snap;
+    return ODINN_OK;
+}
+void* snapshot_ptr(odinn_ensemble* e, int j) { return plane_ptr(e, e->snap, j); }
 
 }  // namespace odinn
 
@@ -759,12 +793,18 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
     void* ptrs[] = {e->d_descs, e->d_tiles, e->d_tile_start, e->d_partial, e->d_items, e->d_item_start, e->d_S,
                     e->snap, e->href, e->wmask, e->work[0], e->work[1], e->d_theta, e->d_J, e->d_dtheta, e->d_temps,
                     e->d_items2, e->d_item2_start, e->d_law_theta, e->lawD, e->lawAl, e->lawBe, e->d_law_partial,
-                    e->d_law_dtheta, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3]};
+                    e->d_law_dtheta, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3], e->ad_plane[0],
+                    e->ad_plane[1], e->ad_plane[2], e->ad_plane[3], e->ad_plane[4], e->ad_plane[5], e->d_ad_state, e->d_ad_dims};
+    for (void* p : e->ext_dev)
+        if (p) cudaFree(p);
+    for (void* p : e->ext_host)
+        if (p) cudaFreeHost(p);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete law_of(e);
     if (e->h_S) cudaFreeHost(e->h_S);
     if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->h_ad_active) cudaFreeHost(e->h_ad_active);
     for (cudaEvent_t ev : e->ev_up) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_done) cudaEventDestroy(ev);
     for (int k = 0; k < 2; ++k)

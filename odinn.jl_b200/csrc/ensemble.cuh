@@ -95,6 +95,21 @@ struct odinn_ensemble {
     std::vector<cudaEvent_t> ev_up, ev_done;
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
+
+    // adaptive forward solve (adaptive.cu): k1..k4, trial state, stage input; per-glacier controller state
+    void* ad_plane[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* d_ad_state = nullptr;
+    int* d_ad_dims = nullptr;     // [nx | ny | n_active]
+    int* h_ad_active = nullptr;   // pinned
+    // device / pinned-host allocations owned by the other translation units (freed by odinn_ensemble_destroy)
+    void* ext_dev[24] = {nullptr};
+    void* ext_host[4] = {nullptr};
+    int ext_int[8] = {0};
+};
+enum {  // ext_dev slots
+    EXT_CA_HT = 0, EXT_CA_HREF_T = 1, EXT_CA_W_T = 2, EXT_CA_LAM1 = 3, EXT_CA_LAM2 = 4, EXT_CA_V = 5,   // continuous adjoint (contadj.cu)
+    EXT_MB = 8, EXT_MB_MASK = 9,                                                                     // mass balance (massbalance.cu)
+    EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15                               // surface velocity / LossV
 };
 
 namespace odinn {
@@ -136,5 +151,17 @@ inline PhysDev<T> make_phys(const odinn_phys& p) {
 
 int ensure_plane(odinn_ensemble* e, int field);
 int sync_descs(odinn_ensemble* e);
+// shared with the other translation units of the library (adaptive.cu, ...)
+int alloc_work_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);      // zero-filled, no-op when *p is set
+int rhs_planes(odinn_ensemble* e, const void* Hin, void* out);              // out <- SIA2D(Hin), whole ensemble, one launch
+int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale = 1.0, int accumulate = 0);  // dst[g] = Σ tiles of g
+int prepare_snapshots(odinn_ensemble* e, int n_snap);
+// A1 (wH: out <- (dSIA/dH)^T lam) and / or A2 (wS: S_dst[g] (+)= scale * S_g; nullptr -> the handle's d_S), discrete or continuous flavour
+int vjp_planes(odinn_ensemble* e, const void* lam, const void* H, void* out, bool wH, bool wS, double* S_dst, double scale,
+               int accumulate, bool continuous);
+// loss_dst[g] (+)= wloss * sum W (H - Href)^2 ; optionally lam_out = lam_in + dt * v + cseed * W * (H - Href)
+int loss_seed_planes(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in, const void* v,
+                     void* lam_out, double dt, double cseed, double* loss_dst, double wloss, int accumulate);
+void* snapshot_ptr(odinn_ensemble* e, int j);
 
 }  // namespace odinn

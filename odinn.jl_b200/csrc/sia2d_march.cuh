@@ -18,7 +18,14 @@
 namespace odinn {
 
 constexpr int STRIP = 30;        // output columns per warp
-constexpr int MARCH_WARPS = 8;   // warps per CTA
+#ifndef ODINN_MARCH_WARPS
+#define ODINN_MARCH_WARPS 4   // (sweep profiles/r01_v6_sweep.txt: fp64 F1 0.340 -> 0.298 ms against 8 warps)
+#endif
+constexpr int MARCH_WARPS = ODINN_MARCH_WARPS;   // warps per CTA
+#ifndef ODINN_VJP1_MIN_CTAS
+#define ODINN_VJP1_MIN_CTAS 4   // resident CTAs per SM the A1+A2 kernel is compiled for: 128 registers instead of 142,
+                                // 16 resident warps instead of 8 (fp64 A1+A2 0.938 -> 0.694 ms)
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 // L2 prefetch distance in rows ahead of the register prefetch queue (0 = off); see sia2d_march2.cuh / profiles/r01_v4_sweep.txt
 #ifndef ODINN_L2PF_ROWS1
@@ -398,7 +405,7 @@ struct VjpMarch {
 };
 
 template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false>
-__global__ void __launch_bounds__(MARCH_WARPS * 32)
+__global__ void __launch_bounds__(MARCH_WARPS * 32, ODINN_VJP1_MIN_CTAS)
 sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ lam, const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af,
                 T* __restrict__ out, T* __restrict__ vjpA, double* __restrict__ partial, PhysDev<T> ph,

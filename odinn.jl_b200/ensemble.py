@@ -219,6 +219,17 @@ class Ensemble:
         m = {"euler": _capi.EULER, "ssprk3": _capi.SSPRK3}[method]
         self._ck(self._lib.odinn_solve_forward(self._h, m, t.size, t.ctypes.data_as(C.POINTER(C.c_double)), int(nsub)))
 
+    def solve_forward_adaptive(self, t, reltol: float = 1e-6, abstol: float = 1e-6, dt0: float = 0.0, max_steps: int = 1_000_000):
+        """BS3 with per-glacier adaptive steps and tstops ``t`` (saveat = tstops); returns (steps, rejected) per glacier."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        steps = np.zeros(self.G, dtype=np.int32)
+        rej = np.zeros(self.G, dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        self._ck(self._lib.odinn_solve_forward_adaptive(self._h, _capi.BS3, t.size, t.ctypes.data_as(C.POINTER(C.c_double)),
+                                                        float(reltol), float(abstol), float(dt0), int(max_steps),
+                                                        steps.ctypes.data_as(ip), rej.ctypes.data_as(ip)))
+        return steps, rej
+
     def get_snapshot(self, g: int, j: int):
         out = np.empty((self.nx[g], self.ny[g]), dtype=self.np_dtype, order="F")
         self._ck(self._lib.odinn_get_snapshot(self._h, g, j, out.ctypes.data, out.shape[0]))
@@ -249,4 +260,22 @@ class Ensemble:
         self._ck(self._lib.odinn_grad_discrete(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), t.size,
                                                loss.ctypes.data_as(C.POINTER(C.c_double)),
                                                Ssum.ctypes.data_as(C.POINTER(C.c_double))))
+        return loss, Ssum
+
+    def grad_continuous(self, t, n_quadrature: int = 200, vjp: str = "discrete", method: str = "ssprk3", nsub: int = 4):
+        """ContinuousAdjoint gradient (gradient.jl:276-538): returns (loss per glacier, Ssum per glacier).
+
+        The Gauss-Legendre rule of GaussQuadrature (gradient.jl:560-566) is built here on the host (n_quadrature = 200 is the
+        reference's default, src/inverse/AdjointTypes.jl)."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        x, w = np.polynomial.legendre.leggauss(int(n_quadrature))
+        qn = np.ascontiguousarray(0.5 * (t[0] + t[-1]) + x * 0.5 * (t[-1] - t[0]))
+        qw = np.ascontiguousarray(0.5 * (t[-1] - t[0]) * w)
+        loss = np.empty(self.G, dtype=np.float64)
+        Ssum = np.empty(self.G, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        m = {"euler": _capi.EULER, "ssprk3": _capi.SSPRK3}[method]
+        self._ck(self._lib.odinn_grad_continuous(self._h, t.ctypes.data_as(dp), t.size, qn.size, qn.ctypes.data_as(dp),
+                                                 qw.ctypes.data_as(dp), 1 if vjp == "continuous" else 0, m, int(nsub),
+                                                 loss.ctypes.data_as(dp), Ssum.ctypes.data_as(dp)))
         return loss, Ssum

@@ -903,6 +903,74 @@ def loss_and_grad_discrete(theta, glacier, target, t, Hs, H_ref, distance=3):
     return ell, dLdtheta, lam[0]
 
 
+def gauss_quadrature(t0, t1, n):
+    """GaussQuadrature (gradient.jl:560-566): Gauss-Legendre nodes / weights mapped to [t0, t1]."""
+    x, w = np.polynomial.legendre.leggauss(int(n))
+    return 0.5 * (t0 + t1) + x * 0.5 * (t1 - t0), 0.5 * (t1 - t0) * w
+
+
+def continuous_adjoint_schedule(t, q_nodes):
+    """Stops of the reverse solve in descending time: the tstops t[j] (loss callbacks, ("t", j)) and the quadrature
+    nodes (("q", m)) -- tstops_adjoint = sort(unique(vcat(-reverse(tstops), -t_nodes))) (gradient.jl:456)."""
+    ev = [(float(tt), "t", j) for j, tt in enumerate(t)] + [(float(tq), "q", m) for m, tq in enumerate(q_nodes)]
+    ev.sort(key=lambda e: (-e[0], e[1] != "q"))  # at equal times the quadrature sample sees λ before the loss jump (dense output)
+    return ev
+
+
+def loss_and_grad_continuous(theta, glacier, target, t, Hs, H_ref, n_quadrature=20, nsub=4, method="ssprk3",
+                             vjp="discrete", distance=3):
+    """ContinuousAdjoint branch of SIA2D_grad_batch! (gradient.jl:276-538) for LossH(L2Sum), no MB, no velocity term:
+
+      * H_itp, H_ref_itp: linear interpolation of the snapshots over t                                  (:285-301)
+      * final condition λ(t_end) = ∂ℓ/∂H at t_end (effect_loss! applied by hand)                        (:439-446)
+      * reverse ODE  dλ/dτ = VJP_H(λ, H_itp(-τ)),  λ += ∂ℓ/∂H at every tstop (DiscreteCallback)          (:316-366, 449-470)
+      * dL/dθ = Σ_m w_m VJP_θ(λ(t_m), H_itp(t_m)) over the Gauss-Legendre nodes                          (:305-306, 495-507)
+
+    The reverse ODE solver is a user parameter of the reference (params.UDE.grad.solver, adaptive); here -- as in the
+    device implementation -- a fixed-step scheme with `nsub` sub-steps between consecutive stops ("euler" | "ssprk3").
+    `vjp`: "discrete" | "continuous" flavour of the two VJPs (the reference accepts either inside ContinuousAdjoint, :310-314).
+    Returns (loss, dLdθ)."""
+    t = np.asarray(t, dtype=np.float64)
+    N = glacier.shape
+    normalization = float(N[0] * N[1])
+    target.precompute_vjp(theta)
+    VH = VJP_dSIA_dH_discrete if vjp == "discrete" else VJP_dSIA_dH_continuous
+    VT = VJP_dSIA_dtheta_discrete if vjp == "discrete" else VJP_dSIA_dtheta_continuous
+    DtH = [0.0] + list(np.diff(t))
+
+    def H_itp(tt):
+        j = int(np.clip(np.searchsorted(t, tt, side="right") - 1, 0, len(t) - 2))
+        a = (tt - t[j]) / (t[j + 1] - t[j])
+        return (1.0 - a) * Hs[j] + a * Hs[j + 1]
+
+    q_nodes, q_w = gauss_quadrature(t[0], t[-1], n_quadrature)
+    f = lambda tt, lam: VH(lam, H_itp(tt), glacier, target, theta)
+    lam = np.zeros(N)
+    ell = 0.0
+    dLdtheta = None
+    t_cur = None
+    for tt, kind, idx in continuous_adjoint_schedule(t, q_nodes):
+        if t_cur is not None and tt < t_cur:
+            h = (t_cur - tt) / nsub  # step in τ = -t
+            for s_ in range(nsub):
+                ta = t_cur - s_ * h
+                if method == "euler":
+                    lam = lam + h * f(ta, lam)
+                else:
+                    u1 = lam + h * f(ta, lam)
+                    u2 = 0.75 * lam + 0.25 * (u1 + h * f(ta - h, u1))
+                    lam = lam / 3.0 + (2.0 / 3.0) * (u2 + h * f(ta - 0.5 * h, u2))
+        t_cur = tt
+        if kind == "t":
+            mask = is_in_glacier(H_ref[idx], distance)
+            ell += loss_L2Sum(Hs[idx], H_ref[idx], mask, normalization) * DtH[idx]
+            lam = lam + backward_loss_L2Sum(Hs[idx], H_ref[idx], mask, normalization) * DtH[idx]
+        else:
+            g = q_w[idx] * VT(lam, H_itp(tt), glacier, target, theta)
+            dLdtheta = g if dLdtheta is None else dLdtheta + g
+    return ell, dLdtheta
+
+
 def loss_forward(Hs, H_ref, t, shape, distance=3):
     """loss_iceflow_transient for LossH(L2Sum) (inversion_utils.jl:383-461)."""
     normalization = float(shape[0] * shape[1])

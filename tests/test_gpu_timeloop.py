@@ -43,6 +43,37 @@ def _ens(ob, gl, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_adaptive_bs3_matches_oracle(ob, dtype):
+    """N1: adaptive BS3 with tstops, one step-size controller per glacier on the device == the oracle's bs3 run glacier
+    by glacier (same error norm, same controller); fp64 takes the same accept/reject sequence (same RHS count)."""
+    gl = _glaciers()
+    As = [4e-17, 2.21e-18, 1.5e-17]
+    t = o.define_callback_steps((2010.0, 2010.5), 1.0 / 12.0)
+    ens = _ens(ob, gl, dtype)
+    rtol = 1e-5 if dtype == "f64" else 1e-4   # solver tolerances (the fp32 error estimate bottoms out near 1e-4)
+    try:
+        for k, a in enumerate(As):
+            ens.set_A_scalar(k, a)
+        steps, rej = ens.solve_forward_adaptive(t, reltol=rtol, abstol=rtol)
+        assert np.all(steps > 0) and np.all(rej >= 0)
+        for k, g in enumerate(gl):
+            if dtype == "f32":
+                g = o.Glacier(B=g.B.astype(np.float32).astype(np.float64), dx=g.dx, dy=g.dy, H0=g.H0.astype(np.float32).astype(np.float64))
+            tg = o.TargetA(o.Phys(**PH), "const", A=As[k])
+            stats = {}
+            Hs = o.solve_forward(g.H0, g, tg, None, t, method="bs3", reltol=rtol, abstol=rtol, stats=stats)
+            if dtype == "f64":
+                assert stats["nrhs"] == 1 + 3 * steps[k], (k, stats, steps[k])
+            for j in (1, len(t) // 2, len(t) - 1):
+                err = rel_l2(ens.get_snapshot(k, j), Hs[j])
+                assert err <= (1e-10 if dtype == "f64" else 1e-3), (k, j, err)
+        # mass is conserved by every accepted step (interior ice, zero border): Σ H changes only through clipping at 0
+        assert np.isfinite(ens.get_snapshot(0, len(t) - 1)).all()
+    finally:
+        ens.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("method", ["euler", "ssprk3"])
 def test_forward_solve_matches_oracle(ob, dtype, method):
     gl = _glaciers()
@@ -166,5 +197,46 @@ def test_snapshots_from_host_and_state_errors(ob):
         tgs.precompute_vjp(theta)
         assert loss[0] == pytest.approx(ell, rel=1e-10)
         assert Ssum[0] * tgs.vjp_theta[0] == pytest.approx(dth[0], rel=1e-8)
+    finally:
+        ens.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("vjp", ["discrete", "continuous"])
+@pytest.mark.parametrize("method", ["ssprk3", "euler"])
+def test_continuous_adjoint_gradient_matches_oracle(ob, dtype, vjp, method):
+    """N4: ContinuousAdjoint (gradient.jl:276-538) on the device == the oracle running the same reverse scheme: loss jumps at
+    the tstops, Gauss-Legendre quadrature of the theta-VJP, linear interpolation of the snapshots."""
+    gl = [o.rough_bed_glacier(30, 31), o.rough_bed_glacier(21, 26)]
+    for g in gl:
+        g.H0 = 0.6 * g.H0
+    t = o.define_callback_steps((2010.0, 2010.25), 1.0 / 12.0)
+    ph = o.Phys(**PH)
+    As = [3e-17, 1.2e-17]
+    ens = _ens(ob, gl, dtype)
+    npdt = np.float32 if dtype == "f32" else np.float64
+    try:
+        refs = []
+        for k, g in enumerate(gl):
+            g32 = o.Glacier(B=g.B.astype(npdt).astype(np.float64), dx=g.dx, dy=g.dy, H0=g.H0)
+            Href = o.solve_forward(g.H0, g, o.TargetA(ph, "const", A=5e-17), None, t, method="ssprk3", nsub=8)
+            Hs = o.solve_forward(g.H0, g, o.TargetA(ph, "const", A=As[k]), None, t, method="ssprk3", nsub=8)
+            Href = [h.astype(npdt).astype(np.float64) for h in Href]
+            Hs = [h.astype(npdt).astype(np.float64) for h in Hs]
+            for j in range(len(t)):
+                ens.set_snapshot(k, j, len(t), Hs[j])
+                ens.set_reference(k, j, len(t), Href[j], o.is_in_glacier(Href[j], 3))
+            ens.set_A_scalar(k, As[k])
+            tgs = o.TargetA(ph, "scalar")
+            theta = np.array([np.arctanh(2 * (As[k] - ph.minA) / (ph.maxA - ph.minA) - 1)])
+            ell, dth = o.loss_and_grad_continuous(theta, g32, tgs, t, Hs, Href, n_quadrature=7, nsub=2, method=method, vjp=vjp)
+            refs.append((ell, dth[0], tgs.vjp_theta[0]))
+        loss, Ssum = ens.grad_continuous(t, n_quadrature=7, vjp=vjp, method=method, nsub=2)
+        rt_l, rt_g = (1e-10, 1e-8) if dtype == "f64" else (2e-4, 2e-3)
+        for k in range(len(gl)):
+            assert loss[k] == pytest.approx(refs[k][0], rel=rt_l), k
+            assert Ssum[k] * refs[k][2] == pytest.approx(refs[k][1], rel=rt_g), (k, Ssum[k] * refs[k][2], refs[k][1])
+        loss2, Ssum2 = ens.grad_continuous(t, n_quadrature=7, vjp=vjp, method=method, nsub=2)
+        assert np.array_equal(loss, loss2) and np.array_equal(Ssum, Ssum2)  # bit-stable run to run
     finally:
         ens.close()
