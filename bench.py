@@ -227,6 +227,8 @@ def run_b200(args, rank, local_rank, world):
     for k in range(G):
         ens.upload(k, _capi.FIELD_H, hH[k].numpy().T)
         ens.upload(k, _capi.FIELD_LAMBDA, hL[k].numpy().T)
+    if args.batch_chunk > 0:
+        ens.set_batch_chunk(args.batch_chunk)
     if args.e2e_steps > 0:
         ens.fwd_adj_batch_host(pH, pL, pdH, pV, S)
 
@@ -342,6 +344,7 @@ def main():
     ap.add_argument("--glaciers", type=int, default=256, help="glaciers per GPU")
     ap.add_argument("--allreduce-every", type=int, default=61)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--batch-chunk", type=int, default=0, help="cells per pipeline chunk of the host-batch call (0: library default)")
     ap.add_argument("--ref-glaciers", type=int, default=16, help="glaciers per CPU pass (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")

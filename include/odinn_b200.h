@@ -205,6 +205,43 @@ int odinn_loss(odinn_ensemble* e, const double* t, int n_t, double* loss_out);
  * Ssum_out[g] = sum_j dt_{j-1} * S_{g,j},  so that  dL/dtheta = sum_g (dA_g/dtheta) * Ssum_out[g]. */
 int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* loss_out, double* Ssum_out);
 
+/* ---- mass-balance callback ---- */
+
+/* n_mb mass-balance steps: step m fires when the forward solve reaches snapshot snapshot_index[m] (the end of its step_MB window,
+ * PeriodicCallback of src/simulations/inversions/inversion_utils.jl:498-517) and its VJP is applied to lambda at the same tstop
+ * in odinn_grad_discrete (VJP_lambda_dMBdH(::DiscreteVJP, ...), src/inverse/SIA2D/VJPs.jl:107-151; gradient.jl:201-207).
+ * params[(m * n_glaciers + g) * 7 + k], k = temp, gradient, ref_hgt, snow, DDF, acc_factor, scale: the cumulative climate of the
+ * window for glacier g (get_cumulative_climate!, independent of H) and the TImodel1 coefficients; scale = 1 / (step_MB * 12).
+ *   PDD = temp + gradient (B + H - ref_hgt);  MB = (acc_factor snow - DDF max(PDD, 0)) scale;  MB_mask = (H > 0 and MB < 0) or
+ *   (H > 10 and MB >= 0);  MB = 0 outside the mask, -H where H + MB < 0;  H += MB.
+ * (The evaluation of TImodel1 lives in Muninn, which is not vendored: the formula is the one the in-tree VJP differentiates.)
+ * n_mb = 0 switches the callback off. */
+int odinn_set_mass_balance(odinn_ensemble* e, int n_mb, const int* snapshot_index, const double* params);
+/* The MB field applied at step m (cache.iceflow.MB_history). */
+int odinn_get_mass_balance(odinn_ensemble* e, int glacier, int m, void* host, int ld);
+
+/* ---- surface velocity and LossV ---- */
+
+/* (Vx, Vy) <- V_from_H(H): Vx = -D_up grad_x S, Vy = -D_up grad_y S on the dual grid, stored in inn1 of nx x ny matrices (last row /
+ * column 0).  Replaces Huginn.V_from_H(simulation, H, t, theta) at its call sites src/losses/Losses.jl:314, 358, with
+ * D_up = Velocity_up of src/models/target/target_A.jl:94-108. */
+int odinn_surface_velocity(odinn_ensemble* e, int glacier, const void* H, int ldH, void* Vx, void* Vy, int ldV, double t);
+/* out_dH <- VJP_lambda_dsurface_VdH(::DiscreteVJP, dVx, dVy, H, ...) (src/inverse/SIA2D/adjoint.jl:268-350) and
+ * *out_S <- the glacier-wide contraction of VJP_lambda_dsurface_Vdtheta (adjoint.jl:352-413, target_A.jl:143-170):
+ * d_theta = (dA/dtheta) * S.  Either output may be NULL. */
+int odinn_sia2d_vjp_surface_V(odinn_ensemble* e, int glacier, const void* dVx, const void* dVy, int ldV, const void* H, int ldH,
+                              void* out_dH, int ldo, double* out_S, double t);
+/* Reference surface velocity at snapshot `snapshot_index` (a tstop that holds velocity data, tV_ref in gradient.jl:118-121), kept in
+ * slot `slot` of `n_slots`: Vx_ref, Vy_ref, Vabs_ref and the weights Wv = (Vabs_ref > 0) / (nx ny [* sqrt(mean(Vx_ref^2 + Vy_ref^2
+ * over the mask)) when scale_loss]) (Losses.jl:316, 327-331), nx x ny matrices. */
+int odinn_set_velocity_reference(odinn_ensemble* e, int glacier, int slot, int n_slots, int snapshot_index, const void* Vx_ref,
+                                 const void* Vy_ref, const void* Vabs_ref, const void* Wv, int ld);
+/* Loss type through per-snapshot multipliers of the two L2Sum terms: loss = sum_j wH[j] * L2Sum_H(H_j) + wV[j] * L2Sum_V(H_j).
+ * LossH: wH = dt_H, wV = 0 (the default when no weights are set); LossV: wV = dt_V; LossHV: wH = dt_H^2, wV = scaling dt_V^2
+ * (Losses.jl:250-268, 293-336, 391-409).  v_component: 0 = :xy, 1 = :abs.  n_t = 0 restores the default.
+ * Used by odinn_loss and odinn_grad_discrete. */
+int odinn_set_loss_weights(odinn_ensemble* e, int n_t, const double* wH, const double* wV, int v_component);
+
 /* The ContinuousAdjoint branch of SIA2D_grad_batch! (src/inverse/SIA2D/gradient.jl:276-538; the reference's default
  * gradient, src/parameters/UDEparameters.jl:63) for LossH(L2Sum): linear interpolation H_itp(t) of the snapshots, reverse
  * ODE d(lambda)/d(tau) = VJP_H(lambda, H_itp(-tau)) with the loss jumps at the tstops t[0..n_t-1], and

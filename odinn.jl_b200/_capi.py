@@ -59,6 +59,12 @@ SIGNATURES = {
     "odinn_set_reference": (_i, [_vp, _i, _i, _i, _vp, _vp, _i]),
     "odinn_loss": (_i, [_vp, _dp, _i, _dp]),
     "odinn_grad_discrete": (_i, [_vp, _dp, _i, _dp, _dp]),
+    "odinn_set_mass_balance": (_i, [_vp, _i, _ip, _dp]),
+    "odinn_get_mass_balance": (_i, [_vp, _i, _i, _vp, _i]),
+    "odinn_surface_velocity": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _d]),
+    "odinn_sia2d_vjp_surface_V": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _dp, _d]),
+    "odinn_set_velocity_reference": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
+    "odinn_set_loss_weights": (_i, [_vp, _i, _dp, _dp, _i]),
     "odinn_grad_continuous": (_i, [_vp, _dp, _i, _i, _dp, _dp, _i, _i, _i, _dp, _dp]),
     "odinn_law_A_nn_apply": (_i, [_vp, _i, _ip, _ip, _dp, _i, _dp]),
     "odinn_law_A_nn_pullback": (_i, [_vp, _dp, _dp, _i]),

@@ -205,6 +205,9 @@ static int solve_bs3_t(odinn_ensemble* e, int n_snap, const double* t, double re
             ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
             if (*e->h_ad_active == 0) break;
         }
+        int mb_applied = 0;
+        if ((rc = mb_apply_step(e, j, H, &mb_applied))) return rc;   // mass-balance callback at the end of its window
+        if (mb_applied && (rc = rhs_planes(e, H, k1))) return rc;    // u was modified by the callback: the FSAL slope is stale
         ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, j), H, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     }
     if (steps_out || rejected_out) {

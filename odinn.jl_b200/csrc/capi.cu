@@ -582,6 +582,9 @@ static int launch_loss_seed(odinn_ensemble* e, const void* H, const void* Href, 
 }
 
 int alloc_work_plane(odinn_ensemble* e, void** p, size_t n_planes) { return alloc_plane(e, p, n_planes); }
+int copy_plane_2d(odinn_ensemble* e, int glacier, void* plane, void* host, int ld, bool to_device) {
+    return copy2d_ptr(e, glacier, (char*)plane, false, host, ld, to_device, e->stream);
+}
 int vjp_planes(odinn_ensemble* e, const void* lam, const void* H, void* out, bool wH, bool wS, double* S_dst, double scale,
                int accumulate, bool continuous) {
     if (!continuous) return launch_vjp_range(e, -1, 0, lam, H, out, wH, wS, S_dst, scale, accumulate, false);
@@ -1050,12 +1053,35 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
                              : cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
         return ODINN_OK;
     };
+    // Packed layout: glaciers whose host matrices are adjacent in memory (a batch held in one array) move as ONE copy per
+    // plane and chunk -- 1 MiB copies reach 28 GB/s each way when both directions run, 64 MiB copies 49 GB/s
+    // (tools/microbench/pcie.py on the B200 box).
+    auto xfer_range = [&](int g0, int g1, int slot, void* const* host, bool to_dev, cudaStream_t st) -> int {
+        if (!packed) {
+            for (int g = g0; g < g1; ++g)
+                if ((rc = xfer(g, slot, host[g], to_dev, st))) return rc;
+            return ODINN_OK;
+        }
+        int r0 = g0;
+        while (r0 < g1) {
+            if (!host[r0]) return fail(e, ODINN_EARG, "null host pointer in a batch array");
+            size_t bytes = (size_t)e->gl[r0].nx * e->gl[r0].ny * e->esize;
+            int r1 = r0 + 1;
+            while (r1 < g1 && host[r1] == (char*)host[r0] + bytes) {
+                bytes += (size_t)e->gl[r1].nx * e->gl[r1].ny * e->esize;
+                ++r1;
+            }
+            char* dev = (char*)e->stage[slot] + (size_t)e->gl[r0].off_packed * e->esize;
+            ODINN_CUDA(e, to_dev ? cudaMemcpyAsync(dev, host[r0], bytes, cudaMemcpyHostToDevice, st)
+                                 : cudaMemcpyAsync(host[r0], dev, bytes, cudaMemcpyDeviceToHost, st));
+            r0 = r1;
+        }
+        return ODINN_OK;
+    };
     for (int c = 0; c < nchunk; ++c) {
         const int g0 = cstart[c], g1 = cstart[c + 1];
-        for (int g = g0; g < g1; ++g) {
-            if ((rc = xfer(g, 0, const_cast<void*>(H[g]), true, up))) return rc;
-            if (adj && (rc = xfer(g, 1, const_cast<void*>(lambda[g]), true, up))) return rc;
-        }
+        if ((rc = xfer_range(g0, g1, 0, const_cast<void* const*>(H), true, up))) return rc;
+        if (adj && (rc = xfer_range(g0, g1, 1, const_cast<void* const*>(lambda), true, up))) return rc;
         ODINN_CUDA(e, cudaEventRecord(e->ev_up[c], up));
         ODINN_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_up[c], 0));
         if (!adj) {
@@ -1065,10 +1091,8 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
             return rc;
         ODINN_CUDA(e, cudaEventRecord(e->ev_done[c], e->stream));
         ODINN_CUDA(e, cudaStreamWaitEvent(dn, e->ev_done[c], 0));
-        for (int g = g0; g < g1; ++g) {
-            if (dH && (rc = xfer(g, 2, dH[g], false, dn))) return rc;
-            if (vjpH && (rc = xfer(g, 3, vjpH[g], false, dn))) return rc;
-        }
+        if (dH && (rc = xfer_range(g0, g1, 2, dH, false, dn))) return rc;
+        if (vjpH && (rc = xfer_range(g0, g1, 3, vjpH, false, dn))) return rc;
     }
     if (S) ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_S, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
     // join: the compute stream (the one callers time / synchronise) waits for both copy streams
@@ -1137,6 +1161,7 @@ int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double*
                 if ((rc = launch_rhs(e, -1, U2, Hs, &s3))) return rc;
             }
         }
+        if ((rc = mb_apply_step(e, j, Hs, nullptr))) return rc;  // mass-balance callback at the end of its window (inversion_utils.jl:498-517)
         ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, j), Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     }
     if (Hs != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H
@@ -1204,10 +1229,12 @@ int odinn_loss(odinn_ensemble* e, const double* t, int n_t, double* loss_out) {
     if (rc) return rc;
     if (!loss_out) return fail(e, ODINN_EARG, "loss_out is null");
     ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
-    for (int j = 1; j < n_t; ++j) {  // Δt_H of the first data point is 0 (safe_slice, gradient.jl:146-149)
-        if ((rc = launch_loss_seed(e, plane_ptr(e, e->snap, j), plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j),
-                                   nullptr, nullptr, nullptr, 0.0, 0.0, e->d_loss, t[j] - t[j - 1], 1)))
+    for (int j = 0; j < n_t; ++j) {  // Δt_H of the first data point is 0 (safe_slice, gradient.jl:146-149)
+        const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
+        if (wH != 0.0 && (rc = launch_loss_seed(e, plane_ptr(e, e->snap, j), plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j),
+                                                nullptr, nullptr, nullptr, 0.0, 0.0, e->d_loss, wH, 1)))
             return rc;
+        if ((rc = velocity_loss_term(e, j, plane_ptr(e, e->snap, j), nullptr, wV, e->d_loss, nullptr))) return rc;
     }
     ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
     ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1233,16 +1260,23 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
     for (int j = n_t - 1; j >= 1; --j) {  // gradient.jl:191-253 (the j = 1 pass of the reference updates nothing)
         const double dt = t[j] - t[j - 1];
         void* Hj = plane_ptr(e, e->snap, j);
+        // λ_j += VJP_λ_∂MB∂H(λ_j, H_j - MB) at the MB tstops                                (gradient.jl:201-207)
+        const bool mb_here = std::find(e->mb_snap.begin(), e->mb_snap.end(), j) != e->mb_snap.end();
+        if (j < n_t - 1 && (rc = mb_adjoint_step(e, j, lam, Hj))) return rc;  // (λ_k = 0 at the last snapshot)
+        (void)mb_here;
         // λ_∂f∂H = VJP_H(λ_j, H_j)                                                     (gradient.jl:235-237)
         if (j < n_t - 1) {
             if ((rc = launch_vjp(e, -1, lam, Hj, vH, true, false))) return rc;
         } else {
             ODINN_CUDA(e, cudaMemsetAsync(vH, 0, pbytes, e->stream));  // λ_k = 0 ⇒ VJP = 0
         }
-        // ℓ += ℓ_j ;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H,  ∂ℓ_j/∂H = 2 Δt_j W (H_j - H_ref,j)   (:218-242)
-        if ((rc = launch_loss_seed(e, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), lam, vH, lam, dt, 2.0 * dt,
-                                   e->d_loss, dt, 1)))
+        // ℓ += ℓ_j ;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H,  ∂ℓ_j/∂H = 2 w_j W (H_j - H_ref,j), w_j = Δt_j for LossH  (:218-242)
+        const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
+        if ((rc = launch_loss_seed(e, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), lam, vH, lam, dt, 2.0 * wH,
+                                   e->d_loss, wH, 1)))
             return rc;
+        // velocity term of LossV / LossHV: ℓ, ∂ℓ/∂H into λ_{j-1} and ∂ℓ/∂θ (Losses.jl:293-390)
+        if ((rc = velocity_loss_term(e, j, Hj, lam, wV, e->d_loss, e->d_Ssum))) return rc;
         // dLdθ += Δt_{j-1} · VJP_θ(λ_{j-1}, H_j)                                        (:245-249)
         if ((rc = launch_vjp(e, -1, lam, Hj, nullptr, false, true, e->d_Ssum, dt, 1))) return rc;
     }

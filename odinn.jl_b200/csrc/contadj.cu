@@ -115,11 +115,13 @@ static int grad_continuous_t(odinn_ensemble* e, const double* t, int n_t, int n_
         t_cur = s.t;
         if (!s.is_q) {
             const int j = s.idx;
-            const double dtj = j > 0 ? t[j] - t[j - 1] : 0.0;  // Δt_HV.H[ind-1] through safe_slice: 0 for the first data point
-            // ℓ += Δt_j Σ W (H_j - H_ref,j)² ;  λ += 2 Δt_j W (H_j - H_ref,j)       (Losses.jl:270-291)
+            // w_j = Δt_HV.H[ind-1] through safe_slice for LossH: 0 for the first data point (odinn_set_loss_weights overrides)
+            const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
+            // ℓ += w_j Σ W (H_j - H_ref,j)² ;  λ += 2 w_j W (H_j - H_ref,j)       (Losses.jl:270-291)
             if ((rc = loss_seed_planes(e, snapshot_ptr(e, j), (char*)e->href + (size_t)j * pbytes, (char*)e->wmask + (size_t)j * pbytes,
-                                       lam, nullptr, lam, 0.0, 2.0 * dtj, e->d_loss, dtj, 1)))
+                                       lam, nullptr, lam, 0.0, 2.0 * wH, e->d_loss, wH, 1)))
                 return rc;
+            (void)wV;  // (a velocity term is refused by odinn_grad_continuous: its ∂ℓ/∂θ is quadrature-weighted upstream, :474-507)
         } else {
             if ((rc = H_itp(s.t))) return rc;
             if ((rc = vjp_planes(e, lam, Ht, nullptr, false, true, e->d_Ssum, qw[s.idx], 1, cont_vjp))) return rc;
@@ -147,6 +149,9 @@ extern "C" int odinn_grad_continuous(odinn_ensemble* e, const double* t, int n_t
     for (int m = 0; m < n_quadrature; ++m)
         if (!(q_nodes[m] >= t[0] && q_nodes[m] <= t[n_t - 1])) return fail(e, ODINN_EARG, "quadrature node outside the time span");
     if (e->a_gridded) return fail(e, ODINN_ESTATE, "odinn_grad_continuous supports glacier-wide A and per-cell laws");
+    for (int j = 0; j < n_t; ++j)
+        if (loss_weight_V(e, n_t, j) != 0.0)
+            return fail(e, ODINN_ESTATE, "odinn_grad_continuous covers LossH; use odinn_grad_discrete for losses with a velocity term");
     if (continuous_vjp && e->law_kind != 0) return fail(e, ODINN_ESTATE, "the continuous VJP flavour is provided for glacier-wide A laws");
     int rc = e->dtype == ODINN_F32 ? grad_continuous_t<float>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, method, nsub)
                                    : grad_continuous_t<double>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, method, nsub);

@@ -105,11 +105,18 @@ struct odinn_ensemble {
     void* ext_dev[24] = {nullptr};
     void* ext_host[4] = {nullptr};
     int ext_int[8] = {0};
+    // loss configuration (odinn_set_loss_weights): per-snapshot multipliers of the thickness / velocity L2 terms; empty = LossH with Δt
+    std::vector<double> loss_wH, loss_wV;
+    int lossV_component = 0;          // 0 :xy, 1 :abs  (Losses.jl:318-325)
+    std::vector<int> v_snap;          // snapshot index of every velocity-reference slot (velocity.cu)
+    // mass balance (massbalance.cu): snapshot indices after which the MB callback fires, per-glacier climate scalars per MB step
+    std::vector<int> mb_snap;
+    std::vector<double> mb_params;    // [n_mb x G x MB_NPAR]
 };
 enum {  // ext_dev slots
     EXT_CA_HT = 0, EXT_CA_HREF_T = 1, EXT_CA_W_T = 2, EXT_CA_LAM1 = 3, EXT_CA_LAM2 = 4, EXT_CA_V = 5,   // continuous adjoint (contadj.cu)
-    EXT_MB = 8, EXT_MB_MASK = 9,                                                                     // mass balance (massbalance.cu)
-    EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15                               // surface velocity / LossV
+    EXT_MB = 8, EXT_MB_PAR = 9,                                                                      // mass balance (massbalance.cu)
+    EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15, EXT_V_PARTIAL = 16           // surface velocity / LossV
 };
 
 namespace odinn {
@@ -159,6 +166,17 @@ int prepare_snapshots(odinn_ensemble* e, int n_snap);
 // A1 (wH: out <- (dSIA/dH)^T lam) and / or A2 (wS: S_dst[g] (+)= scale * S_g; nullptr -> the handle's d_S), discrete or continuous flavour
 int vjp_planes(odinn_ensemble* e, const void* lam, const void* H, void* out, bool wH, bool wS, double* S_dst, double scale,
                int accumulate, bool continuous);
+// one glacier's plane <-> host matrix (column-major, ld elements), on the handle's stream (asynchronous for pinned memory)
+int copy_plane_2d(odinn_ensemble* e, int glacier, void* plane, void* host, int ld, bool to_device);
+// velocity term of snapshot j in the loss / reverse loops (velocity.cu); no-op when there is no velocity data at j or w == 0
+int velocity_loss_term(odinn_ensemble* e, int j, const void* Hj, void* lam, double w, double* loss_dst, double* S_dst);
+// mass-balance callback of snapshot j / its adjoint (massbalance.cu); no-ops when no MB step fires at j
+int mb_apply_step(odinn_ensemble* e, int j, void* H, int* applied);
+int mb_adjoint_step(odinn_ensemble* e, int j, void* lam, const void* Hj);
+inline double loss_weight_H(const odinn_ensemble* e, const double* t, int n_t, int j) {
+    return (int)e->loss_wH.size() == n_t ? e->loss_wH[j] : (j > 0 ? t[j] - t[j - 1] : 0.0);
+}
+inline double loss_weight_V(const odinn_ensemble* e, int n_t, int j) { return (int)e->loss_wV.size() == n_t ? e->loss_wV[j] : 0.0; }
 // loss_dst[g] (+)= wloss * sum W (H - Href)^2 ; optionally lam_out = lam_in + dt * v + cseed * W * (H - Href)
 int loss_seed_planes(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in, const void* v,
                      void* lam_out, double dt, double cseed, double* loss_dst, double wloss, int accumulate);

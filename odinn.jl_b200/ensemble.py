@@ -279,3 +279,59 @@ class Ensemble:
                                                  qw.ctypes.data_as(dp), 1 if vjp == "continuous" else 0, m, int(nsub),
                                                  loss.ctypes.data_as(dp), Ssum.ctypes.data_as(dp)))
         return loss, Ssum
+
+    # -- surface velocity / LossV ---------------------------------------------------------------------
+    def surface_velocity(self, g: int, H, t: float = 0.0):
+        """(Vx, Vy) = V_from_H(H) (Huginn.V_from_H call sites Losses.jl:314, 358)."""
+        H = _as_f(H, self.np_dtype)
+        Vx = np.empty_like(H, order="F")
+        Vy = np.empty_like(H, order="F")
+        self._ck(self._lib.odinn_surface_velocity(self._h, g, H.ctypes.data, H.shape[0], Vx.ctypes.data, Vy.ctypes.data, Vx.shape[0], float(t)))
+        return Vx, Vy
+
+    def vjp_surface_V(self, g: int, dVx, dVy, H, t: float = 0.0):
+        """(VJP_λ_∂surface_V∂H, S) with ∂θ = (∂A/∂θ)·S (adjoint.jl:268-413)."""
+        H = _as_f(H, self.np_dtype)
+        dVx = _as_f(dVx, self.np_dtype)
+        dVy = _as_f(dVy, self.np_dtype)
+        out = np.empty_like(H, order="F")
+        S = C.c_double(0.0)
+        self._ck(self._lib.odinn_sia2d_vjp_surface_V(self._h, g, dVx.ctypes.data, dVy.ctypes.data, dVx.shape[0], H.ctypes.data, H.shape[0],
+                                                     out.ctypes.data, out.shape[0], C.byref(S), float(t)))
+        return out, S.value
+
+    def set_velocity_reference(self, g: int, slot: int, n_slots: int, snapshot_index: int, Vx_ref, Vy_ref, Vabs_ref, scale_loss: bool = True):
+        """Wv = mask / (nx·ny·scale), mask = Vabs_ref > 0, scale = sqrt(mean(Vx_ref² + Vy_ref² over the mask)) (Losses.jl:316-331)."""
+        Vabs = np.asarray(Vabs_ref, dtype=np.float64)
+        mask = Vabs > 0.0
+        sc = float(np.mean(np.asarray(Vx_ref)[mask] ** 2 + np.asarray(Vy_ref)[mask] ** 2) ** 0.5) if (scale_loss and mask.any()) else 1.0
+        W = mask.astype(np.float64) / (float(self.nx[g] * self.ny[g]) * sc)
+        a = [_as_f(x, self.np_dtype) for x in (Vx_ref, Vy_ref, Vabs, W)]
+        self._ck(self._lib.odinn_set_velocity_reference(self._h, g, slot, n_slots, snapshot_index, a[0].ctypes.data, a[1].ctypes.data,
+                                                        a[2].ctypes.data, a[3].ctypes.data, a[0].shape[0]))
+
+    def set_loss_weights(self, wH=None, wV=None, component: str = "xy"):
+        dp = C.POINTER(C.c_double)
+        if wH is None:
+            self._ck(self._lib.odinn_set_loss_weights(self._h, 0, None, None, 0))
+            return
+        wH = np.ascontiguousarray(wH, dtype=np.float64)
+        wV = np.ascontiguousarray(wV if wV is not None else np.zeros_like(wH), dtype=np.float64)
+        self._ck(self._lib.odinn_set_loss_weights(self._h, wH.size, wH.ctypes.data_as(dp), wV.ctypes.data_as(dp), 1 if component == "abs" else 0))
+
+    # -- mass balance -------------------------------------------------------------------------------------
+    def set_mass_balance(self, snapshot_index, params):
+        """params: array [n_mb, G, 7] = (temp, gradient, ref_hgt, snow, DDF, acc_factor, scale) per MB step and glacier."""
+        idx = np.ascontiguousarray(snapshot_index, dtype=np.int32)
+        if idx.size == 0:
+            self._ck(self._lib.odinn_set_mass_balance(self._h, 0, None, None))
+            return
+        par = np.ascontiguousarray(params, dtype=np.float64)
+        assert par.shape == (idx.size, self.G, 7)
+        self._ck(self._lib.odinn_set_mass_balance(self._h, idx.size, idx.ctypes.data_as(C.POINTER(C.c_int)),
+                                                  par.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def get_mass_balance(self, g: int, m: int):
+        out = np.empty((self.nx[g], self.ny[g]), dtype=self.np_dtype, order="F")
+        self._ck(self._lib.odinn_get_mass_balance(self._h, g, m, out.ctypes.data, out.shape[0]))
+        return out

@@ -761,6 +761,59 @@ def VJP_dsurfaceV_dH_discrete(dVx, dVy, H, glacier, target, theta=None):
     return -(dDdH + dgS)
 
 
+def VJP_dsurfaceV_dtheta_discrete(dVx, dVy, H, glacier, target, theta=None):
+    """adjoint.jl:352-413 with ∂Velocityꜛ∂θ of target_A.jl:143-170 for a glacier-wide A law:
+    ∂θ = -vjp_θ · Σ (Γꜛ_noA H̄^{n+1} ∇S^{n-1}) ∘ (∇Sx ∂Vx + ∇Sy ∂Vy)."""
+    return -np.atleast_1d(target.vjp_theta).reshape(-1) * surfaceV_theta_reduction(dVx, dVy, H, glacier, target, theta)
+
+
+def surfaceV_theta_reduction(dVx, dVy, H, glacier, target, theta=None):
+    """Σ_ij ∂A_spatialꜛ[i,j] (∇Sx ∂Vx + ∇Sy ∂Vy)[i,j] -- the scalar the device reduces (sign and vjp_θ applied by the caller)."""
+    f = _recompute_forward(H, glacier, target, theta)
+    ph = target.ph
+    sv = f["gSx"] * inn1(dVx) + f["gSy"] * inn1(dVy)
+    return float(np.sum(Gamma_up(ph) * f["Hb"] ** (ph.n + 1) * f["gS"] ** (ph.n - 1) * sv))
+
+
+def V_from_H(H, glacier, target, theta=None):
+    """Huginn.V_from_H [NOT IN TREE]; call sites Losses.jl:314, 358: (Vx, Vy, |V|) on the primal grid, values on inn1."""
+    Vx, Vy = surface_V(H, glacier, target, theta)
+    return Vx, Vy, (Vx**2 + Vy**2) ** 0.5
+
+
+def loss_V(H, Vabs_ref, Vx_ref, Vy_ref, glacier, target, theta, normalization, component="xy", scale_loss=True):
+    """loss(::LossV, ...) / Δt.V  (Losses.jl:293-336) with the L2Sum inner loss and mask = V_ref > 0."""
+    Vx, Vy, V = V_from_H(H, glacier, target, theta)
+    mask = Vabs_ref > 0.0
+    if component == "xy":
+        ell = loss_L2Sum(Vx, Vx_ref, mask, normalization) + loss_L2Sum(Vy, Vy_ref, mask, normalization)
+    else:
+        ell = loss_L2Sum(V, Vabs_ref, mask, normalization)
+    if scale_loss:
+        ell = ell / np.mean(Vx_ref[mask] ** 2 + Vy_ref[mask] ** 2) ** 0.5
+    return ell
+
+
+def backward_loss_V(H, Vabs_ref, Vx_ref, Vy_ref, glacier, target, theta, normalization, component="xy", scale_loss=True):
+    """backward_loss(::LossV, ...) / Δt.V (Losses.jl:337-390): (∂L/∂H, ∂L/∂θ)."""
+    Vx, Vy, V = V_from_H(H, glacier, target, theta)
+    mask = Vabs_ref > 0.0
+    if component == "xy":
+        dVx = backward_loss_L2Sum(Vx, Vx_ref, mask, normalization)
+        dVy = backward_loss_L2Sum(Vy, Vy_ref, mask, normalization)
+    else:
+        dV = backward_loss_L2Sum(V, Vabs_ref, mask, normalization)
+        with np.errstate(divide="ignore", invalid="ignore"):  # Losses.jl:369-370 (as written upstream)
+            dVx = np.where(mask, dV * (Vx - Vx_ref) / (V - Vabs_ref), 0.0)
+            dVy = np.where(mask, dV * (Vy - Vy_ref) / (V - Vabs_ref), 0.0)
+    if scale_loss:
+        sc = np.mean(Vx_ref[mask] ** 2 + Vy_ref[mask] ** 2) ** 0.5
+        dVx, dVy = dVx / sc, dVy / sc
+    dH = VJP_dsurfaceV_dH_discrete(dVx, dVy, H, glacier, target, theta)
+    dth = VJP_dsurfaceV_dtheta_discrete(dVx, dVy, H, glacier, target, theta)
+    return dH, dth
+
+
 # --------------------------------------------------------------------------
 # L1 -- losses.  L2Sum: src/losses/Losses.jl:116-152; LossH: :250-291.
 # --------------------------------------------------------------------------
@@ -791,6 +844,38 @@ def backward_loss_L2Sum(a, b, mask, normalization):
 
 
 # --------------------------------------------------------------------------
+# N3 -- mass-balance callback and its discrete VJP.
+# Forward: mb_action! (inversion_utils.jl:498-517) = MB_timestep! + apply_MB_mask! [Muninn / Huginn, NOT IN TREE];
+# VJP: VJP_λ_∂MB∂H(::DiscreteVJP, ...) (VJPs.jl:107-151), which fixes PDD, the mask, the clipping and ∂MB/∂H.
+# ASSUMPTION: MB = (acc_factor·snow - DDF·max(PDD, 0)) · scale, scale = 1 / (step_MB · 12), glacier-wide snow.
+# par = (temp, gradient, ref_hgt, snow, DDF, acc_factor, scale).
+# --------------------------------------------------------------------------
+
+
+def mb_TI1(H, B, par):
+    """MB field actually applied to H (masked and clipped) and the bookkeeping masks."""
+    temp, grad, ref_hgt, snow, DDF, acc, scale = par
+    PDD = temp + grad * ((B + H) - ref_hgt)  # VJPs.jl:120-121
+    MB = (acc * snow - DDF * np.maximum(PDD, 0.0)) * scale
+    mask = ((H > 0.0) & (MB < 0.0)) | ((H > 10.0) & (MB >= 0.0))  # VJPs.jl:130
+    MB = np.where(mask, MB, 0.0)  # :132
+    gone = mask & ((H + MB) < 0.0)  # :134-138
+    MB = np.where(gone, -H, MB)  # :140
+    return MB, mask, gone, PDD
+
+
+def VJP_MB_dH(lam, H_preMB, B, par):
+    """VJPs.jl:107-151."""
+    temp, grad, ref_hgt, snow, DDF, acc, scale = par
+    MB, mask, gone, PDD = mb_TI1(H_preMB, B, par)
+    PDD_jac = np.where(PDD < 0.0, 0.0, grad * lam)  # :122-123
+    out = np.zeros_like(lam)
+    out[mask] = (-(DDF * PDD_jac) * scale)[mask]  # :145
+    out[gone] = -lam[gone]  # :146
+    return out
+
+
+# --------------------------------------------------------------------------
 # Time integration.  The reference delegates to OrdinaryDiffEq (RDPK3Sp35 by
 # default, src/inverse/AdjointTypes.jl:60) [NOT IN TREE]; the solver is a user
 # parameter (params.solver.solver).  The B200 on-device loop and this oracle
@@ -809,8 +894,10 @@ def define_callback_steps(tspan, step):
 
 
 def solve_forward(H0, glacier, target, theta, tstops, method="ssprk3", nsub=8, reltol=1e-6, abstol=1e-6, dt0=None,
-                  max_steps=10_000_000, stats=None):
-    """Returns the list of snapshots H(t) at every tstop (incl. the first)."""
+                  max_steps=10_000_000, stats=None, mb=None):
+    """Returns the list of snapshots H(t) at every tstop (incl. the first).
+    mb: {snapshot index j: par} -- the mass-balance callback fires when the solve reaches tstop j, before the state is
+    saved (the solution is stored after MB has been applied, gradient.jl:202); the MB fields go to stats["MB"][j]."""
     f = lambda H: SIA2D(H, glacier, target, theta)
     H = np.array(H0, dtype=np.float64, copy=True)
     out = [H.copy()]
@@ -863,6 +950,15 @@ def solve_forward(H0, glacier, target, theta, tstops, method="ssprk3", nsub=8, r
                     raise RuntimeError("bs3: too many steps")
         else:
             raise ValueError(method)
+        j_stop = len(out)
+        if mb is not None and j_stop in mb:
+            MB, _, _, _ = mb_TI1(H, glacier.B, mb[j_stop])
+            H = H + MB
+            if stats is not None:
+                stats.setdefault("MB", {})[j_stop] = MB
+            if method == "bs3":
+                k1 = f(H)  # the callback modified u: the FSAL slope is recomputed
+                nrhs += 1
         out.append(H.copy())
     if stats is not None:
         stats["nrhs"] = nrhs
@@ -968,6 +1064,63 @@ def loss_and_grad_continuous(theta, glacier, target, t, Hs, H_ref, n_quadrature=
         else:
             g = q_w[idx] * VT(lam, H_itp(tt), glacier, target, theta)
             dLdtheta = g if dLdtheta is None else dLdtheta + g
+    return ell, dLdtheta
+
+
+def loss_weights(kind, t, t_has_V=None, scaling=1.0):
+    """Per-snapshot multipliers (wH, wV) of the L2Sum thickness / velocity terms for the reference's loss types:
+    LossH: ℓ_H Δt.H (Losses.jl:250-268); LossV: ℓ_V Δt.V (:293-336); LossHV: lH Δt.H + scaling lV Δt.V where lH and lV
+    ALREADY carry Δt.H / Δt.V (:404-409 -- the squares are the reference's arithmetic, kept as is).
+    Δt.H[j] = t[j] - t[j-1] (0 for j = 0, safe_slice, gradient.jl:146-149); Δt.V[j]: the same over the times that hold
+    velocity data (t_has_V[j])."""
+    k = len(t)
+    dH = np.array([0.0] + list(np.diff(t)))
+    dV = np.zeros(k)
+    if t_has_V is not None:
+        idx = [j for j in range(k) if t_has_V[j]]
+        for a, b in zip(idx[:-1], idx[1:]):
+            dV[b] = t[b] - t[a]
+    if kind == "H":
+        return dH, np.zeros(k)
+    if kind == "V":
+        return np.zeros(k), dV
+    return dH * dH, scaling * dV * dV
+
+
+def loss_and_grad_discrete_HV(theta, glacier, target, t, Hs, H_ref, V_ref, wH, wV, component="xy", scale_loss=True, distance=3,
+                              mb=None, MB_hist=None):
+    """DiscreteAdjoint reverse loop (gradient.jl:191-253) with thickness AND surface-velocity terms:
+    ℓ = Σ_j wH[j] L2Sum_H(H_j) + wV[j] LossV(H_j);  V_ref[j] = (Vx_ref, Vy_ref, Vabs_ref) or None.
+    mb / MB_hist: {j: par} / {j: MB field} of the mass-balance steps -- λ_j += VJP_λ_∂MB∂H(λ_j, H_j - MB_j) (:201-207).
+    Returns (ℓ, dLdθ)."""
+    k = len(Hs)
+    Dt = np.diff(t)
+    N = glacier.shape
+    normalization = float(N[0] * N[1])
+    target.precompute_vjp(theta)
+    lam = np.zeros(N)
+    ell = 0.0
+    dLdtheta = 0.0
+    for j in reversed(range(k)):
+        dLdH = np.zeros(N)
+        dLdth = 0.0
+        if wH[j] != 0.0:
+            mask = is_in_glacier(H_ref[j], distance)
+            ell += wH[j] * loss_L2Sum(Hs[j], H_ref[j], mask, normalization)
+            dLdH = dLdH + wH[j] * backward_loss_L2Sum(Hs[j], H_ref[j], mask, normalization)
+        if wV[j] != 0.0 and V_ref[j] is not None:
+            Vxr, Vyr, Var = V_ref[j]
+            ell += wV[j] * loss_V(Hs[j], Var, Vxr, Vyr, glacier, target, theta, normalization, component, scale_loss)
+            dH, dth = backward_loss_V(Hs[j], Var, Vxr, Vyr, glacier, target, theta, normalization, component, scale_loss)
+            dLdH = dLdH + wV[j] * dH
+            dLdth = dLdth + wV[j] * dth
+        if mb is not None and j in mb:
+            lam = lam + VJP_MB_dH(lam, Hs[j] - MB_hist[j], glacier.B, mb[j])  # :201-207
+        l_dfdH = VJP_dSIA_dH_discrete(lam, Hs[j], glacier, target, theta)
+        if j > 0:
+            lam = lam + Dt[j - 1] * l_dfdH + dLdH  # :242
+            dLdtheta = dLdtheta + Dt[j - 1] * VJP_dSIA_dtheta_discrete(lam, Hs[j], glacier, target, theta)  # :245-249
+        dLdtheta = dLdtheta + dLdth  # :252
     return ell, dLdtheta
 
 
