@@ -161,7 +161,7 @@ int odinn_vjp_resident(odinn_ensemble* e, int flags, double* S_out);
  * (page-locked) host memory; see odinn_host_register.  The resident planes are not touched. */
 int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void* const* lambda,
                              void* const* dH, void* const* vjpH, double* S);
-/* Cells per pipeline chunk of odinn_fwd_adj_batch_host (default 2 Mi cells). */
+/* Cells per pipeline chunk of odinn_fwd_adj_batch_host (default 8 Mi cells). */
 int odinn_set_batch_chunk(odinn_ensemble* e, long long cells);
 /* Page-lock / release a caller-owned host range (a Julia Array's memory) so that transfers from it are true
  * asynchronous DMA.  Thin wrappers of cudaHostRegister / cudaHostUnregister. */

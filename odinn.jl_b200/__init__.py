@@ -10,6 +10,8 @@ from ._capi import F32, F64, LIB_PATH, OdinnError, Phys, load  # noqa: F401
 from .ensemble import Ensemble  # noqa: F401
 from . import parallel  # noqa: F401
 from .api import (  # noqa: F401
+    ContinuousAdjoint,
+    DiscreteAdjoint,
     FunctionalInversion,
     Inversion,
     LawA,

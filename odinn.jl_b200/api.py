@@ -102,8 +102,29 @@ class SolverParameters:
     "euler" / "ssprk3" with ``nsub`` fixed sub-steps per interval (OrdinaryDiffEq's RDPK3Sp35 is not in the tree)."""
 
     step: float = 1.0 / 12.0
-    solver: str = "ssprk3"
+    solver: str = "ssprk3"     # "euler" | "ssprk3" (nsub fixed sub-steps per tstop interval) | "bs3" (adaptive, reltol / abstol)
     nsub: int = 8
+    reltol: float = 1e-6
+    abstol: float = 1e-6
+    maxiters: int = 1_000_000
+
+
+@dataclass
+class DiscreteAdjoint:
+    """src/inverse/AdjointTypes.jl: reverse loop over the saved steps (gradient.jl:45-274)."""
+
+    VJP_method: str = "discrete"
+
+
+@dataclass
+class ContinuousAdjoint:
+    """src/inverse/AdjointTypes.jl:60-: reverse ODE on interpolated snapshots + Gauss-Legendre quadrature (gradient.jl:276-538).
+    ``solver`` / ``nsub``: the reverse integrator (params.UDE.grad.solver upstream); ``VJP_method``: "discrete" | "continuous"."""
+
+    VJP_method: str = "discrete"
+    n_quadrature: int = 200
+    solver: str = "ssprk3"
+    nsub: int = 4
 
 
 @dataclass
@@ -113,6 +134,7 @@ class Parameters:
     tspan: tuple = (2010.0, 2015.0)
     dtype: str = "f64"
     distance: int = 3          # is_in_glacier erosion distance of LossH (Losses.jl:270-291)
+    grad: object = field(default_factory=DiscreteAdjoint)   # params.UDE.grad (DiscreteAdjoint | ContinuousAdjoint)
     epochs: int = 50
     lr: float = 1e-2
 
@@ -182,7 +204,10 @@ class _Simulation:
     def solve(self):
         if self.ensemble is not None:
             sp = self.parameters.solver
-            self.ensemble.solve_forward(self.t, method=sp.solver, nsub=sp.nsub)
+            if sp.solver == "bs3":
+                self.ensemble.solve_forward_adaptive(self.t, reltol=sp.reltol, abstol=sp.abstol, max_steps=sp.maxiters)
+            else:
+                self.ensemble.solve_forward(self.t, method=sp.solver, nsub=sp.nsub)
 
     def close(self):
         if self.ensemble is not None:
@@ -249,7 +274,12 @@ def SIA2D_grad_(dθ, θ, simulation: Inversion) -> float:
     if ens is not None:
         simulation.apply_laws(θ)
         simulation.solve()
-        losses, Ssum = ens.grad_discrete(simulation.t)
+        gm = simulation.parameters.grad
+        if isinstance(gm, ContinuousAdjoint):
+            losses, Ssum = ens.grad_continuous(simulation.t, n_quadrature=gm.n_quadrature, vjp=gm.VJP_method, method=gm.solver,
+                                               nsub=gm.nsub)
+        else:
+            losses, Ssum = ens.grad_discrete(simulation.t)
         loss = float(losses.sum())
         if law.kind == "nn":
             g_local = ens.law_A_nn_pullback(law.nn.n_params)

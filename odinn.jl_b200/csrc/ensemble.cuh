@@ -88,7 +88,7 @@ struct odinn_ensemble {
 
     // host-batch path (odinn_fwd_adj_batch_host): packed copy of B, chunk events for the
     // H2D -> compute -> D2H pipeline over copy_stream[0] / stream / copy_stream[1]
-    long long batch_chunk_cells = 2LL << 20;
+    long long batch_chunk_cells = 8LL << 20;  // sweep profiles/r01_v6_sweep.txt: 2 Mi 4.94, 4 Mi 5.25, 8 Mi 5.37, 16 Mi 5.04, 32 Mi 4.13 G cell-steps/s
     void* bpack = nullptr;
     bool bpack_dirty = true;
     void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // H, lambda, dH, vjp_H of the host-batch call

@@ -1,0 +1,83 @@
+"""The host-side mirror of ODINN's user API on the GPU: Prediction / Inversion / run! / SIA2D_grad! / loss_iceflow_transient
+(src/simulations/inversions/inversion_utils.jl:21-296, src/inverse/SIA2D/gradient.jl:6-31), in the shape of the reference's
+twin experiment (test/inversion_test.jl:20-170): ground truth from a known A(T) law, a small MLP law trained against it."""
+import numpy as np
+import pytest
+
+from oracle import sia2d_numpy as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import odinn_b200
+
+    return odinn_b200
+
+
+def _setup(ob, grad=None, solver=None):
+    raw = [o.rough_bed_glacier(34, 30), o.rough_bed_glacier(26, 37), o.dome_glacier(29, 29, H0=150.0)]
+    for g in raw[:2]:
+        g.H0 = 0.6 * g.H0
+    glaciers = [ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy, H0=g.H0) for g in raw]
+    temps = [-14.0, -6.0, -2.0]
+    ph = ob.Phys(minA=8e-21, maxA=8e-17)
+    params = ob.Parameters(physical=ph, tspan=(2010.0, 2010.5), dtype="f64", solver=solver or ob.SolverParameters(),
+                           grad=grad or ob.DiscreteAdjoint())
+    A_true = [ph.minA + (ph.maxA - ph.minA) * (0.15 + 0.04 * (T + 20.0)) for T in temps]  # smooth monotone "ground truth" law
+    pred = ob.Prediction(ob.Model(ob.SIA2Dmodel(A=None)), glaciers, params)
+    pred.set_A(A_true)
+    H_ref = ob.run_(pred)
+    pred.close()
+    nn = ob.NeuralNetwork(widths=(1, 4, 1), acts=("softplus", "sigmoid"), seed=3)
+    model = ob.Model(ob.SIA2Dmodel(A=ob.LawA(nn)))
+    inv = ob.Inversion(model, glaciers, params, H_ref, temperatures=temps)
+    return inv, H_ref, raw
+
+
+def test_prediction_and_gradient_against_finite_differences(ob):
+    inv, H_ref, raw = _setup(ob)
+    try:
+        assert len(H_ref) == 3 and len(H_ref[0]) == len(inv.t) and H_ref[0][0].shape == raw[0].B.shape
+        θ = np.array(inv.model.θ)
+        g = np.zeros_like(θ)
+        loss = ob.SIA2D_grad_(g, θ, inv)
+        assert loss == pytest.approx(ob.loss_iceflow_transient(θ, inv), rel=1e-8)  # gradient.jl:259
+        assert np.isfinite(g).all() and np.linalg.norm(g) > 0  # test_grad_loss.jl:269
+        d = np.random.default_rng(0).standard_normal(θ.size)
+        eps = 1e-5
+        fd = (ob.loss_iceflow_transient(θ + eps * d, inv) - ob.loss_iceflow_transient(θ - eps * d, inv)) / (2 * eps)
+        # the DiscreteAdjoint is the adjoint of an explicit-Euler reverse step over the saved snapshots: first order in the tstop
+        # spacing, the reference accepts ratios within [5e-4 .. few %] depending on the setup (test/test_grad_loss.jl)
+        assert abs(g @ d - fd) <= 0.1 * abs(fd), (g @ d, fd)
+    finally:
+        inv.close()
+
+
+def test_continuous_adjoint_and_adaptive_solver_through_the_api(ob):
+    inv, _, _ = _setup(ob, grad=ob.ContinuousAdjoint(n_quadrature=24, nsub=4),
+                       solver=ob.SolverParameters(solver="bs3", reltol=1e-7, abstol=1e-7))
+    try:
+        θ = np.array(inv.model.θ)
+        g = np.zeros_like(θ)
+        loss = ob.SIA2D_grad_(g, θ, inv)
+        d = np.random.default_rng(1).standard_normal(θ.size)
+        eps = 1e-5
+        fd = (ob.loss_iceflow_transient(θ + eps * d, inv) - ob.loss_iceflow_transient(θ - eps * d, inv)) / (2 * eps)
+        assert loss > 0 and abs(g @ d - fd) <= 0.02 * abs(fd), (g @ d, fd)  # the continuous adjoint converges with the reverse step
+    finally:
+        inv.close()
+
+
+def test_twin_experiment_training_reduces_the_loss(ob):
+    # adaptive forward solve: the step follows A as the law moves (a fixed sub-step goes unstable when A overshoots)
+    inv, _, _ = _setup(ob, solver=ob.SolverParameters(solver="bs3", reltol=1e-6, abstol=1e-6))
+    try:
+        θ = ob.run_(inv, epochs=25, lr=0.05)
+        losses = inv.stats["losses"]
+        assert len(losses) == 25 and np.isfinite(losses).all()
+        assert min(losses) < 0.2 * losses[0], losses[::6]  # test/inversion_test.jl:154-163 asks for recovery of the law
+        assert θ.shape == inv.model.θ.shape
+    finally:
+        inv.close()
