@@ -68,6 +68,25 @@ def synthetic_glacier(nx, ny, k):
     return B, H, dx
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank to the CPUs next to its GPU before the pinned host buffers are allocated (first-touch NUMA placement):
+    the e2e arm is PCIe / host-memory bound, and N ranks sharing one socket's memory halve each other's copy rate."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -191,11 +210,27 @@ def run_b200(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
+    # stdout carries ONE JSON line.  The image exports NCCL_DEBUG=VERSION, which makes NCCL print "NCCL version ..." on stdout when
+    # the communicator is created: drop it (ODINN_NCCL_DEBUG re-enables NCCL logging) and create the communicator with fd 1 -> stderr.
+    os.environ.pop("NCCL_DEBUG", None)
+    if "ODINN_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["ODINN_NCCL_DEBUG"]
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)  # communicator creation happens here
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     G, n = args.glaciers, args.grid
     npdt = np.float32 if args.dtype == "f32" else np.float64
