@@ -280,8 +280,8 @@ def run_b200(args, rank, local_rank, world):
     vjp_theta = torch.zeros(322, dtype=torch.float64, device="cuda")  # [loss; dθ] of the 1-16-16-1 law (321 params)
 
     def step(i):
-        # F1 + A1 + A2 of every glacier: dH, (dSIA/dH)^T lambda and S.  fp32: ONE fused kernel (the adjoint pass recomputes
-        # every forward intermediate, so dH costs one more store); fp64 / --no-fuse: an F1 launch + an A1+A2 launch.
+        # F1 + A1 + A2 of every glacier: dH, (dSIA/dH)^T lambda and S -- ONE fused kernel (the adjoint pass recomputes
+        # every forward intermediate, so dH costs one more store); --no-fuse: an F1 launch + an A1+A2 launch.
         if args.no_fuse:
             ens.rhs_resident()
             ens.vjp_resident(True, True, read_S=False)
@@ -329,15 +329,17 @@ def run_b200(args, rank, local_rank, world):
     value = world * cells_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * cells_per_step / (ms_e2e * 1e-3) if e2e_steps > 0 else None
     peak, peak_src = load_peaks()
-    # Roofline of the dominant kernel.  fp32: the fused F1 + A1 + A2 kernel -- 5 words/cell (read λ, H, B; write dH, ∂H);
-    # fp64 / --no-fuse: the A1+A2 kernel -- 4 words/cell.  The F1 kernel (3 words/cell) is reported beside it.
-    fused = (args.dtype == "f32") and not args.no_fuse and os.environ.get("ODINN_NO_FUSE") != "1" and os.environ.get("ODINN_MARCH", "2") == "2"
+    # Roofline of the dominant kernel: the fused F1 + A1 + A2 kernel -- 5 words/cell (read λ, H, B; write dH, ∂H);
+    # --no-fuse: the A1+A2 kernel -- 4 words/cell.  The F1 and A1+A2 kernels timed alone are reported beside it.
+    fused = (not args.no_fuse and os.environ.get("ODINN_NO_FUSE") != "1"
+             and (args.dtype == "f64" or os.environ.get("ODINN_MARCH", "2") == "2"))
     vjp_bytes = 4 * w * cells_per_step
     rhs_bytes = 3 * w * cells_per_step
     sub = lambda nbytes, ms_k, words: {"achieved": nbytes / (ms_k * 1e-3) / 1e9, "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak,
                                        "algorithmic_bytes_per_cell": words * w, "ms_per_launch": ms_k}
     if fused:
-        dom_name, dom_key, dom_words, dom_ms = "sia2d_vjp_march2<WRITE_F> (F1 + A1 + A2 fused: one launch per step)", "sia2d_fused", 5, ms / args.steps
+        dom_name = ("sia2d_vjp_march2<WRITE_F>" if args.dtype == "f32" else "sia2d_vjp_march<double, WRITE_F>") + " (F1 + A1 + A2 fused: one launch per step)"
+        dom_key, dom_words, dom_ms = "sia2d_fused", 5, ms / args.steps
     else:
         dom_name = "sia2d_vjp_march2 (A1+A2 fused)" if args.dtype == "f32" else "sia2d_vjp_march (A1+A2 fused)"
         dom_key, dom_words, dom_ms = "sia2d_vjp_march2" if args.dtype == "f32" else "sia2d_vjp_march", 4, ms_vjp

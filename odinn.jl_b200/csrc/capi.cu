@@ -1,5 +1,6 @@
 // C ABI of libodinn_b200.so (see include/odinn_b200.h for the reference interfaces replaced).
 #include <cstdlib>
+#include <type_traits>
 
 #include "ensemble.cuh"
 #include "sia2d_march.cuh"
@@ -379,7 +380,7 @@ static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, cons
 
 template <typename T>
 static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const void* H_, void* out_, bool wH,
-                        bool wS, bool packed) {
+                        bool wS, bool packed, void* dH_out = nullptr) {
     PhysDev<T> ph = make_phys<T>(e->phys);
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs + (packed ? e->G : 0);
     const T* lam = (const T*)lam_;
@@ -394,9 +395,17 @@ static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_
     dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
 #define L(CUB, AF, WH, WS, E1) \
     sia2d_vjp_march<T, CUB, AF, WH, WS, E1><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph)
+    // fused F1 + A1 + A2 (cubic form, fp64 only: the fp32 product path is the two-column kernel)
+#define LF(AF, E1)                                                                                                            \
+    do {                                                                                                                      \
+        if constexpr (std::is_same<T, double>::value)                                                                         \
+            sia2d_vjp_march<T, true, AF, true, true, E1, false, true><<<grid, block, 0, e->stream>>>(                         \
+                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph, nullptr, nullptr, (T*)dH_out);                  \
+    } while (0)
 #define L3(CUB, AF, E1)                         \
     do {                                        \
-        if (wH && wS) L(CUB, AF, true, true, E1);   \
+        if (dH_out && CUB) LF(AF, E1);              \
+        else if (wH && wS) L(CUB, AF, true, true, E1);   \
         else if (wH) L(CUB, AF, true, false, E1);   \
         else L(CUB, AF, false, true, E1);           \
     } while (0)
@@ -404,6 +413,7 @@ static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_
     ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
+#undef LF
 #undef L
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
@@ -416,7 +426,8 @@ static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, 
 static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS,
                             double* S_dst, double scale, int accumulate, bool packed, void* dH_out = nullptr) {
     int rc;
-    const bool fuse = dH_out && wH && wS && e->law_kind == LAW_NONE && e->dtype == ODINN_F32 && e->march == 2 && !e->no_fuse;
+    const bool fuse = dH_out && wH && wS && e->law_kind == LAW_NONE && !e->no_fuse &&
+                      ((e->dtype == ODINN_F32 && e->march == 2) || (e->dtype == ODINN_F64 && e->cubic));
     if (dH_out && !fuse && (rc = launch_rhs_range(e, g0, g1, H, dH_out, nullptr, packed))) return rc;
     if (!fuse) dH_out = nullptr;
     if (!wH && !wS) return ODINN_OK;
@@ -444,7 +455,7 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
     if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed, dH_out);
     else
         rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
-                                   : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed);
+                                   : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed, dH_out);
     if (rc) return rc;
     if (wS) {
         double* dst = S_dst ? S_dst : e->d_S;

@@ -287,11 +287,18 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 // --------------------------------------------------------------------------------------------
 // DFIELD (with AFIELD): the node planes hold D, α = ∂D/∂H̄ and β (as the target's ∂Diffusivity∂∇H returns it) of a
 // per-cell law; the θ-integrand plane then receives D† itself (gA ≡ 1) for the law's own pullback (sia2d_law.cuh).
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false>
+// WRITE_F (cubic form only): the same pass also writes dH = SIA2D(H) -- see VjpMarch2 in sia2d_march2.cuh.
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false>
 struct VjpMarch {
     static constexpr int PF = PfVjp<T>::value;
+    static constexpr bool CUBIC_FORM = CUBIC && !DFIELD;  // n = 3, C = 0: step_cubic()
     const T *hp, *bp, *lp, *ap, *alp, *bep;
+    const T* pfp;  // CUBIC_FORM: this lane's L2-prefetch sector (10 lanes per input plane), ODINN_L2PF_ROWS1 rows ahead
     T *op, *vp;  // output row pointer; gridded-A integrand pointer (or null)
+    T* fp;       // WRITE_F: dH row pointer
+    // CUBIC_FORM constants and carried values (same scheme as VjpMarch2::compute_cubic)
+    T hdxs, hdys, lmx, lmy, qx2, qy2, nodem;
+    T ly, fx, Qp, cx, Fyp;
     int ld, nym1, ny2, r0;
     T eta0, hdx, hdy, nhx2, nhy2, qx, qy, A, dx, dy;
     T lmask;     // 1 on inner columns, 0 on border columns (λ_inn zero-extension)
@@ -301,8 +308,126 @@ struct VjpMarch {
     T h, b, l, eh, ex, hx, ehE, fxr, px, Dp, aDp, Pp, Qrow_p, yu_p, acc;
     T hq[PF], bq[PF], lq[PF];
 
+    // n = 3, C = 0 form of the step (scalar A or gridded A): shared node products, λ scaled once when loaded, the Q term in the
+    // west-going message, one L2 prefetch per row for all planes, optional F1 output.  Same operator as step().
+    template <bool OUT, bool MASKED>
+    __device__ __forceinline__ void step_cubic(int row) {
+        T h1 = hq[0], b1 = bq[0], l1 = lq[0];
+#pragma unroll
+        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
+        T l1x = l1 * lmx, l1y = l1 * lmy;
+        if (MASKED) {
+            int stp = (row + 1 + PF <= nym1) ? ld : 0;
+            hp += stp;
+            bp += stp;
+            lp += stp;
+            pfp += stp;
+            if (!(row >= 0 && row + 1 < nym1)) l1x = l1y = T(0);  // λ_inn zero-extended on border rows
+        } else {
+            hp += ld;
+            bp += ld;
+            lp += ld;
+            pfp += ld;
+        }
+        hq[PF - 1] = __ldg(hp);
+        bq[PF - 1] = __ldg(bp);
+        lq[PF - 1] = __ldg(lp);
+        if (ODINN_L2PF_ROWS1 > 0 && !MASKED) {
+            if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) prefetch_l2_row(pfp);
+        }
+        h1 = fmx(h1, T(0));
+        b1 = surf_store<T>(b1, h1);
+        T eh1 = ETA1 ? h1 : eta0 * h1;
+        T hE1 = shfl_dn(h1), bE1 = shfl_dn(b1), lE1x = shfl_dn(l1x);
+        // x-edge (i→i+1, row+1)
+        T ex1 = sdiff<T>(bE1, b1, hE1, h1);
+        T hx1 = h1 + hE1;
+        T ehE1 = ETA1 ? hE1 : eta0 * hE1;
+        T fx1 = lE1x - l1x;                                  // -½/Δx² · Fx†   (adjoint.jl:100)
+        const T cx1 = fmx(fmn(ex1, ehE1), -eh1);
+        T px1 = fx1 * cx1;                                   // (adjoint.jl:102)
+        // y-edge (i, row→row+1)
+        T ey = sdiff<T>(b1, b, h1, h);
+        T fy = l1y - ly;
+        const T cy = fmx(fmn(ey, eh1), -eh);
+        T py = fy * cy;
+        T eyE = shfl_dn(ey), pyE = shfl_dn(py);
+        // node (i, row)
+        T gxr = ex + ex1, gyr = ey + eyE;
+        T u = gxr * hdxs, v = gyr * hdys;                    // scaled by √K: u² + v² = K |∇S|²
+        T g2 = u * u + v * v;
+        T Anode = A;
+        if (AFIELD) {
+            Anode = __ldg(ap);
+            bool adv = true;
+            if (MASKED) adv = (row >= 0 && row < ny2);
+            if (adv) ap += ld;
+        }
+        T Hs = hx + hx1;
+        T H2 = Hs * Hs;
+        T H4 = H2 * H2;
+        T mk = g2 * Hs;
+        T D1 = H4 * (mk * Anode);
+        T Dadj = ((py + pyE) + (px + px1)) * nodem;          // D† (adjoint.jl:102-104), zero outside the dual grid
+        bool node_ok = node_col_ok;
+        if (MASKED) { node_ok = node_ok && row >= 0 && row < nym1; if (!(row >= 0 && row < nym1)) Dadj = T(0); }
+        T z = H4 * Dadj;
+        T zA = z * Anode;
+        T aD1 = g2 * zA;                                     // α D† / 5
+        T bD = Hs * zA;                                      // β D† / (2K)
+        T P1 = bD * gxr;
+        T Q1 = bD * gyr;
+        if (WRITE_S) {
+            if (OUT) {
+                T vS = mk * z;                               // ∂A_spatial ∘ D† (adjoint.jl:250)
+                acc += vS;                                   // (halo lanes are dropped when the strip is reduced)
+                if (AFIELD) { if (own_lane && node_ok) *vp = vS; }
+            }
+            if (AFIELD) vp += ld;
+        }
+        T D1W = T(0);
+        if (WRITE_H || WRITE_F) D1W = shfl_up(D1);
+        if (WRITE_F) {
+            T Fy1 = (D1W + D1) * cy;
+            T Fx = (Dp + D1) * cx;
+            T FxW = shfl_up(Fx);
+            if (OUT) {
+                T outv = lmy * (Fyp - Fy1) + lmx * (FxW - Fx);
+                if (MASKED) { if (row < 1 || row >= nym1) outv = T(0); }
+                if (store_lane) *fp = outv;
+            }
+            fp += ld;
+            Fyp = Fy1;
+        }
+        if (WRITE_H) {
+            T yl, yu1, xl, xu;
+            {
+                T dC = fy * (D1W + D1);                      // ∂Cy/Δy = -Fy†·Dy/Δy
+                subgrad<T, ETA1>(dC, ey, -eh, eh1, dy, eta0, yl, yu1);
+            }
+            {
+                T dC = fx * (Dp + D1);
+                subgrad<T, ETA1>(dC, ex, -eh, ehE, dx, eta0, xl, xu);
+            }
+            T SAW = (Qp - Q1) * qy2 + (aDp + aD1) * T(5);
+            T SP = (Pp + P1) * qx2;
+            T ZW = shfl_up(SAW + SP + xu);                   // everything column i-1 sends to cell (i, row)
+            if (OUT) {
+                T res = ZW + (SAW - SP + xl) + (yl + yu_p);
+                if (!(h > T(0))) res = T(0);                 // adjoint.jl:148
+                if (store_lane) *op = res;
+            }
+            op += ld;
+            yu_p = yu1;
+        }
+        h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; cx = cx1;
+        fx = fx1; ly = l1y; px = px1;
+        Dp = D1; aDp = aD1; Pp = P1; Qp = Q1;
+    }
+
     template <bool OUT, bool MASKED>
     __device__ __forceinline__ void step(int row) {
+        if (CUBIC_FORM) { step_cubic<OUT, MASKED>(row); return; }
         T h1 = hq[0], b1 = bq[0], l1 = lq[0] * lmask;
 #pragma unroll
         for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
@@ -404,12 +529,12 @@ struct VjpMarch {
     }
 };
 
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false>
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false>
 __global__ void __launch_bounds__(MARCH_WARPS * 32, ODINN_VJP1_MIN_CTAS)
 sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ lam, const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af,
                 T* __restrict__ out, T* __restrict__ vjpA, double* __restrict__ partial, PhysDev<T> ph,
-                const T* __restrict__ alF = nullptr, const T* __restrict__ beF = nullptr) {
+                const T* __restrict__ alF = nullptr, const T* __restrict__ beF = nullptr, T* __restrict__ dH = nullptr) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -418,7 +543,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, DFIELD> m;
+    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, DFIELD, WRITE_F> m;
     constexpr int PF = PfVjp<T>::value;
     m.ph = ph;
     m.ld = d.ld;
@@ -448,6 +573,15 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.bep = DFIELD ? beF + d.off + min(ic, d.nx - 2) + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
     m.op = WRITE_H ? out + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
     m.vp = (WRITE_S && AFIELD) ? vjpA + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    m.fp = WRITE_F ? dH + d.off + ic + (long long)(r0 - 1) * d.ld : nullptr;
+    {
+        // one prefetch instruction per row covers the three input planes: 10 lanes per plane, one 32-byte sector each
+        // (a 32-column row segment spans up to 9 sectors in fp64; lanes 30, 31 touch the next strip's first sectors)
+        const int pl = min(lane / 10, 2), sec = lane - 10 * pl;
+        const T* pb = pl == 0 ? H : (pl == 1 ? B : lam);
+        constexpr int per = 32 / (int)sizeof(T);  // elements per sector
+        m.pfp = pb + d.off + min(max(it.y + per * sec, 0), d.nx - 1) + (long long)rc * d.ld;
+    }
 
     // ---- cell row r0-1 ----
     m.h = fmx(__ldg(m.hp), T(0));
@@ -461,16 +595,34 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
         m.hx = m.h + hE;
         m.ehE = ETA1 ? hE : m.eta0 * hE;
         m.fxr = lE - m.l;
-        m.px = m.fxr * fmx(fmn(m.ex, m.ehE), -m.eh);
+        m.cx = fmx(fmn(m.ex, m.ehE), -m.eh);
+        m.px = m.fxr * m.cx;
     }
-    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = T(0);
+    if (CUBIC && !DFIELD) {
+        const T Kc = ph.Gam * T(1.0 / 1024.0);  // Γ/4^5
+        const T sK = tsqrt(Kc);
+        m.hdxs = m.hdx * sK;
+        m.hdys = m.hdy * sK;
+        m.lmx = m.lmask * m.nhx2;
+        m.lmy = m.lmask * m.nhy2;
+        m.qx2 = T(2) * Kc * m.qx;
+        m.qy2 = T(2) * Kc * m.qy;
+        m.nodem = m.node_col_ok ? T(1) : T(0);
+        const T lx = m.l * m.nhx2;              // m.l is the masked λ row r0-1
+        m.ly = m.l * m.nhy2;
+        m.fx = shfl_dn(lx) - lx;
+        m.px = m.fx * m.cx;
+        m.Qp = T(0);
+    }
+    m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = m.Fyp = T(0);
 #pragma unroll
     for (int k = 0; k < PF; ++k) {  // rows r0 .. r0+PF-1 (clamped)
-        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; }
+        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; m.pfp += d.ld; }
         m.hq[k] = __ldg(m.hp);
         m.bq[k] = __ldg(m.bp);
         m.lq[k] = __ldg(m.lp);
     }
+    m.pfp += (long long)ODINN_L2PF_ROWS1 * d.ld;
 
     int row = r0 - 1;
     m.template step<false, true>(row);  // warm-up
@@ -482,7 +634,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     for (; row < r1; ++row) m.template step<true, true>(row);
 
     if (WRITE_S) {
-        double a = (double)m.acc;
+        double a = m.own_lane ? (double)m.acc : 0.0;  // (the cubic form accumulates in the halo lanes too)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
         if (lane == 0) partial[item] = a;

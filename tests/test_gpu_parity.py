@@ -259,8 +259,8 @@ def test_host_batch_pipeline(ob, dtype, gridded):
         assert np.array_equal(ens.download(0, _capi.FIELD_H), marker.astype(ens.np_dtype))
         only_dH, none_v, none_S = ens.fwd_adj_batch(Hs, None, want_vjpH=False, want_S=False)
         assert none_v is None and none_S is None
-        # (fp32: dH above came out of the fused F1 + A1 + A2 kernel, whose D is rounded in a different order)
-        assert all(rel_l2(a, b) <= (1e-6 if dtype == "f32" else 0.0) for a, b in zip(only_dH, dH))
+        # (dH above came out of the fused F1 + A1 + A2 kernel, whose D is rounded in a different order)
+        assert all(rel_l2(a, b) <= (1e-6 if dtype == "f32" else 1e-14) for a, b in zip(only_dH, dH))
     finally:
         sim.close()
 
