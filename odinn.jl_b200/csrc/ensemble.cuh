@@ -105,6 +105,12 @@ struct odinn_ensemble {
     void* ext_dev[24] = {nullptr};
     void* ext_host[4] = {nullptr};
     int ext_int[8] = {0};
+    // CUDA graph of one tstop interval of the fixed-step forward loop (odinn_solve_forward) + its device table of step sizes
+    cudaGraphExec_t fwd_graph_exec = nullptr;
+    std::string fwd_graph_key;
+    int fwd_graph_launches = 0;
+    double* d_fwd_tab = nullptr;      // [fwd_tab_len x 9] stage coefficients, then one int: the interval counter
+    int fwd_tab_len = 0;
     // loss configuration (odinn_set_loss_weights): per-snapshot multipliers of the thickness / velocity L2 terms; empty = LossH with Δt
     std::vector<double> loss_wH, loss_wV;
     int lossV_component = 0;          // 0 :xy, 1 :abs  (Losses.jl:318-325)

@@ -220,7 +220,14 @@ template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIEL
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af, T* dH,
-                PhysDev<T> ph, const T* U0, T sa, T sb, T sdt, T A_ovr = T(0), int use_A_ovr = 0) {
+                PhysDev<T> ph, const T* U0, T sa, T sb, T sdt, T A_ovr = T(0), int use_A_ovr = 0,
+                const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr) {
+    // Replayed from a CUDA graph (odinn_solve_forward): the stage coefficients of interval *interval come from a device table
+    // (9 doubles per interval, stage_tab already offset to this launch's stage), so one captured graph serves every interval.
+    if (STAGE && stage_tab != nullptr) {
+        const double* sp = stage_tab + (long long)(*interval) * 9;
+        sa = (T)sp[0]; sb = (T)sp[1]; sdt = (T)sp[2];
+    }
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;

@@ -210,7 +210,12 @@ template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
 __global__ void __launch_bounds__(MARCH2_WARPS * 32)
 sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                  const float* __restrict__ H, const float* __restrict__ B, const float* __restrict__ Af, float* dH,
-                 PhysDev<float> ph, const float* U0, float sa, float sb, float sdt) {
+                 PhysDev<float> ph, const float* U0, float sa, float sb, float sdt,
+                 const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr) {
+    if (STAGE && stage_tab != nullptr) {  // graph replay: stage coefficients from the device table (see sia2d_rhs_march)
+        const double* sp = stage_tab + (long long)(*interval) * 9;
+        sa = (float)sp[0]; sb = (float)sp[1]; sdt = (float)sp[2];
+    }
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;

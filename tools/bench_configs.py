@@ -1,0 +1,102 @@
+"""Wall-clock numbers for the BASELINE.json configs that bench.py's headline line does not cover (configs 1, 3, 4):
+forward time loops and full gradient iterations on device-resident ensembles.  usage: python tools/bench_configs.py [f32|f64]
+Prints one JSON line per measurement.  (Synthetic glaciers: SURVEY.md 8d.)"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import odinn_b200 as ob
+from odinn_b200 import _capi
+from bench import synthetic_glacier
+
+dtype = sys.argv[1] if len(sys.argv) > 1 else "f32"
+PH = dict(minA=8e-21, maxA=8e-17)
+
+
+def make(shapes, seed=0, thin=1.0):
+    G = len(shapes)
+    ens = ob.Ensemble([s[0] for s in shapes], [s[1] for s in shapes], [50.0] * G, [50.0] * G, ob.Phys(**PH), dtype)
+    rng = np.random.default_rng(seed)
+    for k, (nx, ny) in enumerate(shapes):
+        B, H, _ = synthetic_glacier(nx, ny, k)
+        ens.upload(k, _capi.FIELD_B, B)
+        ens.upload(k, _capi.FIELD_H0, thin * H)
+        ens.set_A_scalar(k, float(np.exp(rng.uniform(np.log(2e-18), np.log(2e-17)))))
+    return ens
+
+
+def timed(fn, reps=3):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def report(name, **kw):
+    print(json.dumps(dict(config=name, dtype=dtype, **kw)), flush=True)
+
+
+t5 = np.linspace(2010.0, 2015.0, 61)   # 5 years, monthly tstops
+
+# config 1: single 128x128 glacier, forward 2010-2015
+ens = make([(128, 128)], thin=0.5)
+for nsub in (8,):
+    s = timed(lambda: (ens.solve_forward(t5, method="ssprk3", nsub=nsub), ens.synchronize()))
+    rhs = 60 * nsub * 3
+    report("1: 128x128 forward 2010-2015, SSPRK3", nsub=nsub, seconds=s, rhs_evals=rhs, us_per_rhs=1e6 * s / rhs, cell_steps_per_s=128 * 128 * rhs / s)
+st = None
+def run_bs3():
+    global st
+    st = ens.solve_forward_adaptive(t5, reltol=1e-4, abstol=1e-4)
+    ens.synchronize()
+s = timed(run_bs3)
+report("1: 128x128 forward 2010-2015, adaptive BS3 rtol 1e-4", seconds=s, steps=int(st[0][0]), rejected=int(st[1][0]))
+ens.close()
+
+# config 3: 64 glaciers, sizes U{100..400}, forward Prediction run
+rng = np.random.default_rng(2024)
+shapes = [(int(rng.integers(100, 401)), int(rng.integers(100, 401))) for _ in range(64)]
+cells = sum(a * b for a, b in shapes)
+ens = make(shapes, thin=0.4)
+nsub = 8
+s = timed(lambda: (ens.solve_forward(t5, method="ssprk3", nsub=nsub), ens.synchronize()))
+rhs = 60 * nsub * 3
+report("3: 64 glaciers 100-400 px, forward 2010-2015, SSPRK3 nsub 8", seconds=s, cells=cells, rhs_evals=rhs, cell_steps_per_s=cells * rhs / s,
+       frac_of_hbm_peak=cells * rhs * 4 * (4 if dtype == "f32" else 8) / s / 6550.1e9)
+ens.close()
+
+# config 4: 32 glaciers, LawA(nn 1-16-16-1), one optimiser iteration = law + forward solve + adjoint + pullback
+rng = np.random.default_rng(2025)
+shapes = [(int(rng.integers(100, 401)), int(rng.integers(100, 401))) for _ in range(32)]
+cells = sum(a * b for a, b in shapes)
+ens = make(shapes, thin=0.4)
+widths, acts = [1, 16, 16, 1], ["softplus", "softplus", "sigmoid"]
+nth = sum(o * i + o for i, o in zip(widths[:-1], widths[1:]))
+theta = 0.3 * np.random.default_rng(1).standard_normal(nth)
+for k in range(32):
+    ens.set_temperature(k, float(rng.uniform(-20, 0)))
+ens.law_A_nn_apply(widths, acts, theta - 1.0)
+ens.solve_forward(t5, method="ssprk3", nsub=nsub)
+for k in range(32):
+    for j in range(len(t5)):
+        Hj = ens.get_snapshot(k, j)
+        ens.set_reference(k, j, len(t5), Hj, ob.is_in_glacier(Hj, 3))
+
+def iteration(mode):
+    ens.law_A_nn_apply(widths, acts, theta)
+    ens.solve_forward(t5, method="ssprk3", nsub=nsub)
+    if mode == "discrete":
+        ens.grad_discrete(t5)
+    else:
+        ens.grad_continuous(t5, n_quadrature=200, vjp="discrete", method="ssprk3", nsub=1)
+    return ens.law_A_nn_pullback(nth)
+
+for mode in ("discrete", "continuous"):
+    s = timed(lambda: iteration(mode), reps=2)
+    report(f"4: 32 glaciers, LawA(1-16-16-1), one iteration: law + forward (SSPRK3 nsub 8) + {mode} adjoint + pullback", seconds=s, cells=cells,
+           n_theta=nth)
+s_f = timed(lambda: (ens.solve_forward(t5, method="ssprk3", nsub=nsub), ens.synchronize()), reps=2)
+s_g = timed(lambda: ens.grad_discrete(t5), reps=2)
+report("4: split", forward_seconds=s_f, discrete_adjoint_seconds=s_g, adjoint_cell_steps_per_s=cells * 60 / s_g)
+ens.close()
