@@ -173,6 +173,7 @@ struct RhsMarch {
             if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) {
                 prefetch_l2_row(hp + (long long)ODINN_L2PF_ROWS1 * ld);
                 prefetch_l2_row(bp + (long long)ODINN_L2PF_ROWS1 * ld);
+                if (STAGE) prefetch_l2_row(up + (long long)ODINN_L2PF_ROWS1 * ld);  // U0 has no register queue (see sia2d_rhs_march2)
             }
         }
         T u0 = T(0);

@@ -246,7 +246,11 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.hp = H + d.off + ic + (long long)rc * d.ld;
     m.bp = B + d.off + ic + (long long)rc * d.ld;
     {
-        const float* q = prefetch_lane_ptr<2>(lane, it.y, cmax, d.off, H, B, nullptr);
+        // L2 prefetch: H and B, plus U0 in a stage launch (9 lanes per plane, one 32-byte sector each).  U0 has no register prefetch
+        // queue (it is read at the output row), so the L2 prefetch is what hides its DRAM latency: SSPRK3 stage 0.226 -> 0.197 ms.
+        // (Skipping the U0 read in stages with sa == 0 was measured SLOWER -- 0.35 ms: the branch serialises the load in every stage.)
+        const float* q = STAGE ? prefetch_lane_ptr<3>(lane, it.y, cmax, d.off, H, B, U0)
+                               : prefetch_lane_ptr<2>(lane, it.y, cmax, d.off, H, B, nullptr);
         m.pf_lane = q != nullptr;
         m.pfp = (m.pf_lane ? q : H + d.off) + (long long)rc * d.ld;  // advanced with hp below, then ODINN_L2PF_ROWS rows further
     }

@@ -81,5 +81,44 @@ def main():
     print("lawA_default_nn A = %.6e" % tg.A)
 
 
+def next_rows():
+    """SURVEY 8f rows (N1-N4) on one small glacier: adaptive BS3 run, surface velocity + its VJPs, mass balance + its VJP,
+    discrete (with MB) and continuous adjoint gradients."""
+    rng = np.random.default_rng(4321)
+    g = o.rough_bed_glacier(24, 21)
+    g.H0 = 0.6 * g.H0
+    ph = o.Phys(minA=8e-21, maxA=8e-17)
+    A, Aref = 1.5e-17, 4e-17
+    t = o.define_callback_steps((2010.0, 2010.5), 1.0 / 12.0)
+    tg, tgr = o.TargetA(ph, "const", A=A), o.TargetA(ph, "const", A=Aref)
+    st = {}
+    H_bs3 = o.solve_forward(g.H0, g, tg, None, t, method="bs3", reltol=1e-6, abstol=1e-6, stats=st)
+    Vx, Vy = o.surface_V(g.H0, g, tg)
+    dVx, dVy = rng.standard_normal(g.B.shape), rng.standard_normal(g.B.shape)
+    par = (3.0, -0.0065, 2100.0, 0.9, 0.4, 1.2, 1.0)
+    MB, _, _, _ = o.mb_TI1(g.H0, g.B, par)
+    lam = rng.standard_normal(g.B.shape)
+    mb = {j: par for j in (2, 4, 6)}
+    stm = {}
+    Href = o.solve_forward(g.H0, g, tgr, None, t, method="ssprk3", nsub=8, mb=mb)
+    Hs = o.solve_forward(g.H0, g, tg, None, t, method="ssprk3", nsub=8, mb=mb, stats=stm)
+    tgs = o.TargetA(ph, "scalar")
+    theta = np.array([np.arctanh(2 * (A - ph.minA) / (ph.maxA - ph.minA) - 1)])
+    wH, wV = o.loss_weights("H", t)
+    ell_d, dth_d = o.loss_and_grad_discrete_HV(theta, g, tgs, t, Hs, Href, [None] * len(t), wH, wV, mb=mb, MB_hist=stm["MB"])
+    Href0 = o.solve_forward(g.H0, g, tgr, None, t, method="ssprk3", nsub=8)
+    Hs0 = o.solve_forward(g.H0, g, tg, None, t, method="ssprk3", nsub=8)
+    ell_c, dth_c = o.loss_and_grad_continuous(theta, g, tgs, t, Hs0, Href0, n_quadrature=9, nsub=2, method="ssprk3", vjp="discrete")
+    np.savez_compressed(
+        os.path.join(HERE, "next_24x21.npz"), B=g.B, H0=g.H0, dx=g.dx, dy=g.dy, A=A, Aref=Aref, t=t, minA=ph.minA, maxA=ph.maxA,
+        H_bs3_end=H_bs3[-1], bs3_nrhs=st["nrhs"], Vx=Vx, Vy=Vy, dVx=dVx, dVy=dVy,
+        vjpV_H=o.VJP_dsurfaceV_dH_discrete(dVx, dVy, g.H0, g, tg), vjpV_S=-o.surfaceV_theta_reduction(dVx, dVy, g.H0, g, tg),
+        mb_par=np.array(par), MB=MB, lam=lam, vjp_MB=o.VJP_MB_dH(lam, g.H0, g.B, par), mb_idx=np.array(sorted(mb)),
+        Hs_mb_end=Hs[-1], loss_discrete_mb=ell_d, dtheta_discrete_mb=dth_d[0], vjp_theta=tgs.vjp_theta[0],
+        loss_continuous=ell_c, dtheta_continuous=dth_c[0])
+    print("next_24x21 bs3 nrhs = %d  loss_d = %.6e  dθ_d = %.6e  dθ_c = %.6e" % (st["nrhs"], ell_d, dth_d[0], dth_c[0]))
+
+
 if __name__ == "__main__":
     main()
+    next_rows()
