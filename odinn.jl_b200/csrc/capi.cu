@@ -701,7 +701,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     }
     e->total = off;
     e->n_tiles = tile;
-    if (off + (long long)(ODINN_L2PF_ROWS + 8) * 65536 >= (1LL << 31)) {  // the fp32 A1+A2 kernels index planes with 32-bit element offsets
+    if (dtype == ODINN_F32 && off + (long long)(ODINN_L2PF_ROWS + 8) * 65536 >= (1LL << 31)) {  // the fp32 A1+A2 kernels index planes with 32-bit element offsets
         delete e;
         return fail(nullptr, ODINN_EARG, "ensemble too large for one handle: a plane must stay below 2^31 elements (split the ensemble)");
     }
@@ -1346,9 +1346,7 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
         const double dt = t[j] - t[j - 1];
         void* Hj = plane_ptr(e, e->snap, j);
         // λ_j += VJP_λ_∂MB∂H(λ_j, H_j - MB) at the MB tstops                                (gradient.jl:201-207)
-        const bool mb_here = std::find(e->mb_snap.begin(), e->mb_snap.end(), j) != e->mb_snap.end();
-        if (j < n_t - 1 && (rc = mb_adjoint_step(e, j, lam, Hj))) return rc;  // (λ_k = 0 at the last snapshot)
-        (void)mb_here;
+        if (j < n_t - 1 && (rc = mb_adjoint_step(e, j, lam, Hj))) return rc;  // (λ_k = 0 at the last snapshot: nothing to add)
         // λ_∂f∂H = VJP_H(λ_j, H_j)                                                     (gradient.jl:235-237)
         if (j < n_t - 1) {
             if ((rc = launch_vjp(e, -1, lam, Hj, vH, true, false))) return rc;

@@ -120,7 +120,7 @@ struct odinn_ensemble {
     std::vector<double> mb_params;    // [n_mb x G x MB_NPAR]
 };
 enum {  // ext_dev slots
-    EXT_CA_HT = 0, EXT_CA_HREF_T = 1, EXT_CA_W_T = 2, EXT_CA_LAM1 = 3, EXT_CA_LAM2 = 4, EXT_CA_V = 5,   // continuous adjoint (contadj.cu)
+    EXT_CA_HT = 0, EXT_CA_LAM1 = 3, EXT_CA_LAM2 = 4,                                                   // continuous adjoint (contadj.cu)
     EXT_MB = 8, EXT_MB_PAR = 9,                                                                      // mass balance (massbalance.cu)
     EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15, EXT_V_PARTIAL = 16           // surface velocity / LossV
 };

@@ -170,3 +170,35 @@ def test_mass_balance_forward_and_discrete_gradient(ob, dtype, method):
                 assert Ssum[k] * g._ref[2] == pytest.approx(g._ref[1], rel=rt_g), (k, Ssum[k] * g._ref[2], g._ref[1])
     finally:
         ens.close()
+
+
+def test_error_convention_of_the_new_entry_points(ob):
+    """Bad arguments and call-sequence errors come back as a negative status + message (OdinnError in the mirror), never a crash."""
+    g = o.rough_bed_glacier(12, 11)
+    g.H0 = 0.5 * g.H0
+    ens = _ens(ob, [g], "f64")
+    t = np.array([2010.0, 2010.1, 2010.2])
+    try:
+        with pytest.raises(ob.OdinnError, match="strictly increasing"):
+            ens.solve_forward_adaptive(np.array([2010.0, 2010.0, 2010.1]))
+        with pytest.raises(ob.OdinnError, match="adaptive-solve"):
+            ens.solve_forward_adaptive(t, reltol=-1.0)
+        with pytest.raises(ob.OdinnError, match="snapshots and reference"):
+            ens.grad_continuous(t, n_quadrature=4)
+        ens.set_A_scalar(0, 2.21e-18)
+        ens.solve_forward(t, method="ssprk3", nsub=16)
+        assert np.isfinite(ens.get_snapshot(0, 2)).all()
+        with pytest.raises(ob.OdinnError):  # no reference data yet
+            ens.grad_continuous(t, n_quadrature=4)
+        for j in range(3):
+            ens.set_reference(0, j, 3, ens.get_snapshot(0, j), np.ones(g.B.shape, bool))
+        with pytest.raises(ob.OdinnError, match="count"):
+            ens.grad_continuous(t[:2], n_quadrature=4)
+        with pytest.raises(ob.OdinnError, match="mass-balance step"):
+            ens.get_mass_balance(0, 0)
+        with pytest.raises(ob.OdinnError, match="velocity reference"):
+            ens.set_velocity_reference(0, 3, 2, 1, g.B, g.B, g.B)
+        loss, Ssum = ens.grad_continuous(t, n_quadrature=4)
+        assert loss[0] == 0.0 and Ssum[0] == 0.0, (loss, Ssum)  # reference == prediction: zero loss, zero gradient
+    finally:
+        ens.close()
