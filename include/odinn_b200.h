@@ -278,8 +278,10 @@ int odinn_law_A_nn_pullback(odinn_ensemble* e, const double* S, double* dtheta, 
  * (target_utils.jl:131-141) or NULL for raw inputs; max_NN > 0 enables post() = max_NN exp((y-1)/y)
  * (target_utils.jl:86-93); n_H, n_gS <= 0 default to the Glen exponent n.
  * While a per-cell law is set every RHS / VJP entry point of the handle (per-call, resident, time loop, reverse loop)
- * uses it instead of the A law.  The partials dD/dHbar and dD/dgradS are the reference's finite differences
- * (target_D_pure.jl:105-137, target_D_hybrid.jl:58-73), evaluated in fp64. */
+ * uses it instead of the A law.  LawU: the partials dD/dHbar and dD/dgradS (central differences of the network upstream,
+ * target_D_pure.jl:105-137) are the exact derivatives, propagated alongside the forward evaluation -- within the rounding noise
+ * of the reference's differences (3e-10 / 7e-10 relative on the oracle).  LawY: the reference's one-sided difference
+ * (target_D_hybrid.jl:58-73), evaluated in fp64. */
 int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* widths, const int* acts, const double* theta,
                           int n_theta, const double* prescale_bounds, double max_NN, double n_H, double n_gS);
 int odinn_law_cell_clear(odinn_ensemble* e);

@@ -131,15 +131,21 @@ static int launch_law_nodes_t(odinn_ensemble* e, int g0, int g1, const void* H, 
     }
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
     const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    if (partials) {  // differences of the network: always fp64 (a 1e-6 step is below the fp32 resolution of D)
-        size_t smem = sizeof(double) * lw.arch.n_params;
-        law_nodes_kernel<T, double, true><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
-                                                                          (T*)e->lawD, (T*)e->lawAl, (T*)e->lawBe);
-    } else {
-        size_t smem = sizeof(T) * lw.arch.n_params;
-        law_nodes_kernel<T, T, false><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
-                                                                      (T*)e->lawD, nullptr, nullptr);
-    }
+    int wmax = 0;
+    for (int L = 0; L <= lw.arch.n_layers; ++L) wmax = std::max(wmax, lw.arch.widths[L]);
+    const bool w16 = wmax <= 16;  // register-resident evaluator: compile-time width bound 16 or 32
+#define LN(TT, RR, PP)                                                                                                         \
+    do {                                                                                                                       \
+        const size_t smem = sizeof(RR) * lw.arch.n_params;                                                                     \
+        if (w16) law_nodes_kernel<TT, RR, PP, 16><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, \
+                     (const TT*)H, B, (TT*)e->lawD, PP ? (TT*)e->lawAl : nullptr, PP ? (TT*)e->lawBe : nullptr);               \
+        else law_nodes_kernel<TT, RR, PP, 32><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta,     \
+                     (const TT*)H, B, (TT*)e->lawD, PP ? (TT*)e->lawAl : nullptr, PP ? (TT*)e->lawBe : nullptr);               \
+    } while (0)
+    if (!partials) LN(T, T, false);
+    else if (lw.kind == LAW_U) LN(T, T, true);   // analytic partials ride along the forward evaluation: the ensemble's precision
+    else LN(T, double, true);                    // LawY: one-sided difference of the network (target_D_hybrid.jl:58-73): fp64
+#undef LN
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
@@ -159,11 +165,29 @@ static int launch_law_theta_t(odinn_ensemble* e, int g0, int g1, const void* H, 
     const int np = lw.arch.n_params;
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
     const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const size_t smem = sizeof(double) * np * (1 + LAW_NT / 32);
+    int NA = 0, NZ = 0, wmax = 0;
+    for (int L = 0; L < lw.arch.n_layers; ++L) { NA += lw.arch.widths[L]; NZ += lw.arch.widths[L + 1]; }
+    for (int L = 0; L <= lw.arch.n_layers; ++L) wmax = std::max(wmax, lw.arch.widths[L]);
+    const size_t smem = (sizeof(double) + sizeof(int2)) * (size_t)np + sizeof(T) * (((size_t)np + 3) / 4 * 4 + (size_t)(NA + NZ) * LAW_PITCH);
+    if (smem > 220 * 1024) return fail(e, ODINN_EARG, "per-cell law too large for the shared-memory pullback (reduce depth x width)");
+    const bool w16 = wmax <= 16;
+    {
+        static size_t attr16 = 0, attr32 = 0;  // opt in to > 48 KB dynamic shared memory once per size
+        size_t& cur = w16 ? attr16 : attr32;
+        if (smem > cur) {
+            if (w16) ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
     for (int g = g0; g < g1; ++g) {  // one glacier at a time: the block partials are [tiles of one glacier x n_theta]
         const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
-        law_theta_kernel<T><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
-                                                            (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
+        if (w16)
+            law_theta_kernel<T, T, 16><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                    (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
+        else
+            law_theta_kernel<T, T, 32><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                    (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
         ODINN_CHECK_LAUNCH(e);
         law_theta_reduce_scaled<<<div_up(np, 128), 128, 0, e->stream>>>(e->d_law_partial, nt, np, e->d_law_dtheta + (size_t)g * np,
                                                                        scale, accumulate);
