@@ -5,8 +5,8 @@
 // are instruction-issue bound.  Measured pipe rates on B200 (tools/microbench/pipes.cu): FFMA 3.6, FFMA2 1.8,
 // FMNMX 2.0, SHFL 1.0 warp-instructions / clk / SM.  A packed FFMA2 costs ONE issue slot for two columns, and with
 // two columns per lane only every second x-neighbour is in another lane, so shuffles, loads, stores and address
-// arithmetic per cell halve as well.  Same arithmetic, same operation order per column as sia2d_march.cuh
-// (results are bit-identical to the one-column kernels; the parity tests cover both).
+// arithmetic per cell halve as well.  Same operator as sia2d_march.cuh (F1: same operation order per column; the A1+A2 step in
+// its cubic form shares node products and differs from the generic form in rounding only -- the parity tests cover every form).
 //
 // Geometry: a warp owns 64 consecutive columns  base .. base+63  (base even), lane l holds columns base+2l (.x)
 // and base+2l+1 (.y); lanes 0 and 31 are halo lanes, so a strip produces the 60 columns base+2 .. base+61.
