@@ -211,6 +211,46 @@ def test_vjp_is_transpose_of_jacobian_at_scale(ob):
         sim.close()
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_fused_step_at_bench_size_properties(ob, dtype):
+    """BASELINE-size grids (500 x 500 and odd neighbours) through size-independent properties of the fused F1 + A1 + A2 pass:
+    it reproduces the two separate kernels, the VJP is linear in λ, ∂H vanishes on ice-free cells, and dH conserves mass."""
+    from odinn_b200 import _capi
+
+    shapes = [(500, 500), (499, 501), (501, 487)]
+    gl = [o.rough_bed_glacier(nx, ny) for nx, ny in shapes]
+    rng = np.random.default_rng(11)
+    lams = [rng.standard_normal(g.B.shape) for g in gl]
+    sim = ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy) for g in gl], ob.Phys(), A=[A0, 2 * A0, 3 * A0], dtype=dtype)
+    try:
+        ens = sim.ensemble
+        for k, g in enumerate(gl):
+            ens.upload(k, _capi.FIELD_H, g.H0)
+            ens.upload(k, _capi.FIELD_LAMBDA, lams[k])
+        ens.rhs_resident()
+        S_sep = ens.vjp_resident(True, True)
+        dH_sep = [ens.download(k, _capi.FIELD_DH) for k in range(3)]
+        vH_sep = [ens.download(k, _capi.FIELD_VJP_H) for k in range(3)]
+        S_f = ens.vjp_resident(True, True, want_dH=True)
+        eps = 1e-6 if dtype == "f32" else 1e-14
+        for k, g in enumerate(gl):
+            dH, vH = ens.download(k, _capi.FIELD_DH), ens.download(k, _capi.FIELD_VJP_H)
+            assert rel_l2(dH, dH_sep[k]) <= eps and rel_l2(vH, vH_sep[k]) <= eps, k
+            assert abs(S_f[k] - S_sep[k]) <= 1e-6 * abs(S_sep[k]) + 1e-30, k
+            assert np.all(vH[np.maximum(g.H0, 0) <= 0] == 0)                      # adjoint.jl:148
+            assert abs(dH.astype(np.float64).sum()) <= (1e-4 if dtype == "f32" else 1e-9) * np.abs(dH).sum()
+            assert np.all(dH[0, :] == 0) and np.all(dH[-1, :] == 0) and np.all(dH[:, 0] == 0) and np.all(dH[:, -1] == 0)
+        # linearity in λ: VJP(2λ) == 2 VJP(λ) exactly (scaling by 2 is exact in floating point)
+        for k in range(3):
+            ens.upload(k, _capi.FIELD_LAMBDA, 2.0 * lams[k])
+        ens.vjp_resident(True, True, want_dH=True)
+        for k in range(3):
+            assert np.array_equal(ens.download(k, _capi.FIELD_VJP_H), 2.0 * vH_sep[k].astype(ens.np_dtype)) or \
+                rel_l2(ens.download(k, _capi.FIELD_VJP_H), 2.0 * vH_sep[k]) <= eps, k
+    finally:
+        sim.close()
+
+
 def test_error_convention(ob):
     """Nonzero return code -> exception carrying odinn_last_error (never exit)."""
     with pytest.raises(ob.OdinnError):
