@@ -776,7 +776,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
             long long n = 0;
             for (int g = 0; g < n_glaciers; ++g) n += (long long)div_up(e->gl[g].nx, STRIP2) * div_up(e->gl[g].ny, rows);
             e->chunk_rows2 = rows;
-            if (n >= 148LL * 64) break;
+            if (n >= 148LL * 12) break;  // ~1 wave of warps; shorter chunks only add halo rows (sweep on BASELINE configs 3 / 4: 8 -> 16 rows, 24.7 -> 21.9 ms)
         }
         if (forced >= 4) e->chunk_rows2 = forced;
         for (int g = 0; g < n_glaciers; ++g) {
