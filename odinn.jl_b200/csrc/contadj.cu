@@ -16,35 +16,45 @@
 
 namespace odinn {
 
-#define CA_TILE_LOOP(BODY)                                                        \
-    const int2 tl = tiles[blockIdx.x];                                            \
-    const GDesc<T> d = descs[tl.x];                                               \
-    const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;                  \
-    const int i = x0 + (threadIdx.x & 31), tr = threadIdx.x >> 5;                 \
-    _Pragma("unroll") for (int rr = 0; rr < TY / 8; ++rr) {                       \
-        const int j = y0 + tr + rr * 8;                                           \
-        if (i < d.nx && j < d.ny) {                                               \
-            const long long p = d.off + (long long)j * d.ld + i;                  \
-            BODY                                                                  \
-        }                                                                         \
+// Elementwise kernels over the padded planes of every glacier (grid: chunks x glaciers, 16-byte vector accesses; padding stays zero
+// under these linear combinations) -- the same scheme as the adaptive solve's kernels.
+template <typename T> struct CaVec;
+template <> struct CaVec<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct CaVec<double> { typedef double2 type; static constexpr int N = 2; };
+constexpr int CA_NT = 256;
+constexpr int CA_UNROLL = 4;
+__device__ __forceinline__ float4 ca_axpby(float a, const float4& x, float b, const float4& y) {
+    return make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
+}
+__device__ __forceinline__ double2 ca_axpby(double a, const double2& x, double b, const double2& y) {
+    return make_double2(a * x.x + b * y.x, a * x.y + b * y.y);
+}
+__device__ __forceinline__ float4 ca_scale(float a, const float4& x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+__device__ __forceinline__ double2 ca_scale(double a, const double2& x) { return make_double2(a * x.x, a * x.y); }
+
+#define CA_VEC_LOOP(BODY)                                                                           \
+    typedef typename CaVec<T>::type V;                                                              \
+    const GDesc<T> d = descs[blockIdx.y];                                                           \
+    const long long nvec = (long long)d.ld * d.ny / CaVec<T>::N, base = d.off / CaVec<T>::N;        \
+    _Pragma("unroll") for (int u = 0; u < CA_UNROLL; ++u) {                                         \
+        const long long q = ((long long)blockIdx.x * CA_UNROLL + u) * CA_NT + threadIdx.x;          \
+        if (q < nvec) { const long long p = base + q; BODY }                                        \
     }
 
 // Ht = (1 - a) Ha + a Hb
 template <typename T>
-__global__ void __launch_bounds__(NT)
-ca_lerp(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, const T* __restrict__ Ha,
-        const T* __restrict__ Hb, T* __restrict__ Ht, T a) {
-    CA_TILE_LOOP({ Ht[p] = (T(1) - a) * Ha[p] + a * Hb[p]; })
+__global__ void __launch_bounds__(CA_NT)
+ca_lerp(const GDesc<T>* __restrict__ descs, const T* __restrict__ Ha, const T* __restrict__ Hb, T* __restrict__ Ht, T a) {
+    CA_VEC_LOOP({ reinterpret_cast<V*>(Ht)[p] = ca_axpby(T(1) - a, reinterpret_cast<const V*>(Ha)[p], a, reinterpret_cast<const V*>(Hb)[p]); })
 }
 
 // out = sa U0 + sb (U + h V)      (one Shu-Osher stage of the reverse solve; out may alias U0 or U)
 template <typename T>
-__global__ void __launch_bounds__(NT)
-ca_stage(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, const T* U0, const T* U, const T* __restrict__ V,
-         T* out, T sa, T sb, T h) {
-    CA_TILE_LOOP({
-        const T u = U[p] + h * V[p];
-        out[p] = (sa != T(0)) ? sa * U0[p] + sb * u : sb * u;
+__global__ void __launch_bounds__(CA_NT)
+ca_stage(const GDesc<T>* __restrict__ descs, const T* U0, const T* U, const T* __restrict__ Vp, T* out, T sa, T sb, T h) {
+    CA_VEC_LOOP({
+        const V u = ca_axpby(T(1), reinterpret_cast<const V*>(U)[p], h, reinterpret_cast<const V*>(Vp)[p]);
+        reinterpret_cast<V*>(out)[p] = (sa != T(0)) ? ca_axpby(sa, reinterpret_cast<const V*>(U0)[p], sb, u) : ca_scale(sb, u);
     })
 }
 
@@ -59,6 +69,9 @@ static int grad_continuous_t(odinn_ensemble* e, const double* t, int n_t, int n_
     if ((rc = ensure_plane(e, ODINN_FIELD_LAMBDA)) || (rc = ensure_plane(e, ODINN_FIELD_VJP_H))) return rc;
     if ((rc = sync_descs(e))) return rc;
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
+    long long max_vec = 0;
+    for (int g = 0; g < e->G; ++g) max_vec = std::max(max_vec, (long long)e->gl[g].ld * e->gl[g].ny / CaVec<T>::N);
+    const dim3 egrid((unsigned)((max_vec + (long long)CA_NT * CA_UNROLL - 1) / ((long long)CA_NT * CA_UNROLL)), e->G);
     T* lam = (T*)e->plane[ODINN_FIELD_LAMBDA];
     T* V = (T*)e->plane[ODINN_FIELD_VJP_H];
     T *Ht = (T*)*Htp, *U1 = (T*)*U1p, *U2 = (T*)*U2p;
@@ -73,7 +86,7 @@ static int grad_continuous_t(odinn_ensemble* e, const double* t, int n_t, int n_
         int j = 0;
         while (j + 2 < n_t && tt >= t[j + 1]) ++j;  // interval [t_j, t_{j+1}] with tt >= t_j (clipped to the last one)
         const double a = (tt - t[j]) / (t[j + 1] - t[j]);
-        ca_lerp<T><<<e->n_tiles, NT, 0, e->stream>>>(descs, e->d_tiles, (const T*)snapshot_ptr(e, j), (const T*)snapshot_ptr(e, j + 1), Ht, (T)a);
+        ca_lerp<T><<<egrid, CA_NT, 0, e->stream>>>(descs, (const T*)snapshot_ptr(e, j), (const T*)snapshot_ptr(e, j + 1), Ht, (T)a);
         ODINN_CHECK_LAUNCH(e);
         return ODINN_OK;
     };
@@ -83,7 +96,7 @@ static int grad_continuous_t(odinn_ensemble* e, const double* t, int n_t, int n_
         return vjp_planes(e, u, Ht, V, true, false, nullptr, 1.0, 0, cont_vjp);
     };
     auto stage = [&](const T* U0, const T* U, T* out, double sa, double sb, double h) -> int {
-        ca_stage<T><<<e->n_tiles, NT, 0, e->stream>>>(descs, e->d_tiles, U0, U, V, out, (T)sa, (T)sb, (T)h);
+        ca_stage<T><<<egrid, CA_NT, 0, e->stream>>>(descs, U0, U, V, out, (T)sa, (T)sb, (T)h);
         ODINN_CHECK_LAUNCH(e);
         return ODINN_OK;
     };
