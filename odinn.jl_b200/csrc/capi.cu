@@ -601,26 +601,34 @@ static int copy2d(odinn_ensemble* e, int g, int field, void* host, int ld, bool 
 
 // ---- loss / seed ---------------------------------------------------------------------------------------------
 
-template <typename T>
-static int launch_loss_seed_t(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in,
-                              const void* v, void* lam_out, double dt, double cseed) {
-    loss_seed_kernel<T><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<T>*)e->d_descs, e->d_tiles, (const T*)H,
-                                                          (const T*)Href, (const T*)W, (const T*)lam_in, (const T*)v,
-                                                          (T*)lam_out, e->d_partial, (T)dt, (T)cseed);
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
 // loss_dst[g] (+)= wloss · Σ W (H - Href)² ; optionally λ_out = λ_in + dt·v + cseed·W·(H - Href)
 static int launch_loss_seed(odinn_ensemble* e, const void* H, const void* Href, const void* W, const void* lam_in,
                             const void* v, void* lam_out, double dt, double cseed, double* loss_dst, double wloss,
                             int accumulate) {
     int rc = sync_descs(e);
     if (rc) return rc;
-    rc = e->dtype == ODINN_F32 ? launch_loss_seed_t<float>(e, H, Href, W, lam_in, v, lam_out, dt, cseed)
-                               : launch_loss_seed_t<double>(e, H, Href, W, lam_in, v, lam_out, dt, cseed);
-    if (rc) return rc;
-    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, loss_dst, wloss, accumulate);
+    const int N = e->dtype == ODINN_F32 ? 4 : 2;
+    long long max_vec = 0;
+    for (int g = 0; g < e->G; ++g) max_vec = std::max(max_vec, (long long)e->gl[g].ld * e->gl[g].ny / N);
+    const int nchunk = (int)((max_vec + (long long)NT * LS_UNROLL - 1) / ((long long)NT * LS_UNROLL));
+    if (e->ext_int[1] < nchunk * e->G) {  // per-(glacier, chunk) partial sums of the loss
+        if (e->ext_dev[EXT_LS_PARTIAL]) cudaFree(e->ext_dev[EXT_LS_PARTIAL]);
+        e->ext_dev[EXT_LS_PARTIAL] = nullptr;
+        ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_LS_PARTIAL], sizeof(double) * (size_t)nchunk * e->G));
+        e->ext_int[1] = nchunk * e->G;
+    }
+    double* partial = (double*)e->ext_dev[EXT_LS_PARTIAL];
+    const dim3 grid(nchunk, e->G);
+    if (e->dtype == ODINN_F32)
+        loss_seed_vec_kernel<float><<<grid, NT, 0, e->stream>>>((const GDesc<float>*)e->d_descs, (const float*)H, (const float*)Href,
+                                                               (const float*)W, (const float*)lam_in, (const float*)v, (float*)lam_out,
+                                                               partial, (float)dt, (float)cseed);
+    else
+        loss_seed_vec_kernel<double><<<grid, NT, 0, e->stream>>>((const GDesc<double>*)e->d_descs, (const double*)H, (const double*)Href,
+                                                                (const double*)W, (const double*)lam_in, (const double*)v, (double*)lam_out,
+                                                                partial, dt, cseed);
+    ODINN_CHECK_LAUNCH(e);
+    reduce_chunks_scaled_kernel<<<e->G, NT, 0, e->stream>>>(partial, nchunk, loss_dst, wloss, accumulate);
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }

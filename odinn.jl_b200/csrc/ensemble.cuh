@@ -123,7 +123,8 @@ enum {  // ext_dev slots
     EXT_CA_HT = 0, EXT_CA_LAM1 = 3, EXT_CA_LAM2 = 4,                                                   // continuous adjoint (contadj.cu)
     EXT_MB = 8, EXT_MB_PAR = 9,                                                                      // mass balance (massbalance.cu)
     EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15, EXT_V_PARTIAL = 16,          // surface velocity / LossV
-    EXT_AD_PARTIAL = 17                                                                             // adaptive solve (ext_int[0] = its length)
+    EXT_AD_PARTIAL = 17,                                                                            // adaptive solve (ext_int[0] = its length)
+    EXT_LS_PARTIAL = 18                                                                             // loss / seed pass (ext_int[1] = its length)
 };
 
 namespace odinn {

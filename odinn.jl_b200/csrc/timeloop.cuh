@@ -10,38 +10,65 @@
 
 namespace odinn {
 
-// One CTA per 32x16 tile (so a CTA never straddles two glaciers):
-//   partial[tile] = Σ_tile W (H - Href)²        (W = mask / (nx ny), uploaded pre-divided)
+//   partial = Σ W (H - Href)²        (W = mask / (nx ny), uploaded pre-divided)
 //   lam_out = lam_in + dt·v + cseed·W·(H - Href)  when lam_out != nullptr   (gradient.jl:242, Losses.jl:270-291)
+// One pass over the padded planes with 16-byte vector accesses (grid: chunks x glaciers): padding columns carry W = 0 and
+// λ = v = 0, so they add nothing to the loss and stay zero in λ_out.  partial[glacier * gridDim.x + chunk].
+template <typename T> struct LsVec;
+template <> struct LsVec<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct LsVec<double> { typedef double2 type; static constexpr int N = 2; };
+constexpr int LS_UNROLL = 4;
+template <typename T> __device__ __forceinline__ void ls_unpack(const typename LsVec<T>::type& v, T* x);
+template <> __device__ __forceinline__ void ls_unpack<float>(const float4& v, float* x) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+template <> __device__ __forceinline__ void ls_unpack<double>(const double2& v, double* x) { x[0] = v.x; x[1] = v.y; }
+template <typename T> __device__ __forceinline__ typename LsVec<T>::type ls_pack(const T* x);
+template <> __device__ __forceinline__ float4 ls_pack<float>(const float* x) { return make_float4(x[0], x[1], x[2], x[3]); }
+template <> __device__ __forceinline__ double2 ls_pack<double>(const double* x) { return make_double2(x[0], x[1]); }
+
 template <typename T>
 __global__ void __launch_bounds__(NT)
-loss_seed_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, const T* __restrict__ H,
-                 const T* __restrict__ Href, const T* __restrict__ W, const T* lam_in, const T* __restrict__ v,
-                 T* lam_out, double* __restrict__ partial, T dt, T cseed) {
+loss_seed_vec_kernel(const GDesc<T>* __restrict__ descs, const T* __restrict__ H, const T* __restrict__ Href, const T* __restrict__ W,
+                     const T* lam_in, const T* __restrict__ v, T* lam_out, double* __restrict__ partial, T dt, T cseed) {
+    typedef typename LsVec<T>::type V;
+    constexpr int N = LsVec<T>::N;
     __shared__ double sRed[NT / 32];
-    const int2 tl = tiles[blockIdx.x];
-    const GDesc<T> d = descs[tl.x];
-    const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;
-    const int tx = threadIdx.x & 31, tr = threadIdx.x >> 5;
-    const int i = x0 + tx;
+    const GDesc<T> d = descs[blockIdx.y];
+    const long long nvec = (long long)d.ld * d.ny / N, base = d.off / N;
     double acc = 0.0;
 #pragma unroll
-    for (int rr = 0; rr < TY / 8; ++rr) {
-        int j = y0 + tr + rr * 8;
-        if (i < d.nx && j < d.ny) {
-            long long p = d.off + (long long)j * d.ld + i;
-            T w = __ldg(W + p);
-            T diff = __ldg(H + p) - __ldg(Href + p);
-            acc += (double)(w * diff * diff);
+    for (int u = 0; u < LS_UNROLL; ++u) {
+        const long long q = ((long long)blockIdx.x * LS_UNROLL + u) * NT + threadIdx.x;
+        if (q < nvec) {
+            const long long p = base + q;
+            T h[N], r[N], w[N], l[N], vv[N], o[N];
+            ls_unpack<T>(reinterpret_cast<const V*>(H)[p], h);
+            ls_unpack<T>(reinterpret_cast<const V*>(Href)[p], r);
+            ls_unpack<T>(reinterpret_cast<const V*>(W)[p], w);
             if (lam_out != nullptr) {
-                T lv = lam_in ? lam_in[p] : T(0);
-                T vv = v ? __ldg(v + p) : T(0);
-                lam_out[p] = lv + dt * vv + cseed * (w * diff);
+                if (lam_in) ls_unpack<T>(reinterpret_cast<const V*>(lam_in)[p], l);
+                if (v) ls_unpack<T>(reinterpret_cast<const V*>(v)[p], vv);
             }
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+                const T diff = h[e] - r[e];
+                acc += (double)(w[e] * diff * diff);
+                if (lam_out != nullptr) o[e] = (lam_in ? l[e] : T(0)) + dt * (v ? vv[e] : T(0)) + cseed * (w[e] * diff);
+            }
+            if (lam_out != nullptr) reinterpret_cast<V*>(lam_out)[p] = ls_pack<T>(o);
         }
     }
     double s = block_sum(acc, sRed);
-    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+// out[g] = (accumulate ? out[g] : 0) + scale * Σ_chunks partial[g][chunk]   (fixed order)
+__global__ void __launch_bounds__(NT)
+reduce_chunks_scaled_kernel(const double* __restrict__ partial, int nchunk, double* __restrict__ out, double scale, int accumulate) {
+    __shared__ double sRed[NT / 32];
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < nchunk; c += NT) acc += partial[(long long)blockIdx.x * nchunk + c];
+    double s = block_sum(acc, sRed);
+    if (threadIdx.x == 0) out[blockIdx.x] = (accumulate ? out[blockIdx.x] : 0.0) + scale * s;
 }
 
 // out[g] = (accumulate ? out[g] : 0) + scale * Σ partial[start[g] .. start[g+1])   (fixed order, bit-stable)
