@@ -183,6 +183,7 @@ __global__ void ad_control(AdState* st, const double* __restrict__ sumsq, const 
         s.accept = 0;
         s.dt = s.h * fac;
         s.rejected++;
+        atomicAdd(n_active + 1, 1);  // rejections of this trial step
     }
     s.steps++;
     if (s.t < s.b) {
@@ -220,8 +221,8 @@ static int solve_bs3_t(odinn_ensemble* e, int n_snap, const double* t, double re
         if ((rc = alloc_work_plane(e, &e->ad_plane[k]))) return rc;
     if (!e->d_ad_state) {
         ODINN_CUDA(e, cudaMalloc(&e->d_ad_state, sizeof(AdState) * e->G));
-        ODINN_CUDA(e, cudaMalloc(&e->d_ad_dims, sizeof(int) * 2 * e->G + sizeof(int)));
-        ODINN_CUDA(e, cudaMallocHost(&e->h_ad_active, sizeof(int)));
+        ODINN_CUDA(e, cudaMalloc(&e->d_ad_dims, sizeof(int) * 2 * e->G + 2 * sizeof(int)));
+        ODINN_CUDA(e, cudaMallocHost(&e->h_ad_active, 2 * sizeof(int)));
         std::vector<int> dims(2 * e->G);
         for (int g = 0; g < e->G; ++g) { dims[g] = e->gl[g].nx; dims[e->G + g] = e->gl[g].ny; }
         ODINN_CUDA(e, cudaMemcpy(e->d_ad_dims, dims.data(), sizeof(int) * 2 * e->G, cudaMemcpyHostToDevice));
@@ -271,20 +272,29 @@ static int solve_bs3_t(odinn_ensemble* e, int n_snap, const double* t, double re
             ODINN_CHECK_LAUNCH(e);
             ad_reduce_chunks<<<e->G, AD_NT, 0, e->stream>>>(ad_partial, nchunk, e->d_S);  // per-glacier Σ (fixed order)
             ODINN_CHECK_LAUNCH(e);
-            ODINN_CUDA(e, cudaMemsetAsync(d_active, 0, sizeof(int), e->stream));
+            ODINN_CUDA(e, cudaMemsetAsync(d_active, 0, 2 * sizeof(int), e->stream));
             ad_control<<<gb, 128, 0, e->stream>>>(st, e->d_S, d_nx, d_ny, e->G, d_active);
             ODINN_CHECK_LAUNCH(e);
-            ad_commit<T><<<egrid, AD_NT, 0, e->stream>>>(descs, st, H, Hn, k1, k4);
-            ODINN_CHECK_LAUNCH(e);
-            ODINN_CUDA(e, cudaMemcpyAsync(e->h_ad_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            ODINN_CUDA(e, cudaMemcpyAsync(e->h_ad_active, d_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
-            if (*e->h_ad_active == 0) break;
+            if (e->h_ad_active[1] == 0) {
+                // every glacier accepted (the ones already at the tstop took h = 0: H_new == H and k4 == k1 bit for bit): the
+                // commit is a pointer swap instead of a 4 words/cell copy
+                std::swap(H, Hn);
+                std::swap(k1, k4);
+            } else {
+                ad_commit<T><<<egrid, AD_NT, 0, e->stream>>>(descs, st, H, Hn, k1, k4);
+                ODINN_CHECK_LAUNCH(e);
+            }
+            if (e->h_ad_active[0] == 0) break;
         }
         int mb_applied = 0;
         if ((rc = mb_apply_step(e, j, H, &mb_applied))) return rc;   // mass-balance callback at the end of its window
         if (mb_applied && (rc = rhs_planes(e, H, k1))) return rc;    // u was modified by the callback: the FSAL slope is stale
         ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, j), H, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     }
+    if ((void*)H != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H
+        ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], H, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     if (steps_out || rejected_out) {
         std::vector<AdState> hs(e->G);
         ODINN_CUDA(e, cudaMemcpyAsync(hs.data(), st, sizeof(AdState) * e->G, cudaMemcpyDeviceToHost, e->stream));
