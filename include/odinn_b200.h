@@ -177,7 +177,8 @@ int odinn_host_unregister(odinn_ensemble* e, void* host);
  * simulate_iceflow_UDE! -> solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops)) with saveat = tstops
  * (src/simulations/inversions/inversion_utils.jl:551-572, 584-610, tstops :487-495).  The integrator is a
  * user parameter in the reference (params.solver.solver); offered here: explicit Euler and SSPRK(3,3), each
- * stage fused into the RHS kernel. */
+ * stage fused into the RHS kernel.  The launches of one tstop interval are captured once into a CUDA graph and replayed per
+ * interval (step sizes from a device table, so non-uniform tstops need no re-capture); ODINN_NO_GRAPH=1 disables it. */
 int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double* t, int nsub);
 /* Adaptive forward solve with tstops: replaces solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops), solver;
  * reltol, abstol, maxiters, saveat = tstops) (src/simulations/inversions/inversion_utils.jl:559-568; solver choice
