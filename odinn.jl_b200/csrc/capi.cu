@@ -1074,6 +1074,8 @@ int odinn_fwd_adj_batch_host(odinn_ensemble* e, const void* const* H, const void
         e->bpack_dirty = false;
     }
     // chunks of ~2 M cells: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap
+    // (A ramped schedule -- smaller first and last chunks to shorten the pipeline's fill and drain -- was measured slower, 5.17 vs
+    // 5.37 G cell-steps/s: copies below ~32 MiB lose more PCIe efficiency than the shorter ends gain; profiles/r01_v6_sweep.txt.)
     const long long chunk_cells = e->batch_chunk_cells;
     std::vector<int> cstart{0};
     {
