@@ -111,7 +111,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region (the sampler itself starts earlier, nvidia-smi needs ~0.3 s to come up)."""
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -119,10 +123,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[i0:(None if i1 is None else i1 + 1)] or self.rows[i0:] or self.rows
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
@@ -307,11 +312,12 @@ def run_b200(args, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
-    for i in range(args.warmup):
-        step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step(i)
+    m0 = sampler.mark()
     l0 = ens.launch_count
     ms = timed(step, args.steps)
     launches = ens.launch_count - l0
@@ -324,7 +330,7 @@ def run_b200(args, rank, local_rank, world):
     if e2e_steps > 0:  # (--e2e-steps 0: profiling runs that want the resident launches only)
         ens.fwd_adj_batch_host(pH, pL, pdH, pV, S)
         ms_e2e = timed(lambda i: ens.fwd_adj_batch_host(pH, pL, pdH, pV, S), e2e_steps) / e2e_steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, sampler.mark()) if rank == 0 else None
 
     value = world * cells_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * cells_per_step / (ms_e2e * 1e-3) if e2e_steps > 0 else None
