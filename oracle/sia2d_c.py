@@ -86,3 +86,40 @@ def vjp(lam, H, B, dx, dy, ph, A, dtype=np.float64, want_H=True, want_field=Fals
        C.c_void_p(out.ctypes.data if want_H else None), C.byref(S), C.c_void_p(fld.ctypes.data if want_field else None),
        C.c_void_p(work.ctypes.data), C.byref(p))
     return out, S.value, fld
+
+
+def solve_fixed(H0, B, dx, dy, ph, A, t, nsub=8, method="ssprk3", dtype=np.float64):
+    """oracle.sia2d_numpy.solve_forward("euler" | "ssprk3") as one C loop: returns the (n_t, nx, ny) snapshots
+    (each [j] a column-major (nx, ny) matrix)."""
+    H0 = np.asfortranarray(H0, dtype=dtype)
+    B = np.asfortranarray(B, dtype=dtype)
+    nx, ny = H0.shape
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.empty((t.size, ny, nx), dtype=dtype)  # plane j, C order (ny, nx) == column-major (nx, ny)
+    work = np.empty((nx - 1) * (ny - 1) + 3 * nx * ny, dtype=dtype)
+    p, keep = _par(dx, dy, ph, A, dtype)
+    fn = lib().sia2d_solve_fixed_f64 if dtype == np.float64 else lib().sia2d_solve_fixed_f32
+    fn(C.c_int(nx), C.c_int(ny), C.c_void_p(H0.ctypes.data), C.c_void_p(B.ctypes.data), C.byref(p), C.c_int(t.size),
+       C.c_void_p(t.ctypes.data), C.c_int(nsub), C.c_int({"euler": 0, "ssprk3": 1}[method]), C.c_void_p(out.ctypes.data),
+       C.c_void_p(work.ctypes.data))
+    return [out[j].T for j in range(t.size)]
+
+
+def grad_discrete(B, dx, dy, ph, A, t, Hs, Href, masks, dtype=np.float64):
+    """oracle.sia2d_numpy.loss_and_grad_discrete for a glacier-wide law as one C loop: returns (loss, Ssum, lambda(t_0))
+    with d(theta) = (dA/dtheta) * Ssum."""
+    B = np.asfortranarray(B, dtype=dtype)
+    nx, ny = B.shape
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    pack = lambda arrs: np.ascontiguousarray(np.stack([np.asarray(a, dtype=dtype).T for a in arrs]))
+    hs, hr = pack(Hs), pack(Href)
+    w = pack([np.asarray(m, dtype=np.float64) / float(nx * ny) for m in masks])
+    lam = np.empty((ny, nx), dtype=dtype)
+    work = np.empty(4 * (nx - 1) * (ny - 1) + nx * ny, dtype=dtype)
+    loss, Ssum = C.c_double(0.0), C.c_double(0.0)
+    p, keep = _par(dx, dy, ph, A, dtype)
+    fn = lib().sia2d_grad_discrete_f64 if dtype == np.float64 else lib().sia2d_grad_discrete_f32
+    fn(C.c_int(nx), C.c_int(ny), C.c_void_p(B.ctypes.data), C.byref(p), C.c_int(t.size), C.c_void_p(t.ctypes.data),
+       C.c_void_p(hs.ctypes.data), C.c_void_p(hr.ctypes.data), C.c_void_p(w.ctypes.data), C.byref(loss), C.byref(Ssum),
+       C.c_void_p(lam.ctypes.data), C.c_void_p(work.ctypes.data))
+    return loss.value, Ssum.value, lam.T

@@ -206,6 +206,72 @@ void FN(sia2d_vjp)(int nx, int ny, const REAL* lam, const REAL* H, const REAL* B
     if (S) *S = Sacc;
 }
 
+/* Fixed-step forward solve with tstops, saveat = tstops: the loop of oracle/sia2d_numpy.py::solve_forward for
+ * method 0 = explicit Euler, 1 = Shu-Osher SSPRK(3,3) (the reference's solve call: src/simulations/inversions/
+ * inversion_utils.jl:551-572 with tstops :487-495; the integrator is a user parameter there).  Same operation order as the
+ * NumPy loop:  u1 = H + h f(H);  u2 = 0.75 H + 0.25 (u1 + h f(u1));  H = H/3 + (2/3)(u2 + h f(u2)).
+ * out: n_t planes of nx*ny (out[0] = H0).  work: (nx-1)*(ny-1) + 3*nx*ny REALs. */
+void FN(sia2d_solve_fixed)(int nx, int ny, const REAL* H0, const REAL* B, const FN(sia2d_par) * P, int n_t, const double* t,
+                           int nsub, int method, REAL* out, REAL* work) {
+    const long N = (long)nx * ny;
+    REAL *wk = work, *f = work + (long)(nx - 1) * (ny - 1), *u1 = f + N, *u2 = u1 + N;
+    REAL* H = out;
+    for (long k = 0; k < N; ++k) H[k] = H0[k];
+    for (int j = 1; j < n_t; ++j) {
+        REAL* Hn = out + (long)j * N;
+        for (long k = 0; k < N; ++k) Hn[k] = H[k];
+        H = Hn;
+        const REAL h = (REAL)((t[j] - t[j - 1]) / nsub);
+        for (int s = 0; s < nsub; ++s) {
+            FN(sia2d_rhs)(nx, ny, H, B, f, wk, P);
+            if (method == 0) {
+#pragma omp parallel for schedule(static)
+                for (long k = 0; k < N; ++k) H[k] = H[k] + h * f[k];
+                continue;
+            }
+#pragma omp parallel for schedule(static)
+            for (long k = 0; k < N; ++k) u1[k] = H[k] + h * f[k];
+            FN(sia2d_rhs)(nx, ny, u1, B, f, wk, P);
+#pragma omp parallel for schedule(static)
+            for (long k = 0; k < N; ++k) u2[k] = (REAL)0.75 * H[k] + (REAL)0.25 * (u1[k] + h * f[k]);
+            FN(sia2d_rhs)(nx, ny, u2, B, f, wk, P);
+#pragma omp parallel for schedule(static)
+            for (long k = 0; k < N; ++k) H[k] = H[k] / (REAL)3 + ((REAL)2 / (REAL)3) * (u2[k] + h * f[k]);
+        }
+    }
+}
+
+/* DiscreteAdjoint reverse loop of SIA2D_grad_batch! (src/inverse/SIA2D/gradient.jl:191-253) for LossH(L2Sum), glacier-wide A:
+ * the loop of oracle/sia2d_numpy.py::loss_and_grad_discrete.  Hs, Href, W: n_t planes (W = is_in_glacier mask / (nx ny),
+ * gradient.jl:161; the loss weight of snapshot j is t[j] - t[j-1], 0 for j = 0).  *loss = sum_j dt_j sum W (H_j - Href_j)^2,
+ * *Ssum = sum_j dt_{j-1} S(lambda_{j-1}, H_j)  with  d(theta) = (dA/dtheta) * Ssum;  lam: nx*ny (lambda at t_0 on return).
+ * work: 4*(nx-1)*(ny-1) + nx*ny REALs. */
+void FN(sia2d_grad_discrete)(int nx, int ny, const REAL* B, const FN(sia2d_par) * P, int n_t, const double* t, const REAL* Hs,
+                             const REAL* Href, const REAL* W, double* loss, double* Ssum, REAL* lam, REAL* work) {
+    const long N = (long)nx * ny;
+    REAL* v = work + 4 * (long)(nx - 1) * (ny - 1);
+    double ell = 0.0, Sa = 0.0;
+    for (long k = 0; k < N; ++k) lam[k] = 0;
+    for (int j = n_t - 1; j >= 0; --j) {
+        const REAL *Hj = Hs + (long)j * N, *Rj = Href + (long)j * N, *Wj = W + (long)j * N;
+        const double dtH = j > 0 ? t[j] - t[j - 1] : 0.0;
+        double lj = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : lj)
+        for (long k = 0; k < N; ++k) { double d = (double)Hj[k] - (double)Rj[k]; lj += (double)Wj[k] * d * d; } /* Losses.jl:142-152 */
+        ell += dtH * lj;                                                                  /* gradient.jl:218-232 */
+        if (j == 0) break;
+        FN(sia2d_vjp)(nx, ny, lam, Hj, B, v, NULL, NULL, work, P);                        /* :235-237 */
+        const REAL dt = (REAL)(t[j] - t[j - 1]), c = (REAL)(2.0 * dtH);
+#pragma omp parallel for schedule(static)
+        for (long k = 0; k < N; ++k) lam[k] = lam[k] + dt * v[k] + c * Wj[k] * (Hj[k] - Rj[k]);  /* :242, Losses.jl:270-291 */
+        double S = 0.0;
+        FN(sia2d_vjp)(nx, ny, lam, Hj, B, NULL, &S, NULL, work, P);                       /* :245-246 (the UPDATED lambda) */
+        Sa += (double)dt * S;                                                             /* :249 */
+    }
+    *loss = ell;
+    *Ssum = Sa;
+}
+
 #undef FN
 #undef CAT
 #undef CAT_
