@@ -205,6 +205,7 @@ def cpu_grad_iteration(n, dtype, n_glaciers=1, n_t=61, nsub=8):
     data = []
     for k in range(n_glaciers):
         B, H, dx = synthetic_glacier(n, n, k)
+        H = 0.6 * H  # (GRAD_THIN of the GPU arm)
         Href = oc.solve_fixed(H, B, dx, dx, ph, 1.5 * A0, t[:3], nsub=nsub, dtype=npdt)  # (also warms the thread team)
         masks = [onp.is_in_glacier(Href[-1], 3)] * n_t
         data.append((B, H, dx, [Href[-1]] * n_t, masks))
@@ -258,6 +259,12 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------
 LAW_WIDTHS, LAW_ACTS = [1, 16, 16, 1], ["softplus", "softplus", "sigmoid"]   # BASELINE config 4: 2 hidden layers x 16
 N_THETA = sum(o * i + o for i, o in zip(LAW_WIDTHS[:-1], LAW_WIDTHS[1:]))   # 321
+
+
+# The reference's reverse loop is explicit Euler with the monthly step (gradient.jl:242): on the full 250 m cap it is unstable
+# (|lambda| overflows fp32; gradient.jl:19-24 warns about exactly this), so the gradient iteration runs on 0.6 x the cap -- the work
+# per iteration does not depend on the values.
+GRAD_THIN = 0.6
 
 
 def law_theta():
@@ -528,6 +535,7 @@ def grad_iteration_arm(ob, parallel, args, dtype, rank, local_rank, world, dist)
     for k in range(G):
         if k < nvar:
             B, H, _ = synthetic_glacier(n, n, k + 4 * rank)
+            H = GRAD_THIN * H
             ens.upload(k, _capi.FIELD_B, B)
             hH0[k].copy_(torch.from_numpy(np.ascontiguousarray(H.T.astype(npdt))))
         else:

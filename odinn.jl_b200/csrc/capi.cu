@@ -1325,7 +1325,9 @@ int odinn_set_reference(odinn_ensemble* e, int glacier, int j, int n_snap, const
     }
     int rc;
     if ((rc = alloc_plane(e, &e->href, n_snap)) || (rc = alloc_plane(e, &e->wmask, n_snap))) return rc;
+    if (e->n_ref != n_snap) e->ref_has.assign((size_t)n_snap, 0);   // (planes are zero-filled: W = 0 where no data was given)
     e->n_ref = n_snap;
+    e->ref_has[j] = 1;
     if ((rc = copy2d_ptr(e, glacier, plane_ptr(e, e->href, j), false, const_cast<void*>(Href), ld, true, e->stream)))
         return rc;
     if ((rc = copy2d_ptr(e, glacier, plane_ptr(e, e->wmask, j), false, const_cast<void*>(W), ld, true, e->stream)))
@@ -1396,6 +1398,17 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
         if ((rc = velocity_loss_term(e, j, Hj, lam, wV, e->d_loss, e->d_Ssum))) return rc;
         // dLdθ += Δt_{j-1} · VJP_θ(λ_{j-1}, H_j)                                        (:245-249)
         if ((rc = launch_vjp(e, -1, lam, Hj, nullptr, false, true, e->d_Ssum, dt, 1))) return rc;
+    }
+    {
+        // The j = 1 pass of the reference (snapshot 0 here) updates no λ but still adds its loss terms: ℓ += ℓ_1 and
+        // dLdθ += ∂ℓ∂θ[1] (gradient.jl:218-232, 252).  With the default LossH weights w_0 = 0 (safe_slice); user weights
+        // (odinn_set_loss_weights) may be nonzero there, and the forward / reverse losses must agree (gradient.jl:259).
+        const double wH0 = loss_weight_H(e, t, n_t, 0), wV0 = loss_weight_V(e, n_t, 0);
+        void* H0s = plane_ptr(e, e->snap, 0);
+        if (wH0 != 0.0 && (rc = launch_loss_seed(e, H0s, plane_ptr(e, e->href, 0), plane_ptr(e, e->wmask, 0), nullptr, nullptr,
+                                                 nullptr, 0.0, 0.0, e->d_loss, wH0, 1)))
+            return rc;
+        if ((rc = velocity_loss_term(e, 0, H0s, nullptr, wV0, e->d_loss, e->d_Ssum))) return rc;
     }
     ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
     ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + e->G, e->d_Ssum, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));

@@ -66,6 +66,7 @@ struct odinn_ensemble {
     void* wmask = nullptr;        // n_ref planes: is_in_glacier mask / (nx ny)
     void* work[2] = {nullptr, nullptr};
     int n_snap = 0, n_ref = 0;
+    std::vector<char> ref_has;    // [n_ref] snapshot j holds thickness data (odinn_set_reference was called for it): tH_ref of gradient.jl:79
     // law state (LawA(nn, params))
     void* d_theta = nullptr;
     void* d_J = nullptr;          // [G x n_theta] dA_g/dθ
@@ -181,8 +182,15 @@ int velocity_loss_term(odinn_ensemble* e, int j, const void* Hj, void* lam, doub
 // mass-balance callback of snapshot j / its adjoint (massbalance.cu); no-ops when no MB step fires at j
 int mb_apply_step(odinn_ensemble* e, int j, void* H, int* applied);
 int mb_adjoint_step(odinn_ensemble* e, int j, void* lam, const void* Hj);
+// Default LossH weight of snapshot j: ΔtH = diff(tH_ref) indexed by the position of t_j inside tH_ref -- the time since the PREVIOUS
+// snapshot that holds thickness data, 0 for the first datum (safe_slice) and for tstops without data (gradient.jl:79-80, 144-149).
 inline double loss_weight_H(const odinn_ensemble* e, const double* t, int n_t, int j) {
-    return (int)e->loss_wH.size() == n_t ? e->loss_wH[j] : (j > 0 ? t[j] - t[j - 1] : 0.0);
+    if ((int)e->loss_wH.size() == n_t) return e->loss_wH[j];
+    if ((int)e->ref_has.size() != n_t) return j > 0 ? t[j] - t[j - 1] : 0.0;
+    if (!e->ref_has[j]) return 0.0;
+    for (int p = j - 1; p >= 0; --p)
+        if (e->ref_has[p]) return t[j] - t[p];
+    return 0.0;
 }
 inline double loss_weight_V(const odinn_ensemble* e, int n_t, int j) { return (int)e->loss_wV.size() == n_t ? e->loss_wV[j] : 0.0; }
 // loss_dst[g] (+)= wloss * sum W (H - Href)^2 ; optionally lam_out = lam_in + dt * v + cseed * W * (H - Href)

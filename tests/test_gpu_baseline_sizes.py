@@ -158,7 +158,10 @@ def test_config2_61_snapshot_forward_and_discrete_adjoint(ob, dtype):
 
     nx = ny = 500
     g0 = o.rough_bed_glacier(nx, ny)
-    g = o.Glacier(B=_r(g0.B, dtype), dx=g0.dx, dy=g0.dy, H0=_r(g0.H0, dtype))
+    # 0.6 x the 250 m cap: the reference's reverse loop is explicit Euler with the MONTHLY step (gradient.jl:242), stable only while
+    # dt * rho(dSIA/dH) < 2.  On the full-thickness cap it is not (|lambda| reaches 1e28 and a 1e-13 perturbation of the snapshots
+    # flips the sign of d(theta) in the fp64 oracle -- the situation gradient.jl:19-24 warns about), so no two implementations agree there.
+    g = o.Glacier(B=_r(g0.B, dtype), dx=g0.dx, dy=g0.dy, H0=_r(0.6 * g0.H0, dtype))
     t = np.linspace(2010.0, 2015.0, 61)
     ph = o.Phys(**PH)
     A_true, A_inv, nsub = 4.0e-18, A0, 8
