@@ -2,46 +2,16 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "ensemble.cuh"
-#include "sia2d_march.cuh"
-#include "sia2d_march2.cuh"
-#ifndef ODINN_NO_BULK
-#include "sia2d_bulk.cuh"
-#endif
-#include "sia2d_cont.cuh"
+#include "launch.cuh"
+#include "sia2d_march2.cuh"  // (geometry constants of the work-item tables; no kernel is instantiated here)
 #include "timeloop.cuh"
 #include "sia2d_law.cuh"
-
-// Template dispatch on (n == 3 && C == 0, gridded A, eta0 == 1).  ODINN_BENCH_ONLY (developer builds for kernel
-// tuning) instantiates the benchmark configuration only; every other configuration then fails loudly.
-#ifdef ODINN_BENCH_ONLY
-#define ODINN_DISPATCH(L2)                                                                            \
-    do {                                                                                              \
-        if (e->cubic && !e->a_gridded) L2(true, false);                                               \
-        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (n = 3, C = 0, scalar A only)"); \
-    } while (0)
-#define ODINN_ETA(L3, CUB, AF)                                                                        \
-    do {                                                                                              \
-        if (eta1) L3(CUB, AF, true);                                                                  \
-        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (eta0 = 1 only)");       \
-    } while (0)
-#else
-#define ODINN_DISPATCH(L2)                                                                            \
-    do {                                                                                              \
-        if (e->cubic) {                                                                               \
-            if (e->a_gridded) L2(true, true); else L2(true, false);                                   \
-        } else {                                                                                      \
-            if (e->a_gridded) L2(false, true); else L2(false, false);                                 \
-        }                                                                                             \
-    } while (0)
-#define ODINN_ETA(L3, CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
-#endif
 
 namespace odinn {
 
 thread_local std::string g_create_error;
 
-static int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1) {
+int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes) {
     if (*p) return ODINN_OK;
     size_t bytes = (size_t)e->total * e->esize * n_planes;
     cudaError_t st = cudaMalloc(p, bytes);
@@ -98,15 +68,6 @@ static inline char* plane_ptr(odinn_ensemble* e, void* base, long long plane_ind
     return (char*)base + (size_t)plane_index * (size_t)e->total * e->esize;
 }
 
-__global__ void law_theta_reduce_scaled(const double* __restrict__ block_partial, int n_tiles, int n_params,
-                                        double* __restrict__ out, double scale, int accumulate) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_params) return;
-    double s = 0.0;
-    for (int t = 0; t < n_tiles; ++t) s += block_partial[(long long)t * n_params + k];  // tile order: deterministic
-    out[k] = (accumulate ? out[k] : 0.0) + scale * s;
-}
-
 // ---- per-cell laws (sia2d_law.cuh) --------------------------------------------------------------------------------
 
 static inline CellLaw* law_of(odinn_ensemble* e) { return static_cast<CellLaw*>(e->law_cfg); }
@@ -120,211 +81,10 @@ static void law_refresh_phys(odinn_ensemble* e) {
     lw->q = e->phys.q;
 }
 
-// Pass 1 over the tiles of glaciers [g0, g1) (g0 < 0: all): node planes D (and alpha, beta when partials).
-template <typename T>
-static int launch_law_nodes_t(odinn_ensemble* e, int g0, int g1, const void* H, bool partials) {
-    const CellLaw lw = *law_of(e);
-    int t0 = 0, nt = e->n_tiles;
-    if (g0 >= 0) {
-        t0 = e->gl[g0].tile0;
-        nt = e->gl[g1 - 1].tile0 + e->gl[g1 - 1].ntx * e->gl[g1 - 1].nty - t0;
-    }
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    int wmax = 0;
-    for (int L = 0; L <= lw.arch.n_layers; ++L) wmax = std::max(wmax, lw.arch.widths[L]);
-    const bool w16 = wmax <= 16;  // register-resident evaluator: compile-time width bound 16 or 32
-#define LN(TT, RR, PP)                                                                                                         \
-    do {                                                                                                                       \
-        const size_t smem = sizeof(RR) * lw.arch.n_params;                                                                     \
-        if (w16) law_nodes_kernel<TT, RR, PP, 16><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, \
-                     (const TT*)H, B, (TT*)e->lawD, PP ? (TT*)e->lawAl : nullptr, PP ? (TT*)e->lawBe : nullptr);               \
-        else law_nodes_kernel<TT, RR, PP, 32><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta,     \
-                     (const TT*)H, B, (TT*)e->lawD, PP ? (TT*)e->lawAl : nullptr, PP ? (TT*)e->lawBe : nullptr);               \
-    } while (0)
-    if (!partials) LN(T, T, false);
-    else if (lw.kind == LAW_U) LN(T, T, true);   // analytic partials ride along the forward evaluation: the ensemble's precision
-    else LN(T, double, true);                    // LawY: one-sided difference of the network (target_D_hybrid.jl:58-73): fp64
-#undef LN
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
-static int launch_law_nodes(odinn_ensemble* e, int g0, int g1, const void* H, bool partials) {
-    int rc;
-    if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = alloc_plane(e, &e->lawD))) return rc;
-    if (partials && ((rc = alloc_plane(e, &e->lawAl)) || (rc = alloc_plane(e, &e->lawBe)))) return rc;
-    if ((rc = sync_descs(e))) return rc;
-    return e->dtype == ODINN_F32 ? launch_law_nodes_t<float>(e, g0, g1, H, partials) : launch_law_nodes_t<double>(e, g0, g1, H, partials);
-}
-
-// Pass 3 for glaciers [g0, g1): d_law_dtheta[g] = (accumulate ? old : 0) + scale * sum_nodes D_adj s dNN/dtheta.
-template <typename T>
-static int launch_law_theta_t(odinn_ensemble* e, int g0, int g1, const void* H, double scale, int accumulate) {
-    const CellLaw lw = *law_of(e);
-    const int np = lw.arch.n_params;
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    int NA = 0, NZ = 0, wmax = 0;
-    for (int L = 0; L < lw.arch.n_layers; ++L) { NA += lw.arch.widths[L]; NZ += lw.arch.widths[L + 1]; }
-    for (int L = 0; L <= lw.arch.n_layers; ++L) wmax = std::max(wmax, lw.arch.widths[L]);
-    const size_t smem = (sizeof(double) + sizeof(int2)) * (size_t)np + sizeof(T) * (((size_t)np + 3) / 4 * 4 + (size_t)(NA + NZ) * LAW_PITCH);
-    if (smem > 220 * 1024) return fail(e, ODINN_EARG, "per-cell law too large for the shared-memory pullback (reduce depth x width)");
-    const bool w16 = wmax <= 16;
-    {
-        static size_t attr16 = 0, attr32 = 0;  // opt in to > 48 KB dynamic shared memory once per size
-        size_t& cur = w16 ? attr16 : attr32;
-        if (smem > cur) {
-            if (w16) ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cur = smem;
-        }
-    }
-    for (int g = g0; g < g1; ++g) {  // one glacier at a time: the block partials are [tiles of one glacier x n_theta]
-        const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
-        if (w16)
-            law_theta_kernel<T, T, 16><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
-                                                                    (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
-        else
-            law_theta_kernel<T, T, 32><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
-                                                                    (const T*)e->plane[ODINN_FIELD_VJP_A], e->d_law_partial);
-        ODINN_CHECK_LAUNCH(e);
-        law_theta_reduce_scaled<<<div_up(np, 128), 128, 0, e->stream>>>(e->d_law_partial, nt, np, e->d_law_dtheta + (size_t)g * np,
-                                                                       scale, accumulate);
-        ODINN_CHECK_LAUNCH(e);
-    }
-    return ODINN_OK;
-}
-
-static int launch_law_theta(odinn_ensemble* e, int g0, int g1, const void* H, double scale = 1.0, int accumulate = 0) {
-    if (g0 < 0) { g0 = 0; g1 = e->G; }
-    return e->dtype == ODINN_F32 ? launch_law_theta_t<float>(e, g0, g1, H, scale, accumulate)
-                                 : launch_law_theta_t<double>(e, g0, g1, H, scale, accumulate);
-}
-
 // ---- F1 launch: out = SIA2D(Hin)   or, with a stage,  out = sa·U0 + sb·(Hin + sdt·SIA2D(Hin)) ----------------
-
-struct Stage {
-    const void* U0;
-    double sa, sb, sdt;
-    const double* tab = nullptr;   // graph replay: device table of stage coefficients (offset to this stage) + interval counter
-    const int* interval = nullptr;
-};
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 __global__ void advance_interval_kernel(int* p) { *p += 1; }
-
-// fp32, two columns per lane (sia2d_march2.cuh)
-static int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
-    PhysDev<float> ph = make_phys<float>(e->phys);
-    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
-    int i0 = 0, n_items = e->n_items2;
-    if (g0 >= 0) {
-        i0 = e->gl[g0].item20;
-        n_items = e->gl[g1 - 1].item20 + e->gl[g1 - 1].n_items2 - i0;
-    }
-    const int4* items = e->d_items2 + i0;
-    const float* H = (const float*)Hin;
-    const float* B = (const float*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
-    const float* Af = (const float*)e->plane[ODINN_FIELD_A];
-    float* dH = (float*)out;
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    const float* U0 = st ? (const float*)st->U0 : nullptr;
-    const float sa = st ? (float)st->sa : 0.f, sb = st ? (float)st->sb : 0.f, sdt = st ? (float)st->sdt : 0.f;
-    const double* stab = st ? st->tab : nullptr;
-    const int* sint = st ? st->interval : nullptr;
-    const bool bulk = (e->march == 3) && !packed;  // bulk copies need the padded (16-byte aligned) layout
-    dim3 grid(div_up(n_items, bulk ? BK_WARPS : MARCH2_WARPS)), block((bulk ? BK_WARPS : MARCH2_WARPS) * 32);
-#define L(CUB, AF, E1, STG)                                                                                              \
-    do {                                                                                                                 \
-        if (bulk) {                                                                                                      \
-            constexpr size_t smem = bulk_smem_bytes<2 + (AF ? 1 : 0) + (STG ? 1 : 0)>();                                  \
-            static bool attr_set = false;                                                                                \
-            if (!attr_set) {                                                                                             \
-                ODINN_CUDA(e, cudaFuncSetAttribute(sia2d_rhs_bulk<CUB, AF, E1, STG>,                                      \
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-                attr_set = true;                                                                                         \
-            }                                                                                                            \
-            sia2d_rhs_bulk<CUB, AF, E1, STG><<<grid, block, smem, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph,   \
-                                                                               U0, sa, sb, sdt);                         \
-        } else {                                                                                                         \
-            sia2d_rhs_march2<CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph,    \
-                                                                              U0, sa, sb, sdt, stab, sint);              \
-        }                                                                                                                \
-    } while (0)
-#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
-#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
-    ODINN_DISPATCH(L2);
-#undef L2
-#undef L3
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
-template <typename T>
-static int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs + (packed ? e->G : 0);
-    const int4* items = e->d_items + i0;
-    const T* H = (const T*)Hin;
-    const T* B = (const T*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
-    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
-    T* dH = (T*)out;
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    const T* U0 = st ? (const T*)st->U0 : nullptr;
-    const T sa = st ? (T)st->sa : T(0), sb = st ? (T)st->sb : T(0), sdt = st ? (T)st->sdt : T(0);
-    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
-    const double* stab = st ? st->tab : nullptr;
-    const int* sint = st ? st->interval : nullptr;
-#define L(CUB, AF, E1, STG) \
-    sia2d_rhs_march<T, CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, T(0), 0, stab, sint)
-#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
-#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
-    ODINN_DISPATCH(L2);
-#undef L2
-#undef L3
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
-template <typename T>
-static int launch_rhs_law_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const int4* items = e->d_items + i0;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const T* Dn = (const T*)e->lawD;
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    const T* U0 = st ? (const T*)st->U0 : nullptr;
-    const T sa = st ? (T)st->sa : T(0), sb = st ? (T)st->sb : T(0), sdt = st ? (T)st->sdt : T(0);
-    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
-#define LL(E1, STG) sia2d_rhs_march<T, true, true, E1, STG, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)Hin, B, Dn, (T*)out, ph, U0, sa, sb, sdt)
-    if (eta1) { if (st) LL(true, true); else LL(true, false); }
-    else { if (st) LL(false, true); else LL(false, false); }
-#undef LL
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
-template <typename T>
-static int launch_vjp_law_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out, bool wH, bool wS) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const int4* items = e->d_items + i0;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    T* vjpA = wS ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
-    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
-#define LL(WH, WS, E1) sia2d_vjp_march<T, true, true, WH, WS, E1, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)lam, (const T*)H, B, (const T*)e->lawD, (T*)out, vjpA, e->d_partial + i0, ph, (const T*)e->lawAl, (const T*)e->lawBe)
-#define LL2(E1) do { if (wH && wS) LL(true, true, E1); else if (wH) LL(true, false, E1); else LL(false, true, E1); } while (0)
-    if (eta1) LL2(true); else LL2(false);
-#undef LL2
-#undef LL
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
 
 // Glaciers [g0, g1); g0 < 0: whole ensemble.  `packed` selects the packed descriptor table (host-batch path).
 static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
@@ -348,108 +108,6 @@ static int launch_rhs_range(odinn_ensemble* e, int g0, int g1, const void* Hin, 
 }
 static int launch_rhs(odinn_ensemble* e, int g, const void* Hin, void* out, const Stage* st = nullptr) {
     return launch_rhs_range(e, g, g + 1, Hin, out, st, false);
-}
-
-// ---- A1 / A2 launch --------------------------------------------------------------------------------------------
-
-// fp32, two columns per lane (sia2d_march2.cuh).  Partials are indexed by the two-column work items.
-// dH_out != nullptr (with wH && wS, no bulk variant): the fused F1 + A1 + A2 pass.
-static int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void* H_, void* out_, bool wH, bool wS,
-                       bool packed, void* dH_out = nullptr) {
-    PhysDev<float> ph = make_phys<float>(e->phys);
-    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
-    int i0 = 0, n_items = e->n_items2;
-    if (g0 >= 0) {
-        i0 = e->gl[g0].item20;
-        n_items = e->gl[g1 - 1].item20 + e->gl[g1 - 1].n_items2 - i0;
-    }
-    const float* lam = (const float*)lam_;
-    const float* H = (const float*)H_;
-    const float* B = (const float*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
-    const float* Af = (const float*)e->plane[ODINN_FIELD_A];
-    float* out = (float*)out_;
-    float* vjpA = (wS && e->a_gridded) ? (float*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
-    double* partial = e->d_partial + i0;
-    const int4* items = e->d_items2 + i0;
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    const bool bulk = (e->march == 3) && !packed;
-    dim3 grid(div_up(n_items, bulk ? BK_WARPS : MARCH2_WARPS)), block((bulk ? BK_WARPS : MARCH2_WARPS) * 32);
-#define L(CUB, AF, WH, WS, E1)                                                                                           \
-    do {                                                                                                                 \
-        if (bulk) {                                                                                                      \
-            constexpr size_t smem = bulk_smem_bytes<3 + (AF ? 1 : 0)>();                                                  \
-            static bool attr_set = false;                                                                                \
-            if (!attr_set) {                                                                                             \
-                ODINN_CUDA(e, cudaFuncSetAttribute(sia2d_vjp_bulk<CUB, AF, WH, WS, E1>,                                   \
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-                attr_set = true;                                                                                         \
-            }                                                                                                            \
-            sia2d_vjp_bulk<CUB, AF, WH, WS, E1><<<grid, block, smem, e->stream>>>(descs, items, n_items, lam, H, B, Af,   \
-                                                                                  out, vjpA, partial, ph);               \
-        } else {                                                                                                         \
-            sia2d_vjp_march2<CUB, AF, WH, WS, E1><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af,    \
-                                                                                 out, vjpA, partial, ph);                \
-        }                                                                                                                \
-    } while (0)
-#define LF(CUB, AF, E1)                                                                                                  \
-    sia2d_vjp_march2<CUB, AF, true, true, E1, true><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af,  \
-                                                                                   out, vjpA, partial, ph, (float*)dH_out)
-#define L3(CUB, AF, E1)                         \
-    do {                                        \
-        if (dH_out) LF(CUB, AF, E1);                \
-        else if (wH && wS) L(CUB, AF, true, true, E1);   \
-        else if (wH) L(CUB, AF, true, false, E1);   \
-        else L(CUB, AF, false, true, E1);           \
-    } while (0)
-#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
-    ODINN_DISPATCH(L2);
-#undef L2
-#undef L3
-#undef LF
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
-template <typename T>
-static int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const void* H_, void* out_, bool wH,
-                        bool wS, bool packed, void* dH_out = nullptr) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs + (packed ? e->G : 0);
-    const T* lam = (const T*)lam_;
-    const T* H = (const T*)H_;
-    const T* B = (const T*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
-    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
-    T* out = (T*)out_;
-    T* vjpA = (wS && e->a_gridded) ? (T*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
-    double* partial = e->d_partial + i0;
-    const int4* items = e->d_items + i0;
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
-#define L(CUB, AF, WH, WS, E1) \
-    sia2d_vjp_march<T, CUB, AF, WH, WS, E1><<<grid, block, 0, e->stream>>>(descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph)
-    // fused F1 + A1 + A2 (cubic form, fp64 only: the fp32 product path is the two-column kernel)
-#define LF(AF, E1)                                                                                                            \
-    do {                                                                                                                      \
-        if constexpr (std::is_same<T, double>::value)                                                                         \
-            sia2d_vjp_march<T, true, AF, true, true, E1, false, true><<<grid, block, 0, e->stream>>>(                         \
-                descs, items, n_items, lam, H, B, Af, out, vjpA, partial, ph, nullptr, nullptr, (T*)dH_out);                  \
-    } while (0)
-#define L3(CUB, AF, E1)                         \
-    do {                                        \
-        if (dH_out && CUB) LF(AF, E1);              \
-        else if (wH && wS) L(CUB, AF, true, true, E1);   \
-        else if (wH) L(CUB, AF, true, false, E1);   \
-        else L(CUB, AF, false, true, E1);           \
-    } while (0)
-#define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
-    ODINN_DISPATCH(L2);
-#undef L2
-#undef L3
-#undef LF
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
 }
 
 // Glaciers [g0, g1); g0 < 0: whole ensemble.  S_dst: where the per-glacier sums go (d_S or an accumulator), scaled by `scale`.
@@ -508,21 +166,6 @@ static int launch_vjp(odinn_ensemble* e, int g, const void* lam, const void* H, 
 
 // ---- continuous VJPs (sia2d_cont.cuh) ---------------------------------------------------------------------------
 
-template <typename T>
-static int launch_vjpc_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out) {
-    PhysDev<T> ph = make_phys<T>(e->phys);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    const int4* items = e->d_items + i0;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    const T* Af = (const T*)e->plane[ODINN_FIELD_A];
-    dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
-#define L(CUB, AF) sia2d_vjpc_march<T, CUB, AF><<<grid, block, 0, e->stream>>>(descs, items, n_items, (const T*)lam, (const T*)H, B, Af, (T*)out, ph)
-    ODINN_DISPATCH(L);
-#undef L
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
-}
-
 // out = (dSIA/dH)^T lam, continuous form (adjoint.jl:442-555).  g < 0: whole ensemble.
 static int launch_vjpc(odinn_ensemble* e, int g, const void* lam, const void* H, void* out) {
     int rc;
@@ -532,36 +175,6 @@ static int launch_vjpc(odinn_ensemble* e, int g, const void* lam, const void* H,
     int i0 = 0, ni = e->n_items;
     if (g >= 0) { i0 = e->gl[g].item0; ni = e->gl[g].n_items; }
     return e->dtype == ODINN_F32 ? launch_vjpc_t<float>(e, i0, ni, lam, H, out) : launch_vjpc_t<double>(e, i0, ni, lam, H, out);
-}
-
-template <typename T>
-static int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst, double scale, int accumulate) {
-    odinn_phys p1 = e->phys;
-    p1.C = 0.0;  // ∂D/∂A carries no sliding term (target_A.jl:71-72)
-    PhysDev<T> ph = make_phys<T>(p1);
-    const bool cubic = (p1.n == 3.0);
-    const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
-    int i0 = 0, ni = e->n_items, t0 = 0, nt = e->n_tiles;
-    if (g >= 0) {
-        i0 = e->gl[g].item0; ni = e->gl[g].n_items;
-        t0 = e->gl[g].tile0; nt = e->gl[g].ntx * e->gl[g].nty;
-    }
-    const int4* items = e->d_items + i0;
-    const T* B = (const T*)e->plane[ODINN_FIELD_B];
-    T* scratch = (T*)e->work[0];
-    const bool eta1 = (e->phys.eta0 == 1.0);
-    dim3 grid(div_up(ni, MARCH_WARPS)), block(MARCH_WARPS * 32);
-#define LU(CUB, E1) sia2d_rhs_march<T, CUB, false, E1, false><<<grid, block, 0, e->stream>>>(descs, items, ni, (const T*)H, B, nullptr, scratch, ph, nullptr, T(0), T(0), T(0), T(1), 1)
-    if (cubic) { if (eta1) LU(true, true); else LU(true, false); }
-    else { if (eta1) LU(false, true); else LU(false, false); }
-#undef LU
-    ODINN_CHECK_LAUNCH(e);
-    dot_inner_kernel<T><<<nt, NT, 0, e->stream>>>(descs, e->d_tiles + t0, (const T*)lam, scratch, e->d_partial + t0);
-    ODINN_CHECK_LAUNCH(e);
-    if (g >= 0) reduce_scaled_kernel<<<1, NT, 0, e->stream>>>(e->d_tile_start + g, e->d_partial, S_dst + g, scale, accumulate);
-    else reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, e->d_partial, S_dst, scale, accumulate);
-    ODINN_CHECK_LAUNCH(e);
-    return ODINN_OK;
 }
 
 // S[g] = Σ λ ⊙ pad(∇·(avg(∂A_spatial)·clamp(∇S)))  (adjoint.jl:582-662, glacier-wide law).  g < 0: whole ensemble.

@@ -1,0 +1,64 @@
+// Kernel launchers of libodinn_b200.so, one translation unit per kernel family so that the host logic (capi.cu) and the
+// families compile in parallel and an edit of one does not rebuild the others:
+//   launch_march2.cu            fp32 two-column marching kernels (sia2d_march2.cuh) + the 2-D TMA ring variant (sia2d_tma.cuh)
+//   launch_march_f32.cu / _f64  one-column marching kernels (sia2d_march.cuh), continuous VJPs (sia2d_cont.cuh), D-field mode
+//   launch_law.cu               per-cell law node pass and theta pullback (sia2d_law.cuh)
+#pragma once
+#include "ensemble.cuh"
+
+// Template dispatch on (n == 3 && C == 0, gridded A, eta0 == 1).  ODINN_BENCH_ONLY (developer builds for kernel
+// tuning) instantiates the benchmark configuration only; every other configuration then fails loudly.
+#ifdef ODINN_BENCH_ONLY
+#define ODINN_DISPATCH(L2)                                                                            \
+    do {                                                                                              \
+        if (e->cubic && !e->a_gridded) L2(true, false);                                               \
+        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (n = 3, C = 0, scalar A only)"); \
+    } while (0)
+#define ODINN_ETA(L3, CUB, AF)                                                                        \
+    do {                                                                                              \
+        if (eta1) L3(CUB, AF, true);                                                                  \
+        else return fail(e, ODINN_ESTATE, "this is an ODINN_BENCH_ONLY build (eta0 = 1 only)");       \
+    } while (0)
+#else
+#define ODINN_DISPATCH(L2)                                                                            \
+    do {                                                                                              \
+        if (e->cubic) {                                                                               \
+            if (e->a_gridded) L2(true, true); else L2(true, false);                                   \
+        } else {                                                                                      \
+            if (e->a_gridded) L2(false, true); else L2(false, false);                                 \
+        }                                                                                             \
+    } while (0)
+#define ODINN_ETA(L3, CUB, AF) do { if (eta1) L3(CUB, AF, true); else L3(CUB, AF, false); } while (0)
+#endif
+
+namespace odinn {
+
+// F1 with a fused Runge-Kutta stage:  out = sa U0 + sb (Hin + sdt SIA2D(Hin))
+struct Stage {
+    const void* U0;
+    double sa, sb, sdt;
+    const double* tab = nullptr;   // graph replay: device table of stage coefficients (offset to this stage) + interval counter
+    const int* interval = nullptr;
+};
+
+int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);
+
+// fp32, two columns per lane.  g0 < 0: whole ensemble.  `packed`: packed descriptor table / packed B of the host-batch path.
+int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed);
+int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS, bool packed,
+                void* dH_out = nullptr);
+
+// one column per lane (fp32 generation 1 and fp64); items [i0, i0 + n_items)
+template <typename T> int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed);
+template <typename T> int launch_rhs_law_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st);
+template <typename T> int launch_vjp_law_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out, bool wH, bool wS);
+template <typename T> int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out, bool wH, bool wS,
+                                       bool packed, void* dH_out = nullptr);
+template <typename T> int launch_vjpc_t(odinn_ensemble* e, int i0, int n_items, const void* lam, const void* H, void* out);
+template <typename T> int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst, double scale, int accumulate);
+
+// per-cell laws: node pass (D, and alpha / beta when partials) and theta pullback for glaciers [g0, g1) (g0 < 0: all)
+int launch_law_nodes(odinn_ensemble* e, int g0, int g1, const void* H, bool partials);
+int launch_law_theta(odinn_ensemble* e, int g0, int g1, const void* H, double scale = 1.0, int accumulate = 0);
+
+}  // namespace odinn

@@ -650,7 +650,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 }
 
 // Second stage of the A2 reduction: one CTA per glacier sums its work items' partials in a fixed order.
-__global__ void __launch_bounds__(NT)
+static __global__ void __launch_bounds__(NT)
 reduce_items_kernel(const int* __restrict__ item_start, const double* __restrict__ partial, double* __restrict__ S) {
     __shared__ double sRed[NT / 32];
     int g = blockIdx.x;

@@ -62,7 +62,7 @@ loss_seed_vec_kernel(const GDesc<T>* __restrict__ descs, const T* __restrict__ H
 }
 
 // out[g] = (accumulate ? out[g] : 0) + scale * Σ_chunks partial[g][chunk]   (fixed order)
-__global__ void __launch_bounds__(NT)
+static __global__ void __launch_bounds__(NT)
 reduce_chunks_scaled_kernel(const double* __restrict__ partial, int nchunk, double* __restrict__ out, double scale, int accumulate) {
     __shared__ double sRed[NT / 32];
     double acc = 0.0;
@@ -72,7 +72,7 @@ reduce_chunks_scaled_kernel(const double* __restrict__ partial, int nchunk, doub
 }
 
 // out[g] = (accumulate ? out[g] : 0) + scale * Σ partial[start[g] .. start[g+1])   (fixed order, bit-stable)
-__global__ void __launch_bounds__(NT)
+static __global__ void __launch_bounds__(NT)
 reduce_scaled_kernel(const int* __restrict__ start, const double* __restrict__ partial, double* __restrict__ out,
                      double scale, int accumulate) {
     __shared__ double sRed[NT / 32];
@@ -119,7 +119,7 @@ __host__ __device__ inline double act_bwd(int a, double z, double y) {
 
 // One thread per glacier (the law is evaluated once per glacier and solve: callback_freq = 0, Laws.jl:346).
 // Double precision regardless of the ensemble dtype.  J is [G x n_params], row-major.
-__global__ void law_A_nn_kernel(MlpArch arch, const double* __restrict__ theta, const double* __restrict__ temps,
+static __global__ void law_A_nn_kernel(MlpArch arch, const double* __restrict__ theta, const double* __restrict__ temps,
                                 int G, double minA, double maxA, double* __restrict__ A_out, double* __restrict__ J) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -164,7 +164,7 @@ __global__ void law_A_nn_kernel(MlpArch arch, const double* __restrict__ theta, 
 }
 
 // dθ[k] = Σ_g J[g,k] · S[g]   (glaciers in fixed order: aggregate∇θ, Model.jl:208-224)
-__global__ void law_pullback_kernel(const double* __restrict__ J, const double* __restrict__ S, int G, int n_params,
+static __global__ void law_pullback_kernel(const double* __restrict__ J, const double* __restrict__ S, int G, int n_params,
                                     double* __restrict__ dtheta) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_params) return;

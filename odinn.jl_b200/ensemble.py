@@ -57,6 +57,25 @@ class Ensemble:
     def _ck(self, rc):
         _capi.check(self._h, rc)
 
+    def _mat(self, g: int, a, name: str = "matrix", dual: bool = False):
+        """Column-major (nx, ny) [dual grid: (nx-1, ny-1)] matrix of glacier g in the ensemble dtype.  The C side only sees a
+        pointer and a leading dimension, so a wrong shape would read or write past the host buffer: refuse it here."""
+        if not (0 <= int(g) < self.G):
+            raise _capi.OdinnError(f"glacier index {g} out of range (0..{self.G - 1})")
+        a = _as_f(a, self.np_dtype)
+        want = (self.nx[g] - 1, self.ny[g] - 1) if dual else (self.nx[g], self.ny[g])
+        if a.shape != want:
+            raise _capi.OdinnError(f"{name} of glacier {g} has shape {a.shape}, expected {want}")
+        return a
+
+    def _out(self, g: int, out, name: str = "out"):
+        """A caller-supplied output matrix must already be what the C side writes: right shape, dtype, column-major."""
+        want = (self.nx[g], self.ny[g])
+        if not isinstance(out, np.ndarray) or out.shape != want or out.dtype != self.np_dtype or not out.flags.f_contiguous \
+                or not out.flags.writeable:
+            raise _capi.OdinnError(f"{name} of glacier {g} must be a writeable column-major {self.np_dtype.__name__} array of shape {want}")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.odinn_launch_count(self._h))
@@ -71,10 +90,12 @@ class Ensemble:
 
     # -- state -----------------------------------------------------------------------------
     def upload(self, g: int, field: int, a):
-        a = _as_f(a, self.np_dtype)
+        a = self._mat(g, a, "field", dual=field in (_capi.FIELD_A, _capi.FIELD_VJP_A))
         self._ck(self._lib.odinn_upload(self._h, g, field, a.ctypes.data, a.shape[0]))
 
     def download(self, g: int, field: int):
+        if not (0 <= int(g) < self.G):
+            raise _capi.OdinnError(f"glacier index {g} out of range (0..{self.G - 1})")
         dual = field in (_capi.FIELD_A, _capi.FIELD_VJP_A)
         shape = (self.nx[g] - 1, self.ny[g] - 1) if dual else (self.nx[g], self.ny[g])
         out = np.empty(shape, dtype=self.np_dtype, order="F")
@@ -97,14 +118,14 @@ class Ensemble:
 
     # -- reference-facing per-call operators (host in, host out) ----------------------------------
     def sia2d_rhs(self, g: int, H, t: float = 0.0, out=None):
-        H = _as_f(H, self.np_dtype)
-        dH = np.empty_like(H, order="F") if out is None else out
+        H = self._mat(g, H, "H")
+        dH = np.empty_like(H, order="F") if out is None else self._out(g, out, "dH")
         self._ck(self._lib.odinn_sia2d_rhs(self._h, g, H.ctypes.data, H.shape[0], dH.ctypes.data, dH.shape[0], float(t)))
         return dH
 
     def sia2d_vjp_H(self, g: int, lam, H, t: float = 0.0, continuous: bool = False):
-        H = _as_f(H, self.np_dtype)
-        lam = _as_f(lam, self.np_dtype)
+        H = self._mat(g, H, "H")
+        lam = self._mat(g, lam, "lambda")
         out = np.empty_like(H, order="F")
         fn = self._lib.odinn_sia2d_vjp_H_continuous if continuous else self._lib.odinn_sia2d_vjp_H
         self._ck(fn(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
@@ -112,8 +133,8 @@ class Ensemble:
         return out
 
     def sia2d_vjp_theta(self, g: int, lam, H, t: float = 0.0, continuous: bool = False) -> float:
-        H = _as_f(H, self.np_dtype)
-        lam = _as_f(lam, self.np_dtype)
+        H = self._mat(g, H, "H")
+        lam = self._mat(g, lam, "lambda")
         S = C.c_double(0.0)
         fn = self._lib.odinn_sia2d_vjp_theta_continuous if continuous else self._lib.odinn_sia2d_vjp_theta
         self._ck(fn(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
@@ -144,10 +165,12 @@ class Ensemble:
 
     def fwd_adj_batch(self, Hs, lams=None, want_dH=True, want_vjpH=True, want_S=True):
         """NumPy front end of ``odinn_fwd_adj_batch_host``: lists of (nx, ny) matrices in, (dH list, vjpH list, S) out."""
-        Hs = [_as_f(h, self.np_dtype) for h in Hs]
+        if len(Hs) != self.G or (lams is not None and len(lams) != self.G):
+            raise _capi.OdinnError(f"one matrix per glacier expected ({self.G})")
+        Hs = [self._mat(g, h, "H") for g, h in enumerate(Hs)]
         mk = lambda arrs: (C.c_void_p * self.G)(*[a.ctypes.data for a in arrs])
         adj = want_vjpH or want_S
-        ls = [_as_f(l, self.np_dtype) for l in lams] if adj else None
+        ls = [self._mat(g, l, "lambda") for g, l in enumerate(lams)] if adj else None
         dH = [np.empty_like(h, order="F") for h in Hs] if want_dH else None
         vH = [np.empty_like(h, order="F") for h in Hs] if want_vjpH else None
         S = np.empty(self.G, dtype=np.float64) if want_S else None
@@ -190,8 +213,8 @@ class Ensemble:
 
     def sia2d_vjp_theta_cell(self, g: int, lam, H, t: float = 0.0):
         """∂θ (vector) of the per-cell law for one glacier: Σ (∂D/∂θ_k)·D†."""
-        H = _as_f(H, self.np_dtype)
-        lam = _as_f(lam, self.np_dtype)
+        H = self._mat(g, H, "H")
+        lam = self._mat(g, lam, "lambda")
         out = np.empty(self._law_n_theta, dtype=np.float64)
         self._ck(self._lib.odinn_sia2d_vjp_theta_cell(self._h, g, lam.ctypes.data, lam.shape[0], H.ctypes.data, H.shape[0],
                                                       out.ctypes.data_as(C.POINTER(C.c_double)), out.size, float(t)))
@@ -236,13 +259,13 @@ class Ensemble:
         return out
 
     def set_snapshot(self, g: int, j: int, n_snap: int, H):
-        H = _as_f(H, self.np_dtype)
+        H = self._mat(g, H, "snapshot")
         self._ck(self._lib.odinn_set_snapshot(self._h, g, j, n_snap, H.ctypes.data, H.shape[0]))
 
     def set_reference(self, g: int, j: int, n_snap: int, Href, mask):
         """mask: boolean is_in_glacier(H_ref, distance); stored as W = mask / (nx·ny) (gradient.jl:161)."""
-        Href = _as_f(Href, self.np_dtype)
-        W = _as_f(np.asarray(mask, dtype=np.float64) / float(self.nx[g] * self.ny[g]), self.np_dtype)
+        Href = self._mat(g, Href, "H_ref")
+        W = self._mat(g, np.asarray(mask, dtype=np.float64) / float(self.nx[g] * self.ny[g]), "mask")
         self._ck(self._lib.odinn_set_reference(self._h, g, j, n_snap, Href.ctypes.data, W.ctypes.data, Href.shape[0]))
 
     def loss(self, t):
@@ -283,7 +306,7 @@ class Ensemble:
     # -- surface velocity / LossV ---------------------------------------------------------------------
     def surface_velocity(self, g: int, H, t: float = 0.0):
         """(Vx, Vy) = V_from_H(H) (Huginn.V_from_H call sites Losses.jl:314, 358)."""
-        H = _as_f(H, self.np_dtype)
+        H = self._mat(g, H, "H")
         Vx = np.empty_like(H, order="F")
         Vy = np.empty_like(H, order="F")
         self._ck(self._lib.odinn_surface_velocity(self._h, g, H.ctypes.data, H.shape[0], Vx.ctypes.data, Vy.ctypes.data, Vx.shape[0], float(t)))
@@ -291,9 +314,9 @@ class Ensemble:
 
     def vjp_surface_V(self, g: int, dVx, dVy, H, t: float = 0.0):
         """(VJP_λ_∂surface_V∂H, S) with ∂θ = (∂A/∂θ)·S (adjoint.jl:268-413)."""
-        H = _as_f(H, self.np_dtype)
-        dVx = _as_f(dVx, self.np_dtype)
-        dVy = _as_f(dVy, self.np_dtype)
+        H = self._mat(g, H, "H")
+        dVx = self._mat(g, dVx, "dVx")
+        dVy = self._mat(g, dVy, "dVy")
         out = np.empty_like(H, order="F")
         S = C.c_double(0.0)
         self._ck(self._lib.odinn_sia2d_vjp_surface_V(self._h, g, dVx.ctypes.data, dVy.ctypes.data, dVx.shape[0], H.ctypes.data, H.shape[0],
@@ -306,7 +329,7 @@ class Ensemble:
         mask = Vabs > 0.0
         sc = float(np.mean(np.asarray(Vx_ref)[mask] ** 2 + np.asarray(Vy_ref)[mask] ** 2) ** 0.5) if (scale_loss and mask.any()) else 1.0
         W = mask.astype(np.float64) / (float(self.nx[g] * self.ny[g]) * sc)
-        a = [_as_f(x, self.np_dtype) for x in (Vx_ref, Vy_ref, Vabs, W)]
+        a = [self._mat(g, x, "velocity reference") for x in (Vx_ref, Vy_ref, Vabs, W)]
         self._ck(self._lib.odinn_set_velocity_reference(self._h, g, slot, n_slots, snapshot_index, a[0].ctypes.data, a[1].ctypes.data,
                                                         a[2].ctypes.data, a[3].ctypes.data, a[0].shape[0]))
 

