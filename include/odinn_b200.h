@@ -30,7 +30,11 @@ typedef struct odinn_ensemble odinn_ensemble;
 
 enum odinn_dtype { ODINN_F32 = 0, ODINN_F64 = 1 };
 
-enum odinn_method { ODINN_EULER = 0, ODINN_SSPRK3 = 1, ODINN_BS3 = 2 /* adaptive, odinn_solve_forward_adaptive */ };
+enum odinn_method {
+    ODINN_EULER = 0, ODINN_SSPRK3 = 1,  /* fixed sub-steps, odinn_solve_forward */
+    ODINN_BS3 = 2,                      /* adaptive Bogacki-Shampine 3(2), odinn_solve_forward_adaptive */
+    ODINN_RDPK3SP35 = 3                 /* adaptive RDPK3Sp35 + PID controller: the reference's default solver (src/inverse/AdjointTypes.jl:60) */
+};
 
 enum odinn_activation { ODINN_ACT_IDENTITY = 0, ODINN_ACT_SOFTPLUS = 1, ODINN_ACT_SIGMOID = 2, ODINN_ACT_TANH = 3, ODINN_ACT_RELU = 4 };
 
@@ -187,6 +191,10 @@ int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double*
  * advances with its OWN adaptive step (independent ODEs, one pmap task each in the reference); the controller runs on the
  * device.  dt0 <= 0: (t[1] - t[0]) / 16.  max_steps bounds the number of ensemble-wide trial steps (maxiters).
  * steps_out / rejected_out (n_glaciers ints, optional): trial steps and rejected steps per glacier.
+ * method = ODINN_RDPK3SP35: the reference's default integrator (OrdinaryDiffEq's RDPK3Sp35, src/inverse/AdjointTypes.jl:60,
+ * test/test_grad_loss.jl:143): 5-stage 3rd-order 3S*+ low-storage scheme of Ranocha et al. (2021), FSAL, 5 RHS per trial step, PID
+ * step-size controller beta = (0.64, -0.31, 0.04) with the limiter 1 + atan(x - 1) and acceptance threshold 0.81, OrdinaryDiffEq's
+ * automatic initial step when dt0 <= 0 (for BS3 dt0 <= 0 means (t[1] - t[0]) / 16).
  * Snapshots are kept as by odinn_solve_forward. */
 int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n_snap, const double* t, double reltol, double abstol,
                                  double dt0, int max_steps, int* steps_out, int* rejected_out);
@@ -254,6 +262,22 @@ int odinn_set_loss_weights(odinn_ensemble* e, int n_t, const double* wH, const d
 int odinn_grad_continuous(odinn_ensemble* e, const double* t, int n_t, int n_quadrature, const double* q_nodes,
                           const double* q_weights, int continuous_vjp, int method, int nsub, double* loss_out,
                           double* Ssum_out);
+
+/* The same branch with the reverse ODE solved as the reference solves it by default (gradient.jl:449-467 with the defaults of
+ * src/inverse/AdjointTypes.jl:53-66): adaptive RDPK3Sp35 + PID controller in tau = -t, every glacier with its own step,
+ * tstops_adjoint = sort(unique(-reverse(tstops) U -q_nodes)), reltol, abstol (reference default 1e-8 each), dtmax (1/12), maxiters.
+ * Callbacks as upstream: lambda_1 = effect_loss!(t_end); the mass-balance PeriodicCallback (initial_affect: also at t_end, not at t_0)
+ * lambda += VJP_lambda_dMBdH(lambda, H - MB) BEFORE the loss jump of the same tstop (CallbackSet order, gradient.jl:407-426); the
+ * loss jumps use the weights of odinn_set_loss_weights, thickness AND velocity terms (gradient.jl:326-366); the velocity term's
+ * dl/dtheta is quadrature-weighted (odinn_set_velocity_quadrature).  steps_out (optional): trial steps per glacier. */
+int odinn_grad_continuous_adaptive(odinn_ensemble* e, const double* t, int n_t, int n_quadrature, const double* q_nodes,
+                                   const double* q_weights, int continuous_vjp, double reltol, double abstol, double dtmax,
+                                   int max_steps, double* loss_out, double* Ssum_out, int* steps_out);
+/* Continuous adjoint with a velocity loss: dL/dtheta += sum_m q_weights[m] * theta_scale * dl_V/dtheta(H_itp(t_m), V_ref_itp(t_m)),
+ * the references interpolated linearly over the data times (one datum: constant) and Delta_t = (1, 1) inside the quadrature
+ * (gradient.jl:289-301, 474-507): theta_scale = 1 for LossV, LossHV.scaling for LossHV, 0 switches the term off.
+ * scale_loss: LossV.scale_loss (Losses.jl:327-331), needed to rebuild the weights of the interpolated references. */
+int odinn_set_velocity_quadrature(odinn_ensemble* e, double theta_scale, int scale_loss);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Laws                                                                                      */

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ODINN_B200_LIB") or os.path.join(_HERE, "lib", "libod
 F32, F64 = 0, 1
 
 FIELD_B, FIELD_H, FIELD_DH, FIELD_LAMBDA, FIELD_VJP_H, FIELD_A, FIELD_VJP_A, FIELD_H0 = range(8)
-EULER, SSPRK3, BS3 = 0, 1, 2
+EULER, SSPRK3, BS3, RDPK3SP35 = 0, 1, 2, 3
 LAW_U, LAW_Y = 1, 2
 ACT = {"identity": 0, "softplus": 1, "sigmoid": 2, "tanh": 3, "relu": 4}
 
@@ -66,6 +66,8 @@ SIGNATURES = {
     "odinn_set_velocity_reference": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "odinn_set_loss_weights": (_i, [_vp, _i, _dp, _dp, _i]),
     "odinn_grad_continuous": (_i, [_vp, _dp, _i, _i, _dp, _dp, _i, _i, _i, _dp, _dp]),
+    "odinn_grad_continuous_adaptive": (_i, [_vp, _dp, _i, _i, _dp, _dp, _i, _d, _d, _d, _i, _dp, _dp, _ip]),
+    "odinn_set_velocity_quadrature": (_i, [_vp, _d, _i]),
     "odinn_law_A_nn_apply": (_i, [_vp, _i, _ip, _ip, _dp, _i, _dp]),
     "odinn_law_A_nn_pullback": (_i, [_vp, _dp, _dp, _i]),
     "odinn_set_phys": (_i, [_vp, C.POINTER(Phys)]),

@@ -318,7 +318,7 @@ extern "C" int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n
         cudaError_t s_ = cudaSetDevice(e->device);
         if (s_ != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(s_));
     }
-    if (method != ODINN_BS3) return fail(e, ODINN_EARG, "adaptive solve: method must be ODINN_BS3");
+    if (method != ODINN_BS3 && method != ODINN_RDPK3SP35) return fail(e, ODINN_EARG, "adaptive solve: method must be ODINN_BS3 or ODINN_RDPK3SP35");
     if (n_snap < 1 || !t || !(reltol > 0.0) || !(abstol > 0.0) || max_steps < 1) return fail(e, ODINN_EARG, "bad adaptive-solve arguments");
     for (int j = 1; j < n_snap; ++j)
         if (!(t[j] > t[j - 1])) return fail(e, ODINN_EARG, "tstops must be strictly increasing");
@@ -326,6 +326,7 @@ extern "C" int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n
     if ((rc = ensure_plane(e, ODINN_FIELD_H0)) || (rc = ensure_plane(e, ODINN_FIELD_H))) return rc;
     if ((rc = prepare_snapshots(e, n_snap))) return rc;
     if ((rc = sync_descs(e))) return rc;
+    if (method == ODINN_RDPK3SP35) return solve_forward_rdpk(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
     return e->dtype == ODINN_F32 ? solve_bs3_t<float>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out)
                                  : solve_bs3_t<double>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
 }

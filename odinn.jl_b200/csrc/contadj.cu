@@ -130,14 +130,25 @@ static int grad_continuous_t(odinn_ensemble* e, const double* t, int n_t, int n_
             const int j = s.idx;
             // w_j = Δt_HV.H[ind-1] through safe_slice for LossH: 0 for the first data point (odinn_set_loss_weights overrides)
             const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
+            // Callback order of the reference: interior tstops run CallbackSet(cb_adjoint_MB, cb_adjoint_loss) -- the mass-balance VJP
+            // first (not at t_0: final_affect = false), then the loss jump; at t_end the loss is applied by hand to λ₁ BEFORE the solve
+            // starts and the PeriodicCallback's initial_affect adds the MB term afterwards (gradient.jl:407-446).
+            const bool at_end = (j == n_t - 1);
+            if (!at_end && j != 0 && (rc = mb_adjoint_step(e, j, lam, snapshot_ptr(e, j)))) return rc;
             // ℓ += w_j Σ W (H_j - H_ref,j)² ;  λ += 2 w_j W (H_j - H_ref,j)       (Losses.jl:270-291)
-            if ((rc = loss_seed_planes(e, snapshot_ptr(e, j), (char*)e->href + (size_t)j * pbytes, (char*)e->wmask + (size_t)j * pbytes,
-                                       lam, nullptr, lam, 0.0, 2.0 * wH, e->d_loss, wH, 1)))
+            if (wH != 0.0 && (rc = loss_seed_planes(e, snapshot_ptr(e, j), (char*)e->href + (size_t)j * pbytes, (char*)e->wmask + (size_t)j * pbytes,
+                                                    lam, nullptr, lam, 0.0, 2.0 * wH, e->d_loss, wH, 1)))
                 return rc;
-            (void)wV;  // (a velocity term is refused by odinn_grad_continuous: its ∂ℓ/∂θ is quadrature-weighted upstream, :474-507)
+            // velocity term: ℓ and ∂ℓ/∂H at the tstop (its ∂ℓ/∂θ is quadrature-weighted, below)   (Losses.jl:293-390, gradient.jl:326-366)
+            if ((rc = velocity_loss_term(e, j, snapshot_ptr(e, j), lam, wV, e->d_loss, nullptr))) return rc;
+            if (at_end && (rc = mb_adjoint_step(e, j, lam, snapshot_ptr(e, j)))) return rc;
         } else {
             if ((rc = H_itp(s.t))) return rc;
             if ((rc = vjp_planes(e, lam, Ht, nullptr, false, true, e->d_Ssum, qw[s.idx], 1, cont_vjp))) return rc;
+            // + w_m ∂ℓ/∂θ(t_m): velocity references interpolated at the node, Δt = (1, 1)   (gradient.jl:474-507)
+            if (e->lossV_theta_scale != 0.0 &&
+                (rc = velocity_theta_term_interp(e, s.t, t, n_t, Ht, e->lossV_theta_scale * qw[s.idx], e->d_Ssum)))
+                return rc;
         }
     }
     return ODINN_OK;
@@ -162,9 +173,6 @@ extern "C" int odinn_grad_continuous(odinn_ensemble* e, const double* t, int n_t
     for (int m = 0; m < n_quadrature; ++m)
         if (!(q_nodes[m] >= t[0] && q_nodes[m] <= t[n_t - 1])) return fail(e, ODINN_EARG, "quadrature node outside the time span");
     if (e->a_gridded) return fail(e, ODINN_ESTATE, "odinn_grad_continuous supports glacier-wide A and per-cell laws");
-    for (int j = 0; j < n_t; ++j)
-        if (loss_weight_V(e, n_t, j) != 0.0)
-            return fail(e, ODINN_ESTATE, "odinn_grad_continuous covers LossH; use odinn_grad_discrete for losses with a velocity term");
     if (continuous_vjp && e->law_kind != 0) return fail(e, ODINN_ESTATE, "the continuous VJP flavour is provided for glacier-wide A laws");
     int rc = e->dtype == ODINN_F32 ? grad_continuous_t<float>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, method, nsub)
                                    : grad_continuous_t<double>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, method, nsub);

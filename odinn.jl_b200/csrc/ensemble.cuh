@@ -115,6 +115,8 @@ struct odinn_ensemble {
     // loss configuration (odinn_set_loss_weights): per-snapshot multipliers of the thickness / velocity L2 terms; empty = LossH with Δt
     std::vector<double> loss_wH, loss_wV;
     int lossV_component = 0;          // 0 :xy, 1 :abs  (Losses.jl:318-325)
+    double lossV_theta_scale = 0.0;   // continuous adjoint: multiplier of the quadrature-weighted dl_V/dtheta (1 LossV, `scaling` LossHV; gradient.jl:474-507)
+    int lossV_scale_loss = 1;         // LossV.scale_loss (Losses.jl:327-331), needed to rebuild the weights of interpolated references
     std::vector<int> v_snap;          // snapshot index of every velocity-reference slot (velocity.cu)
     // mass balance (massbalance.cu): snapshot indices after which the MB callback fires, per-glacier climate scalars per MB step
     std::vector<int> mb_snap;
@@ -125,7 +127,10 @@ enum {  // ext_dev slots
     EXT_MB = 8, EXT_MB_PAR = 9,                                                                      // mass balance (massbalance.cu)
     EXT_V_REF = 12, EXT_V_WORK0 = 13, EXT_V_WORK1 = 14, EXT_V_WORK2 = 15, EXT_V_PARTIAL = 16,          // surface velocity / LossV
     EXT_AD_PARTIAL = 17,                                                                            // adaptive solve (ext_int[0] = its length)
-    EXT_LS_PARTIAL = 18                                                                             // loss / seed pass (ext_int[1] = its length)
+    EXT_LS_PARTIAL = 18,                                                                            // loss / seed pass (ext_int[1] = its length)
+    EXT_RK_STATE = 19,                                                                              // RDPK3Sp35 per-glacier controller state (rdpk.cu)
+    EXT_VQ_WORK = 20,                                                                               // 4 planes: velocity references interpolated at a quadrature node
+    EXT_VQ_RED = 21                                                                                 // [2 G] mask count and sum of squares of those references
 };
 
 namespace odinn {
@@ -182,6 +187,12 @@ int velocity_loss_term(odinn_ensemble* e, int j, const void* Hj, void* lam, doub
 // mass-balance callback of snapshot j / its adjoint (massbalance.cu); no-ops when no MB step fires at j
 int mb_apply_step(odinn_ensemble* e, int j, void* H, int* applied);
 int mb_adjoint_step(odinn_ensemble* e, int j, void* lam, const void* Hj);
+// S_dst[g] += scale * dl_V/dtheta-scalar evaluated on the plane H against the velocity references interpolated linearly at time tq
+// (one datum: constant; flat outside the data range) -- the quadrature-node term of the continuous adjoint (gradient.jl:289-301, 474-507)
+int velocity_theta_term_interp(odinn_ensemble* e, double tq, const double* t, int n_t, const void* H, double scale, double* S_dst);
+// adaptive forward solve with the reference's default integrator (rdpk.cu)
+int solve_forward_rdpk(odinn_ensemble* e, int n_snap, const double* t, double reltol, double abstol, double dt0, int max_steps,
+                       int* steps_out, int* rejected_out);
 // Default LossH weight of snapshot j: ΔtH = diff(tH_ref) indexed by the position of t_j inside tH_ref -- the time since the PREVIOUS
 // snapshot that holds thickness data, 0 for the first datum (safe_slice) and for tstops without data (gradient.jl:79-80, 144-149).
 inline double loss_weight_H(const odinn_ensemble* e, const double* t, int n_t, int j) {

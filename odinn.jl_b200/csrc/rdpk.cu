@@ -1,0 +1,646 @@
+// RDPK3Sp35 + PID step-size controller on the device: the reference's DEFAULT integrator, for the forward solve and for the
+// reverse ODE of the continuous adjoint.
+//
+// Replaces (VERDICT round 1 "missing" 1-2):
+//   solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops), RDPK3Sp35(); reltol, maxiters, tstops)
+//       src/simulations/inversions/inversion_utils.jl:559-568, solver default test/test_grad_loss.jl:143
+//   solve(adjoint_PDE_rev, RDPK3Sp35(); callback, tstops = tstops_adjoint, dtmax = 1/12, reltol = abstol = 1e-8)
+//       src/inverse/SIA2D/gradient.jl:449-467 with the defaults of src/inverse/AdjointTypes.jl:53-66
+// The integrator itself is OrdinaryDiffEq's (not in the tree): 5-stage 3rd-order 3S*+ low-storage scheme of Ranocha, Dalcin,
+// Parsani & Ketcheson (2021) with its embedded error estimator and the PID controller beta = (0.64, -0.31, 0.04), limiter
+// 1 + atan(x - 1), acceptance threshold 0.81 -- step by step the scheme of oracle/sia2d_numpy.py::integrate_rdpk3sp35 (whose
+// header says how the coefficients are pinned: order conditions to 1e-37 for the main scheme).
+//
+// As in adaptive.cu every glacier is an independent ODE and carries its OWN (t, dt, PID history) in a device state table: the
+// elementwise kernels read their glacier's step, one controller thread per glacier accepts / rejects and plans the next step, and the
+// host reads back two integers per trial step.  Low-storage registers: S1 (stage value), S2, the step's start state u, the error
+// accumulator -- plus the stage slope k and the FSAL pair (k1, k_new): 6 work planes besides the state.
+#include <vector>
+
+#include "ensemble.cuh"
+
+namespace odinn {
+
+// ---- coefficients (identical digit strings to the oracle) -----------------------------------------------------------------
+__constant__ double c_G1[4] = {2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
+                               5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01};
+__constant__ double c_G2[4] = {5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
+                               2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01};
+__constant__ double c_G3[4] = {0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01};
+__constant__ double c_D[4] = {3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
+                              7.229275366787987419692007421895451953e-01, 0.0};
+__constant__ double c_B[5] = {2.300298624518076223899418286314123354e-01, 3.021434166948288809034402119555380003e-01,
+                              8.025606185416310937583009085873554681e-01, 4.362158943603440930655148245148766471e-01,
+                              1.129272530455059129782111662594436580e-01};
+static const double h_C[6] = {0.0, 2.300298624518076223899418286314123354e-01, 4.050046072094990912268498160116125481e-01,
+                              8.947822893693433545220710894560512805e-01, 7.235136928826589010272834603680114769e-01, 1.0};
+static const double h_BHAT[5] = {1.046363371354093758897668305991705199e-01, 9.520431574956758809511173383346476348e-02,
+                                 4.482446645568668405072421350300379357e-01, 2.449030295461310135957132640369862245e-01,
+                                 1.070116530120251819121660365003405564e-01};
+__constant__ double c_E[5];   // bhat - b, b from the 3S* recurrence (rdpk_error_weights)
+
+// b of the scheme the recurrence defines (oracle: rdpk_butcher), then E = bhat - b.
+static void rdpk_error_weights(double E[5]) {
+    static const double G1[4] = {2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
+                                 5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01};
+    static const double G2[4] = {5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
+                                 2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01};
+    static const double G3[4] = {0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01};
+    static const double D[4] = {3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
+                                7.229275366787987419692007421895451953e-01, 0.0};
+    static const double B[5] = {2.300298624518076223899418286314123354e-01, 3.021434166948288809034402119555380003e-01,
+                                8.025606185416310937583009085873554681e-01, 4.362158943603440930655148245148766471e-01,
+                                1.129272530455059129782111662594436580e-01};
+    double u[6] = {1, B[0], 0, 0, 0, 0}, tmp[6] = {1, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 6; ++j) tmp[j] = tmp[j] + D[i] * u[j];
+        for (int j = 0; j < 6; ++j) u[j] = G1[i] * u[j] + G2[i] * tmp[j] + G3[i] * (j == 0 ? 1.0 : 0.0);
+        u[i + 2] += B[i + 1];
+    }
+    for (int i = 0; i < 5; ++i) E[i] = h_BHAT[i] - u[i + 1];
+}
+
+struct RkState {
+    double t, tstop, dt, h, EEst;
+    double err2, err3;      // PID history: 1 / EEst of the last two accepted steps
+    double sk0, sk1;        // scratch of the initial-step algorithm (d0, d1)
+    int last, accept, done;
+    int steps, rejected;
+};
+
+__device__ __forceinline__ void rk_plan_step(RkState& s, double dtmax) {
+    double h = fmin(fmin(s.dt, dtmax), s.tstop - s.t);
+    s.last = (s.t + h >= s.tstop) || (s.tstop - (s.t + h) < 1e-14 * fmax(1.0, fabs(s.tstop)));
+    s.h = s.last ? (s.tstop - s.t) : h;
+}
+
+__global__ void rk_reset(RkState* st, int G, double t0) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    RkState s{};
+    s.t = t0;
+    s.err2 = s.err3 = 1.0;
+    st[g] = s;
+}
+
+// New stop interval (a, b]: every glacier restarts from t = a with the step it carried over.
+__global__ void rk_begin_interval(RkState* st, int G, double a, double b, double dtmax) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    RkState s = st[g];
+    s.t = a;
+    s.tstop = b;
+    s.done = 0;
+    s.accept = 0;
+    rk_plan_step(s, dtmax);
+    st[g] = s;
+}
+
+template <typename T> struct RkVec;
+template <> struct RkVec<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct RkVec<double> { typedef double2 type; static constexpr int N = 2; };
+constexpr int RK_NT = 256;
+constexpr int RK_UNROLL = 4;
+template <typename T> __device__ __forceinline__ void rk_unpack(const typename RkVec<T>::type& v, T* x);
+template <> __device__ __forceinline__ void rk_unpack<float>(const float4& v, float* x) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+template <> __device__ __forceinline__ void rk_unpack<double>(const double2& v, double* x) { x[0] = v.x; x[1] = v.y; }
+template <typename T> __device__ __forceinline__ typename RkVec<T>::type rk_pack(const T* x);
+template <> __device__ __forceinline__ float4 rk_pack<float>(const float* x) { return make_float4(x[0], x[1], x[2], x[3]); }
+template <> __device__ __forceinline__ double2 rk_pack<double>(const double* x) { return make_double2(x[0], x[1]); }
+
+// Elementwise kernels over the padded planes (grid: chunks x glaciers, 16-byte vectors; padding stays zero under these linear
+// combinations and contributes zero to the norms).
+#define RK_PROLOGUE                                                                                 \
+    typedef typename RkVec<T>::type V;                                                              \
+    constexpr int N = RkVec<T>::N;                                                                  \
+    const GDesc<T> d = descs[blockIdx.y];                                                           \
+    const RkState s = st[blockIdx.y];                                                               \
+    const long long nvec = (long long)d.ld * d.ny / N;                                              \
+    const long long v0 = ((long long)blockIdx.x * RK_UNROLL) * RK_NT + threadIdx.x;                 \
+    const long long base = d.off / N;
+#define RK_LD(P, q) (reinterpret_cast<const V*>(P)[base + (q)])
+#define RK_ST(P, q, x) (reinterpret_cast<V*>(P)[base + (q)] = rk_pack<T>(x))
+
+// S1 = u + (b h) k1 ;  est = (e h) k1      (est == nullptr: S1 only -- the Euler probe of the initial-step algorithm, b = 1)
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_stage1(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, const T* __restrict__ u, const T* __restrict__ k1,
+          T* __restrict__ S1, T* __restrict__ est, double b, double e) {
+    RK_PROLOGUE
+    const T bh = (T)(b * s.h), eh = (T)(e * s.h);
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            T a[N], k[N], x[N], y[N];
+            rk_unpack<T>(RK_LD(u, q), a);
+            rk_unpack<T>(RK_LD(k1, q), k);
+#pragma unroll
+            for (int c = 0; c < N; ++c) { x[c] = a[c] + bh * k[c]; y[c] = eh * k[c]; }
+            RK_ST(S1, q, x);
+            if (est) RK_ST(est, q, y);
+        }
+    }
+}
+
+// Stage i (0..3) after k = f(S1):  S2 = S2in + d S1 ;  S1 = g1 S1 + g2 S2 + g3 u + (b h) k ;  est += (e h) k
+// S2in = u for i = 0; the S2 write is skipped when it is not read again (i = 3, d = 0).
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_stage(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, const T* __restrict__ u, const T* S2in, T* S2out,
+         T* __restrict__ S1, const T* __restrict__ kp, T* __restrict__ est, int i) {
+    RK_PROLOGUE
+    const T g1 = (T)c_G1[i], g2 = (T)c_G2[i], g3 = (T)c_G3[i], dd = (T)c_D[i];
+    const T bh = (T)(c_B[i + 1] * s.h), eh = (T)(c_E[i + 1] * s.h);
+    const bool use_u = (c_G3[i] != 0.0);
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            T s1[N], s2[N], uu[N], k[N], er[N];
+            rk_unpack<T>(RK_LD(S1, q), s1);
+            rk_unpack<T>(RK_LD(S2in, q), s2);
+            rk_unpack<T>(RK_LD(kp, q), k);
+            rk_unpack<T>(RK_LD(est, q), er);
+            if (use_u) rk_unpack<T>(RK_LD(u, q), uu);
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                s2[c] = s2[c] + dd * s1[c];
+                T v = g1 * s1[c] + g2 * s2[c];
+                if (use_u) v = v + g3 * uu[c];
+                s1[c] = v + bh * k[c];
+                er[c] = er[c] + eh * k[c];
+            }
+            if (S2out) RK_ST(S2out, q, s2);
+            RK_ST(S1, q, s1);
+            RK_ST(est, q, er);
+        }
+    }
+}
+
+// partial[glacier * gridDim.x + chunk] = sum ((a - b) / (abstol + reltol max(|u|, |v|)))^2     (b, v optional)
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_sumsq(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, const T* __restrict__ a, const T* __restrict__ b,
+         const T* __restrict__ u, const T* __restrict__ v, double* __restrict__ partial, double reltol, double abstol) {
+    __shared__ double sRed[RK_NT / 32];
+    RK_PROLOGUE
+    (void)s;
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            T xa[N], xb[N], xu[N], xv[N];
+            rk_unpack<T>(RK_LD(a, q), xa);
+            rk_unpack<T>(RK_LD(u, q), xu);
+            if (b) rk_unpack<T>(RK_LD(b, q), xb);
+            if (v) rk_unpack<T>(RK_LD(v, q), xv);
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const double m = v ? fmax(fabs((double)xu[c]), fabs((double)xv[c])) : fabs((double)xu[c]);
+                const double r = (double)(b ? xa[c] - xb[c] : xa[c]) / (abstol + reltol * m);
+                acc += r * r;
+            }
+        }
+    }
+    double sum = block_sum(acc, sRed);
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = sum;
+}
+
+__global__ void __launch_bounds__(RK_NT)
+rk_reduce_chunks(const double* __restrict__ partial, int nchunk, double* __restrict__ sumsq) {
+    __shared__ double sRed[RK_NT / 32];
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < nchunk; c += RK_NT) acc += partial[(long long)blockIdx.x * nchunk + c];
+    double sum = block_sum(acc, sRed);
+    if (threadIdx.x == 0) sumsq[blockIdx.x] = sum;
+}
+
+// Initial step, OrdinaryDiffEq's ode_determine_initdt (Hairer-Wanner), per glacier.
+// phase 0: d0 = ||u / sk|| ;  phase 1: d1 = ||f0 / sk|| -> h0 (the Euler probe runs with s.h = h0) ;  phase 2: d2 -> dt
+__global__ void rk_init_control(RkState* st, const double* __restrict__ sumsq, const int* __restrict__ nx, const int* __restrict__ ny,
+                                int G, int phase, double dtmax) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    RkState s = st[g];
+    const double nrm = sqrt(sumsq[g] / ((double)nx[g] * (double)ny[g]));
+    if (phase == 0) {
+        s.sk0 = nrm;
+    } else if (phase == 1) {
+        s.sk1 = nrm;
+        double h0 = (s.sk0 < 1e-5 || s.sk1 < 1e-5) ? 1e-6 : 0.01 * s.sk0 / s.sk1;
+        s.h = fmin(h0, dtmax);
+    } else {
+        const double h0 = s.h;
+        const double d2 = nrm / h0;
+        const double md = fmax(s.sk1, d2);
+        const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 3.0);
+        s.dt = fmin(fmin(100.0 * h0, h1), dtmax);
+        s.h = 0.0;
+    }
+    st[g] = s;
+}
+
+__global__ void rk_set_dt(RkState* st, int G, double dt) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) st[g].dt = dt;
+}
+
+// One thread per glacier: error norm -> PID factor -> accept / reject -> next step (the `while t < tstop` body of the oracle).
+__global__ void rk_control(RkState* st, const double* __restrict__ sumsq, const int* __restrict__ nx, const int* __restrict__ ny,
+                           int G, int* counters, double dtmax) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    RkState s = st[g];
+    if (s.done) {
+        s.accept = 0;
+        st[g] = s;
+        return;
+    }
+    const double EEst = sqrt(sumsq[g] / ((double)nx[g] * (double)ny[g]));
+    const double e1 = 1.0 / fmax(EEst, 1e-300);
+    double fac = pow(e1, 0.64 / 3.0) * pow(s.err2, -0.31 / 3.0) * pow(s.err3, 0.04 / 3.0);
+    fac = 1.0 + atan(fac - 1.0);
+    s.EEst = EEst;
+    s.steps++;
+    if (fac >= 0.81) {
+        s.accept = 1;
+        s.t = s.last ? s.tstop : s.t + s.h;
+        s.err3 = s.err2;
+        s.err2 = e1;
+        s.dt = s.h * fac;
+    } else {
+        s.accept = 0;
+        s.rejected++;
+        s.dt = s.h * fac;
+        atomicAdd(counters + 1, 1);
+    }
+    if (s.t < s.tstop) {
+        rk_plan_step(s, dtmax);
+        atomicAdd(counters, 1);
+    } else {
+        s.done = 1;
+        s.h = 0.0;
+    }
+    st[g] = s;
+}
+
+// accepted glaciers: u <- S1, k1 <- knew
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_commit(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, T* __restrict__ u, const T* __restrict__ S1,
+          T* __restrict__ k1, const T* __restrict__ knew) {
+    RK_PROLOGUE
+    if (!s.accept) return;
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            reinterpret_cast<V*>(u)[base + q] = RK_LD(S1, q);
+            reinterpret_cast<V*>(k1)[base + q] = RK_LD(knew, q);
+        }
+    }
+}
+
+// Ht = (1 - a_g) Ha + a_g Hb with a_g = (tt_g - ta) / (tb - ta), tt_g = sign (t_g + c h_g): the linear interpolant of the forward
+// snapshots at each glacier's OWN stage time (gradient.jl:285-301; the reverse solve runs in tau = -t, sign = -1).
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_lerp(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, const T* __restrict__ Ha, const T* __restrict__ Hb,
+        T* __restrict__ Ht, double c, double sign, double ta, double tb) {
+    RK_PROLOGUE
+    const double tt = sign * (s.t + c * s.h);
+    const T a1 = (T)((tt - ta) / (tb - ta)), a0 = T(1) - a1;
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            T x[N], y[N], z[N];
+            rk_unpack<T>(RK_LD(Ha, q), x);
+            rk_unpack<T>(RK_LD(Hb, q), y);
+#pragma unroll
+            for (int k = 0; k < N; ++k) z[k] = a0 * x[k] + a1 * y[k];
+            RK_ST(Ht, q, z);
+        }
+    }
+}
+
+// First stage of a trial step:  S1 = u + (B1 h) k1 ;  est = (E1 h) k1   (weights from the constant tables)
+template <typename T>
+__global__ void __launch_bounds__(RK_NT)
+rk_stage1_main(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, const T* __restrict__ u, const T* __restrict__ k1,
+               T* __restrict__ S1, T* __restrict__ est) {
+    RK_PROLOGUE
+    const T bh = (T)(c_B[0] * s.h), eh = (T)(c_E[0] * s.h);
+#pragma unroll
+    for (int w = 0; w < RK_UNROLL; ++w) {
+        const long long q = v0 + (long long)w * RK_NT;
+        if (q < nvec) {
+            T a[N], k[N], x[N], y[N];
+            rk_unpack<T>(RK_LD(u, q), a);
+            rk_unpack<T>(RK_LD(k1, q), k);
+#pragma unroll
+            for (int c = 0; c < N; ++c) { x[c] = a[c] + bh * k[c]; y[c] = eh * k[c]; }
+            RK_ST(S1, q, x);
+            RK_ST(est, q, y);
+        }
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------------------------------
+// The engine: integrate every glacier from stops[0] to stops[n_stops-1], landing on every stop.
+//   rhs(u_in, k_out, c): k_out <- f(t_g + c h_g, u_in) for every glacier (c: stage abscissa; the state table holds t_g, h_g)
+//   on_stop(i, u, modified): callback at stop i >= 1 (may modify u; sets *modified so that the FSAL slope is re-evaluated)
+// -------------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct RkCtx {
+    odinn_ensemble* e;
+    RkState* st;
+    const GDesc<T>* descs;
+    dim3 egrid;
+    int nchunk, gb;
+    double* partial;
+    const int *d_nx, *d_ny;
+    int* d_counters;
+    T *k1, *S1, *S2, *est, *k, *knew;
+};
+
+template <typename T>
+static int rk_setup(odinn_ensemble* e, RkCtx<T>& c) {
+    int rc;
+    for (int k = 0; k < 6; ++k)
+        if ((rc = alloc_work_plane(e, &e->ad_plane[k]))) return rc;
+    if (!e->d_ad_dims) {
+        ODINN_CUDA(e, cudaMalloc(&e->d_ad_dims, sizeof(int) * 2 * e->G + 2 * sizeof(int)));
+        std::vector<int> dims(2 * e->G);
+        for (int g = 0; g < e->G; ++g) { dims[g] = e->gl[g].nx; dims[e->G + g] = e->gl[g].ny; }
+        ODINN_CUDA(e, cudaMemcpy(e->d_ad_dims, dims.data(), sizeof(int) * 2 * e->G, cudaMemcpyHostToDevice));
+    }
+    if (!e->h_ad_active) ODINN_CUDA(e, cudaMallocHost(&e->h_ad_active, 2 * sizeof(int)));
+    if (!e->ext_dev[EXT_RK_STATE]) ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_RK_STATE], sizeof(RkState) * e->G));
+    {   // host constants -> __constant__ memory of the CURRENT device (per call: handles on several GPUs may share the process)
+        double E[5];
+        rdpk_error_weights(E);
+        ODINN_CUDA(e, cudaMemcpyToSymbolAsync(c_E, E, sizeof(E), 0, cudaMemcpyHostToDevice, e->stream));
+    }
+    c.e = e;
+    c.st = (RkState*)e->ext_dev[EXT_RK_STATE];
+    c.descs = (const GDesc<T>*)e->d_descs;
+    long long max_vec = 0;
+    for (int g = 0; g < e->G; ++g) max_vec = std::max(max_vec, (long long)e->gl[g].ld * e->gl[g].ny / RkVec<T>::N);
+    c.nchunk = (int)((max_vec + (long long)RK_NT * RK_UNROLL - 1) / ((long long)RK_NT * RK_UNROLL));
+    c.egrid = dim3(c.nchunk, e->G);
+    c.gb = (e->G + 127) / 128;
+    if (e->ext_int[0] < c.nchunk * e->G) {
+        if (e->ext_dev[EXT_AD_PARTIAL]) cudaFree(e->ext_dev[EXT_AD_PARTIAL]);
+        e->ext_dev[EXT_AD_PARTIAL] = nullptr;
+        ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_AD_PARTIAL], sizeof(double) * (size_t)c.nchunk * e->G));
+        e->ext_int[0] = c.nchunk * e->G;
+    }
+    c.partial = (double*)e->ext_dev[EXT_AD_PARTIAL];
+    c.d_nx = e->d_ad_dims;
+    c.d_ny = e->d_ad_dims + e->G;
+    c.d_counters = e->d_ad_dims + 2 * e->G;
+    c.k1 = (T*)e->ad_plane[0]; c.S1 = (T*)e->ad_plane[1]; c.S2 = (T*)e->ad_plane[2];
+    c.est = (T*)e->ad_plane[3]; c.k = (T*)e->ad_plane[4]; c.knew = (T*)e->ad_plane[5];
+    return ODINN_OK;
+}
+
+template <typename T>
+static int rk_norm(RkCtx<T>& c, const T* a, const T* b, const T* u, const T* v, double reltol, double abstol) {
+    odinn_ensemble* e = c.e;
+    rk_sumsq<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, a, b, u, v, c.partial, reltol, abstol);
+    ODINN_CHECK_LAUNCH(e);
+    rk_reduce_chunks<<<e->G, RK_NT, 0, e->stream>>>(c.partial, c.nchunk, e->d_S);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
+template <typename T, typename Rhs, typename OnStop>
+static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, double reltol, double abstol, double dtmax, double dt0,
+                        int max_steps, Rhs rhs, OnStop on_stop) {
+    odinn_ensemble* e = c.e;
+    int rc;
+    const int G = e->G;
+    rk_reset<<<c.gb, 128, 0, e->stream>>>(c.st, G, stops[0]);
+    ODINN_CHECK_LAUNCH(e);
+    if ((rc = rhs(u, c.k1, 0.0))) return rc;  // FSAL seed f(t0, u0)
+    if (dt0 > 0.0) {
+        rk_set_dt<<<c.gb, 128, 0, e->stream>>>(c.st, G, std::min(dt0, dtmax));
+        ODINN_CHECK_LAUNCH(e);
+    } else {
+        if ((rc = rk_norm<T>(c, u, nullptr, u, nullptr, reltol, abstol))) return rc;
+        rk_init_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, 0, dtmax);
+        ODINN_CHECK_LAUNCH(e);
+        if ((rc = rk_norm<T>(c, c.k1, nullptr, u, nullptr, reltol, abstol))) return rc;
+        rk_init_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, 1, dtmax);
+        ODINN_CHECK_LAUNCH(e);
+        rk_stage1<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.k1, c.S1, (T*)nullptr, 1.0, 0.0);  // u1 = u0 + h0 f0
+        ODINN_CHECK_LAUNCH(e);
+        if ((rc = rhs(c.S1, c.k, 1.0))) return rc;                                                            // f1 = f(t0 + h0, u1)
+        if ((rc = rk_norm<T>(c, c.k, c.k1, u, nullptr, reltol, abstol))) return rc;
+        rk_init_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, 2, dtmax);
+        ODINN_CHECK_LAUNCH(e);
+    }
+    int total = 0;
+    for (size_t i = 1; i < stops.size(); ++i) {
+        rk_begin_interval<<<c.gb, 128, 0, e->stream>>>(c.st, G, stops[i - 1], stops[i], dtmax);
+        ODINN_CHECK_LAUNCH(e);
+        for (;;) {
+            if (++total > max_steps) return fail(e, ODINN_ESTATE, "rdpk3sp35: too many steps (maxiters)");
+            rk_stage1_main<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.k1, c.S1, c.est);
+            ODINN_CHECK_LAUNCH(e);
+            for (int s = 0; s < 4; ++s) {
+                if ((rc = rhs(c.S1, c.k, h_C[s + 1]))) return rc;
+                rk_stage<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, s == 0 ? u : c.S2, s == 3 ? (T*)nullptr : c.S2, c.S1, c.k,
+                                                              c.est, s);
+                ODINN_CHECK_LAUNCH(e);
+            }
+            if ((rc = rhs(c.S1, c.knew, 1.0))) return rc;
+            if ((rc = rk_norm<T>(c, c.est, nullptr, u, c.S1, reltol, abstol))) return rc;
+            ODINN_CUDA(e, cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(int), e->stream));
+            rk_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, c.d_counters, dtmax);
+            ODINN_CHECK_LAUNCH(e);
+            ODINN_CUDA(e, cudaMemcpyAsync(e->h_ad_active, c.d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+            if (e->h_ad_active[1] == 0) {  // every glacier accepted (idle ones took h = 0: S1 == u, knew == k1 bit for bit): swap
+                std::swap(u, c.S1);
+                std::swap(c.k1, c.knew);
+            } else {
+                rk_commit<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.S1, c.k1, c.knew);
+                ODINN_CHECK_LAUNCH(e);
+            }
+            if (e->h_ad_active[0] == 0) break;
+        }
+        bool modified = false;
+        if ((rc = on_stop((int)i, u, &modified))) return rc;
+        if (modified && (rc = rhs(u, c.k1, 0.0))) return rc;  // u_modified: the FSAL slope is re-evaluated (h = 0 at a stop)
+    }
+    return ODINN_OK;
+}
+
+
+// ---- forward solve ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int solve_rdpk_t(odinn_ensemble* e, int n_snap, const double* t, double reltol, double abstol, double dt0, int max_steps,
+                        int* steps_out, int* rejected_out) {
+    RkCtx<T> c;
+    int rc = rk_setup<T>(e, c);
+    if (rc) return rc;
+    const size_t pbytes = (size_t)e->total * e->esize;
+    T* u = (T*)e->plane[ODINN_FIELD_H];
+    ODINN_CUDA(e, cudaMemcpyAsync(u, e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, 0), u, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    std::vector<double> stops(t, t + n_snap);
+    const double dtmax = std::fabs(t[n_snap - 1] - t[0]);
+    auto rhs = [&](const T* in, T* out, double) -> int { return rhs_planes(e, in, out); };   // autonomous: SIA2D(H)
+    auto on_stop = [&](int j, T* state, bool* modified) -> int {
+        int applied = 0, r = mb_apply_step(e, j, state, &applied);   // mass-balance callback at the end of its window
+        if (r) return r;
+        *modified = applied != 0;
+        ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, j), state, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+        return ODINN_OK;
+    };
+    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop))) return rc;
+    if ((void*)u != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H (the planes rotate through pointer swaps)
+        ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], u, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    if (steps_out || rejected_out) {
+        std::vector<RkState> hs(e->G);
+        ODINN_CUDA(e, cudaMemcpyAsync(hs.data(), c.st, sizeof(RkState) * e->G, cudaMemcpyDeviceToHost, e->stream));
+        ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+        for (int g = 0; g < e->G; ++g) {
+            if (steps_out) steps_out[g] = hs[g].steps;
+            if (rejected_out) rejected_out[g] = hs[g].rejected;
+        }
+    }
+    return ODINN_OK;
+}
+
+int solve_forward_rdpk(odinn_ensemble* e, int n_snap, const double* t, double reltol, double abstol, double dt0, int max_steps,
+                       int* steps_out, int* rejected_out) {
+    return e->dtype == ODINN_F32 ? solve_rdpk_t<float>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out)
+                                 : solve_rdpk_t<double>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
+}
+
+// ---- continuous adjoint with the adaptive reverse solve (gradient.jl:276-538) ------------------------------------------------
+template <typename T>
+static int grad_continuous_adaptive_t(odinn_ensemble* e, const double* t, int n_t, int n_q, const double* qn, const double* qw,
+                                      bool cont_vjp, double reltol, double abstol, double dtmax, int max_steps, int* steps_out) {
+    RkCtx<T> c;
+    int rc = rk_setup<T>(e, c);
+    if (rc) return rc;
+    void** Htp = &e->ext_dev[EXT_CA_HT];
+    if ((rc = alloc_work_plane(e, Htp))) return rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_LAMBDA))) return rc;
+    T* Ht = (T*)*Htp;
+    T* lam = (T*)e->plane[ODINN_FIELD_LAMBDA];
+    const size_t pbytes = (size_t)e->total * e->esize;
+    ODINN_CUDA(e, cudaMemsetAsync(lam, 0, pbytes, e->stream));
+    ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
+    ODINN_CUDA(e, cudaMemsetAsync(e->d_Ssum, 0, sizeof(double) * e->G, e->stream));
+    if (e->law_kind != 0)
+        ODINN_CUDA(e, cudaMemsetAsync(e->d_law_dtheta, 0, sizeof(double) * (size_t)e->G * e->law_n_theta, e->stream));
+
+    // stops in tau = -t, ascending:  sort(unique(vcat(-reverse(tstops), -t_nodes)))   (gradient.jl:456)
+    struct Ev { double tau; int is_q; int idx; };
+    std::vector<Ev> ev;
+    for (int j = 0; j < n_t; ++j) ev.push_back({-t[j], 0, j});
+    for (int m = 0; m < n_q; ++m) {
+        bool dup = false;
+        for (int j = 0; j < n_t; ++j) dup |= (qn[m] == t[j]);
+        if (!dup) ev.push_back({-qn[m], 1, m});
+    }
+    std::stable_sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.tau < b.tau; });
+    std::vector<double> stops;
+    for (const Ev& s : ev) stops.push_back(s.tau);
+
+    // effect_loss! at tstop j:  loss += w_j l_j ;  lambda += dl_j/dH   (thickness term + velocity term, Losses.jl:270-390)
+    auto loss_jump = [&](int j, T* u) -> int {
+        const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
+        int r;
+        if (wH != 0.0 && (r = loss_seed_planes(e, snapshot_ptr(e, j), (char*)e->href + (size_t)j * pbytes, (char*)e->wmask + (size_t)j * pbytes,
+                                               u, nullptr, u, 0.0, 2.0 * wH, e->d_loss, wH, 1)))
+            return r;
+        return velocity_loss_term(e, j, snapshot_ptr(e, j), u, wV, e->d_loss, nullptr);   // (its dl/dtheta is quadrature-weighted: below)
+    };
+    // lambda_1 = effect_loss!(t_end, 0), then the PeriodicCallback's initial_affect (MB at t_end)   (gradient.jl:407-446)
+    if ((rc = loss_jump(n_t - 1, lam))) return rc;
+    if ((rc = mb_adjoint_step(e, n_t - 1, lam, snapshot_ptr(e, n_t - 1)))) return rc;
+
+    int jint = n_t - 2;  // tstop interval [t_jint, t_jint+1] the reverse solve is in
+    auto rhs = [&](const T* in, T* out, double cc) -> int {   // dlambda/dtau = VJP_H(lambda, H_itp(-tau))   (gradient.jl:316-324)
+        rk_lerp<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, (const T*)snapshot_ptr(e, jint), (const T*)snapshot_ptr(e, jint + 1), Ht, cc,
+                                                     -1.0, t[jint], t[jint + 1]);
+        ODINN_CHECK_LAUNCH(e);
+        return vjp_planes(e, in, Ht, out, true, false, nullptr, 1.0, 0, cont_vjp);
+    };
+    const double cV = e->lossV_theta_scale;
+    auto on_stop = [&](int i, T* u, bool* modified) -> int {
+        const Ev& s = ev[i];
+        int r;
+        if (!s.is_q) {
+            const int j = s.idx;
+            // CallbackSet(cb_adjoint_MB, cb_adjoint_loss): MB first (not at t_0: final_affect = false), then the loss jump
+            if (j != 0 && (r = mb_adjoint_step(e, j, u, snapshot_ptr(e, j)))) return r;
+            if ((r = loss_jump(j, u))) return r;
+            *modified = true;   // a DiscreteCallback's affect! marks u as modified whatever it added
+            if (j >= 1) jint = std::max(j - 1, 0);   // the solve continues in [t_{j-1}, t_j]
+            return ODINN_OK;
+        }
+        // quadrature node:  dL/dtheta += w_m (VJP_theta(lambda(t_m), H_itp(t_m)) + dl/dtheta(t_m))   (gradient.jl:495-507)
+        rk_lerp<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, (const T*)snapshot_ptr(e, jint), (const T*)snapshot_ptr(e, jint + 1), Ht, 0.0,
+                                                     -1.0, t[jint], t[jint + 1]);
+        ODINN_CHECK_LAUNCH(e);
+        if ((r = vjp_planes(e, u, Ht, nullptr, false, true, e->d_Ssum, qw[s.idx], 1, cont_vjp))) return r;
+        if (cV != 0.0 && (r = velocity_theta_term_interp(e, qn[s.idx], t, n_t, Ht, cV * qw[s.idx], e->d_Ssum))) return r;
+        return ODINN_OK;
+    };
+    if ((rc = rk_integrate<T>(c, lam, stops, reltol, abstol, dtmax, 0.0, max_steps, rhs, on_stop))) return rc;
+    if ((void*)lam != e->plane[ODINN_FIELD_LAMBDA])
+        ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_LAMBDA], lam, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    if (steps_out) {
+        std::vector<RkState> hs(e->G);
+        ODINN_CUDA(e, cudaMemcpyAsync(hs.data(), c.st, sizeof(RkState) * e->G, cudaMemcpyDeviceToHost, e->stream));
+        ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+        for (int g = 0; g < e->G; ++g) steps_out[g] = hs[g].steps;
+    }
+    return ODINN_OK;
+}
+
+}  // namespace odinn
+
+using namespace odinn;
+
+extern "C" int odinn_grad_continuous_adaptive(odinn_ensemble* e, const double* t, int n_t, int n_quadrature, const double* q_nodes,
+                                              const double* q_weights, int continuous_vjp, double reltol, double abstol, double dtmax,
+                                              int max_steps, double* loss_out, double* Ssum_out, int* steps_out) {
+    if (!e) return fail(nullptr, ODINN_EARG, "null ensemble");
+    {
+        cudaError_t s_ = cudaSetDevice(e->device);
+        if (s_ != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(s_));
+    }
+    if (!e->snap || !e->href) return fail(e, ODINN_ESTATE, "snapshots and reference data must be set first");
+    if (e->n_snap != e->n_ref || n_t != e->n_snap) return fail(e, ODINN_ESTATE, "snapshot / reference / time counts differ");
+    if (!t || n_t < 2 || n_quadrature < 1 || !q_nodes || !q_weights || !(reltol > 0.0) || !(abstol > 0.0) || !(dtmax > 0.0) || max_steps < 1)
+        return fail(e, ODINN_EARG, "bad continuous-adjoint arguments");
+    for (int j = 1; j < n_t; ++j)
+        if (!(t[j] > t[j - 1])) return fail(e, ODINN_EARG, "tstops must be strictly increasing");
+    for (int m = 0; m < n_quadrature; ++m)
+        if (!(q_nodes[m] >= t[0] && q_nodes[m] <= t[n_t - 1])) return fail(e, ODINN_EARG, "quadrature node outside the time span");
+    if (e->a_gridded) return fail(e, ODINN_ESTATE, "odinn_grad_continuous_adaptive supports glacier-wide A and per-cell laws");
+    if (continuous_vjp && e->law_kind != 0) return fail(e, ODINN_ESTATE, "the continuous VJP flavour is provided for glacier-wide A laws");
+    int rc;
+    if ((rc = sync_descs(e))) return rc;
+    rc = e->dtype == ODINN_F32
+             ? grad_continuous_adaptive_t<float>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, reltol, abstol, dtmax, max_steps, steps_out)
+             : grad_continuous_adaptive_t<double>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, reltol, abstol, dtmax, max_steps, steps_out);
+    if (rc) return rc;
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + e->G, e->d_Ssum, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (loss_out) memcpy(loss_out, e->h_S, sizeof(double) * e->G);
+    if (Ssum_out) memcpy(Ssum_out, e->h_S + e->G, sizeof(double) * e->G);
+    return ODINN_OK;
+}

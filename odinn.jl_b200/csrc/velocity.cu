@@ -11,6 +11,8 @@
 //   cA = α sv,  cX = β ∇Sx sv + Dꜛ ∂Vx,  cY = β ∇Sy sv + Dꜛ ∂Vy,   sv = ∇Sx ∂Vx + ∇Sy ∂Vy
 // the cell pass gathers  -(avg†(cA) + diff_x†(avg_y†(cX), Δx) + diff_y†(avg_x†(cY), Δy))  from the four nodes of a cell and adds
 // it (weighted) to λ.  Evaluated at the tstops that hold velocity data only -- not on the per-step hot path.
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "ensemble.cuh"
@@ -254,6 +256,115 @@ int velocity_loss_term(odinn_ensemble* e, int j, const void* Hj, void* lam, doub
     return ODINN_OK;
 }
 
+
+// ---- velocity references interpolated at a quadrature node of the continuous adjoint (gradient.jl:289-301, 474-507) ----------
+
+// out{0,1,2} = (1 - a) ref_a{Vx, Vy, Vabs} + a ref_b{...};  partial[2 tile] = #(Vabs > 0), partial[2 tile + 1] = sum_mask (Vx^2 + Vy^2)
+template <typename T>
+__global__ void __launch_bounds__(NT)
+vq_lerp_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, const T* __restrict__ ra, const T* __restrict__ rb,
+               T* __restrict__ out, long long plane, double a, double* __restrict__ partial) {
+    __shared__ double sRed[NT / 32];
+    const int2 tl = tiles[blockIdx.x];
+    const GDesc<T> d = descs[tl.x];
+    const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;
+    const int i = x0 + (threadIdx.x & 31), tr = threadIdx.x >> 5;
+    double cnt = 0.0, ss = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < TY / 8; ++rr) {
+        const int j = y0 + tr + rr * 8;
+        if (i < d.nx && j < d.ny) {
+            const long long p = d.off + (long long)j * d.ld + i;
+            double v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[c] = (1.0 - a) * (double)ra[c * plane + p] + a * (double)rb[c * plane + p];
+                out[c * plane + p] = (T)v[c];
+            }
+            if (v[2] > 0.0) { cnt += 1.0; ss += v[0] * v[0] + v[1] * v[1]; }
+        }
+    }
+    double s0 = block_sum(cnt, sRed);
+    __syncthreads();
+    double s1 = block_sum(ss, sRed);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1; }
+}
+
+// W = (Vabs > 0) / (nx ny [sqrt(mean_mask(Vx^2 + Vy^2))])      (Losses.jl:316, 327-331)
+template <typename T>
+__global__ void __launch_bounds__(NT)
+vq_weight_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, const T* __restrict__ Vabs, T* __restrict__ W,
+                 const double* __restrict__ red, int G, int scale_loss) {
+    const int2 tl = tiles[blockIdx.x];
+    const GDesc<T> d = descs[tl.x];
+    const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;
+    const int i = x0 + (threadIdx.x & 31), tr = threadIdx.x >> 5;
+    const double cnt = red[tl.x], ss = red[G + tl.x];
+    const double sc = (scale_loss && cnt > 0.0) ? sqrt(ss / cnt) : 1.0;
+    const double w = 1.0 / ((double)d.nx * (double)d.ny * sc);
+#pragma unroll
+    for (int rr = 0; rr < TY / 8; ++rr) {
+        const int j = y0 + tr + rr * 8;
+        if (i < d.nx && j < d.ny) {
+            const long long p = d.off + (long long)j * d.ld + i;
+            W[p] = ((double)Vabs[p] > 0.0) ? (T)w : T(0);
+        }
+    }
+}
+
+int velocity_theta_term_interp(odinn_ensemble* e, double tq, const double* t, int n_t, const void* H, double scale, double* S_dst) {
+    if (scale == 0.0 || e->v_snap.empty()) return ODINN_OK;
+    int rc = vel_prepare(e);
+    if (rc) return rc;
+    // data times in ascending order
+    std::vector<std::pair<double, int>> data;
+    for (size_t m = 0; m < e->v_snap.size(); ++m)
+        if (e->v_snap[m] >= 0 && e->v_snap[m] < n_t) data.push_back({t[e->v_snap[m]], (int)m});
+    if (data.empty()) return ODINN_OK;
+    std::sort(data.begin(), data.end());
+    const void *Vx, *Vy, *Vabs, *W;
+    if (data.size() == 1) {  // "when there is only one reference velocity data we use a constant interpolator"
+        const int m = data[0].second;
+        Vx = vref_plane(e, m, 0); Vy = vref_plane(e, m, 1); Vabs = vref_plane(e, m, 2); W = vref_plane(e, m, 3);
+    } else {
+        size_t k = 0;
+        while (k + 2 < data.size() && tq >= data[k + 1].first) ++k;
+        double a = (tq - data[k].first) / (data[k + 1].first - data[k].first);
+        a = std::min(1.0, std::max(0.0, a));
+        if ((rc = alloc_work_plane(e, &e->ext_dev[EXT_VQ_WORK], 4))) return rc;
+        if (!e->ext_dev[EXT_VQ_RED]) ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_VQ_RED], sizeof(double) * 2 * e->G));
+        char* wk = (char*)e->ext_dev[EXT_VQ_WORK];
+        const size_t pb = (size_t)e->total * e->esize;
+        double* red = (double*)e->ext_dev[EXT_VQ_RED];
+        double* partial = (double*)e->ext_dev[EXT_V_PARTIAL];
+        if (e->dtype == ODINN_F32) {
+            vq_lerp_kernel<float><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<float>*)e->d_descs, e->d_tiles, (const float*)vref_plane(e, data[k].second, 0),
+                                                                   (const float*)vref_plane(e, data[k + 1].second, 0), (float*)wk, e->total, a, partial);
+        } else {
+            vq_lerp_kernel<double><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<double>*)e->d_descs, e->d_tiles, (const double*)vref_plane(e, data[k].second, 0),
+                                                                    (const double*)vref_plane(e, data[k + 1].second, 0), (double*)wk, e->total, a, partial);
+        }
+        ODINN_CHECK_LAUNCH(e);
+        vel_reduce_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, partial, 0, red, 1.0, 0);
+        ODINN_CHECK_LAUNCH(e);
+        vel_reduce_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, partial, 1, red + e->G, 1.0, 0);
+        ODINN_CHECK_LAUNCH(e);
+        if (e->dtype == ODINN_F32)
+            vq_weight_kernel<float><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<float>*)e->d_descs, e->d_tiles, (const float*)(wk + 2 * pb), (float*)(wk + 3 * pb),
+                                                                     red, e->G, e->lossV_scale_loss);
+        else
+            vq_weight_kernel<double><<<e->n_tiles, NT, 0, e->stream>>>((const GDesc<double>*)e->d_descs, e->d_tiles, (const double*)(wk + 2 * pb),
+                                                                      (double*)(wk + 3 * pb), red, e->G, e->lossV_scale_loss);
+        ODINN_CHECK_LAUNCH(e);
+        Vx = wk; Vy = wk + pb; Vabs = wk + 2 * pb; W = wk + 3 * pb;
+    }
+    const int mode = e->lossV_component == 1 ? 3 : 2;
+    if ((rc = vel_launch(e, mode, 0, e->n_tiles, H, Vx, Vy, Vabs, W, nullptr, nullptr, false))) return rc;
+    vel_reduce_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, (const double*)e->ext_dev[EXT_V_PARTIAL], 1, S_dst, -scale, 1);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
 }  // namespace odinn
 
 using namespace odinn;
@@ -349,3 +460,10 @@ int odinn_set_loss_weights(odinn_ensemble* e, int n_t, const double* wH, const d
 }
 
 }  // extern "C"
+
+extern "C" int odinn_set_velocity_quadrature(odinn_ensemble* e, double theta_scale, int scale_loss) {
+    VGUARD(e);
+    e->lossV_theta_scale = theta_scale;
+    e->lossV_scale_loss = scale_loss ? 1 : 0;
+    return ODINN_OK;
+}

@@ -242,13 +242,16 @@ class Ensemble:
         m = {"euler": _capi.EULER, "ssprk3": _capi.SSPRK3}[method]
         self._ck(self._lib.odinn_solve_forward(self._h, m, t.size, t.ctypes.data_as(C.POINTER(C.c_double)), int(nsub)))
 
-    def solve_forward_adaptive(self, t, reltol: float = 1e-6, abstol: float = 1e-6, dt0: float = 0.0, max_steps: int = 1_000_000):
-        """BS3 with per-glacier adaptive steps and tstops ``t`` (saveat = tstops); returns (steps, rejected) per glacier."""
+    def solve_forward_adaptive(self, t, reltol: float = 1e-6, abstol: float = 1e-6, dt0: float = 0.0, max_steps: int = 1_000_000,
+                               method: str = "bs3"):
+        """Adaptive solve with per-glacier steps and tstops ``t`` (saveat = tstops); returns (steps, rejected) per glacier.
+        method: "rdpk3sp35" (the reference's default solver: RDPK3Sp35 + PID controller) | "bs3"."""
         t = np.ascontiguousarray(t, dtype=np.float64)
         steps = np.zeros(self.G, dtype=np.int32)
         rej = np.zeros(self.G, dtype=np.int32)
         ip = C.POINTER(C.c_int)
-        self._ck(self._lib.odinn_solve_forward_adaptive(self._h, _capi.BS3, t.size, t.ctypes.data_as(C.POINTER(C.c_double)),
+        m = {"bs3": _capi.BS3, "rdpk3sp35": _capi.RDPK3SP35}[method]
+        self._ck(self._lib.odinn_solve_forward_adaptive(self._h, m, t.size, t.ctypes.data_as(C.POINTER(C.c_double)),
                                                         float(reltol), float(abstol), float(dt0), int(max_steps),
                                                         steps.ctypes.data_as(ip), rej.ctypes.data_as(ip)))
         return steps, rej
@@ -302,6 +305,29 @@ class Ensemble:
                                                  qw.ctypes.data_as(dp), 1 if vjp == "continuous" else 0, m, int(nsub),
                                                  loss.ctypes.data_as(dp), Ssum.ctypes.data_as(dp)))
         return loss, Ssum
+
+    def grad_continuous_adaptive(self, t, n_quadrature: int = 200, vjp: str = "discrete", reltol: float = 1e-8, abstol: float = 1e-8,
+                                 dtmax: float = 1.0 / 12.0, max_steps: int = 1_000_000):
+        """ContinuousAdjoint gradient with the reference's default reverse solve: adaptive RDPK3Sp35, reltol = abstol = 1e-8,
+        dtmax = 1/12, n_quadrature = 200 (src/inverse/AdjointTypes.jl:53-66).  Returns (loss, Ssum, trial steps) per glacier."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        x, w = np.polynomial.legendre.leggauss(int(n_quadrature))
+        qn = np.ascontiguousarray(0.5 * (t[0] + t[-1]) + x * 0.5 * (t[-1] - t[0]))
+        qw = np.ascontiguousarray(0.5 * (t[-1] - t[0]) * w)
+        loss = np.empty(self.G, dtype=np.float64)
+        Ssum = np.empty(self.G, dtype=np.float64)
+        steps = np.zeros(self.G, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        self._ck(self._lib.odinn_grad_continuous_adaptive(self._h, t.ctypes.data_as(dp), t.size, qn.size, qn.ctypes.data_as(dp),
+                                                          qw.ctypes.data_as(dp), 1 if vjp == "continuous" else 0, float(reltol),
+                                                          float(abstol), float(dtmax), int(max_steps), loss.ctypes.data_as(dp),
+                                                          Ssum.ctypes.data_as(dp), steps.ctypes.data_as(C.POINTER(C.c_int))))
+        return loss, Ssum, steps
+
+    def set_velocity_quadrature(self, theta_scale: float, scale_loss: bool = True):
+        """Continuous adjoint with a velocity loss: multiplier of the quadrature-weighted dl_V/dtheta term (1 for LossV,
+        LossHV.scaling for LossHV, 0 = off) and LossV.scale_loss (gradient.jl:474-507)."""
+        self._ck(self._lib.odinn_set_velocity_quadrature(self._h, float(theta_scale), int(bool(scale_loss))))
 
     # -- surface velocity / LossV ---------------------------------------------------------------------
     def surface_velocity(self, g: int, H, t: float = 0.0):

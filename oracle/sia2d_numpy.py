@@ -887,6 +887,144 @@ def VJP_MB_dH(lam, H_preMB, B, par):
 # --------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------
+# RDPK3Sp35 + PID controller: the reference's DEFAULT integrator for the forward solve and for the reverse ODE of the
+# continuous adjoint (src/inverse/AdjointTypes.jl:60-63, test/test_grad_loss.jl:143, solve calls
+# src/simulations/inversions/inversion_utils.jl:559-568 and src/inverse/SIA2D/gradient.jl:459-467).
+#
+# The integrator itself lives in OrdinaryDiffEq 6 [NOT IN TREE] (compat Project.toml:101).  Restated here from its published
+# algorithm: Ranocha, Dalcin, Parsani, Ketcheson, "Optimized Runge-Kutta methods with automatic step size control for
+# compressible computational fluid dynamics" (2021): a 5-stage, 3rd-order 3S*+ low-storage scheme with an embedded 2nd-order
+# error estimator, driven by a PID step-size controller with beta = (0.64, -0.31, 0.04), the limiter 1 + atan(x - 1) and
+# the acceptance threshold 0.81 (Soderlind & Wang 2006), as OrdinaryDiffEq's `PIDController` implements it.
+#
+# PINNING of the coefficients (no Julia, no network): the 3S* coefficients below reproduce, in 40-digit arithmetic, the
+# order conditions  sum b = 1, b.c = 1/2, b.c^2 = 1/3, b.A.c = 1/6  and the published abscissae c to 1e-37 (tests/
+# test_oracle_rdpk.py repeats the check in float64), so the main scheme is digit-exact.  The embedded weights bhat sum to 1
+# to 2e-38 but satisfy bhat.c = 1/2 only to 2.8e-7: one digit string may deviate from the published one at the 1e-6 level
+# (the error ESTIMATE, hence the step-size sequence, would differ from OrdinaryDiffEq's at that relative level; the
+# solution itself is controlled by the tolerances either way).  PARITY UNPINNED against the Julia integrator.
+# --------------------------------------------------------------------------
+RDPK_G1 = (2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
+           5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01)
+RDPK_G2 = (5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
+           2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01)
+RDPK_G3 = (0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01)
+RDPK_D = (3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
+          7.229275366787987419692007421895451953e-01, 0.0)
+RDPK_B1 = 2.300298624518076223899418286314123354e-01
+RDPK_B = (3.021434166948288809034402119555380003e-01, 8.025606185416310937583009085873554681e-01,
+          4.362158943603440930655148245148766471e-01, 1.129272530455059129782111662594436580e-01)
+RDPK_C = (2.300298624518076223899418286314123354e-01, 4.050046072094990912268498160116125481e-01,
+          8.947822893693433545220710894560512805e-01, 7.235136928826589010272834603680114769e-01)
+RDPK_BHAT = (1.046363371354093758897668305991705199e-01, 9.520431574956758809511173383346476348e-02,
+             4.482446645568668405072421350300379357e-01, 2.449030295461310135957132640369862245e-01,
+             1.070116530120251819121660365003405564e-01)
+PID_BETA = (0.64, -0.31, 0.04)   # RDPK3Sp35 (Ranocha et al. 2021, table of controller parameters)
+PID_ACCEPT_SAFETY = 0.81
+
+
+def rdpk_butcher():
+    """(A, b, c) of the scheme the 3S* recurrence  S2 += delta S1;  S1 = g1 S1 + g2 S2 + g3 u_n + beta dt f(S1)  defines."""
+    n = 5
+    u = np.zeros(n + 1); u[0] = 1.0          # coefficients of (u_n, dt k_1 .. dt k_5)
+    tmp = u.copy()
+    u = tmp.copy(); u[1] = RDPK_B1
+    A = np.zeros((n, n))
+    for i in range(4):
+        A[i + 1, :] = u[1:]
+        tmp = tmp + RDPK_D[i] * u
+        e0 = np.zeros(n + 1); e0[0] = 1.0
+        u = RDPK_G1[i] * u + RDPK_G2[i] * tmp + RDPK_G3[i] * e0
+        u[i + 2] += RDPK_B[i]
+    return A, u[1:].copy(), A.sum(axis=1)
+
+
+RDPK_E = tuple(np.asarray(RDPK_BHAT) - rdpk_butcher()[1])   # bhat - b: weights of the error estimate (OrdinaryDiffEq stores this difference)
+
+
+def ode_norm(r):
+    """ODE_DEFAULT_NORM of OrdinaryDiffEq: sqrt(sum(abs2, r) / length(r))."""
+    return float(np.sqrt(np.mean(np.square(r))))
+
+
+def integrate_rdpk3sp35(f, u0, stops, reltol, abstol, dtmax=None, dt0=None, on_stop=None, maxiters=1_000_000, stats=None):
+    """Adaptive RDPK3Sp35 solve of u' = f(t, u) from stops[0] to stops[-1], landing exactly on every stop (tstops).
+
+    on_stop(j, t, u) -> None | new u : callback at stop j >= 1 (DiscreteCallback / PeriodicCallback at a tstop); a returned
+    array replaces u and the FSAL slope is re-evaluated (u_modified).  Returns the list of states at the stops.
+    Step mechanics as in OrdinaryDiffEq: FSAL first stage (the low-storage caches evaluate f(u_new) at the end of a step),
+    5 RHS per trial step; error norm sqrt(mean((est / (abstol + reltol max(|u|, |u_new|)))^2)); PID controller
+        factor = limiter(e1^(b1/k) e2^(b2/k) e3^(b3/k)),  e1 = 1/EEst, k = min(3, 2) + 1,  limiter(x) = 1 + atan(x - 1),
+    accept iff factor >= 0.81; accepted: dt_next = dt * factor (the step that was TAKEN, i.e. after truncation at a tstop) and the error
+    history shifts; rejected: dt *= factor, history kept.  dt is capped by dtmax and by the distance to the next stop.
+    Automatic initial step: Hairer-Wanner (OrdinaryDiffEq's ode_determine_initdt) unless dt0 is given."""
+    u = np.array(u0, dtype=np.float64, copy=True)
+    t = float(stops[0])
+    tdir_end = float(stops[-1])
+    if dtmax is None:
+        dtmax = abs(tdir_end - t)
+    nrhs = 0
+    k1 = f(t, u); nrhs += 1
+    if dt0 is None:
+        sk = abstol + np.abs(u) * reltol
+        d0, d1 = ode_norm(u / sk), ode_norm(k1 / sk)
+        h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        h0 = min(h0, dtmax)
+        f1 = f(t + h0, u + h0 * k1); nrhs += 1
+        d2 = ode_norm((f1 - k1) / sk) / h0
+        md = max(d1, d2)
+        h1 = max(1e-6, h0 * 1e-3) if md <= 1e-15 else 10.0 ** (-(2.0 + np.log10(md)) / 3.0)   # (OrdinaryDiffEq divides by alg_order = 3)
+        dt = min(100.0 * h0, h1, dtmax)
+    else:
+        dt = min(float(dt0), dtmax)
+    err = [1.0, 1.0, 1.0]
+    out = [u.copy()]
+    steps = rejected = 0
+    for j in range(1, len(stops)):
+        tstop = float(stops[j])
+        while t < tstop:
+            h = min(dt, dtmax, tstop - t)
+            last = (t + h >= tstop) or (tstop - (t + h) < 1e-14 * max(1.0, abs(tstop)))
+            if last:
+                h = tstop - t
+            # ---- one trial step: 3S*+ recurrence ----
+            S1 = u + (RDPK_B1 * h) * k1
+            S2 = u.copy()
+            est = (RDPK_E[0] * h) * k1
+            for i in range(4):
+                k = f(t + RDPK_C[i] * h, S1); nrhs += 1
+                S2 = S2 + RDPK_D[i] * S1
+                S1 = RDPK_G1[i] * S1 + RDPK_G2[i] * S2 + RDPK_G3[i] * u + (RDPK_B[i] * h) * k
+                est = est + (RDPK_E[i + 1] * h) * k
+            knew = f(t + h, S1); nrhs += 1           # "for interpolation, then FSAL'd"
+            EEst = ode_norm(est / (abstol + np.maximum(np.abs(u), np.abs(S1)) * reltol))
+            # ---- PID controller ----
+            e1 = 1.0 / max(EEst, 1e-300)
+            fac = e1 ** (PID_BETA[0] / 3.0) * err[1] ** (PID_BETA[1] / 3.0) * err[2] ** (PID_BETA[2] / 3.0)
+            fac = 1.0 + np.arctan(fac - 1.0)
+            steps += 1
+            if steps > maxiters:
+                raise RuntimeError("rdpk3sp35: maxiters reached")
+            if fac >= PID_ACCEPT_SAFETY:
+                t = tstop if last else t + h
+                u, k1 = S1, knew
+                err = [1.0, e1, err[1]]
+                dt = h * fac
+            else:
+                rejected += 1
+                dt = h * fac
+        if on_stop is not None:
+            un = on_stop(j, t, u)
+            if un is not None:
+                u = np.array(un, dtype=np.float64, copy=True)
+                k1 = f(t, u); nrhs += 1
+        out.append(u.copy())
+    if stats is not None:
+        stats.update(nrhs=nrhs, steps=steps, rejected=rejected)
+    return out
+
+
 def define_callback_steps(tspan, step):
     """Huginn.define_callback_steps [NOT IN TREE]; call site gradient.jl:96."""
     n = int(round((tspan[1] - tspan[0]) / step))
@@ -894,11 +1032,23 @@ def define_callback_steps(tspan, step):
 
 
 def solve_forward(H0, glacier, target, theta, tstops, method="ssprk3", nsub=8, reltol=1e-6, abstol=1e-6, dt0=None,
-                  max_steps=10_000_000, stats=None, mb=None):
+                  max_steps=10_000_000, stats=None, mb=None, dtmax=None):
     """Returns the list of snapshots H(t) at every tstop (incl. the first).
     mb: {snapshot index j: par} -- the mass-balance callback fires when the solve reaches tstop j, before the state is
-    saved (the solution is stored after MB has been applied, gradient.jl:202); the MB fields go to stats["MB"][j]."""
+    saved (the solution is stored after MB has been applied, gradient.jl:202); the MB fields go to stats["MB"][j].
+    method "rdpk3sp35": the reference's default solver (adaptive, PID controller; integrate_rdpk3sp35)."""
     f = lambda H: SIA2D(H, glacier, target, theta)
+    if method == "rdpk3sp35":
+        def on_stop(j, t, u):
+            if mb is not None and j in mb:
+                MB, _, _, _ = mb_TI1(u, glacier.B, mb[j])
+                if stats is not None:
+                    stats.setdefault("MB", {})[j] = MB
+                return u + MB
+            return None
+
+        return integrate_rdpk3sp35(lambda t, u: f(u), H0, tstops, reltol, abstol, dtmax=dtmax, dt0=dt0, on_stop=on_stop,
+                                   maxiters=max_steps, stats=stats)
     H = np.array(H0, dtype=np.float64, copy=True)
     out = [H.copy()]
     nrhs = 0
@@ -1065,6 +1215,120 @@ def loss_and_grad_continuous(theta, glacier, target, t, Hs, H_ref, n_quadrature=
             g = q_w[idx] * VT(lam, H_itp(tt), glacier, target, theta)
             dLdtheta = g if dLdtheta is None else dLdtheta + g
     return ell, dLdtheta
+
+
+def loss_and_grad_continuous_adaptive(theta, glacier, target, t, Hs, H_ref, n_quadrature=200, reltol=1e-8, abstol=1e-8,
+                                      dtmax=1.0 / 12.0, vjp="discrete", distance=3, wH=None, wV=None, V_ref=None, cV=0.0,
+                                      component="xy", scale_loss=True, mb=None, MB_hist=None, stats=None, fixed=None):
+    """The ContinuousAdjoint branch of SIA2D_grad_batch! (gradient.jl:276-538) as the reference runs it by default
+    (src/inverse/AdjointTypes.jl:53-66): the reverse ODE is solved ADAPTIVELY with RDPK3Sp35, reltol = abstol = 1e-8,
+    dtmax = 1/12, tstops_adjoint = sort(unique(-reverse(tstops) U -t_nodes)) (:456-466), n_quadrature = 200.
+
+      lambda_1 = effect_loss!(t_end, 0)                                                (:439-446)
+      PeriodicCallback(effect_MB!, step_MB; initial_affect = true, final_affect = false): at every MB tstop (t_end included)
+          lambda += VJP_lambda_dMBdH(lambda, H_itp(t) - MB)                          (:407-424); CallbackSet order: MB, then loss
+      DiscreteCallback at every tstop: lambda += dl/dH with the per-snapshot weights wH / wV   (:326-366)
+      dL/dtheta = sum_m w_m (VJP_theta(lambda(t_m), H_itp(t_m)) + dl/dtheta(t_m))        (:474-507)
+          with dl/dtheta(t_m) = cV * d(l_V)/dtheta evaluated on H_itp(t_m) and the velocity references interpolated
+          linearly over the data times (one datum: constant, :289-301; flat outside the data range -- Interpolations would
+          throw there) -- Delta_t = (1, 1) inside the quadrature (:475), so cV = 1 for LossV and `scaling` for LossHV.
+
+    wH / wV: per-snapshot multipliers as in loss_and_grad_discrete_HV (default: LossH, wH = Delta t_H).
+    V_ref[j] = (Vx_ref, Vy_ref, Vabs_ref) or None.  mb / MB_hist: {j: par} / {j: MB field}.
+    fixed = ("euler" | "ssprk3", nsub): the same callbacks around a fixed-step reverse integrator with nsub sub-steps between
+    consecutive stops (the scheme of loss_and_grad_continuous; params.UDE.grad.solver is a user parameter upstream).
+    Returns (loss, dL/dtheta)."""
+    t = np.asarray(t, dtype=np.float64)
+    k = len(t)
+    N = glacier.shape
+    normalization = float(N[0] * N[1])
+    target.precompute_vjp(theta)
+    VH = VJP_dSIA_dH_discrete if vjp == "discrete" else VJP_dSIA_dH_continuous
+    VT = VJP_dSIA_dtheta_discrete if vjp == "discrete" else VJP_dSIA_dtheta_continuous
+    if wH is None:
+        wH = np.array([0.0] + list(np.diff(t)))
+    if wV is None:
+        wV = np.zeros(k)
+
+    def H_itp(tt):
+        j = int(np.clip(np.searchsorted(t, tt, side="right") - 1, 0, k - 2))
+        a = (tt - t[j]) / (t[j + 1] - t[j])
+        return (1.0 - a) * Hs[j] + a * Hs[j + 1]
+
+    jV = [j for j in range(k) if V_ref is not None and V_ref[j] is not None]
+
+    def V_itp(tt):
+        if len(jV) == 1:
+            return V_ref[jV[0]]
+        tv = t[jV]
+        m = int(np.clip(np.searchsorted(tv, tt, side="right") - 1, 0, len(jV) - 2))
+        a = float(np.clip((tt - tv[m]) / (tv[m + 1] - tv[m]), 0.0, 1.0))
+        return tuple((1.0 - a) * V_ref[jV[m]][c] + a * V_ref[jV[m + 1]][c] for c in range(3))
+
+    ell = [0.0]
+
+    def loss_jump(j, lam):
+        """effect_loss! at tstop j: returns lambda + dl/dH, accumulates the loss value."""
+        out = lam
+        if wH[j] != 0.0:
+            mask = is_in_glacier(H_ref[j], distance)
+            ell[0] += wH[j] * loss_L2Sum(Hs[j], H_ref[j], mask, normalization)
+            out = out + wH[j] * backward_loss_L2Sum(Hs[j], H_ref[j], mask, normalization)
+        if wV[j] != 0.0 and V_ref is not None and V_ref[j] is not None:
+            Vxr, Vyr, Var = V_ref[j]
+            ell[0] += wV[j] * loss_V(Hs[j], Var, Vxr, Vyr, glacier, target, theta, normalization, component, scale_loss)
+            out = out + wV[j] * backward_loss_V(Hs[j], Var, Vxr, Vyr, glacier, target, theta, normalization, component, scale_loss)[0]
+        return out
+
+    def mb_jump(j, lam):
+        if mb is not None and j in mb and j != 0:
+            return lam + VJP_MB_dH(lam, Hs[j] - MB_hist[j], glacier.B, mb[j])
+        return lam
+
+    q_nodes, q_w = gauss_quadrature(t[0], t[-1], n_quadrature)
+    ev = {}  # tau -> ("t", j) | ("q", m)
+    for m, tq in enumerate(q_nodes):
+        ev[-float(tq)] = ("q", m)
+    for j, tt in enumerate(t):
+        ev[-float(tt)] = ("t", j)  # (a node that coincides with a tstop is not sampled: irrational nodes never do)
+    stops = sorted(ev)
+    dLdtheta = [None]
+
+    def on_stop(i, tau, lam):
+        kind, idx = ev[stops[i]]
+        if kind == "t":
+            return loss_jump(idx, mb_jump(idx, lam))      # CallbackSet(cb_adjoint_MB, cb_adjoint_loss, ...)
+        tt = -tau
+        Ht = H_itp(tt)
+        g = VT(lam, Ht, glacier, target, theta)
+        if cV != 0.0 and jV:
+            Vxr, Vyr, Var = V_itp(tt)
+            g = g + cV * backward_loss_V(Ht, Var, Vxr, Vyr, glacier, target, theta, normalization, component, scale_loss)[1]
+        dLdtheta[0] = q_w[idx] * g if dLdtheta[0] is None else dLdtheta[0] + q_w[idx] * g
+        return None
+
+    lam1 = loss_jump(k - 1, np.zeros(N))                    # effect_loss!(tspan[2], lambda_1)
+    lam1 = mb_jump(k - 1, lam1)                             # PeriodicCallback initial_affect
+    f = lambda tau, lam: VH(lam, H_itp(-tau), glacier, target, theta)
+    if fixed is None:
+        integrate_rdpk3sp35(f, lam1, stops, reltol, abstol, dtmax=dtmax, on_stop=on_stop, stats=stats)
+    else:
+        method, nsub = fixed
+        lam = lam1
+        for i in range(1, len(stops)):
+            h = (stops[i] - stops[i - 1]) / nsub
+            for s_ in range(nsub):
+                ta = stops[i - 1] + s_ * h
+                if method == "euler":
+                    lam = lam + h * f(ta, lam)
+                else:
+                    u1 = lam + h * f(ta, lam)
+                    u2 = 0.75 * lam + 0.25 * (u1 + h * f(ta + h, u1))
+                    lam = lam / 3.0 + (2.0 / 3.0) * (u2 + h * f(ta + 0.5 * h, u2))
+            un = on_stop(i, stops[i], lam)
+            if un is not None:
+                lam = un
+    return ell[0], dLdtheta[0]
 
 
 def loss_weights(kind, t, t_has_V=None, scaling=1.0):

@@ -229,7 +229,7 @@ def test_config1_forward_2010_2015(ob, dtype, case, method):
         # adaptive fp32: the accept / reject sequence may differ from the fp64 oracle's, so the bound is the solver tolerance
         # adaptive fp64: same accept / reject sequence, but every step size is a function of the error norm, so the RHS roundings
         # (the cubic kernel groups the node products differently from the oracle) feed back into dt over 5 years: 5e-10 measured
-        st = (1e-10 if method == "ssprk3" else 5e-9) if dtype == "f64" else (1e-3 if method == "ssprk3" else 3e-3)
+        st = (1e-10 if method == "ssprk3" else 2e-8) if dtype == "f64" else (1e-3 if method == "ssprk3" else 3e-3)
         for j in range(0, 61, 6):
             err = rel_l2(ens.get_snapshot(0, j), Hs[j])
             assert err <= st, (j, err)
