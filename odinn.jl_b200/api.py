@@ -98,11 +98,13 @@ class Model:
 
 @dataclass
 class SolverParameters:
-    """params.solver: ``step`` = tstops spacing (default 1/12 yr).  The integrator of the device loop is one of
-    "euler" / "ssprk3" with ``nsub`` fixed sub-steps per interval (OrdinaryDiffEq's RDPK3Sp35 is not in the tree)."""
+    """params.solver: ``step`` = tstops spacing (default 1/12 yr).  ``solver``: "rdpk3sp35" -- the reference's default,
+    OrdinaryDiffEq's RDPK3Sp35 with its PID controller restated on the device (csrc/rdpk.cu; adaptive, reltol / abstol) --
+    "bs3" (adaptive), or "euler" / "ssprk3" with ``nsub`` fixed sub-steps per tstop interval (each stage fused into the RHS
+    kernel, the interval replayed as a CUDA graph: the throughput configuration)."""
 
     step: float = 1.0 / 12.0
-    solver: str = "ssprk3"     # "euler" | "ssprk3" (nsub fixed sub-steps per tstop interval) | "bs3" (adaptive, reltol / abstol)
+    solver: str = "ssprk3"     # "rdpk3sp35" | "bs3" (adaptive) | "euler" | "ssprk3" (nsub fixed sub-steps per tstop interval)
     nsub: int = 8
     reltol: float = 1e-6
     abstol: float = 1e-6
@@ -118,12 +120,17 @@ class DiscreteAdjoint:
 
 @dataclass
 class ContinuousAdjoint:
-    """src/inverse/AdjointTypes.jl:60-: reverse ODE on interpolated snapshots + Gauss-Legendre quadrature (gradient.jl:276-538).
-    ``solver`` / ``nsub``: the reverse integrator (params.UDE.grad.solver upstream); ``VJP_method``: "discrete" | "continuous"."""
+    """src/inverse/AdjointTypes.jl:53-66: reverse ODE on interpolated snapshots + Gauss-Legendre quadrature (gradient.jl:276-538).
+    Defaults as upstream: ``solver`` RDPK3Sp35 (adaptive), reltol = abstol = 1e-8, dtmax = 1/12, n_quadrature = 200.
+    ``solver`` "euler" | "ssprk3": fixed-step reverse integrator with ``nsub`` sub-steps between consecutive stops.
+    ``VJP_method``: "discrete" | "continuous"."""
 
     VJP_method: str = "discrete"
     n_quadrature: int = 200
-    solver: str = "ssprk3"
+    solver: str = "rdpk3sp35"
+    reltol: float = 1e-8
+    abstol: float = 1e-8
+    dtmax: float = 1.0 / 12.0
     nsub: int = 4
 
 
@@ -204,8 +211,8 @@ class _Simulation:
     def solve(self):
         if self.ensemble is not None:
             sp = self.parameters.solver
-            if sp.solver == "bs3":
-                self.ensemble.solve_forward_adaptive(self.t, reltol=sp.reltol, abstol=sp.abstol, max_steps=sp.maxiters)
+            if sp.solver in ("bs3", "rdpk3sp35"):
+                self.ensemble.solve_forward_adaptive(self.t, reltol=sp.reltol, abstol=sp.abstol, max_steps=sp.maxiters, method=sp.solver)
             else:
                 self.ensemble.solve_forward(self.t, method=sp.solver, nsub=sp.nsub)
 
@@ -231,9 +238,12 @@ class Inversion(_Simulation):
         super().__init__(model, glaciers, parameters, **kw)
         n = len(self.t)
         for k, gid in enumerate(self.my_ids):
-            assert len(H_ref[gid]) == n, "one reference thickness per tstop"
+            # H_ref[gid][j] is None at tstops without thickness data (tH_ref a strict subset of the tstops): the library then weights
+            # snapshot j by the time since the previous datum, 0 for the first one (diff(tH_ref), gradient.jl:79-80, 144-149)
+            assert len(H_ref[gid]) == n, "one entry per tstop (None where there is no thickness data)"
             for j in range(n):
-                self.ensemble.set_reference(k, j, n, H_ref[gid][j], is_in_glacier(H_ref[gid][j], parameters.distance))
+                if H_ref[gid][j] is not None:
+                    self.ensemble.set_reference(k, j, n, H_ref[gid][j], is_in_glacier(H_ref[gid][j], parameters.distance))
         self.stats = {"losses": [], "grad_norms": []}
 
 
@@ -275,7 +285,10 @@ def SIA2D_grad_(dθ, θ, simulation: Inversion) -> float:
         simulation.apply_laws(θ)
         simulation.solve()
         gm = simulation.parameters.grad
-        if isinstance(gm, ContinuousAdjoint):
+        if isinstance(gm, ContinuousAdjoint) and gm.solver == "rdpk3sp35":
+            losses, Ssum, _ = ens.grad_continuous_adaptive(simulation.t, n_quadrature=gm.n_quadrature, vjp=gm.VJP_method, reltol=gm.reltol,
+                                                           abstol=gm.abstol, dtmax=gm.dtmax, max_steps=simulation.parameters.solver.maxiters)
+        elif isinstance(gm, ContinuousAdjoint):
             losses, Ssum = ens.grad_continuous(simulation.t, n_quadrature=gm.n_quadrature, vjp=gm.VJP_method, method=gm.solver,
                                                nsub=gm.nsub)
         else:

@@ -55,9 +55,18 @@ def test_prediction_and_gradient_against_finite_differences(ob):
         inv.close()
 
 
-def test_continuous_adjoint_and_adaptive_solver_through_the_api(ob):
-    inv, _, _ = _setup(ob, grad=ob.ContinuousAdjoint(n_quadrature=24, nsub=4),
-                       solver=ob.SolverParameters(solver="bs3", reltol=1e-7, abstol=1e-7))
+@pytest.mark.parametrize("variant", ["reference defaults", "fixed-step reverse, bs3 forward"])
+def test_continuous_adjoint_and_adaptive_solver_through_the_api(ob, variant):
+    """ContinuousAdjoint() as the reference configures it by default -- RDPK3Sp35 forward and reverse solves, reltol = abstol = 1e-8,
+    dtmax = 1/12 (src/inverse/AdjointTypes.jl:53-66; n_quadrature reduced from 200 to keep the test short) -- and the
+    fixed-step reverse integrator behind the same API."""
+    if variant == "reference defaults":
+        inv, _, _ = _setup(ob, grad=ob.ContinuousAdjoint(n_quadrature=24),
+                           solver=ob.SolverParameters(solver="rdpk3sp35", reltol=1e-8, abstol=1e-8))
+        assert inv.parameters.grad.solver == "rdpk3sp35" and inv.parameters.grad.reltol == 1e-8 and inv.parameters.grad.dtmax == 1.0 / 12.0
+    else:
+        inv, _, _ = _setup(ob, grad=ob.ContinuousAdjoint(n_quadrature=24, solver="ssprk3", nsub=4),
+                           solver=ob.SolverParameters(solver="bs3", reltol=1e-7, abstol=1e-7))
     try:
         θ = np.array(inv.model.θ)
         g = np.zeros_like(θ)
