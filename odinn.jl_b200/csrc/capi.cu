@@ -118,7 +118,7 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
                             double* S_dst, double scale, int accumulate, bool packed, void* dH_out = nullptr) {
     int rc;
     const bool fuse = dH_out && wH && wS && e->law_kind == LAW_NONE && !e->no_fuse &&
-                      ((e->dtype == ODINN_F32 && e->march == 2) || (e->dtype == ODINN_F64 && e->cubic));
+                      ((e->dtype == ODINN_F32 && (e->march == 2 || e->march == 4)) || (e->dtype == ODINN_F64 && e->cubic));
     if (dH_out && !fuse && (rc = launch_rhs_range(e, g0, g1, H, dH_out, nullptr, packed))) return rc;
     if (!fuse) dH_out = nullptr;
     if (!wH && !wS) return ODINN_OK;
@@ -143,18 +143,20 @@ static int launch_vjp_range(odinn_ensemble* e, int g0, int g1, const void* lam, 
         return ODINN_OK;
     }
     const bool two = (e->dtype == ODINN_F32 && e->march >= 2);
-    if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed, dH_out);
+    const int* starts2 = e->d_item2_start;
+    if (two) rc = launch_vjp2(e, g0, g1, lam, H, out, wH, wS, packed, dH_out, &starts2);
     else
         rc = e->dtype == ODINN_F32 ? launch_vjp_t<float>(e, i0, ni, lam, H, out, wH, wS, packed)
                                    : launch_vjp_t<double>(e, i0, ni, lam, H, out, wH, wS, packed, dH_out);
     if (rc) return rc;
     if (wS) {
         double* dst = S_dst ? S_dst : e->d_S;
-        const int* starts = two ? e->d_item2_start : e->d_item_start;
+        const int* starts = two ? starts2 : e->d_item_start;
+        const double* part = (two && e->tma_partial_live) ? e->tma_partial_live : e->d_partial;
         if (g0 >= 0)
-            reduce_scaled_kernel<<<g1 - g0, NT, 0, e->stream>>>(starts + g0, e->d_partial, dst + g0, scale, accumulate);
+            reduce_scaled_kernel<<<g1 - g0, NT, 0, e->stream>>>(starts + g0, part, dst + g0, scale, accumulate);
         else
-            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(starts, e->d_partial, dst, scale, accumulate);
+            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(starts, part, dst, scale, accumulate);
         ODINN_CHECK_LAUNCH(e);
     }
     return ODINN_OK;
@@ -388,7 +390,7 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     std::vector<int> istart2(n_glaciers + 1);
     {
         const char* env = getenv("ODINN_MARCH");
-        if (env && env[0] >= '1' && env[0] <= '3') e->march = env[0] - '0';
+        if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) e->march = env[0] - '0';
         const char* envf = getenv("ODINN_NO_FUSE");  // developer switch: F1 and A1+A2 as two launches even where a fused kernel exists
         e->no_fuse = envf && envf[0] == '1';
         const char* envr = getenv("ODINN_CHUNK_ROWS2");
@@ -463,6 +465,7 @@ void odinn_ensemble_destroy(odinn_ensemble* e) {
                     e->d_items2, e->d_item2_start, e->d_law_theta, e->lawD, e->lawAl, e->lawBe, e->d_law_partial,
                     e->d_law_dtheta, e->bpack, e->stage[0], e->stage[1], e->stage[2], e->stage[3], e->ad_plane[0],
                     e->ad_plane[1], e->ad_plane[2], e->ad_plane[3], e->ad_plane[4], e->ad_plane[5], e->d_ad_state, e->d_ad_dims};
+    tma_cache_free(e);
     for (void* p : e->ext_dev)
         if (p) cudaFree(p);
     for (void* p : e->ext_host)
@@ -837,7 +840,7 @@ int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double*
     // kernel): it is captured ONCE into a CUDA graph and replayed per interval; the step sizes come from a device table indexed by an
     // interval counter that the graph itself advances.  (Euler swaps H and the work plane every sub-step: even nsub only.)
     const char* nog = getenv("ODINN_NO_GRAPH");
-    const bool use_graph = !(nog && nog[0] == '1') && e->law_kind == LAW_NONE && !(e->dtype == ODINN_F32 && e->march == 3) &&
+    const bool use_graph = !(nog && nog[0] == '1') && e->law_kind == LAW_NONE && 
                            (method == ODINN_SSPRK3 || nsub % 2 == 0) && n_snap > 2;
     if (use_graph) {
         std::vector<double> tab((size_t)n_snap * 9, 0.0);

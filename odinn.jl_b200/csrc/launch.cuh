@@ -45,8 +45,10 @@ int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);
 
 // fp32, two columns per lane.  g0 < 0: whole ensemble.  `packed`: packed descriptor table / packed B of the host-batch path.
 int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed);
+// *starts_used: the per-glacier start table (device) that indexes the partial sums this launch wrote
 int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS, bool packed,
-                void* dH_out = nullptr);
+                void* dH_out, const int** starts_used);
+void tma_cache_free(odinn_ensemble* e);
 
 // one column per lane (fp32 generation 1 and fp64); items [i0, i0 + n_items)
 template <typename T> int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed);

@@ -1,8 +1,138 @@
-// Launchers of the fp32 two-column marching kernels (sia2d_march2.cuh).
+// Launchers of the fp32 two-column marching kernels (sia2d_march2.cuh) and of the 2-D TMA ring variant of the fused step
+// (sia2d_tma.cuh).
+#include <cstdlib>
+#include <unordered_map>
+
 #include "launch.cuh"
 #include "sia2d_march2.cuh"
+#include "sia2d_tma.cuh"
 
 namespace odinn {
+
+// ---- 2-D TMA ring variant: tensor maps (one per glacier and plane pointer) and band work items --------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmaCache {
+    EncodeTiledFn encode = nullptr;
+    std::unordered_map<const void*, CUtensorMap*> maps;   // plane base pointer -> device array of G tensor maps
+    int4* d_bitems = nullptr;
+    int* d_bstart = nullptr;                              // [G + 1] first partial slot of every glacier
+    int n_bitems = 0;
+    double* d_partial = nullptr;
+    bool usable = false;
+};
+#ifndef ODINN_TMA_CHUNK_ROWS
+#define ODINN_TMA_CHUNK_ROWS 62   // + 2 halo rows = 16 boxes of TMA_R = 4 rows: no row is loaded that is not used
+#endif
+
+void tma_cache_free(odinn_ensemble* e) {
+    TmaCache* c = static_cast<TmaCache*>(e->tma_cache);
+    if (!c) return;
+    for (auto& kv : c->maps) cudaFree(kv.second);
+    if (c->d_bitems) cudaFree(c->d_bitems);
+    if (c->d_bstart) cudaFree(c->d_bstart);
+    if (c->d_partial) cudaFree(c->d_partial);
+    delete c;
+    e->tma_cache = nullptr;
+}
+
+static int tma_prepare(odinn_ensemble* e, TmaCache*& c) {
+    c = static_cast<TmaCache*>(e->tma_cache);
+    if (c) return ODINN_OK;
+    c = new TmaCache();
+    e->tma_cache = c;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return ODINN_OK;  // (usable stays false: the caller falls back to the marching kernel)
+    }
+    c->encode = (EncodeTiledFn)fn;
+    std::vector<int4> items;
+    std::vector<int> start(e->G + 1, 0);
+    for (int g = 0; g < e->G; ++g) {
+        const GlacierHost& s = e->gl[g];
+        start[g] = (int)items.size() * TMA_NW;
+        const int nstrips = div_up(s.nx, STRIP2), nbands = div_up(nstrips, TMA_NW);
+        // row chunks of 4k - 2 rows (+ 2 halo rows = k boxes of TMA_R = 4 rows: no row is loaded that is not used), balanced so that
+        // the last chunk of a glacier is not a sliver: 500 rows -> 7 x 66 + 38
+        const int nch = std::max(1, (s.ny + ODINN_TMA_CHUNK_ROWS / 2) / ODINN_TMA_CHUNK_ROWS);
+        const int rows = (div_up(s.ny, nch) + 2 + TMA_R - 1) / TMA_R * TMA_R - 2;
+        for (int r0 = 0; r0 < s.ny; r0 += rows)
+            for (int b = 0; b < nbands; ++b)
+                items.push_back(make_int4(g, b * TMA_NW * STRIP2 - 2, r0, std::min(r0 + rows, s.ny)));
+    }
+    start[e->G] = (int)items.size() * TMA_NW;
+    c->n_bitems = (int)items.size();
+    ODINN_CUDA(e, cudaMalloc(&c->d_bitems, sizeof(int4) * items.size()));
+    ODINN_CUDA(e, cudaMalloc(&c->d_bstart, sizeof(int) * start.size()));
+    ODINN_CUDA(e, cudaMalloc(&c->d_partial, sizeof(double) * items.size() * TMA_NW));
+    ODINN_CUDA(e, cudaMemcpy(c->d_bitems, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
+    ODINN_CUDA(e, cudaMemcpy(c->d_bstart, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+    c->usable = true;
+    return ODINN_OK;
+}
+
+// Device array of G tensor maps describing the plane at `base`: glacier g is an (nx x ny) fp32 matrix at element offset off[g] with
+// row pitch ld[g]; box = TMA_BOXW columns x TMA_R rows, no swizzle, out-of-bounds elements read as zero.
+static int tma_maps_for(odinn_ensemble* e, TmaCache* c, const void* base, const CUtensorMap** out) {
+    auto it = c->maps.find(base);
+    if (it != c->maps.end()) { *out = it->second; return ODINN_OK; }
+    std::vector<CUtensorMap> h(e->G);
+    for (int g = 0; g < e->G; ++g) {
+        const GlacierHost& s = e->gl[g];
+        const cuuint64_t dims[2] = {(cuuint64_t)s.nx, (cuuint64_t)s.ny};
+        const cuuint64_t strides[1] = {(cuuint64_t)s.ld * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)TMA_BOXW, (cuuint32_t)TMA_R};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = c->encode(&h[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)((const float*)base + s.off), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(e, ODINN_ECUDA, "cuTensorMapEncodeTiled failed (plane offsets must be 16-byte aligned)");
+    }
+    CUtensorMap* d = nullptr;
+    ODINN_CUDA(e, cudaMalloc(&d, sizeof(CUtensorMap) * e->G));
+    ODINN_CUDA(e, cudaMemcpyAsync(d, h.data(), sizeof(CUtensorMap) * e->G, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));  // (h goes out of scope)
+    c->maps[base] = d;
+    *out = d;
+    return ODINN_OK;
+}
+
+// The fused F1 + A1 + A2 step through the TMA ring (whole ensemble, padded layout, n = 3, C = 0, glacier-wide A, eta0 = 1).
+// *done = false when the variant does not apply (the caller then launches the marching kernel).
+static int launch_fused_tma(odinn_ensemble* e, const float* lam, const float* H, const float* B, float* out, float* dH, bool* done,
+                            const int** starts_used, double** partial_used) {
+    *done = false;
+    TmaCache* c = nullptr;
+    int rc = tma_prepare(e, c);
+    if (rc) return rc;
+    if (!c->usable) return ODINN_OK;
+    const CUtensorMap *mL, *mH, *mB;
+    if ((rc = tma_maps_for(e, c, lam, &mL)) || (rc = tma_maps_for(e, c, H, &mH)) || (rc = tma_maps_for(e, c, B, &mB))) return rc;
+    PhysDev<float> ph = make_phys<float>(e->phys);
+    static const int variant = []() { const char* v = getenv("ODINN_TMA_VARIANT"); return v ? atoi(v) : 0; }();   // (tuning sweeps)
+#define LT(ST, MC)                                                                                                                    \
+    do {                                                                                                                              \
+        if (tma_smem_bytes(ST) > 48 * 1024)                                                                                           \
+            ODINN_CUDA(e, cudaFuncSetAttribute(sia2d_fused_tma<true, ST, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                               tma_smem_bytes(ST)));                                                                  \
+        sia2d_fused_tma<true, ST, MC><<<c->n_bitems, TMA_NW * 32, tma_smem_bytes(ST), e->stream>>>(                                    \
+            (const GDesc<float>*)e->d_descs, c->d_bitems, mL, mH, mB, out, dH, c->d_partial, ph);                                      \
+    } while (0)
+    if (variant == 1) LT(3, 6);
+    else if (variant == 2) LT(3, 5);
+    else if (variant == 3) LT(6, 5);
+    else LT(4, 5);
+#undef LT
+    ODINN_CHECK_LAUNCH(e);
+    *done = true;
+    *starts_used = c->d_bstart;
+    *partial_used = c->d_partial;
+    return ODINN_OK;
+}
 
 // fp32, two columns per lane (sia2d_march2.cuh)
 int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed) {
@@ -39,7 +169,20 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
 // fp32, two columns per lane (sia2d_march2.cuh).  Partials are indexed by the two-column work items.
 // dH_out != nullptr (with wH && wS): the fused F1 + A1 + A2 pass.
 int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void* H_, void* out_, bool wH, bool wS,
-                bool packed, void* dH_out) {
+                bool packed, void* dH_out, const int** starts_used) {
+    *starts_used = e->d_item2_start;
+    if (e->march == 4 && dH_out && wH && wS && g0 < 0 && !packed && e->cubic && !e->a_gridded && e->phys.eta0 == 1.0) {
+        bool done = false;
+        double* part = nullptr;
+        int rc = launch_fused_tma(e, (const float*)lam_, (const float*)H_, (const float*)e->plane[ODINN_FIELD_B], (float*)out_,
+                                  (float*)dH_out, &done, starts_used, &part);
+        if (rc) return rc;
+        if (done) {  // the partial sums live in the variant's own buffer: hand them over through d_partial's reduce below
+            e->tma_partial_live = part;
+            return ODINN_OK;
+        }
+    }
+    e->tma_partial_live = nullptr;
     PhysDev<float> ph = make_phys<float>(e->phys);
     const GDesc<float>* descs = (const GDesc<float>*)e->d_descs + (packed ? e->G : 0);
     int i0 = 0, n_items = e->n_items2;

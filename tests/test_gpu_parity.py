@@ -236,7 +236,7 @@ def test_fused_step_at_bench_size_properties(ob, dtype):
         for k, g in enumerate(gl):
             dH, vH = ens.download(k, _capi.FIELD_DH), ens.download(k, _capi.FIELD_VJP_H)
             assert rel_l2(dH, dH_sep[k]) <= eps and rel_l2(vH, vH_sep[k]) <= eps, k
-            assert abs(S_f[k] - S_sep[k]) <= 1e-6 * abs(S_sep[k]) + 1e-30, k
+            assert abs(S_f[k] - S_sep[k]) <= 5e-6 * abs(S_sep[k]) + 1e-30, k   # (a cancelling fp32 sum accumulated over different row chunks)
             assert np.all(vH[np.maximum(g.H0, 0) <= 0] == 0)                      # adjoint.jl:148
             assert abs(dH.astype(np.float64).sum()) <= (1e-4 if dtype == "f32" else 1e-9) * np.abs(dH).sum()
             assert np.all(dH[0, :] == 0) and np.all(dH[-1, :] == 0) and np.all(dH[:, 0] == 0) and np.all(dH[:, -1] == 0)
