@@ -277,7 +277,8 @@ def law_theta():
 
 def dominant_kernel(dtype, fused):
     if fused:
-        return ("sia2d_vjp_march2<WRITE_F>" if dtype == "f32" else "sia2d_vjp_march<double, WRITE_F>") + " (F1 + A1 + A2 fused: one launch per step)", "sia2d_fused", 5
+        k32 = "sia2d_vjp_march2<WRITE_F>" if os.environ.get("ODINN_MARCH", "4") == "2" else "sia2d_fused_tma (2-D TMA ring)"
+        return (k32 if dtype == "f32" else "sia2d_vjp_march<double, WRITE_F>") + " (F1 + A1 + A2 fused: one launch per step)", "sia2d_fused", 5
     return ("sia2d_vjp_march2 (A1+A2 fused)" if dtype == "f32" else "sia2d_vjp_march (A1+A2 fused)"), ("sia2d_vjp_march2" if dtype == "f32" else "sia2d_vjp_march"), 4
 
 
@@ -457,7 +458,7 @@ def run_b200(args, rank, local_rank, world):
     e2e_value = world * cells_per_step / (ms_e2e * 1e-3) if e2e_steps > 0 else None
     peak, peak_src = load_peaks()
     fused = (not args.no_fuse and os.environ.get("ODINN_NO_FUSE") != "1"
-             and (dtype == "f64" or os.environ.get("ODINN_MARCH", "2") in ("2", "4")))
+             and (dtype == "f64" or os.environ.get("ODINN_MARCH", "4") in ("2", "4")))
     sub = lambda nbytes, ms_k, words, wd=w: {"achieved": nbytes / (ms_k * 1e-3) / 1e9, "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak,
                                              "algorithmic_bytes_per_cell": words * wd, "ms_per_launch": ms_k}
     dom_name, dom_key, dom_words = dominant_kernel(dtype, fused)

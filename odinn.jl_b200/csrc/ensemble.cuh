@@ -51,7 +51,7 @@ struct odinn_ensemble {
     int* d_item2_start = nullptr;
     int n_items2 = 0;
     int chunk_rows2 = 32;
-    int march = 2;                // fp32 kernel generation: 1 = one column per lane, 2 = two columns + f32x2, 4 = 2 + the fused step through the 2-D TMA ring
+    int march = 4;                // fp32 kernel generation: 1 = one column per lane, 2 = two columns + f32x2, 4 = 2 + the fused step through the 2-D TMA ring
     void* tma_cache = nullptr;    // tensor maps per plane pointer, band work items (launch_march2.cu)
     double* tma_partial_live = nullptr;  // partial sums of the last fused launch when it went through the TMA variant (else nullptr)
     bool all_nx_even = true;
