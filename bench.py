@@ -278,7 +278,8 @@ def law_theta():
 def dominant_kernel(dtype, fused):
     if fused:
         k32 = "sia2d_vjp_march2<WRITE_F>" if os.environ.get("ODINN_MARCH", "4") == "2" else "sia2d_fused_tma (2-D TMA ring)"
-        return (k32 if dtype == "f32" else "sia2d_vjp_march<double, WRITE_F>") + " (F1 + A1 + A2 fused: one launch per step)", "sia2d_fused", 5
+        key = "sia2d_fused_march2" if (dtype == "f32" and os.environ.get("ODINN_MARCH", "4") == "2") else "sia2d_fused"
+        return (k32 if dtype == "f32" else "sia2d_vjp_march<double, WRITE_F>") + " (F1 + A1 + A2 fused: one launch per step)", key, 5
     return ("sia2d_vjp_march2 (A1+A2 fused)" if dtype == "f32" else "sia2d_vjp_march (A1+A2 fused)"), ("sia2d_vjp_march2" if dtype == "f32" else "sia2d_vjp_march"), 4
 
 

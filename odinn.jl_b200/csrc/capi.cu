@@ -994,27 +994,42 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
     ODINN_CUDA(e, cudaMemsetAsync(lam, 0, pbytes, e->stream));  // λ_k = 0 (gradient.jl:140)
     ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
     ODINN_CUDA(e, cudaMemsetAsync(e->d_Ssum, 0, sizeof(double) * e->G, e->stream));
+    // fp32 two-column kernels, glacier-wide A: the reverse time step is folded into the A1 pass (SEED variant of sia2d_vjp_march2:
+    // lambda_{j-1} = lambda_j + dt VJP_H + dl_j/dH written to the other lambda plane, loss term reduced per strip): 9 words/cell per
+    // saved step (A1+seed 6, A2 3) instead of 13 (A1 4, loss / seed 6, A2 3).  ODINN_NO_FUSE=1 keeps the three-pass form.
+    const bool fused_seed = e->dtype == ODINN_F32 && e->march >= 2 && e->law_kind == LAW_NONE && !e->no_fuse;
     for (int j = n_t - 1; j >= 1; --j) {  // gradient.jl:191-253 (the j = 1 pass of the reference updates nothing)
         const double dt = t[j] - t[j - 1];
         void* Hj = plane_ptr(e, e->snap, j);
+        const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
         // λ_j += VJP_λ_∂MB∂H(λ_j, H_j - MB) at the MB tstops                                (gradient.jl:201-207)
         if (j < n_t - 1 && (rc = mb_adjoint_step(e, j, lam, Hj))) return rc;  // (λ_k = 0 at the last snapshot: nothing to add)
-        // λ_∂f∂H = VJP_H(λ_j, H_j)                                                     (gradient.jl:235-237)
-        if (j < n_t - 1) {
-            if ((rc = launch_vjp(e, -1, lam, Hj, vH, true, false))) return rc;
+        if (fused_seed && j < n_t - 1) {
+            // λ_∂f∂H = VJP_H(λ_j, H_j);  ℓ += ℓ_j;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H   in ONE pass        (:218-242)
+            if ((rc = sync_descs(e))) return rc;
+            if ((rc = launch_vjp2_seed(e, lam, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), vH, dt, 2.0 * wH))) return rc;
+            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_item2_start, e->d_partial, e->d_loss, wH, 1);
+            ODINN_CHECK_LAUNCH(e);
+            std::swap(lam, vH);
         } else {
-            ODINN_CUDA(e, cudaMemsetAsync(vH, 0, pbytes, e->stream));  // λ_k = 0 ⇒ VJP = 0
+            // λ_∂f∂H = VJP_H(λ_j, H_j)                                                     (gradient.jl:235-237)
+            if (j < n_t - 1) {
+                if ((rc = launch_vjp(e, -1, lam, Hj, vH, true, false))) return rc;
+            } else {
+                ODINN_CUDA(e, cudaMemsetAsync(vH, 0, pbytes, e->stream));  // λ_k = 0 ⇒ VJP = 0
+            }
+            // ℓ += ℓ_j ;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H,  ∂ℓ_j/∂H = 2 w_j W (H_j - H_ref,j), w_j = Δt_j for LossH  (:218-242)
+            if ((rc = launch_loss_seed(e, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), lam, vH, lam, dt, 2.0 * wH,
+                                       e->d_loss, wH, 1)))
+                return rc;
         }
-        // ℓ += ℓ_j ;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H,  ∂ℓ_j/∂H = 2 w_j W (H_j - H_ref,j), w_j = Δt_j for LossH  (:218-242)
-        const double wH = loss_weight_H(e, t, n_t, j), wV = loss_weight_V(e, n_t, j);
-        if ((rc = launch_loss_seed(e, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), lam, vH, lam, dt, 2.0 * wH,
-                                   e->d_loss, wH, 1)))
-            return rc;
         // velocity term of LossV / LossHV: ℓ, ∂ℓ/∂H into λ_{j-1} and ∂ℓ/∂θ (Losses.jl:293-390)
         if ((rc = velocity_loss_term(e, j, Hj, lam, wV, e->d_loss, e->d_Ssum))) return rc;
         // dLdθ += Δt_{j-1} · VJP_θ(λ_{j-1}, H_j)                                        (:245-249)
         if ((rc = launch_vjp(e, -1, lam, Hj, nullptr, false, true, e->d_Ssum, dt, 1))) return rc;
     }
+    if (lam != e->plane[ODINN_FIELD_LAMBDA])  // (the two λ planes alternate in the fused form: leave λ(t_0) in FIELD_LAMBDA)
+        ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_LAMBDA], lam, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     {
         // The j = 1 pass of the reference (snapshot 0 here) updates no λ but still adds its loss terms: ℓ += ℓ_1 and
         // dLdθ += ∂ℓ∂θ[1] (gradient.jl:218-232, 252).  With the default LossH weights w_0 = 0 (safe_slice); user weights

@@ -49,6 +49,9 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
 int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam, const void* H, void* out, bool wH, bool wS, bool packed,
                 void* dH_out, const int** starts_used);
 void tma_cache_free(odinn_ensemble* e);
+// A1 + reverse time step in one pass (fp32 two-column kernel, whole ensemble, glacier-wide A):
+//   lam_new = lam + dt (dSIA/dH)^T lam + cseed W (H - Href);   partial sums of  sum W (H - Href)^2  per work item -> d_partial / d_item2_start
+int launch_vjp2_seed(odinn_ensemble* e, const void* lam, const void* H, const void* Href, const void* W, void* lam_new, double dt, double cseed);
 
 // one column per lane (fp32 generation 1 and fp64); items [i0, i0 + n_items)
 template <typename T> int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed);

@@ -222,4 +222,24 @@ int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void*
     return ODINN_OK;
 }
 
+
+int launch_vjp2_seed(odinn_ensemble* e, const void* lam_, const void* H_, const void* Href_, const void* W_, void* lam_new, double dt,
+                     double cseed) {
+    PhysDev<float> ph = make_phys<float>(e->phys);
+    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs;
+    const int n_items = e->n_items2;
+    const float* B = (const float*)e->plane[ODINN_FIELD_B];
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
+#define LS(CUB, E1)                                                                                                                      \
+    sia2d_vjp_march2<CUB, false, true, false, E1, false, true><<<grid, block, 0, e->stream>>>(                                            \
+        descs, e->d_items2, n_items, (const float*)lam_, (const float*)H_, B, nullptr, (float*)lam_new, nullptr, e->d_partial, ph, nullptr, \
+        (const float*)Href_, (const float*)W_, (float)dt, (float)cseed)
+    if (e->cubic) { if (eta1) LS(true, true); else LS(true, false); }
+    else { if (eta1) LS(false, true); else LS(false, false); }
+#undef LS
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
 }  // namespace odinn

@@ -363,7 +363,11 @@ __device__ __forceinline__ void subgrad2(f2 dC, f2 e, f2 lo, f2 up, float eta0, 
 
 // WRITE_F: the same pass also writes dH = SIA2D(H) (F1): every forward intermediate is recomputed here anyway, so the
 // forward costs one more shuffle, ~8 packed operations and one store per row instead of a second pass over H and B.
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false>
+// SEED (with WRITE_H): the reverse time step of the discrete adjoint folded into the A1 epilogue -- instead of storing
+// v = (dSIA/dH)^T lambda the pass writes  lambda_new = lambda + dt v + cseed W (H - H_ref)  (gradient.jl:242 with the LossH seed of
+// Losses.jl:270-291) to a SECOND lambda plane (the neighbours still read the old one) and accumulates the loss term sum W (H - H_ref)^2
+// per strip: 5 reads + 1 write per cell instead of the 4 + 6 words of an A1 pass followed by a loss / seed pass.
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false>
 struct VjpMarch2 {
     static constexpr int PF = ODINN_PF2_VJP;
     // Every plane shares one (offset, pitch) layout, so the kernel keeps 32-bit ELEMENT offsets and adds them to the
@@ -371,6 +375,8 @@ struct VjpMarch2 {
     // registers instead of 14 for the 7 pointers (the kernel sits at the 128-register cap of 4 CTAs/SM).
     const float *Hb, *Bb, *Lb, *Ab;
     float *Ob, *Vb, *Fb;
+    const float *Rb, *Wb;   // SEED: H_ref and W planes
+    f2 sdt, scs, lossacc;   // SEED: dt, cseed (broadcast), loss accumulator
     const float* pfb;  // per lane: base of the plane this lane prefetches + its sector's column delta + ODINN_L2PF_ROWS rows
     int oin, oout, oa;  // offsets of the row being loaded / the row being written / the A-field node row
     int ld, nym1, ny2;
@@ -389,6 +395,21 @@ struct VjpMarch2 {
     f2 ly, fx, Qp;   // scaled λ row (y form), scaled Fx† of the carried row, Q of the previous node row
     f2 hq[PF], bq[PF], lq[PF];
 
+
+    // Output of row `oout`: res = (dSIA/dH)^T lambda, or -- SEED -- the reverse time step built on it.
+    __device__ __forceinline__ void emit(f2 res) {
+        if (SEED) {
+            if (!(store_pair || store_x)) return;
+            f2 l0, h0, r0, w0;
+            if (store_pair) { l0 = ldg2(Lb + oout); h0 = ldg2(Hb + oout); r0 = ldg2(Rb + oout); w0 = ldg2(Wb + oout); }
+            else { l0 = mk2(__ldg(Lb + oout), 0.0f); h0 = mk2(__ldg(Hb + oout), 0.0f); r0 = mk2(__ldg(Rb + oout), 0.0f); w0 = mk2(__ldg(Wb + oout), 0.0f); }
+            const f2 df = sub2(h0, r0), wd = mul2(w0, df);
+            lossacc = fma2(wd, df, lossacc);
+            res = fma2(sdt, res, fma2(scs, wd, l0));
+        }
+        if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
+        if (store_x) Ob[oout] = res.x;
+    }
 
     template <bool OUT, bool MASKED, int SLOT = -1>
     __device__ __forceinline__ void step(int row) {
@@ -504,8 +525,7 @@ struct VjpMarch2 {
                 f2 own = fma2(myl, dCy, fma2(mxl, dCx, sub2(SP, SAW)));   // minus the cell's own share
                 f2 res = sub2(ZW, sub2(own, yu_p));
                 res = mul2(res, mk2(mask_gt(h.x, 0.0f), mask_gt(h.y, 0.0f)));  // adjoint.jl:148
-                if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
-                if (store_x) Ob[oout] = res.x;
+                emit(res);
             }
             yu_p = yu1;
         }
@@ -597,8 +617,7 @@ struct VjpMarch2 {
                 f2 res = add2(add2(add2(ZW, add2(sub2(aDc, Pc), xl)), mul2(qy, sub2(Qrow_p, Qrow1))), add2(yl, yu_p));
                 if (!(h.x > 0.0f)) res.x = 0.0f;  // adjoint.jl:148
                 if (!(h.y > 0.0f)) res.y = 0.0f;
-                if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
-                if (store_x) Ob[oout] = res.x;
+                emit(res);
             }
             Qrow_p = Qrow1;
             yu_p = yu1;
@@ -610,12 +629,13 @@ struct VjpMarch2 {
     }
 };
 
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false>
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false>
 __global__ void __launch_bounds__(MARCH2_WARPS * 32, ODINN_VJP2_MIN_CTAS)
 sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                  const float* __restrict__ lam, const float* __restrict__ H, const float* __restrict__ B,
                  const float* __restrict__ Af, float* __restrict__ out, float* __restrict__ vjpA,
-                 double* __restrict__ partial, PhysDev<float> ph, float* __restrict__ dH = nullptr) {
+                 double* __restrict__ partial, PhysDev<float> ph, float* __restrict__ dH = nullptr,
+                 const float* __restrict__ Href = nullptr, const float* __restrict__ Wm = nullptr, float sdt = 0.0f, float scs = 0.0f) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -624,8 +644,10 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const int c0 = it.y + 2 * lane, r0 = it.z, r1 = it.w;
     const int cmax = (d.nx - 1) & ~1;
     const int ic = min(max(c0, 0), cmax);
-    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, WRITE_F> m;
+    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, WRITE_F, SEED> m;
     constexpr int PF = ODINN_PF2_VJP;
+    m.Rb = Href; m.Wb = Wm;
+    m.sdt = bc2(sdt); m.scs = bc2(scs); m.lossacc = bc2(0.0f);
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
@@ -714,6 +736,12 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
 
+    if (SEED) {   // (exclusive with WRITE_S: the strip's loss term goes where S would)
+        double a = (double)m.lossacc.x + (double)m.lossacc.y;   // (only storing lanes accumulated)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+        if (lane == 0) partial[item] = a;
+    }
     if (WRITE_S) {
         double a = m.own_lane ? (double)m.acc.x + (double)m.acc.y : 0.0;  // (the CUBIC form accumulates in the halo lanes too)
 #pragma unroll

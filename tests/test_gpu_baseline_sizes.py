@@ -226,10 +226,15 @@ def test_config1_forward_2010_2015(ob, dtype, case, method):
             ens.solve_forward(t, method="ssprk3", nsub=8)
         else:
             ens.solve_forward_adaptive(t, reltol=rtol, abstol=rtol)
-        # adaptive fp32: the accept / reject sequence may differ from the fp64 oracle's, so the bound is the solver tolerance
-        # adaptive fp64: same accept / reject sequence, but every step size is a function of the error norm, so the RHS roundings
-        # (the cubic kernel groups the node products differently from the oracle) feed back into dt over 5 years: 5e-10 measured
-        st = (1e-10 if method == "ssprk3" else 2e-8) if dtype == "f64" else (1e-3 if method == "ssprk3" else 3e-3)
+        # adaptive: every step size is a function of the error norm, so the RHS roundings (the cubic kernel groups the node products
+        # differently from the oracle) feed back into dt, and over 5 years ONE accept / reject decision flips: from then on the two
+        # runs are two different discretisations of the same solve and agree at the level of the solver tolerance (rtol 1e-6: 3e-6
+        # measured), not of rounding.  The first half year -- before any flip -- agrees to 1e-9.
+        st = 1e-10 if method == "ssprk3" else 2e-5
+        if dtype == "f32":
+            st = 1e-3 if method == "ssprk3" else 3e-3
+        if method == "bs3" and dtype == "f64":
+            assert rel_l2(ens.get_snapshot(0, 6), Hs[6]) <= 1e-9
         for j in range(0, 61, 6):
             err = rel_l2(ens.get_snapshot(0, j), Hs[j])
             assert err <= st, (j, err)
