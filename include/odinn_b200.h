@@ -310,6 +310,15 @@ int odinn_law_A_nn_pullback(odinn_ensemble* e, const double* S, double* dtheta, 
 int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* widths, const int* acts, const double* theta,
                           int n_theta, const double* prescale_bounds, double max_NN, double n_H, double n_gS);
 int odinn_law_cell_clear(odinn_ensemble* e);
+/* interpolation = :Linear of the law pullback (the default of SIA2D_D_hybrid_target, src/models/target/target_D_hybrid.jl:13, 136-166;
+ * optional for SIA2D_D_target, target_D_pure.jl:180-193 with the lattice of src/laws/Laws.jl:140-168): the network gradient is taken at
+ * the knots -- knots0 x knots1 = (Hbar, gradS) for LawU, knots0 = Hbar for LawY (n1 = 0) -- and interpolated (bi)linearly per cell
+ * (Interpolations.jl Gridded(Linear())).  The knots are what the reference's create_interpolation (target_utils.jl:245-299) returns:
+ * computed by the caller (feed_input_cache!, src/laws/Cache.jl:130-154, from the forward solve for LawU; from the current Hbar for
+ * LawY), 2 * n_interp_half values, strictly increasing; inputs outside the knot range are clamped to it.  On the device the contraction
+ * with D_adj is reordered as a sum over KNOTS: the cells scatter D_adj * s to their bracketing knots, then the knots are back-propagated
+ * -- cost independent of |theta| x cells.  n0 = 0 restores the exact per-node gradient (interpolation = :None). */
+int odinn_law_cell_interp_set(odinn_ensemble* e, int n0, const double* knots0, int n1, const double* knots1);
 /* out_theta[k] = sum_ij (dD/dtheta_k)[i,j] * D_adj[i,j]: VJP_lambda_dSIAdtheta(::DiscreteVJP, ...) for a per-cell law
  * (adjoint.jl:235-250 with dDiffusivity/dtheta of target_D_pure.jl:139-199 / target_D_hybrid.jl:98-166,
  * interpolation = :None, i.e. the exact per-node network gradient). */

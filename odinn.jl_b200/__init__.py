@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     SIA2Dmodel,
     SolverParameters,
     define_callback_steps,
+    create_interpolation,
     is_in_glacier,
     loss_iceflow_transient,
     run_,

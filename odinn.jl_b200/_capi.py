@@ -78,6 +78,7 @@ SIGNATURES = {
     "odinn_sia2d_vjp_theta_continuous": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _d]),
     "odinn_law_cell_nn_set": (_i, [_vp, _i, _i, _ip, _ip, _dp, _i, _dp, _d, _d, _d]),
     "odinn_law_cell_clear": (_i, [_vp]),
+    "odinn_law_cell_interp_set": (_i, [_vp, _i, _dp, _i, _dp]),
     "odinn_sia2d_vjp_theta_cell": (_i, [_vp, _i, _vp, _i, _vp, _i, _dp, _i, _d]),
     "odinn_law_cell_grad": (_i, [_vp, _dp, _i]),
     "odinn_rhs_resident": (_i, [_vp]),

@@ -152,6 +152,29 @@ def define_callback_steps(tspan, step):
     return tspan[0] + step * np.arange(n + 1)
 
 
+def create_interpolation(A, n_interp_half: int, dilation_factor: float = 1.0, minA_unif=None, minA_quantile=None,
+                         maxA_unif=None, maxA_quantile=None) -> np.ndarray:
+    """``create_interpolation`` (src/models/target/target_utils.jl:245-299): the 2·n_interp_half knots of the law-gradient
+    interpolation -- n_interp_half equally spaced points of [minA_unif, dilation_factor·max(A)] united with n_interp_half
+    interior quantiles of the values inside (minA_quantile, maxA_quantile).  Feed the result to
+    ``Ensemble.law_cell_interp_set`` (what ``feed_input_cache!`` does upstream, src/laws/Cache.jl:130-154: H̄ knots with
+    dilation 1.05 and quantiles from 10 m, ∇S knots with dilation 1.05, over ALL snapshots of the forward solve)."""
+    A = np.asarray(A, dtype=np.float64).reshape(-1)
+    minA_unif = 0.0 if minA_unif is None else minA_unif
+    minA_quantile = 0.0 if minA_quantile is None else minA_quantile
+    maxA_unif = dilation_factor * A.max() if maxA_unif is None else maxA_unif
+    maxA_quantile = A.max() if maxA_quantile is None else maxA_quantile
+    if not (minA_unif < maxA_unif and minA_quantile < maxA_quantile):
+        raise ValueError("There are not enough different values of A to create a proper interpolation.")
+    unif = np.linspace(minA_unif, maxA_unif, n_interp_half)
+    quant = np.quantile(A[(minA_quantile < A) & (A < maxA_quantile)], np.linspace(0.0, 1.0, n_interp_half + 2)[1:-1])
+    knots = np.unique(np.concatenate([unif, quant]))
+    if knots.size < 2 * n_interp_half:  # coinciding knots: top up with midpoints (the reference picks the gaps at random)
+        n_left = 2 * n_interp_half - knots.size
+        knots = np.sort(np.concatenate([knots, 0.5 * (knots[:n_left] + knots[1:n_left + 1])]))
+    return knots
+
+
 def is_in_glacier(A: np.ndarray, distance: int) -> np.ndarray:
     """Sleipnir.is_in_glacier [not in tree].  Assumption: `distance` erosions of the mask A != 0 with the
     5-point cross and circular shifts."""

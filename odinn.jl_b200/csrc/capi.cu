@@ -1099,6 +1099,43 @@ int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* 
     return ODINN_OK;
 }
 
+int odinn_law_cell_interp_set(odinn_ensemble* e, int n0, const double* knots0, int n1, const double* knots1) {
+    GUARD(e);
+    if (n0 == 0) {  // exact per-node gradients (interpolation = :None)
+        e->ext_int[2] = e->ext_int[3] = 0;
+        return ODINN_OK;
+    }
+    if (e->law_kind == LAW_NONE) return fail(e, ODINN_ESTATE, "set a per-cell law first (odinn_law_cell_nn_set)");
+    if (n0 < 2 || !knots0 || n1 < 0 || (n1 > 0 && (n1 < 2 || !knots1))) return fail(e, ODINN_EARG, "an interpolation axis needs at least 2 knots");
+    if (e->law_kind == LAW_U && n1 == 0) return fail(e, ODINN_EARG, "LawU interpolates over (Hbar, gradS): two knot vectors");
+    if (e->law_kind == LAW_Y && n1 != 0) return fail(e, ODINN_EARG, "LawY interpolates over Hbar only: one knot vector");
+    for (int k = 1; k < n0; ++k) if (!(knots0[k] > knots0[k - 1])) return fail(e, ODINN_EARG, "knots must be strictly increasing");
+    for (int k = 1; k < n1; ++k) if (!(knots1[k] > knots1[k - 1])) return fail(e, ODINN_EARG, "knots must be strictly increasing");
+    if (e->ext_dev[EXT_LAT_KNOTS]) cudaFree(e->ext_dev[EXT_LAT_KNOTS]);
+    if (e->ext_dev[EXT_LAT_W]) cudaFree(e->ext_dev[EXT_LAT_W]);
+    e->ext_dev[EXT_LAT_KNOTS] = e->ext_dev[EXT_LAT_W] = nullptr;
+    e->ext_int[2] = e->ext_int[3] = 0;
+    ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_LAT_KNOTS], sizeof(double) * (n0 + n1)));
+    ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_LAT_W], sizeof(double) * (size_t)n0 * std::max(n1, 1)));
+    ODINN_CUDA(e, cudaMemcpyAsync(e->ext_dev[EXT_LAT_KNOTS], knots0, sizeof(double) * n0, cudaMemcpyHostToDevice, e->stream));
+    if (n1 > 0)
+        ODINN_CUDA(e, cudaMemcpyAsync((double*)e->ext_dev[EXT_LAT_KNOTS] + n0, knots1, sizeof(double) * n1, cudaMemcpyHostToDevice, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    {   // the knot pass writes one row of block partials per 512 knots: grow the partial buffer when the lattice has more blocks than
+        // the largest glacier has tiles
+        const int nb = div_up(n0 * std::max(n1, 1), TX * TY);
+        if (nb > e->max_tiles_per_glacier) {
+            if (e->d_law_partial) cudaFree(e->d_law_partial);
+            e->d_law_partial = nullptr;
+            ODINN_CUDA(e, cudaMalloc(&e->d_law_partial, sizeof(double) * (size_t)e->law_n_theta * nb));
+            e->max_tiles_per_glacier = nb;
+        }
+    }
+    e->ext_int[2] = n0;
+    e->ext_int[3] = n1;
+    return ODINN_OK;
+}
+
 int odinn_law_cell_clear(odinn_ensemble* e) {
     GUARD(e);
     e->law_kind = LAW_NONE;

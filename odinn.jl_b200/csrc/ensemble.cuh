@@ -132,7 +132,8 @@ enum {  // ext_dev slots
     EXT_LS_PARTIAL = 18,                                                                            // loss / seed pass (ext_int[1] = its length)
     EXT_RK_STATE = 19,                                                                              // RDPK3Sp35 per-glacier controller state (rdpk.cu)
     EXT_VQ_WORK = 20,                                                                               // 4 planes: velocity references interpolated at a quadrature node
-    EXT_VQ_RED = 21                                                                                 // [2 G] mask count and sum of squares of those references
+    EXT_VQ_RED = 21,                                                                                // [2 G] mask count and sum of squares of those references
+    EXT_LAT_KNOTS = 22, EXT_LAT_W = 23                                                              // law pullback with interpolation = :Linear: knots, knot weights (ext_int[2], [3] = n0, n1)
 };
 
 namespace odinn {

@@ -72,6 +72,35 @@ static int launch_law_theta_t(odinn_ensemble* e, int g0, int g1, const void* H, 
         if (w16) ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    const int n0 = e->ext_int[2], n1 = e->ext_int[3];
+    if (n0 > 0) {
+        // interpolation = :Linear: scatter D†·s onto the knots (one lattice per glacier pass), then back-propagate the KNOTS
+        const double* knots = (const double*)e->ext_dev[EXT_LAT_KNOTS];
+        double* Wlat = (double*)e->ext_dev[EXT_LAT_W];
+        const int nk = n0 * std::max(n1, 1);
+        const int nb = div_up(nk, TX * TY);
+        if (nb > e->max_tiles_per_glacier) return fail(e, ODINN_EARG, "interpolation lattice larger than the largest glacier: reduce n_interp_half");
+        if (w16) { if (smem > 48 * 1024) ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+        else if (smem > 48 * 1024) ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int g = g0; g < g1; ++g) {
+            const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
+            ODINN_CUDA(e, cudaMemsetAsync(Wlat, 0, sizeof(double) * nk, e->stream));
+            law_lattice_scatter<T><<<nt, LAW_NT, sizeof(double) * (n0 + n1), e->stream>>>(descs, e->d_tiles + t0, lw, (const T*)H, B,
+                                                                                       (const T*)e->plane[ODINN_FIELD_VJP_A], knots, n0, n1, Wlat);
+            ODINN_CHECK_LAUNCH(e);
+            if (w16)
+                law_theta_kernel<T, T, 16, true><<<nb, LAW_NT, smem, e->stream>>>(descs, nullptr, lw, e->d_law_theta, nullptr, nullptr, nullptr,
+                                                                                e->d_law_partial, knots, n0, n1, Wlat, g);
+            else
+                law_theta_kernel<T, T, 32, true><<<nb, LAW_NT, smem, e->stream>>>(descs, nullptr, lw, e->d_law_theta, nullptr, nullptr, nullptr,
+                                                                                e->d_law_partial, knots, n0, n1, Wlat, g);
+            ODINN_CHECK_LAUNCH(e);
+            law_theta_reduce_scaled<<<div_up(np, 128), 128, 0, e->stream>>>(e->d_law_partial, nb, np, e->d_law_dtheta + (size_t)g * np, scale,
+                                                                           accumulate);
+            ODINN_CHECK_LAUNCH(e);
+        }
+        return ODINN_OK;
+    }
     for (int g = g0; g < g1; ++g) {  // one glacier at a time: the block partials are [tiles of one glacier x n_theta]
         const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
         if (w16)

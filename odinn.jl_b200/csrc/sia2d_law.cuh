@@ -296,6 +296,51 @@ law_nodes_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ ti
     }
 }
 
+// interpolation = :Linear, step 1: every dual node adds  D†·s  (s as in pass 3) to the knots that bracket its (H̄, ∇S) [LawU] or its
+// H̄ [LawY], split by the (bi)linear interpolation weights of Gridded(Linear()); inputs beyond the knot range are clamped to it
+// (Interpolations.jl would throw; the reference dilates the range by 1.05).  Wlat: [n0 x max(n1, 1)] doubles of ONE glacier.
+template <typename T>
+__global__ void __launch_bounds__(LAW_NT)
+law_lattice_scatter(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, CellLaw lw, const T* __restrict__ H,
+                    const T* __restrict__ B, const T* __restrict__ Dadj, const double* __restrict__ knots, int n0, int n1,
+                    double* __restrict__ Wlat) {
+    extern __shared__ __align__(16) unsigned char law_smem[];
+    double* kn = reinterpret_cast<double*>(law_smem);
+    for (int k = threadIdx.x; k < n0 + n1; k += LAW_NT) kn[k] = knots[k];
+    __syncthreads();
+    const int2 tl = tiles[blockIdx.x];
+    const GDesc<T> d = descs[tl.x];
+    const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;
+    auto locate = [&](const double* k, int nk, double x, int& a, double& w) {
+        x = fmin(fmax(x, k[0]), k[nk - 1]);
+        int lo = 0, hi = nk - 1;              // largest a in [0, nk-2] with k[a] <= x  (searchsorted(side = right) - 1, clipped)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (k[mid] <= x) lo = mid; else hi = mid; }
+        a = lo;
+        w = (x - k[a]) / (k[a + 1] - k[a]);
+    };
+    for (int c = threadIdx.x; c < TX * TY; c += LAW_NT) {
+        const int an = x0 + (c % TX), bn = y0 + (c / TX);
+        if (an > d.nx - 2 || bn > d.ny - 2) continue;
+        double Hb, gS;
+        node_inputs<T>(d, H, B, an, bn, Hb, gS);
+        double sc;
+        if (lw.kind == LAW_U) sc = (Hb > 0.0) ? Hb : 0.0;
+        else sc = lw.Gam * pow(Hb, lw.n_H + 2.0) * pow(gS, lw.n_gS - 1.0);
+        double v = (double)__ldg(Dadj + d.off + (long long)bn * d.ld + an) * sc;
+        if (!(v == v) || v == 0.0) continue;
+        int a, b = 0;
+        double wa, wb = 0.0;
+        locate(kn, n0, Hb, a, wa);
+        if (n1 > 0) locate(kn + n0, n1, gS, b, wb);
+        atomicAdd(Wlat + a + (long long)n0 * b, v * (1.0 - wa) * (1.0 - wb));
+        atomicAdd(Wlat + a + 1 + (long long)n0 * b, v * wa * (1.0 - wb));
+        if (n1 > 0) {
+            atomicAdd(Wlat + a + (long long)n0 * (b + 1), v * (1.0 - wa) * wb);
+            atomicAdd(Wlat + a + 1 + (long long)n0 * (b + 1), v * wa * wb);
+        }
+    }
+}
+
 // Pass 3.  ∂θ_k = Σ_nodes D†·s·post'(y)·∂NN/∂θ_k ,  s = H̄·[H̄ > 0] (LawU, nodes with H̄ == 0 skipped: target_D_pure.jl:169-171)
 // or Γ H̄^{n_H+2} ∇S^{n_∇S-1} (LawY).  One block per tile; block_partial[block][k] written in full (fixed order).
 //
@@ -308,11 +353,17 @@ constexpr int LAW_PITCH = LAW_NT + 1;
 
 // R: precision of the per-node forward / backward and of the contraction inside one pass (the ensemble's precision; the passes and
 // tiles are accumulated in double).
-template <typename T, typename R, int MAXW>
+//
+// LATTICE (interpolation = :Linear, target_D_pure.jl:180-193 / target_D_hybrid.jl:136-166): the nodes are not the dual nodes of a
+// tile but the knots of the interpolation lattice (n0 x n1 for LawU's (H̄, ∇S), n0 x 1 for LawY's H̄ with T fixed), and the weight of
+// a knot is what law_lattice_scatter accumulated there -- sum over the cells of D†·s times the cell's (bi)linear interpolation
+// weight -- times post'(y) at the knot: the contraction of the interpolated gradient tensor, reordered as a sum over knots.
+template <typename T, typename R, int MAXW, bool LATTICE = false>
 __global__ void __launch_bounds__(LAW_NT)
 law_theta_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ tiles, CellLaw lw,
                  const double* __restrict__ theta, const T* __restrict__ H, const T* __restrict__ B,
-                 const T* __restrict__ Dadj, double* __restrict__ block_partial) {
+                 const T* __restrict__ Dadj, double* __restrict__ block_partial, const double* __restrict__ knots = nullptr,
+                 int n0 = 0, int n1 = 0, const double* __restrict__ Wlat = nullptr, int glacier = 0) {
     extern __shared__ __align__(16) unsigned char law_smem[];
     const int np = lw.arch.n_params, nl = lw.arch.n_layers;
     int NA = 0, NZ = 0;
@@ -335,16 +386,27 @@ law_theta_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ ti
         }
     }
     __syncthreads();
-    const int2 tl = tiles[blockIdx.x];
+    const int2 tl = LATTICE ? make_int2(glacier, 0) : tiles[blockIdx.x];
     const GDesc<T> d = descs[tl.x];
     const int x0 = (tl.y & 0xffff) * TX, y0 = (tl.y >> 16) * TY;
     const int n = threadIdx.x;
+    const int n1e = n1 > 0 ? n1 : 1;
     for (int c0 = 0; c0 < TX * TY; c0 += LAW_NT) {
         const int c = c0 + n;
-        const int an = x0 + (c % TX), bn = y0 + (c / TX);
-        const bool in_grid = (an <= d.nx - 2 && bn <= d.ny - 2);
+        int an = x0 + (c % TX), bn = y0 + (c / TX);
+        bool in_grid = (an <= d.nx - 2 && bn <= d.ny - 2);
         double Hb = 0.0, gS = 0.0;
-        if (in_grid) node_inputs<T>(d, H, B, an, bn, Hb, gS);
+        long long lc = 0;
+        if (LATTICE) {
+            lc = (long long)blockIdx.x * (TX * TY) + c;   // knot index: a + n0 * b
+            in_grid = lc < (long long)n0 * n1e;
+            if (in_grid) {
+                Hb = knots[lc % n0];
+                gS = n1 > 0 ? knots[n0 + lc / n0] : 0.0;
+            }
+        } else if (in_grid) {
+            node_inputs<T>(d, H, B, an, bn, Hb, gS);
+        }
         const double in0 = lw.kind == LAW_U ? Hb : (double)d.temp, in1 = lw.kind == LAW_U ? gS : Hb;
         // ---- forward: layer inputs -> As, act'(z) -> Zs ----
         R cur[MAXW];
@@ -391,10 +453,14 @@ law_theta_kernel(const GDesc<T>* __restrict__ descs, const int2* __restrict__ ti
         double w = 0.0;
         if (in_grid) {
             const double dpost = lw.postscale ? lw.max_NN * exp((y - 1.0) / y) / (y * y) : 1.0;
-            double sc;
-            if (lw.kind == LAW_U) sc = (Hb > 0.0) ? Hb : 0.0;
-            else sc = lw.Gam * pow(Hb, lw.n_H + 2.0) * pow(gS, lw.n_gS - 1.0);
-            w = (double)__ldg(Dadj + d.off + (long long)bn * d.ld + an) * sc * dpost;
+            if (LATTICE) {
+                w = Wlat[lc] * dpost;
+            } else {
+                double sc;
+                if (lw.kind == LAW_U) sc = (Hb > 0.0) ? Hb : 0.0;
+                else sc = lw.Gam * pow(Hb, lw.n_H + 2.0) * pow(gS, lw.n_gS - 1.0);
+                w = (double)__ldg(Dadj + d.off + (long long)bn * d.ld + an) * sc * dpost;
+            }
             if (!(w == w)) w = 0.0;  // 0·inf from a degenerate node (H̄ = 0 with a negative exponent) contributes nothing
         }
         // ---- backward: dz -> Zs ----

@@ -397,15 +397,26 @@ struct VjpMarch2 {
 
 
     // Output of row `oout`: res = (dSIA/dH)^T lambda, or -- SEED -- the reverse time step built on it.
+    // SEED operands of the row this step emits (raw lambda, raw H, H_ref, W), loaded at the TOP of the step so that the whole step
+    // hides their latency (lambda and H were read two rows ago by this warp: L1 / L2 hits; H_ref and W are new DRAM streams,
+    // L2-prefetched ODINN_L2PF_ROWS ahead by seed_loads).
+    f2 s_l, s_h, s_r, s_w;
+    bool seed_lane;   // store_pair || store_x
+    const float* pfs;   // per lane: H_ref (lanes 0-8) or W (lanes 9-17) sector of the row ODINN_L2PF_ROWS ahead, or nullptr
+    template <bool MASKED>
+    __device__ __forceinline__ void seed_loads(int row) {
+        if (!SEED) return;
+        // (the pair that straddles the last column of an odd-nx grid reads the zero padding column: its second element contributes 0
+        //  to the loss and is never stored; the packed layout, which has no padding, only takes even nx)
+        if (seed_lane) { s_l = ldg2(Lb + oout); s_h = ldg2(Hb + oout); s_r = ldg2(Rb + oout); s_w = ldg2(Wb + oout); }
+        if (ODINN_L2PF_ROWS > 0 && !MASKED && pfs != nullptr && row + ODINN_L2PF_ROWS <= nym1) prefetch_l2(pfs + oout);
+    }
     __device__ __forceinline__ void emit(f2 res) {
         if (SEED) {
-            if (!(store_pair || store_x)) return;
-            f2 l0, h0, r0, w0;
-            if (store_pair) { l0 = ldg2(Lb + oout); h0 = ldg2(Hb + oout); r0 = ldg2(Rb + oout); w0 = ldg2(Wb + oout); }
-            else { l0 = mk2(__ldg(Lb + oout), 0.0f); h0 = mk2(__ldg(Hb + oout), 0.0f); r0 = mk2(__ldg(Rb + oout), 0.0f); w0 = mk2(__ldg(Wb + oout), 0.0f); }
-            const f2 df = sub2(h0, r0), wd = mul2(w0, df);
+            if (!seed_lane) return;
+            const f2 df = sub2(s_h, s_r), wd = mul2(s_w, df);
             lossacc = fma2(wd, df, lossacc);
-            res = fma2(sdt, res, fma2(scs, wd, l0));
+            res = fma2(sdt, res, fma2(scs, wd, s_l));
         }
         if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = res;
         if (store_x) Ob[oout] = res.x;
@@ -433,6 +444,7 @@ struct VjpMarch2 {
             Anode = ldg2(Ab + oa);
             if (MASKED) { if (row >= 0 && row < ny2) oa += ld; } else oa += ld;
         }
+        if (OUT) seed_loads<MASKED>(row);
         if (CUBIC) compute_cubic<OUT, MASKED>(row, h1, b1, l1, Anode);
         else compute<OUT, MASKED>(row, h1, b1, l1, Anode);
     }
@@ -648,6 +660,9 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     constexpr int PF = ODINN_PF2_VJP;
     m.Rb = Href; m.Wb = Wm;
     m.sdt = bc2(sdt); m.scs = bc2(scs); m.lossacc = bc2(0.0f);
+    m.s_l = m.s_h = m.s_r = m.s_w = bc2(0.0f);
+    m.pfs = nullptr;
+    m.seed_lane = false;
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
@@ -668,6 +683,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.store_pair = out_lane && (c1 < d.nx);
     m.store_x = out_lane && (c1 == d.nx);
     m.own_lane = (lane >= 1 && lane <= 30);
+    m.seed_lane = m.store_pair || m.store_x;
     m.vstore_pair = out_lane && (c1 <= d.nx - 2);
     m.vstore_x = out_lane && (c1 == d.nx - 1);
     const int rc = max(r0 - 1, 0);
@@ -683,6 +699,10 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
         const int pl = min(lane / 10, 2), sec = lane - 10 * pl;
         const float* pb = pl == 0 ? H : (pl == 1 ? B : lam);
         m.pfb = pb + (min(max(it.y + 8 * sec, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
+        if (SEED && lane < 18) {
+            const int sp = lane / 9, ss = lane - 9 * sp;
+            m.pfs = (sp == 0 ? Href : Wm) + (min(max(it.y + 8 * ss, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
+        }
     }
 
     // ---- cell row r0-1 ----

@@ -208,6 +208,18 @@ class Ensemble:
                                                  float(max_NN) if max_NN else 0.0, float(n_H) if n_H else 0.0,
                                                  float(n_gS) if n_gS else 0.0))
 
+    def law_cell_interp_set(self, knots0=None, knots1=None):
+        """interpolation = :Linear of the law pullback: knots of H̄ (and of ∇S for LawU), e.g. from ``create_interpolation``;
+        ``law_cell_interp_set()`` restores the exact per-node gradient."""
+        dp = C.POINTER(C.c_double)
+        if knots0 is None:
+            self._ck(self._lib.odinn_law_cell_interp_set(self._h, 0, None, 0, None))
+            return
+        k0 = np.ascontiguousarray(knots0, dtype=np.float64)
+        k1 = np.ascontiguousarray(knots1, dtype=np.float64) if knots1 is not None else None
+        self._ck(self._lib.odinn_law_cell_interp_set(self._h, k0.size, k0.ctypes.data_as(dp), 0 if k1 is None else k1.size,
+                                                     None if k1 is None else k1.ctypes.data_as(dp)))
+
     def law_cell_clear(self):
         self._ck(self._lib.odinn_law_cell_clear(self._h))
 

@@ -405,6 +405,38 @@ class TargetA:
         ) + self.A * Gamma_up(ph) * (ph.n - 1) * Hb ** (ph.n + 1) * gS ** (ph.n - 3)
 
 
+def create_interpolation(A, n_interp_half, dilation_factor=1.0, minA_unif=None, minA_quantile=None, maxA_unif=None,
+                         maxA_quantile=None):
+    """create_interpolation (target_utils.jl:245-299): 2 * n_interp_half knots = n_interp_half equally spaced points of
+    [minA_unif, dilation_factor * max(A)] united with n_interp_half interior quantiles of the values strictly inside
+    (minA_quantile, maxA_quantile), sorted.  (`quantile!` is Julia's default definition 7 == numpy's default.)  When the two sets
+    share values the reference tops the knots up with midpoints at RANDOM positions (`sample`); here the first gaps are used --
+    a deterministic choice, irrelevant unless knots coincide."""
+    A = np.asarray(A, dtype=np.float64).reshape(-1)
+    minA_unif = 0.0 if minA_unif is None else minA_unif
+    minA_quantile = 0.0 if minA_quantile is None else minA_quantile
+    maxA_unif = dilation_factor * A.max() if maxA_unif is None else maxA_unif
+    maxA_quantile = A.max() if maxA_quantile is None else maxA_quantile
+    assert minA_unif < maxA_unif and minA_quantile < maxA_quantile
+    unif = np.linspace(minA_unif, maxA_unif, n_interp_half)
+    qr = np.linspace(0.0, 1.0, n_interp_half + 2)[1:-1]
+    quant = np.quantile(A[(minA_quantile < A) & (A < maxA_quantile)], qr)
+    knots = np.unique(np.concatenate([unif, quant]))
+    if knots.size < 2 * n_interp_half:
+        n_left = 2 * n_interp_half - knots.size
+        knots = np.sort(np.concatenate([knots, 0.5 * (knots[:n_left] + knots[1:n_left + 1])]))
+    assert knots.size == 2 * n_interp_half
+    return knots
+
+
+def _interp_weights(knots, x):
+    """Gridded(Linear()) on one axis: (index of the lower knot, weight of the upper knot); x is clamped to the knot range
+    (Interpolations.jl throws outside it; the reference dilates the range by 1.05 so that this never happens)."""
+    x = np.clip(np.asarray(x, dtype=np.float64), knots[0], knots[-1])
+    a = np.clip(np.searchsorted(knots, x, side="right") - 1, 0, knots.size - 2)
+    return a, (x - knots[a]) / (knots[a + 1] - knots[a])
+
+
 class TargetD:
     """SIA2D_D_target (src/models/target/target_D_pure.jl): D = H̄ * U,
     U = post(NN(pre([H̄, ∇S]); theta))  (LawU, src/laws/Laws.jl:97-123).
@@ -414,8 +446,12 @@ class TargetD:
     Note that the reference's ∂Diffusivity∂∇H returns ∂D/∂|∇S| (not divided by
     |∇S|); we follow the reference."""
 
-    def __init__(self, ph: Phys, mlp: MLP, prescale_bounds=None, max_NN=None):
+    def __init__(self, ph: Phys, mlp: MLP, prescale_bounds=None, max_NN=None, interpolation="None", nodes_H=None, nodes_S=None):
+        """interpolation "Linear" (target_D_pure.jl:180-193): the network gradient is evaluated on the lattice nodes_H x nodes_S
+        (the knots feed_input_cache! derives from the forward solve, src/laws/Cache.jl:130-154) and interpolated bilinearly per
+        cell (LawU's MatrixCacheInterp, Laws.jl:140-168).  The default of SIA2D_D_target is "None" (:35)."""
         self.ph, self.mlp, self.bounds, self.max_NN = ph, mlp, prescale_bounds, max_NN
+        self.interpolation, self.nodes_H, self.nodes_S = interpolation, nodes_H, nodes_S
         self.U = None
 
     def _pre(self, Hb, gS):
@@ -467,9 +503,24 @@ class TargetD:
         dth[Hb == 0.0] = 0.0  # `continue` at target_D_pure.jl:169-171
         return dth
 
+    def dU_dtheta_interp(self, Hb, gS, theta):
+        """grad_itp(H̄[i,j], ∇S[i,j]) (target_D_pure.jl:186-192): lattice of exact gradients, bilinear interpolation per cell."""
+        kh, ks = np.asarray(self.nodes_H, dtype=np.float64), np.asarray(self.nodes_S, dtype=np.float64)
+        Hn, Sn = np.meshgrid(kh, ks, indexing="ij")
+        X = self._pre(Hn, Sn)
+        y = self.mlp.forward(theta, X)[:, 0]
+        gout = (ml_model_postscale(y, self.max_NN) / (y * y))[:, None] if self.max_NN is not None else np.ones((X.shape[0], 1))
+        grads = self.mlp.backward(theta, X, gout)[0].reshape(kh.size, ks.size, -1)   # (no H̄ == 0 skip on the lattice, Laws.jl:158-166)
+        a, wa = _interp_weights(kh, Hb)
+        b, wb = _interp_weights(ks, gS)
+        wa, wb = wa[..., None], wb[..., None]
+        return ((1 - wa) * (1 - wb) * grads[a, b] + wa * (1 - wb) * grads[a + 1, b] + (1 - wa) * wb * grads[a, b + 1]
+                + wa * wb * grads[a + 1, b + 1])
+
     def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
         dspatial = np.where(Hb > 0.0, 1.0, 0.0)
-        T3 = dspatial[:, :, None] * self.dU_dtheta(Hb, gS, theta) * Hb[:, :, None]
+        dU = self.dU_dtheta_interp(Hb, gS, theta) if self.interpolation == "Linear" else self.dU_dtheta(Hb, gS, theta)
+        T3 = dspatial[:, :, None] * dU * Hb[:, :, None]
         return np.einsum("ijk,ij->k", T3, D_adjoint)
 
 
@@ -482,7 +533,11 @@ class TargetDHybrid:
     δH = 1e-4 (target_D_hybrid.jl:58-73)."""
 
     def __init__(self, ph: Phys, mlp: MLP, T: float, prescale_bounds=((-25.0, 0.0), (0.0, 500.0)), max_NN=None,
-                 n_H=None, n_gS=None):
+                 n_H=None, n_gS=None, interpolation="None", n_interp_half=20, nodes_H=None):
+        """interpolation "Linear" -- the DEFAULT of SIA2D_D_hybrid_target (target_D_hybrid.jl:13, 136-166): the network gradient at
+        2 * n_interp_half knots of H̄ (create_interpolation(H̄) of the CURRENT field, :143) interpolated linearly per cell;
+        nodes_H overrides the knots (the device-resident reverse loop keeps one set of knots for all snapshots)."""
+        self.interpolation, self.n_interp_half, self.nodes_H = interpolation, n_interp_half, nodes_H
         self.ph, self.mlp, self.T, self.bounds = ph, mlp, T, prescale_bounds
         self.max_NN = ph.maxA if max_NN is None else max_NN
         self.n_H = ph.n if n_H is None else n_H
@@ -529,12 +584,21 @@ class TargetDHybrid:
     def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
         ph = self.ph
         dA_spatial = Gamma(ph) * Hb ** (self.n_H + 2) * gS ** (self.n_gS - 1)
-        X = np.stack([np.full(Hb.size, normalize(self.T, self.bounds[0])), normalize(Hb.reshape(-1), self.bounds[1])],
-                     axis=1)
-        y = self.mlp.forward(theta, X)[:, 0]
-        gout = (ml_model_postscale(y, self.max_NN) / (y * y))[:, None]
-        dth, _ = self.mlp.backward(theta, X, gout)
-        T3 = dA_spatial[:, :, None] * dth.reshape(Hb.shape + (-1,))
+
+        def grad_at(h):
+            X = np.stack([np.full(h.size, normalize(self.T, self.bounds[0])), normalize(h.reshape(-1), self.bounds[1])], axis=1)
+            y = self.mlp.forward(theta, X)[:, 0]
+            gout = (ml_model_postscale(y, self.max_NN) / (y * y))[:, None]
+            return self.mlp.backward(theta, X, gout)[0]
+
+        if self.interpolation == "Linear":
+            kh = create_interpolation(Hb, self.n_interp_half) if self.nodes_H is None else np.asarray(self.nodes_H, dtype=np.float64)
+            grads = grad_at(kh)
+            a, wa = _interp_weights(kh, Hb)
+            dth = (1 - wa[..., None]) * grads[a] + wa[..., None] * grads[a + 1]
+        else:
+            dth = grad_at(Hb).reshape(Hb.shape + (-1,))
+        T3 = dA_spatial[:, :, None] * dth
         return np.einsum("ijk,ij->k", T3, D_adjoint)
 
 

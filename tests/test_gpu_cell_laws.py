@@ -134,3 +134,58 @@ def test_lawU_ragged_resident_and_determinism(ob):
         assert np.array_equal(G1, ens.law_cell_grad())
     finally:
         sim.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("kind", ["U", "Y"])
+def test_law_pullback_with_linear_interpolation(ob, dtype, kind):
+    """M2 with interpolation = :Linear -- the default of SIA2D_D_hybrid_target (1-D lattice over Hbar, target_D_hybrid.jl:136-166)
+    and the optional mode of SIA2D_D_target (2-D lattice over (Hbar, gradS), target_D_pure.jl:180-193, Laws.jl:140-168): the device
+    reorders the contraction as a sum over knots; it must equal the oracle's per-cell interpolated gradient tensor contracted with
+    D_adj, converge to the exact gradient with the knot count, and fall back to the exact gradient when the knots are cleared."""
+    import odinn_b200
+
+    nx, ny = 37, 29
+    g, H, lam = _inputs(nx, ny, dtype, 21)
+    widths, acts = (2, 16, 16, 1), ("softplus", "softplus", "sigmoid")
+    mlp, theta = _mlp(widths, acts, 123)
+    ph = o.Phys()
+    sim = ob.Simulation([ob.Glacier2D(B=g.B, Δx=g.dx, Δy=g.dy)], ob.Phys(), A=1e-17, dtype=dtype)
+    tol = 1e-10 if dtype == "f64" else 5e-5
+    try:
+        ens = sim.ensemble
+        if kind == "U":
+            bounds, max_NN = ((0.0, 300.0), (0.0, 0.5)), 50.0
+            exact = o.TargetD(ph, mlp, prescale_bounds=bounds, max_NN=max_NN)
+            f = o._recompute_forward(H, g, exact, theta)
+            ens.law_cell_nn_set("U", widths, acts, theta, prescale_bounds=bounds, max_NN=max_NN)
+        else:
+            T = -7.5
+            exact = o.TargetDHybrid(ph, mlp, T)
+            f = o._recompute_forward(H, g, exact, theta)
+            ens.set_temperature(0, T)
+            ens.law_cell_nn_set("Y", widths, acts, theta, prescale_bounds=exact.bounds, max_NN=exact.max_NN)
+        ref_exact = o.VJP_dSIA_dtheta_discrete(lam, H, g, exact, theta)
+        errs = []
+        for nh in (6, 40):
+            kh = o.create_interpolation(f["Hb"], nh, dilation_factor=1.05, minA_quantile=10.0 if kind == "U" else None)
+            assert np.array_equal(kh, odinn_b200.create_interpolation(f["Hb"], nh, dilation_factor=1.05,
+                                                                      minA_quantile=10.0 if kind == "U" else None))
+            if kind == "U":
+                ks = o.create_interpolation(f["gS"], nh, dilation_factor=1.05)
+                tgi = o.TargetD(ph, mlp, prescale_bounds=bounds, max_NN=max_NN, interpolation="Linear", nodes_H=kh, nodes_S=ks)
+                ens.law_cell_interp_set(kh, ks)
+            else:
+                tgi = o.TargetDHybrid(ph, mlp, T, interpolation="Linear", nodes_H=kh)
+                ens.law_cell_interp_set(kh)
+            ref = o.VJP_dSIA_dtheta_discrete(lam, H, g, tgi, theta)
+            dth = ens.sia2d_vjp_theta_cell(0, lam, H)
+            assert rel_l2(dth, ref) <= tol, (nh, rel_l2(dth, ref))
+            errs.append(rel_l2(dth, ref_exact))
+        assert errs[1] < 0.2 * errs[0] and errs[1] < 2e-3   # second-order convergence to the exact gradient
+        ens.law_cell_interp_set()
+        assert rel_l2(ens.sia2d_vjp_theta_cell(0, lam, H), ref_exact) <= (1e-11 if dtype == "f64" else 2e-5)
+        with pytest.raises(ob.OdinnError):
+            ens.law_cell_interp_set(np.array([1.0, 0.5]), np.array([0.0, 1.0]) if kind == "U" else None)   # knots must increase
+    finally:
+        sim.close()
