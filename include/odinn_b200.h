@@ -136,7 +136,9 @@ int odinn_sia2d_vjp_theta(odinn_ensemble* e, int glacier, const void* lambda, in
 /* Continuous-adjoint flavours (differentiate-then-discretise; no flux clamp, no H > 0 mask, border 0).
  * Replace VJP_lambda_dSIAdH(::ContinuousVJP, ...) (src/inverse/SIA2D/VJPs.jl:7-10 -> adjoint.jl:442-555) and
  * VJP_lambda_dSIAdtheta(::ContinuousVJP, ...) (VJPs.jl:35-38 -> adjoint.jl:582-662).  As for the discrete flavour the
- * theta-VJP of a glacier-wide law returns the scalar S with d_theta = (dA/dtheta) * S. */
+ * theta-VJP of a glacier-wide law returns the scalar S with d_theta = (dA/dtheta) * S; with the gridded A mode the per-node
+ * integrand is left in ODINN_FIELD_VJP_A, with a per-cell law the vector is read with odinn_law_cell_grad (adjoint.jl:646-657 is
+ * the transpose of the discrete contraction of adjoint.jl:250, so these two cases run the discrete A2 kernels). */
 int odinn_sia2d_vjp_H_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,
                                  void* out, int ldo, double t);
 int odinn_sia2d_vjp_theta_continuous(odinn_ensemble* e, int glacier, const void* lambda, int ldl, const void* H, int ldH,

@@ -182,7 +182,12 @@ static int launch_vjpc(odinn_ensemble* e, int g, const void* lam, const void* H,
 // S[g] = Σ λ ⊙ pad(∇·(avg(∂A_spatial)·clamp(∇S)))  (adjoint.jl:582-662, glacier-wide law).  g < 0: whole ensemble.
 static int launch_unitA_dot(odinn_ensemble* e, int g, const void* lam, const void* H, double* S_dst, double scale = 1.0,
                             int accumulate = 0) {
-    if (e->a_gridded) return fail(e, ODINN_ESTATE, "the continuous theta-VJP is provided for glacier-wide A laws");
+    // The Tullio chain of adjoint.jl:646-657 is linear in the tensor dD/dtheta and uses the CLAMPED edge slopes: transposed, it is the
+    // discrete contraction sum_nodes dD/dtheta[node] D_adj[node] of adjoint.jl:250 (identical to rounding: tests/test_oracle_identities.py).
+    // For a glacier-wide law that sum factorises and the unit-A forward + dot product below is the cheapest way to get it; for a gridded A
+    // (one parameter per node) and for per-cell laws (a network gradient per node) the discrete A2 kernels already produce exactly it.
+    if (e->a_gridded || e->law_kind != LAW_NONE)
+        return launch_vjp_range(e, g, g + 1, lam, H, nullptr, false, true, S_dst, scale, accumulate, false);
     int rc;
     if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = alloc_plane(e, &e->work[0]))) return rc;
     if ((rc = sync_descs(e))) return rc;

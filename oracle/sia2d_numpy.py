@@ -385,6 +385,24 @@ class TargetA:
             return (dA_spatial * self.vjp_theta.reshape(dA_spatial.shape) * D_adjoint).reshape(-1, order="F")
         return np.zeros(0)
 
+    def dD_dtheta_dense(self, Hb, gS, theta):
+        """∂Diffusivity∂θ as the dense tensor of target_A.jl:64-92: cartesian_tensor for glacier-wide laws, sparse_cartesian_tensor
+        (one parameter per dual node, column-major) for the gridded law (target_utils.jl:156-173)."""
+        ph = self.ph
+        dA_spatial = Gamma(ph) * Hb ** (ph.n + 2) * gS ** (ph.n - 1)
+        if self.vjp_theta is None:
+            self.precompute_vjp(theta)
+        if self.kind in ("nn", "scalar"):
+            return dA_spatial[:, :, None] * np.atleast_1d(self.vjp_theta).reshape(-1)[None, None, :]
+        if self.kind == "gridded":
+            n0, n1 = dA_spatial.shape
+            T3 = np.zeros((n0, n1, n0 * n1))
+            v = (dA_spatial * self.vjp_theta.reshape(dA_spatial.shape))
+            ii, jj = np.meshgrid(np.arange(n0), np.arange(n1), indexing="ij")
+            T3[ii, jj, ii + n0 * jj] = v
+            return T3
+        return np.zeros(Hb.shape + (0,))
+
     # -- surface velocity pieces, target_A.jl:94-141 -----------------------
     def Velocity_up(self, Hb, gS):
         ph = self.ph
@@ -517,11 +535,13 @@ class TargetD:
         return ((1 - wa) * (1 - wb) * grads[a, b] + wa * (1 - wb) * grads[a + 1, b] + (1 - wa) * wb * grads[a, b + 1]
                 + wa * wb * grads[a + 1, b + 1])
 
-    def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
+    def dD_dtheta_dense(self, Hb, gS, theta):
         dspatial = np.where(Hb > 0.0, 1.0, 0.0)
         dU = self.dU_dtheta_interp(Hb, gS, theta) if self.interpolation == "Linear" else self.dU_dtheta(Hb, gS, theta)
-        T3 = dspatial[:, :, None] * dU * Hb[:, :, None]
-        return np.einsum("ijk,ij->k", T3, D_adjoint)
+        return dspatial[:, :, None] * dU * Hb[:, :, None]
+
+    def dD_dtheta_contract(self, Hb, gS, theta, D_adjoint, dense=False):
+        return np.einsum("ijk,ij->k", self.dD_dtheta_dense(Hb, gS, theta), D_adjoint)
 
 
 class TargetDHybrid:
@@ -599,7 +619,10 @@ class TargetDHybrid:
         else:
             dth = grad_at(Hb).reshape(Hb.shape + (-1,))
         T3 = dA_spatial[:, :, None] * dth
-        return np.einsum("ijk,ij->k", T3, D_adjoint)
+        return T3 if D_adjoint is None else np.einsum("ijk,ij->k", T3, D_adjoint)
+
+    def dD_dtheta_dense(self, Hb, gS, theta):
+        return self.dD_dtheta_contract(Hb, gS, theta, None)
 
 
 # --------------------------------------------------------------------------
@@ -770,13 +793,30 @@ def VJP_dSIA_dH_continuous(lam, H, glacier, target, theta=None):
     return out
 
 
-def VJP_dSIA_dtheta_continuous(lam, H, glacier, target, theta=None):
-    """adjoint.jl:582-662 for glacier-wide A (the dense tensor factorises as
-    ∂A_spatial ⊗ vjp_θ, so the Tullio chain acts on ∂A_spatial alone)."""
+def VJP_dSIA_dtheta_continuous_dense(lam, H, glacier, target, theta=None):
+    """adjoint.jl:582-662 literally, for ANY target: the dense tensor ∂D∂θ[i, j, k] pushed through the Tullio chain
+    Fx = avg_y(∂D∂θ) clamp(dSdx), Fy = avg_x(∂D∂θ) clamp(dSdy) (:646-647), Fxx + Fyy padded with a zero border (:649-654),
+    contracted with λ (:657).  Because the chain is linear in ∂D∂θ and uses the CLAMPED edge slopes, it equals the discrete
+    contraction Σ ∂D∂θ[i, j, k] D†[i, j] (adjoint.jl:250) -- tests/test_oracle_identities.py checks that identity, which is what
+    lets the device serve the continuous θ-VJP of gridded-A and per-cell laws with the discrete A2 kernels."""
     dx, dy = glacier.dx, glacier.dy
     f = _recompute_forward(H, glacier, target, theta)
+    T3 = target.dD_dtheta_dense(f["Hb"], f["gS"], theta)                      # (nx-1, ny-1, K)
+    Fx = 0.5 * (T3[:, :-1, :] + T3[:, 1:, :]) * f["cx"][:, :, None]           # :646
+    Fy = 0.5 * (T3[:-1, :, :] + T3[1:, :, :]) * f["cy"][:, :, None]           # :647
+    Fxx = (Fx[1:, :, :] - Fx[:-1, :, :]) / dx
+    Fyy = (Fy[:, 1:, :] - Fy[:, :-1, :]) / dy
+    return np.einsum("ijk,ij->k", Fxx + Fyy, lam[1:-1, 1:-1])                 # :649-657 (zero-padded border)
+
+
+def VJP_dSIA_dtheta_continuous(lam, H, glacier, target, theta=None):
+    """adjoint.jl:582-662 for glacier-wide A (the dense tensor factorises as
+    ∂A_spatial ⊗ vjp_θ, so the Tullio chain acts on ∂A_spatial alone); other targets: the dense chain."""
+    dx, dy = glacier.dx, glacier.dy
+    if not (isinstance(target, TargetA) and target.kind in ("nn", "scalar")):
+        return VJP_dSIA_dtheta_continuous_dense(lam, H, glacier, target, theta)
+    f = _recompute_forward(H, glacier, target, theta)
     ph = target.ph
-    assert isinstance(target, TargetA) and target.kind in ("nn", "scalar")
     if target.vjp_theta is None:
         target.precompute_vjp(theta)
     dA = Gamma(ph) * f["Hb"] ** (ph.n + 2) * f["gS"] ** (ph.n - 1)

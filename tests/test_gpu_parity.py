@@ -368,8 +368,18 @@ def test_continuous_vjp_generic_physics_and_gridded_A(ob, dtype):
         tg = o.TargetA(o.Phys(), "const", A=Af)
         vH, _ = ob.VJP_λ_dSIAdH(ob.ContinuousVJP(), lam, H, None, sim, 0.0)
         assert rel_l2(vH, o.VJP_dSIA_dH_continuous(lam, H, g, tg)) <= TOL[dtype]
-        with pytest.raises(ob.OdinnError):  # the continuous θ-VJP is provided for glacier-wide laws only
-            ob.VJP_λ_dSIAdθ(ob.ContinuousVJP(), lam, H, None, None, sim, 0.0)
+        # continuous θ-VJP with a gridded A: the per-node integrand, identical to the discrete one (adjoint.jl:646-657 is the
+        # transpose of the contraction at adjoint.jl:250)
+        from odinn_b200 import _capi
+
+        S = ob.VJP_λ_dSIAdθ(ob.ContinuousVJP(), lam, H, None, None, sim, 0.0)
+        tgg = o.TargetA(o.Phys(), "gridded")
+        thg = np.arctanh(2 * (Af - o.Phys().minA) / (o.Phys().maxA - o.Phys().minA) - 1)
+        ref = np.asarray(o.VJP_dSIA_dtheta_continuous(lam, H, g, tgg, thg)).reshape(Af.shape, order="F")
+        tgg.precompute_vjp(thg)
+        got = sim.ensemble.download(0, _capi.FIELD_VJP_A) * tgg.vjp_theta.reshape(Af.shape)
+        assert rel_l2(got, ref) <= TOL[dtype] * 5
+        assert abs(S - sim.ensemble.download(0, _capi.FIELD_VJP_A).astype(np.float64).sum()) <= 1e-4 * abs(S) + 1e-30
     finally:
         sim.close()
 

@@ -72,3 +72,25 @@ def test_shapes_follow_reference():
     assert o.avg(A).shape == (9, 10) and o.inn(A).shape == (8, 9) and o.inn1(A).shape == (9, 10)
     assert o.clamp_borders_dx(np.zeros((9, 9)), A, 1.0, 1.0).shape == (9, 9)
     assert o.clamp_borders_dy(np.zeros((8, 10)), A, 1.0, 1.0).shape == (8, 10)
+
+
+def test_continuous_theta_vjp_is_the_transpose_of_the_discrete_contraction():
+    """adjoint.jl:646-657 (dense tensor dD/dtheta through avg, the CLAMPED edge slopes, the divergence, then contracted with lambda)
+    == adjoint.jl:250 (sum_nodes dD/dtheta D_adj) for every law kind: glacier-wide, gridded (one parameter per node), per-cell
+    networks.  The device relies on it to serve the continuous theta-VJP of gridded-A and per-cell laws with the discrete A2 kernels."""
+    ph = o.Phys()
+    g = o.rough_bed_glacier(23, 19)
+    lam = np.random.default_rng(1).standard_normal(g.B.shape)
+    mlp = o.MLP([2, 8, 8, 1], ["softplus", "softplus", "sigmoid"])
+    thm = 0.4 * np.random.default_rng(3).standard_normal(mlp.n_params)
+    cases = [
+        (o.TargetA(ph, "scalar"), np.array([0.3])),
+        (o.TargetA(ph, "gridded"), 0.1 * np.random.default_rng(2).standard_normal((22, 18))),
+        (o.TargetD(ph, mlp, prescale_bounds=((0.0, 300.0), (0.0, 0.6)), max_NN=60.0), thm),
+        (o.TargetDHybrid(ph, mlp, T=-7.0), thm),
+        (o.TargetDHybrid(ph, mlp, T=-7.0, interpolation="Linear", n_interp_half=8), thm),
+    ]
+    for tg, th in cases:
+        a = o.VJP_dSIA_dtheta_continuous_dense(lam, g.H0, g, tg, th)
+        b = np.asarray(o.VJP_dSIA_dtheta_discrete(lam, g.H0, g, tg, th)).reshape(-1)
+        assert a.shape == b.shape and np.linalg.norm(a - b) <= 1e-13 * np.linalg.norm(b), type(tg).__name__
