@@ -1090,7 +1090,9 @@ int odinn_law_cell_nn_set(odinn_ensemble* e, int kind, int n_layers, const int* 
         e->d_law_theta = e->d_law_partial = e->d_law_dtheta = nullptr;
         e->law_n_theta = 0;
         ODINN_CUDA(e, cudaMalloc(&e->d_law_theta, sizeof(double) * np));
-        ODINN_CUDA(e, cudaMalloc(&e->d_law_partial, sizeof(double) * (size_t)np * e->max_tiles_per_glacier));
+        // block partials of the theta pullback: one row per tile of the WHOLE ensemble (the fixed-architecture kernel covers every glacier
+        // in one launch); the generic kernel and the knot pass use the first max_tiles_per_glacier rows
+        ODINN_CUDA(e, cudaMalloc(&e->d_law_partial, sizeof(double) * (size_t)np * std::max(e->n_tiles, e->max_tiles_per_glacier)));
         ODINN_CUDA(e, cudaMalloc(&e->d_law_dtheta, sizeof(double) * (size_t)np * e->G));
         ODINN_CUDA(e, cudaMemsetAsync(e->d_law_dtheta, 0, sizeof(double) * (size_t)np * e->G, e->stream));
         e->law_n_theta = np;
@@ -1129,12 +1131,12 @@ int odinn_law_cell_interp_set(odinn_ensemble* e, int n0, const double* knots0, i
     {   // the knot pass writes one row of block partials per 512 knots: grow the partial buffer when the lattice has more blocks than
         // the largest glacier has tiles
         const int nb = div_up(n0 * std::max(n1, 1), TX * TY);
-        if (nb > e->max_tiles_per_glacier) {
+        if (nb > std::max(e->n_tiles, e->max_tiles_per_glacier)) {
             if (e->d_law_partial) cudaFree(e->d_law_partial);
             e->d_law_partial = nullptr;
             ODINN_CUDA(e, cudaMalloc(&e->d_law_partial, sizeof(double) * (size_t)e->law_n_theta * nb));
-            e->max_tiles_per_glacier = nb;
         }
+        e->max_tiles_per_glacier = std::max(e->max_tiles_per_glacier, nb);
     }
     e->ext_int[2] = n0;
     e->ext_int[3] = n1;

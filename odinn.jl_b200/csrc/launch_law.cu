@@ -1,10 +1,21 @@
 // Launchers of the per-cell law kernels (sia2d_law.cuh): node pass and theta pullback.
+#include <cstdlib>
+
 #include "launch.cuh"
 #include "sia2d_law.cuh"
+#include "sia2d_law_fixed.cuh"
 
 namespace odinn {
 
 static inline CellLaw* law_of(odinn_ensemble* e) { return static_cast<CellLaw*>(e->law_cfg); }
+
+// The compile-time architecture of sia2d_law_fixed.cuh: 2 -> 16 -> 16 -> 1, softplus / softplus / sigmoid (ODINN_LAW_GENERIC=1: never).
+static bool lf_match(const CellLaw& lw) {
+    static const bool off = []() { const char* v = getenv("ODINN_LAW_GENERIC"); return v && v[0] == '1'; }();
+    const MlpArch& a = lw.arch;
+    return !off && a.n_layers == 3 && a.widths[0] == 2 && a.widths[1] == 16 && a.widths[2] == 16 && a.widths[3] == 1 &&
+           a.acts[0] == ACT_SOFTPLUS && a.acts[1] == ACT_SOFTPLUS && a.acts[2] == ACT_SIGMOID;
+}
 
 static __global__ void law_theta_reduce_scaled(const double* __restrict__ block_partial, int n_tiles, int n_params,
                                         double* __restrict__ out, double scale, int accumulate) {
@@ -37,6 +48,16 @@ static int launch_law_nodes_t(odinn_ensemble* e, int g0, int g1, const void* H, 
         else law_nodes_kernel<TT, RR, PP, 32><<<nt, LAW_NT, smem, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta,     \
                      (const TT*)H, B, (TT*)e->lawD, PP ? (TT*)e->lawAl : nullptr, PP ? (TT*)e->lawBe : nullptr);               \
     } while (0)
+    if (lf_match(lw) && (!partials || lw.kind == LAW_U)) {
+        if (partials)
+            law_nodes_fixed_kernel<T, 16, 16, true><<<nt, LAW_NT, 0, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                                 (T*)e->lawD, (T*)e->lawAl, (T*)e->lawBe);
+        else
+            law_nodes_fixed_kernel<T, 16, 16, false><<<nt, LAW_NT, 0, e->stream>>>(descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B,
+                                                                                  (T*)e->lawD, nullptr, nullptr);
+        ODINN_CHECK_LAUNCH(e);
+        return ODINN_OK;
+    }
     if (!partials) LN(T, T, false);
     else if (lw.kind == LAW_U) LN(T, T, true);   // analytic partials ride along the forward evaluation: the ensemble's precision
     else LN(T, double, true);                    // LawY: one-sided difference of the network (target_D_hybrid.jl:58-73): fp64
@@ -73,6 +94,42 @@ static int launch_law_theta_t(odinn_ensemble* e, int g0, int g1, const void* H, 
         else ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_kernel<T, T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int n0 = e->ext_int[2], n1 = e->ext_int[3];
+    if (lf_match(lw)) {
+        constexpr size_t fsmem = lf_theta_smem<T, 16, 16>();
+        if (fsmem > 48 * 1024) {
+            ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_fixed_kernel<T, 16, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            ODINN_CUDA(e, cudaFuncSetAttribute(law_theta_fixed_kernel<T, 16, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        }
+        if (n0 == 0) {
+            // ONE launch over the tiles of glaciers [g0, g1), ONE reduction launch (block partials indexed by global tile)
+            const int t0 = e->gl[g0].tile0, t1 = e->gl[g1 - 1].tile0 + e->gl[g1 - 1].ntx * e->gl[g1 - 1].nty;
+            law_theta_fixed_kernel<T, 16, 16, false><<<t1 - t0, LAW_NT, fsmem, e->stream>>>(
+                descs, e->d_tiles + t0, lw, e->d_law_theta, (const T*)H, B, (const T*)e->plane[ODINN_FIELD_VJP_A],
+                e->d_law_partial + (size_t)t0 * np, nullptr, 0, 0, nullptr, 0);
+            ODINN_CHECK_LAUNCH(e);
+            law_theta_reduce_all<<<dim3(div_up(np, 128), g1 - g0), 128, 0, e->stream>>>(e->d_tile_start + g0, e->d_law_partial, np,
+                                                                                      e->d_law_dtheta + (size_t)g0 * np, scale, accumulate);
+            ODINN_CHECK_LAUNCH(e);
+            return ODINN_OK;
+        }
+        const double* knots = (const double*)e->ext_dev[EXT_LAT_KNOTS];
+        double* Wlat = (double*)e->ext_dev[EXT_LAT_W];
+        const int nk = n0 * std::max(n1, 1), nb = div_up(nk, TX * TY);
+        for (int g = g0; g < g1; ++g) {
+            const int t0 = e->gl[g].tile0, nt = e->gl[g].ntx * e->gl[g].nty;
+            ODINN_CUDA(e, cudaMemsetAsync(Wlat, 0, sizeof(double) * nk, e->stream));
+            law_lattice_scatter<T><<<nt, LAW_NT, sizeof(double) * (n0 + n1), e->stream>>>(descs, e->d_tiles + t0, lw, (const T*)H, B,
+                                                                                       (const T*)e->plane[ODINN_FIELD_VJP_A], knots, n0, n1, Wlat);
+            ODINN_CHECK_LAUNCH(e);
+            law_theta_fixed_kernel<T, 16, 16, true><<<nb, LAW_NT, fsmem, e->stream>>>(descs, nullptr, lw, e->d_law_theta, nullptr, nullptr, nullptr,
+                                                                                     e->d_law_partial, knots, n0, n1, Wlat, g);
+            ODINN_CHECK_LAUNCH(e);
+            law_theta_reduce_scaled<<<div_up(np, 128), 128, 0, e->stream>>>(e->d_law_partial, nb, np, e->d_law_dtheta + (size_t)g * np, scale,
+                                                                           accumulate);
+            ODINN_CHECK_LAUNCH(e);
+        }
+        return ODINN_OK;
+    }
     if (n0 > 0) {
         // interpolation = :Linear: scatter D†·s onto the knots (one lattice per glacier pass), then back-propagate the KNOTS
         const double* knots = (const double*)e->ext_dev[EXT_LAT_KNOTS];
