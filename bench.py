@@ -364,23 +364,20 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     bind_to_gpu_numa_node(local_rank)
     dist = None
+    json_fd = 1
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries ONE JSON line: NCCL (NCCL_DEBUG=VERSION in the image, INFO when the driver asks for it) logs to stdout while
-        # the communicator comes up, so fd 1 points at stderr during the initialisation.  NCCL_DEBUG itself is left as the caller set it.
+        # stdout carries ONE JSON line: NCCL (NCCL_DEBUG=VERSION in the image, INFO when the driver asks for it) logs to fd 1 while
+        # the communicator comes up AND when it is destroyed, so fd 1 points at stderr for the rest of the process and the JSON line
+        # is written to the saved descriptor.  NCCL_DEBUG itself is left as the caller set it.
         sys.stdout.flush()
-        saved_stdout = os.dup(1)
+        json_fd = os.dup(1)
         os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            warm = torch.zeros(1 + N_THETA, dtype=torch.float64, device="cuda")
-            dist.all_reduce(warm)  # communicator creation happens here
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        warm = torch.zeros(1 + N_THETA, dtype=torch.float64, device="cuda")
+        dist.all_reduce(warm)  # communicator creation happens here
+        torch.cuda.synchronize()
 
     def barrier(arm):
         arm.ens.synchronize()
@@ -513,7 +510,8 @@ def run_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cpu.cores, "kind": "port",
                                     "sample": f"{args.ref_glaciers} glaciers of {n}x{n} per step, best of {blocks} blocks of {args.steps} steps "
                                               f"({best:.2f} s per block) after a >= 1.5 s warm-up, C oracle + OpenMP, {dtype}"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     arm.close()
     if dist is not None:
         dist.barrier()

@@ -186,6 +186,14 @@ int odinn_host_unregister(odinn_ensemble* e, void* host);
  * stage fused into the RHS kernel.  The launches of one tstop interval are captured once into a CUDA graph and replayed per
  * interval (step sizes from a device table, so non-uniform tstops need no re-capture); ODINN_NO_GRAPH=1 disables it. */
 int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double* t, int nsub);
+/* Small ensembles (the reference's usual workload: a few glaciers of 100 - 400 px, src/simulations/inversions/inversion_utils.jl:551-610
+ * called once per glacier) run odinn_solve_forward shared-memory resident: one thread-block cluster per glacier keeps the state on the
+ * SMs and ONE launch runs every sub-step and stage of a whole range of tstop intervals, writing the snapshots as it goes.  mode = -1
+ * (default): automatic (used when every glacier fits the shared memory of a cluster of <= 16 CTAs and all clusters are co-resident,
+ * glacier-wide A, no per-cell law); 0: never (marching kernels + CUDA graph); 1, 2, 4, 8, 16: this cluster size.  Same results either
+ * way up to rounding.  odinn_solve_forward_adaptive(ODINN_RDPK3SP35) takes the same path: the whole adaptive loop of a glacier (stages,
+ * error norm reduced over the cluster, PID controller, tstops) then runs on the device without a host round trip per trial step. */
+int odinn_set_cluster_mode(odinn_ensemble* e, int mode);
 /* Adaptive forward solve with tstops: replaces solve(ODEProblem(SIA2D_UDE!, H0, tspan; tstops), solver;
  * reltol, abstol, maxiters, saveat = tstops) (src/simulations/inversions/inversion_utils.jl:559-568; solver choice
  * src/parameters ... AdjointTypes.jl:60, test/test_grad_loss.jl:143).  method = ODINN_BS3: Bogacki-Shampine 3(2) with FSAL,

@@ -85,6 +85,7 @@ SIGNATURES = {
     "odinn_vjp_resident": (_i, [_vp, _i, _dp]),
     "odinn_fwd_adj_batch_host": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _dp]),
     "odinn_set_batch_chunk": (_i, [_vp, C.c_longlong]),
+    "odinn_set_cluster_mode": (_i, [_vp, _i]),
     "odinn_host_register": (_i, [_vp, _vp, C.c_size_t]),
     "odinn_host_unregister": (_i, [_vp, _vp]),
 }

@@ -326,7 +326,13 @@ extern "C" int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n
     if ((rc = ensure_plane(e, ODINN_FIELD_H0)) || (rc = ensure_plane(e, ODINN_FIELD_H))) return rc;
     if ((rc = prepare_snapshots(e, n_snap))) return rc;
     if ((rc = sync_descs(e))) return rc;
-    if (method == ODINN_RDPK3SP35) return solve_forward_rdpk(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
+    if (method == ODINN_RDPK3SP35) {
+        if ((rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+        // small ensembles: the whole adaptive loop of every glacier runs inside one thread-block cluster (sia2d_cluster.cuh)
+        if (const int cs = cluster_plan(e, 1))
+            return solve_forward_rdpk_cluster(e, cs, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
+        return solve_forward_rdpk(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
+    }
     return e->dtype == ODINN_F32 ? solve_bs3_t<float>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out)
                                  : solve_bs3_t<double>(e, n_snap, t, reltol, abstol, dt0, max_steps, steps_out, rejected_out);
 }

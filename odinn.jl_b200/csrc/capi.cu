@@ -838,6 +838,29 @@ int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double*
     void* Hs = e->plane[ODINN_FIELD_H];  // current state; H and the work planes rotate by pointer
     void* U1 = e->work[0];
     void* U2 = e->work[1];
+
+    // Small glaciers (every glacier of the ensemble fits the shared memory of one thread-block cluster): the state stays on the SMs
+    // and ONE launch runs a whole range of intervals, writing the snapshots as it goes (sia2d_cluster.cuh).  A range ends where a
+    // mass-balance callback fires (inversion_utils.jl:498-517): it is applied to the global plane between two launches.
+    if (const int cs = cluster_plan(e, 0)) {
+        const double* d_t = nullptr;
+        if ((rc = upload_time_grid(e, t, n_snap, &d_t))) return rc;
+        ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, 0), e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
+        if (n_snap == 1) ODINN_CUDA(e, cudaMemcpyAsync(Hs, e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
+        const void* Hin = e->plane[ODINN_FIELD_H0];
+        int j0 = 0;
+        while (j0 < n_snap - 1) {
+            int j1 = n_snap - 1;
+            for (int m : e->mb_snap) if (m > j0 && m < j1) j1 = m;
+            if ((rc = launch_interval_cluster(e, cs, method, nsub, j0, j1, Hin, Hs, e->snap, d_t))) return rc;
+            int applied = 0;
+            if ((rc = mb_apply_step(e, j1, Hs, &applied))) return rc;
+            if (applied) ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, j1), Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+            Hin = Hs;
+            j0 = j1;
+        }
+        return ODINN_OK;
+    }
     ODINN_CUDA(e, cudaMemcpyAsync(Hs, e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
     ODINN_CUDA(e, cudaMemcpyAsync(plane_ptr(e, e->snap, 0), Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
 
@@ -906,6 +929,14 @@ int odinn_solve_forward(odinn_ensemble* e, int method, int n_snap, const double*
     }
     if (Hs != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], Hs, pbytes, cudaMemcpyDeviceToDevice, e->stream));
+    return ODINN_OK;
+}
+
+int odinn_set_cluster_mode(odinn_ensemble* e, int mode) {
+    GUARD(e);
+    if (mode != -1 && mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8 && mode != 16)
+        return fail(e, ODINN_EARG, "cluster mode must be -1 (automatic), 0 (off) or a cluster size 1, 2, 4, 8, 16");
+    e->cluster_mode = mode;
     return ODINN_OK;
 }
 

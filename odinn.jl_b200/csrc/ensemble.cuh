@@ -55,6 +55,7 @@ struct odinn_ensemble {
     void* tma_cache = nullptr;    // tensor maps per plane pointer, band work items (launch_march2.cu)
     double* tma_partial_live = nullptr;  // partial sums of the last fused launch when it went through the TMA variant (else nullptr)
     bool all_nx_even = true;
+    int cluster_mode = -1;        // odinn_set_cluster_mode: -1 automatic, 0 off, else the forced cluster size (launch_cluster.cu)
     bool no_fuse = false;         // ODINN_NO_FUSE=1: never use the fused F1 + A1 + A2 kernel
     double* d_partial = nullptr;  // per-item / per-tile partial sums (two-stage, fixed-order reductions)
     double* d_S = nullptr;        // [4 x G]: S | Ssum | loss | A
@@ -105,7 +106,7 @@ struct odinn_ensemble {
     int* d_ad_dims = nullptr;     // [nx | ny | n_active]
     int* h_ad_active = nullptr;   // pinned
     // device / pinned-host allocations owned by the other translation units (freed by odinn_ensemble_destroy)
-    void* ext_dev[24] = {nullptr};
+    void* ext_dev[32] = {nullptr};
     void* ext_host[4] = {nullptr};
     int ext_int[8] = {0};
     // CUDA graph of one tstop interval of the fixed-step forward loop (odinn_solve_forward) + its device table of step sizes
@@ -133,6 +134,7 @@ enum {  // ext_dev slots
     EXT_RK_STATE = 19,                                                                              // RDPK3Sp35 per-glacier controller state (rdpk.cu)
     EXT_VQ_WORK = 20,                                                                               // 4 planes: velocity references interpolated at a quadrature node
     EXT_VQ_RED = 21,                                                                                // [2 G] mask count and sum of squares of those references
+    EXT_CL_TIMES = 24, EXT_CL_RKSTATE = 25,                                                                              // cluster-resident forward solve: time grid on the device (ext_int[4] = its length)
     EXT_LAT_KNOTS = 22, EXT_LAT_W = 23                                                              // law pullback with interpolation = :Linear: knots, knot weights (ext_int[2], [3] = n0, n1)
 };
 
@@ -193,6 +195,16 @@ int mb_adjoint_step(odinn_ensemble* e, int j, void* lam, const void* Hj);
 // S_dst[g] += scale * dl_V/dtheta-scalar evaluated on the plane H against the velocity references interpolated linearly at time tq
 // (one datum: constant; flat outside the data range) -- the quadrature-node term of the continuous adjoint (gradient.jl:289-301, 474-507)
 int velocity_theta_term_interp(odinn_ensemble* e, double tq, const double* t, int n_t, const void* H, double scale, double* S_dst);
+// cluster-resident forward solves of small glaciers (launch_cluster.cu).  kind: 0 fixed-step (Euler / SSPRK3), 1 RDPK3Sp35.
+// cluster_plan: the cluster size the ensemble would run with (0: not eligible).  launch_interval_cluster: intervals j0+1 .. j1 of the
+// time grid in one launch (snapshots j0+1 .. j1 and the final state written by the kernel).
+int cluster_plan(odinn_ensemble* e, int kind);
+int launch_interval_cluster(odinn_ensemble* e, int cs, int method, int nsub, int j0, int j1, const void* Hin, void* Hout, void* snap,
+                            const double* d_t);
+int solve_forward_rdpk_cluster(odinn_ensemble* e, int cs, int n_snap, const double* t, double reltol, double abstol, double dt0,
+                               int max_steps, int* steps_out, int* rejected_out);
+void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5]);
+int upload_time_grid(odinn_ensemble* e, const double* t, int n_snap, const double** d_t);   // device copy of the tstops (EXT_CL_TIMES)
 // adaptive forward solve with the reference's default integrator (rdpk.cu)
 int solve_forward_rdpk(odinn_ensemble* e, int n_snap, const double* t, double reltol, double abstol, double dt0, int max_steps,
                        int* steps_out, int* rejected_out);

@@ -39,25 +39,33 @@ static const double h_BHAT[5] = {1.046363371354093758897668305991705199e-01, 9.5
                                  1.070116530120251819121660365003405564e-01};
 __constant__ double c_E[5];   // bhat - b, b from the 3S* recurrence (rdpk_error_weights)
 
+static const double h_G1[4] = {2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
+                               5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01};
+static const double h_G2[4] = {5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
+                               2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01};
+static const double h_G3[4] = {0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01};
+static const double h_D[4] = {3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
+                              7.229275366787987419692007421895451953e-01, 0.0};
+static const double h_B[5] = {2.300298624518076223899418286314123354e-01, 3.021434166948288809034402119555380003e-01,
+                              8.025606185416310937583009085873554681e-01, 4.362158943603440930655148245148766471e-01,
+                              1.129272530455059129782111662594436580e-01};
+
 // b of the scheme the recurrence defines (oracle: rdpk_butcher), then E = bhat - b.
 static void rdpk_error_weights(double E[5]) {
-    static const double G1[4] = {2.587771979725733308135192812685323706e-01, -1.324380360140723382965420909764953437e-01,
-                                 5.056033948190826045833606441415585735e-02, 5.670532000739313812633197158607642990e-01};
-    static const double G2[4] = {5.528354909301389892439698870483746541e-01, 6.731871608203061824849561782794643600e-01,
-                                 2.803103963297672407841316576323901761e-01, 5.521525447020610386070346724931300367e-01};
-    static const double G3[4] = {0.0, 0.0, 2.752563273304676380891217287572780582e-01, -8.950526174674033822276061734289327568e-01};
-    static const double D[4] = {3.407655879334525365094815965895763636e-01, 3.414382655003386206551709871126405331e-01,
-                                7.229275366787987419692007421895451953e-01, 0.0};
-    static const double B[5] = {2.300298624518076223899418286314123354e-01, 3.021434166948288809034402119555380003e-01,
-                                8.025606185416310937583009085873554681e-01, 4.362158943603440930655148245148766471e-01,
-                                1.129272530455059129782111662594436580e-01};
-    double u[6] = {1, B[0], 0, 0, 0, 0}, tmp[6] = {1, 0, 0, 0, 0, 0};
+    double u[6] = {1, h_B[0], 0, 0, 0, 0}, tmp[6] = {1, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; ++i) {
-        for (int j = 0; j < 6; ++j) tmp[j] = tmp[j] + D[i] * u[j];
-        for (int j = 0; j < 6; ++j) u[j] = G1[i] * u[j] + G2[i] * tmp[j] + G3[i] * (j == 0 ? 1.0 : 0.0);
-        u[i + 2] += B[i + 1];
+        for (int j = 0; j < 6; ++j) tmp[j] = tmp[j] + h_D[i] * u[j];
+        for (int j = 0; j < 6; ++j) u[j] = h_G1[i] * u[j] + h_G2[i] * tmp[j] + h_G3[i] * (j == 0 ? 1.0 : 0.0);
+        u[i + 2] += h_B[i + 1];
     }
     for (int i = 0; i < 5; ++i) E[i] = h_BHAT[i] - u[i + 1];
+}
+
+// the same tables for the cluster-resident solver (launch_cluster.cu passes them as a kernel argument)
+void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5]) {
+    for (int i = 0; i < 4; ++i) { G1[i] = h_G1[i]; G2[i] = h_G2[i]; G3[i] = h_G3[i]; D[i] = h_D[i]; }
+    for (int i = 0; i < 5; ++i) B[i] = h_B[i];
+    rdpk_error_weights(E);
 }
 
 struct RkState {

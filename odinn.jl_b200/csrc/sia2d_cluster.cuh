@@ -1,0 +1,500 @@
+// Shared-memory-resident forward solves of SMALL glaciers: one thread-block cluster per glacier, a whole range of
+// tstop intervals (every sub-step and Runge-Kutta stage of it) in ONE launch.
+//
+// Why: the reference's real workloads are small grids (BASELINE config 1: one 128 x 128 glacier, config 3 / 4: 32 - 64
+// glaciers of 100 - 400 px).  One F1 launch over such a grid lasts 2 - 4 us even when replayed from a CUDA graph, and a
+// 5-year SSPRK3 run is 1440 of them: launch-latency bound at 1 - 2 % of what the marching kernels reach on a large ensemble
+// (profiles/r01_v6_configs_f32.jsonl); the adaptive solvers add a host round trip per trial step.  Here the state never
+// leaves the SMs between stages:
+//   * the glacier is cut into CS row bands, one per CTA of the cluster; each CTA keeps B, the stage planes and the dual-node
+//     diffusivity plane of its band (+ one halo row on each side) in shared memory;
+//   * an RHS evaluation is two sweeps over the band -- nodes (D, once per node), then cells (edge fluxes, divergence, and the
+//     Runge-Kutta update of the scheme as the epilogue) -- with 16-byte shared-memory accesses, four cells per thread;
+//   * the first / last row of a new stage value is also stored into the neighbouring CTA's halo row through distributed shared
+//     memory, and ONE cluster barrier (arrive.release / wait.acquire) per stage orders those stores before the next sweep;
+//   * at every tstop the band is written to the snapshot plane (gradient.jl:73: the forward states the adjoint re-reads);
+//   * the adaptive scheme reduces its error norm over the cluster in a fixed order (every CTA receives every partial through
+//     DSMEM and forms the same sum), so every CTA takes the same accept / reject decision without a host round trip.
+// Two kernels: sia2d_interval_cluster (Euler / SSPRK(3,3) with fixed sub-steps, odinn_solve_forward) and
+// sia2d_rdpk_cluster (RDPK3Sp35 + PID controller, the reference's default integrator, odinn_solve_forward_adaptive).
+// The arithmetic is that of sia2d_rhs_march (same raw sums, same clamp, same RK forms): reference semantics and citations
+// in sia2d_kernels.cuh -- SIA2D! as restated at src/inverse/SIA2D/adjoint.jl:47-104, solve with tstops
+// src/simulations/inversions/inversion_utils.jl:551-610, solver default src/inverse/AdjointTypes.jl:60.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "sia2d_march.cuh"
+
+namespace odinn {
+
+namespace cg = cooperative_groups;
+
+constexpr int CL_NT = 512;         // threads per CTA
+constexpr int CL_PAD = 4;          // zero columns left of column 0 (the row pitch also leaves >= 4 right of column nx-1)
+constexpr int CL_PLANES_FIXED = 5; // B, D, three rotating H planes
+constexpr int CL_PLANES_RDPK = 8;  // B, D, three rotating planes (u, S1, S1'), S2, est, k1
+constexpr int CL_MAX_CS = 16;
+
+__host__ __device__ inline int cl_pitch(int nx) { return ((nx + 3) & ~3) + 2 * CL_PAD; }
+__host__ __device__ inline int cl_band_rows(int ny, int cs) { return (ny + cs - 1) / cs; }
+// bytes of dynamic shared memory one CTA needs for a glacier: n_planes planes of (R + 2) rows
+inline size_t cl_smem_bytes(int nx, int ny, int cs, size_t esize, int n_planes) {
+    return (size_t)n_planes * (size_t)(cl_band_rows(ny, cs) + 2) * (size_t)cl_pitch(nx) * esize;
+}
+
+template <typename T> struct Quad { T v[4]; };
+__device__ __forceinline__ Quad<float> ld4(const float* p) {
+    float4 q = *reinterpret_cast<const float4*>(p);
+    return {{q.x, q.y, q.z, q.w}};
+}
+__device__ __forceinline__ Quad<double> ld4(const double* p) {
+    double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    return {{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void st4(float* p, const Quad<float>& q) {
+    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
+    *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+}
+
+// One CTA's band of one glacier.  Plane k of the carve-up is sm + k * plane; plane 0 is B, plane 1 is D (node row m of the band
+// in local row m), the others belong to the scheme.  Local row l <-> grid row row0 - 1 + l (l = 0 and l = Rown + 1: halo rows).
+template <typename T, bool CUBIC, bool ETA1>
+struct ClBand {
+    int nx, ny, P, R, Q, row0, Rown, CS, rank, tid;
+    size_t plane;
+    T *sm, *sB, *sD, *sm_lo, *sm_hi;
+    T eta0, hdx, hdy, kx, ky, A;
+    PhysDev<T> ph;
+    long long goff;
+    int gld;
+
+    __device__ __forceinline__ void init(cg::cluster_group& cluster, const GDesc<T>& d, const PhysDev<T>& phys, unsigned char* raw, int n_planes) {
+        CS = (int)cluster.num_blocks();
+        rank = (int)cluster.block_rank();
+        tid = threadIdx.x;
+        nx = d.nx; ny = d.ny;
+        P = cl_pitch(nx); R = cl_band_rows(ny, CS); Q = (nx + 3) >> 2;
+        row0 = min(rank * R, ny);
+        Rown = min(row0 + R, ny) - row0;
+        plane = (size_t)(R + 2) * P;
+        sm = reinterpret_cast<T*>(raw);
+        sB = sm;
+        sD = sm + plane;
+        // the same carve-up in the neighbours' shared memory (halo rows of the stage values)
+        sm_lo = (rank > 0 && Rown > 0) ? cluster.map_shared_rank(sm, rank - 1) : nullptr;
+        sm_hi = (rank + 1 < CS && row0 + Rown < ny) ? cluster.map_shared_rank(sm, rank + 1) : nullptr;
+        ph = phys;
+        eta0 = phys.eta0;
+        hdx = T(0.5) * d.inv_dx; hdy = T(0.5) * d.inv_dy;
+        kx = hdx * d.inv_dx; ky = hdy * d.inv_dy;   // ½/Δx², ½/Δy²
+        A = d.A;
+        goff = d.off; gld = d.ld;
+        for (size_t k = tid; k < (size_t)n_planes * plane; k += CL_NT) sm[k] = T(0);
+        __syncthreads();
+    }
+    __device__ __forceinline__ T* pl(int k) const { return sm + (size_t)k * plane; }
+
+    // band rows row0-1 .. row1 (clipped to the grid) of a global plane into shared plane k
+    __device__ __forceinline__ void load(int k, const T* __restrict__ g) {
+        T* dst = pl(k);
+        for (int q = tid; q < (Rown + 2) * Q; q += CL_NT) {
+            const int l = q / Q, i0 = (q - l * Q) << 2, j = row0 - 1 + l;
+            if (Rown == 0 || j < 0 || j >= ny) continue;
+            // (rows of the global planes are padded to 32 elements with zeros: a full quad is readable)
+            st4(dst + (size_t)l * P + CL_PAD + i0, ld4(g + goff + (long long)j * gld + i0));
+        }
+    }
+    // own rows of shared plane k to one or two global planes (16-byte stores; the row padding receives zeros)
+    __device__ __forceinline__ void store(int k, T* __restrict__ g0, T* __restrict__ g1) {
+        const T* src = pl(k);
+        for (int q = tid; q < Rown * Q; q += CL_NT) {
+            const int lr = q / Q, i0 = (q - lr * Q) << 2;
+            const Quad<T> v = ld4(src + (size_t)(lr + 1) * P + CL_PAD + i0);
+            const long long go = goff + (long long)(row0 + lr) * gld + i0;
+            if (g0) st4(g0 + go, v);
+            if (g1) st4(g1 + go, v);
+        }
+    }
+    // a quad of local row l of plane k; the first / last own row also goes to the neighbour's halo row
+    __device__ __forceinline__ void put(int k, int l, size_t o, const Quad<T>& v) {
+        st4(pl(k) + o, v);
+        if (l == 1 && sm_lo) st4(sm_lo + (size_t)k * plane + o + (size_t)R * P, v);        // its local row R + 1
+        if (l == Rown && sm_hi) st4(sm_hi + (size_t)k * plane + o - (size_t)Rown * P, v);  // its local row 0
+    }
+
+    // ---- nodes: local node row m <-> grid node row row0 - 1 + m, between cell rows m and m + 1 ----
+    __device__ __forceinline__ void nodes(const T* __restrict__ cur) {
+        for (int q = tid; q < (Rown + 1) * Q; q += CL_NT) {
+            const int m = q / Q, a0 = (q - m * Q) << 2, b = row0 - 1 + m;
+            if (Rown == 0 || b < 0 || b > ny - 2) continue;
+            const T* c0 = cur + (size_t)m * P + CL_PAD + a0;
+            const T* c1 = c0 + P;
+            const T* b0 = sB + (size_t)m * P + CL_PAD + a0;
+            const T* b1 = b0 + P;
+            Quad<T> h0 = ld4(c0), h1 = ld4(c1), z0 = ld4(b0), z1 = ld4(b1);
+            T h0e[5], h1e[5], s0e[5], s1e[5];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { h0e[k] = h0.v[k]; h1e[k] = h1.v[k]; s0e[k] = z0.v[k]; s1e[k] = z1.v[k]; }
+            h0e[4] = c0[4]; h1e[4] = c1[4]; s0e[4] = b0[4]; s1e[4] = b1[4];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                h0e[k] = fmx(h0e[k], T(0));                     // adjoint.jl:52
+                h1e[k] = fmx(h1e[k], T(0));
+                s0e[k] = surf_store<T>(s0e[k], h0e[k]);        // fp64: S = B + H rounded first (adjoint.jl:54); fp32: B kept
+                s1e[k] = surf_store<T>(s1e[k], h1e[k]);
+            }
+            Quad<T> Dq;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const T ex0 = sdiff<T>(s0e[k + 1], s0e[k], h0e[k + 1], h0e[k]);
+                const T ex1 = sdiff<T>(s1e[k + 1], s1e[k], h1e[k + 1], h1e[k]);
+                const T ey0 = sdiff<T>(s1e[k], s0e[k], h1e[k], h0e[k]);
+                const T ey1 = sdiff<T>(s1e[k + 1], s0e[k + 1], h1e[k + 1], h0e[k + 1]);
+                const T u = (ex0 + ex1) * hdx, v = (ey0 + ey1) * hdy;   // ∇Sx, ∇Sy at the node (adjoint.jl:58-67)
+                const T g2 = u * u + v * v;
+                T Dn, al, be, gA;
+                node_raw<T, CUBIC, false>(ph, A, (h0e[k] + h0e[k + 1]) + (h1e[k] + h1e[k + 1]), g2, Dn, al, be, gA);
+                Dq.v[k] = (a0 + k <= nx - 2) ? Dn : T(0);
+            }
+            st4(sD + (size_t)m * P + CL_PAD + a0, Dq);
+        }
+        __syncthreads();
+    }
+
+    // ---- cells of the band: ep(l, o, hc, f) with hc the quad of `cur` and f = SIA2D(cur) on it (0 on the border) ----
+    template <class Ep>
+    __device__ __forceinline__ void cells(const T* __restrict__ cur, Ep&& ep) {
+        for (int q = tid; q < Rown * Q; q += CL_NT) {
+            const int lr = q / Q, i0 = (q - lr * Q) << 2, l = lr + 1, j = row0 + lr;
+            const size_t o = (size_t)l * P + CL_PAD + i0;
+            const Quad<T> hc = ld4(cur + o);
+            Quad<T> f;
+            if (j >= 1 && j <= ny - 2) {
+                const Quad<T> hs = ld4(cur + o - P), hn = ld4(cur + o + P);
+                const Quad<T> zc = ld4(sB + o), zs = ld4(sB + o - P), zn = ld4(sB + o + P);
+                const Quad<T> Ds = ld4(sD + o - P), Dc = ld4(sD + o);   // node rows j-1 and j, nodes i0 .. i0+3
+                const T DsW = sD[o - P - 1], DcW = sD[o - 1];           // node i0-1
+                T he[6], se[6];
+                he[0] = fmx(cur[o - 1], T(0));
+                he[5] = fmx(cur[o + 4], T(0));
+                se[0] = surf_store<T>(sB[o - 1], he[0]);
+                se[5] = surf_store<T>(sB[o + 4], he[5]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { he[k + 1] = fmx(hc.v[k], T(0)); se[k + 1] = surf_store<T>(zc.v[k], he[k + 1]); }
+                // x-edge fluxes (raw): edge e joins cells i0-1+e and i0+e                      (adjoint.jl:93-97)
+                T Fx[5];
+#pragma unroll
+                for (int e = 0; e < 5; ++e) {
+                    const T ex = sdiff<T>(se[e + 1], se[e], he[e + 1], he[e]);
+                    const T up = ETA1 ? he[e + 1] : eta0 * he[e + 1], lo = ETA1 ? he[e] : eta0 * he[e];
+                    const T Dsum = (e == 0) ? (DsW + DcW) : (Ds.v[e - 1] + Dc.v[e - 1]);
+                    Fx[e] = Dsum * fmx(fmn(ex, up), -lo);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const T h = he[k + 1], s = se[k + 1];
+                    const T hS = fmx(hs.v[k], T(0)), hN = fmx(hn.v[k], T(0));
+                    const T sS = surf_store<T>(zs.v[k], hS), sN = surf_store<T>(zn.v[k], hN);
+                    const T eyN = sdiff<T>(sN, s, hN, h), eyS = sdiff<T>(s, sS, h, hS);
+                    const T eh = ETA1 ? h : eta0 * h, ehN = ETA1 ? hN : eta0 * hN, ehS = ETA1 ? hS : eta0 * hS;
+                    const T DW_c = (k == 0) ? DcW : Dc.v[k - 1], DW_s = (k == 0) ? DsW : Ds.v[k - 1];
+                    const T FyN = (DW_c + Dc.v[k]) * fmx(fmn(eyN, ehN), -eh);
+                    const T FyS = (DW_s + Ds.v[k]) * fmx(fmn(eyS, eh), -ehS);
+                    // dH = ½/Δx² ΔFx_raw + ½/Δy² ΔFy_raw  (see RhsMarch::step)
+                    const T fv = kx * (Fx[k + 1] - Fx[k]) + ky * (FyN - FyS);
+                    const int i = i0 + k;
+                    f.v[k] = (i >= 1 && i <= nx - 2) ? fv : T(0);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f.v[k] = T(0);   // border rows: dH = 0
+            }
+            ep(l, o, hc, f);
+        }
+    }
+    // elementwise sweep over the own cells: ep(l, o)
+    template <class Ep>
+    __device__ __forceinline__ void own(Ep&& ep) {
+        for (int q = tid; q < Rown * Q; q += CL_NT) {
+            const int lr = q / Q, i0 = (q - lr * Q) << 2;
+            ep(lr + 1, (size_t)(lr + 1) * P + CL_PAD + i0);
+        }
+    }
+};
+
+// method: 0 Euler, 1 SSPRK(3,3) (Shu-Osher form, as forward_interval in capi.cu).  Intervals j0+1 .. j1 of the time grid t.
+template <typename T, bool CUBIC, bool ETA1>
+__global__ void __launch_bounds__(CL_NT, 1)
+sia2d_interval_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
+                       T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, int nsub,
+                       int method, PhysDev<T> ph) {
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    ClBand<T, CUBIC, ETA1> bd;
+    bd.init(cluster, descs[blockIdx.x / cluster.num_blocks()], ph, cl_smem_raw, CL_PLANES_FIXED);
+    bd.load(0, Bg);
+    bd.load(2, Hin);
+    cluster.sync();  // every CTA of the cluster has initialised its planes before a neighbour stores into them
+
+    // out = sa·u0 + sb·(cur + sdt·SIA2D(cur)) on the band; halo rows of `nxt` in the neighbours; cluster barrier
+    auto stage = [&](int cur, int u0, int nxt, T sa, T sb, T sdt) {
+        const T* pc = bd.pl(cur);
+        const T* pu = bd.pl(u0);
+        bd.nodes(pc);
+        bd.cells(pc, [&](int l, size_t o, const Quad<T>& hc, const Quad<T>& f) {
+            Quad<T> out;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out.v[k] = sb * (hc.v[k] + sdt * f.v[k]);
+            if (sa != T(0)) {
+                const Quad<T> uq = ld4(pu + o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) out.v[k] = sa * uq.v[k] + out.v[k];
+            }
+            bd.put(nxt, l, o, out);
+        });
+        cluster.sync();
+    };
+
+    int a = 2, b = 3, c = 4;   // plane a: state u0; planes b, c: stage values
+    const T third = (T)(1.0 / 3.0), twothirds = (T)(2.0 / 3.0);
+    for (int j = j0 + 1; j <= j1; ++j) {
+        const T h = (T)((t[j] - t[j - 1]) / nsub);
+        for (int s = 0; s < nsub; ++s) {
+            if (method == 0) {
+                stage(a, a, b, T(0), T(1), h);                 // H + h f(H)
+            } else {
+                stage(a, a, b, T(0), T(1), h);                 // u1 = H + h f(H)
+                stage(b, a, c, T(0.75), T(0.25), h);           // u2 = 3/4 H + 1/4 (u1 + h f(u1))
+                stage(c, a, b, third, twothirds, h);           // H  = 1/3 H + 2/3 (u2 + h f(u2))
+            }
+            const int tmp = a; a = b; b = tmp;
+        }
+        bd.store(a, snap ? snap + (long long)j * plane_stride : nullptr, j == j1 ? Hout : nullptr);   // snapshot j (and the final state)
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+// RDPK3Sp35 + PID controller (the scheme of rdpk.cu / oracle integrate_rdpk3sp35, step for step), one cluster per glacier.
+// -------------------------------------------------------------------------------------------------------------------------
+struct RdpkCoef { double G1[4], G2[4], G3[4], D[4], B[5], E[5]; };
+
+// per-glacier controller state carried between launches (a launch range ends at a mass-balance callback)
+struct ClRkState {
+    double t, dt, err2, err3;
+    int steps, rejected, started, pad;
+};
+
+// Fixed-order sum over the cluster of up to two values per thread: every CTA receives every CTA's partial through DSMEM and adds
+// them in rank order, so all CTAs hold the same bits.  Contains one cluster barrier (which also orders the halo stores of the pass).
+__device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double& v0, double& v1, double (*red)[2][CL_MAX_CS], double* sRed,
+                                             int& slot) {
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const double s0 = block_sum(v0, sRed);
+    __syncthreads();
+    const double s1 = block_sum(v1, sRed + CL_NT / 32);
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < CS; ++r) {
+            double(*rr)[2][CL_MAX_CS] = cluster.map_shared_rank(red, r);
+            rr[slot][0][rank] = s0;
+            rr[slot][1][rank] = s1;
+        }
+    }
+    cluster.sync();
+    double a0 = 0.0, a1 = 0.0;
+    for (int r = 0; r < CS; ++r) { a0 += red[slot][0][r]; a1 += red[slot][1][r]; }
+    v0 = a0; v1 = a1;
+    slot ^= 1;
+}
+
+template <typename T, bool CUBIC, bool ETA1>
+__global__ void __launch_bounds__(CL_NT, 1)
+sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
+                   T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, ClRkState* __restrict__ states,
+                   double reltol, double abstol, double dtmax, double dt0, int max_steps, RdpkCoef cf, PhysDev<T> ph) {
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    __shared__ double red[2][2][CL_MAX_CS];
+    __shared__ double sRed[2 * CL_NT / 32];
+    __shared__ double ctl[4];   // h, accept, done, fac  (thread 0 -> CTA)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x / cluster.num_blocks();
+    ClBand<T, CUBIC, ETA1> bd;
+    bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_RDPK);
+    int a = 2, b = 3, c = 4;             // rotating planes with halos: a = u (state at the start of the step), b / c = stage values
+    constexpr int pS2 = 5, pE = 6, pK1 = 7;
+    bd.load(0, Bg);
+    bd.load(a, Hin);
+    cluster.sync();
+
+    ClRkState s = states[g];
+    const double ncell = (double)bd.nx * (double)bd.ny;
+    int slot = 0;
+    bool k1_valid = false;
+
+    if (!s.started) {
+        s.started = 1;
+        s.t = t[j0];
+        s.err2 = s.err3 = 1.0;
+        s.steps = s.rejected = 0;
+        if (dt0 > 0.0) {
+            s.dt = fmin(dt0, dtmax);
+        } else {
+            // OrdinaryDiffEq's ode_determine_initdt (Hairer-Wanner); sk = abstol + |u| reltol
+            double d0 = 0.0, d1 = 0.0;
+            const T* pu = bd.pl(a);
+            bd.nodes(pu);
+            bd.cells(pu, [&](int, size_t o, const Quad<T>& hc, const Quad<T>& f) {
+                st4(bd.pl(pK1) + o, f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double sk = abstol + fabs((double)hc.v[k]) * reltol;
+                    const double r0 = (double)hc.v[k] / sk, r1 = (double)f.v[k] / sk;
+                    d0 += r0 * r0; d1 += r1 * r1;
+                }
+            });
+            cluster_sum2(cluster, d0, d1, red, sRed, slot);
+            d0 = sqrt(d0 / ncell); d1 = sqrt(d1 / ncell);
+            const double h0 = fmin((d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1, dtmax);
+            const T h0T = (T)(1.0 * h0);
+            bd.own([&](int l, size_t o) {   // Euler probe u1 = u + h0 f0
+                const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
+                Quad<T> x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x.v[k] = uq.v[k] + h0T * kq.v[k];
+                bd.put(b, l, o, x);
+            });
+            cluster.sync();
+            double d2 = 0.0, dz = 0.0;
+            bd.nodes(bd.pl(b));
+            bd.cells(bd.pl(b), [&](int, size_t o, const Quad<T>&, const Quad<T>& f) {
+                const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double sk = abstol + fabs((double)uq.v[k]) * reltol;
+                    const double r = (double)(f.v[k] - kq.v[k]) / sk;
+                    d2 += r * r;
+                }
+            });
+            cluster_sum2(cluster, d2, dz, red, sRed, slot);
+            d2 = sqrt(d2 / ncell) / h0;
+            const double md = fmax(d1, d2);
+            const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 3.0);
+            s.dt = fmin(fmin(100.0 * h0, h1), dtmax);
+            k1_valid = true;
+        }
+    }
+
+    int total = 0;
+    for (int j = j0 + 1; j <= j1; ++j) {
+        s.t = t[j - 1];
+        const double tstop = t[j];
+        while (s.t < tstop) {
+            if (++total > max_steps) break;
+            // plan the step (rk_plan_step)
+            double h = fmin(fmin(s.dt, dtmax), tstop - s.t);
+            const bool last = (s.t + h >= tstop) || (tstop - (s.t + h) < 1e-14 * fmax(1.0, fabs(tstop)));
+            if (last) h = tstop - s.t;
+            const T* pu = bd.pl(a);
+            {   // S1 = u + (B1 h) k1 ;  est = (E1 h) k1      with k1 = f(u) (re-evaluated after an accepted step: FSAL)
+                const T bh = (T)(cf.B[0] * h), eh = (T)(cf.E[0] * h);
+                if (!k1_valid) {
+                    bd.nodes(pu);
+                    bd.cells(pu, [&](int l, size_t o, const Quad<T>& hc, const Quad<T>& f) {
+                        Quad<T> x, y;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { x.v[k] = hc.v[k] + bh * f.v[k]; y.v[k] = eh * f.v[k]; }
+                        st4(bd.pl(pK1) + o, f);
+                        st4(bd.pl(pE) + o, y);
+                        bd.put(b, l, o, x);
+                    });
+                    k1_valid = true;
+                } else {
+                    bd.own([&](int l, size_t o) {
+                        const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
+                        Quad<T> x, y;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { x.v[k] = uq.v[k] + bh * kq.v[k]; y.v[k] = eh * kq.v[k]; }
+                        st4(bd.pl(pE) + o, y);
+                        bd.put(b, l, o, x);
+                    });
+                }
+                cluster.sync();
+            }
+            int cur = b, nxt = c;
+            double acc = 0.0, accz = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                // k = f(S1);  S2 = S2in + d S1;  S1 = g1 S1 + g2 S2 + g3 u + (b h) k;  est += (e h) k       (rk_stage)
+                const T g1 = (T)cf.G1[i], g2 = (T)cf.G2[i], g3 = (T)cf.G3[i], dd = (T)cf.D[i];
+                const T bh = (T)(cf.B[i + 1] * h), eh = (T)(cf.E[i + 1] * h);
+                const bool use_u = (cf.G3[i] != 0.0);
+                const T* pc = bd.pl(cur);
+                bd.nodes(pc);
+                bd.cells(pc, [&](int l, size_t o, const Quad<T>& s1, const Quad<T>& f) {
+                    const Quad<T> uq = ld4(pu + o), er = ld4(bd.pl(pE) + o);
+                    const Quad<T> s2in = (i == 0) ? uq : ld4(bd.pl(pS2) + o);
+                    Quad<T> s2, x, y;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        s2.v[k] = s2in.v[k] + dd * s1.v[k];
+                        T v = g1 * s1.v[k] + g2 * s2.v[k];
+                        if (use_u) v = v + g3 * uq.v[k];
+                        x.v[k] = v + bh * f.v[k];
+                        y.v[k] = er.v[k] + eh * f.v[k];
+                    }
+                    if (i < 3) st4(bd.pl(pS2) + o, s2);
+                    st4(bd.pl(pE) + o, y);
+                    bd.put(nxt, l, o, x);
+                    if (i == 3) {   // error norm of the step: sum (est / (abstol + reltol max(|u|, |u_new|)))^2        (rk_sumsq)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double m = fmax(fabs((double)uq.v[k]), fabs((double)x.v[k]));
+                            const double r = (double)y.v[k] / (abstol + reltol * m);
+                            acc += r * r;
+                        }
+                    }
+                });
+                if (i < 3) cluster.sync();
+                const int tmp = cur; cur = nxt; nxt = tmp;
+            }
+            cluster_sum2(cluster, acc, accz, red, sRed, slot);
+            // PID controller (rk_control): every thread of every CTA evaluates the same expression on the same bits
+            if (threadIdx.x == 0) {
+                const double EEst = sqrt(acc / ncell);
+                const double e1 = 1.0 / fmax(EEst, 1e-300);
+                double fac = pow(e1, 0.64 / 3.0) * pow(s.err2, -0.31 / 3.0) * pow(s.err3, 0.04 / 3.0);
+                fac = 1.0 + atan(fac - 1.0);
+                ctl[0] = fac;
+                ctl[1] = e1;
+            }
+            __syncthreads();
+            const double fac = ctl[0], e1 = ctl[1];
+            __syncthreads();
+            s.steps++;
+            if (fac >= 0.81) {
+                s.t = last ? tstop : s.t + h;
+                s.err3 = s.err2;
+                s.err2 = e1;
+                s.dt = h * fac;
+                // u <- S1 (plane `cur` after the last swap); the old u plane becomes a stage plane
+                const int old_a = a;
+                a = cur;
+                b = old_a;
+                c = nxt;
+                k1_valid = false;
+            } else {
+                s.rejected++;
+                s.dt = h * fac;
+                b = cur; c = nxt;   // (any two planes other than a)
+                if (b == a || c == a) { b = (a == 2) ? 3 : 2; c = 9 - a - b; }
+            }
+        }
+        bd.store(a, snap ? snap + (long long)j * plane_stride : nullptr, j == j1 ? Hout : nullptr);
+    }
+    if (total > max_steps) s.started = -1;   // maxiters: reported by the launcher
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) states[g] = s;
+}
+
+}  // namespace odinn

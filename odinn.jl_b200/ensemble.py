@@ -163,6 +163,10 @@ class Ensemble:
     def set_batch_chunk(self, cells: int):
         self._ck(self._lib.odinn_set_batch_chunk(self._h, int(cells)))
 
+    def set_cluster_mode(self, mode: int):
+        """-1 automatic, 0 marching kernels only, 1/2/4/8/16: cluster size of the shared-memory-resident forward solve."""
+        self._ck(self._lib.odinn_set_cluster_mode(self._h, int(mode)))
+
     def fwd_adj_batch(self, Hs, lams=None, want_dH=True, want_vjpH=True, want_S=True):
         """NumPy front end of ``odinn_fwd_adj_batch_host``: lists of (nx, ny) matrices in, (dH list, vjpH list, S) out."""
         if len(Hs) != self.G or (lams is not None and len(lams) != self.G):

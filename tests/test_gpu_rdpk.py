@@ -48,7 +48,8 @@ def _ens(ob, gl, dtype):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("with_mb", [False, True])
-def test_forward_rdpk3sp35_matches_oracle(ob, dtype, with_mb):
+@pytest.mark.parametrize("cluster", [0, -1, 2])   # 0: host-driven engine (rdpk.cu); -1 / 2: the cluster-resident solver (sia2d_cluster.cuh)
+def test_forward_rdpk3sp35_matches_oracle(ob, dtype, with_mb, cluster):
     gl = _glaciers()
     As = [4e-17, 2.21e-18, 1.5e-17]
     t = o.define_callback_steps((2010.0, 2010.5), 1.0 / 12.0)
@@ -61,7 +62,11 @@ def test_forward_rdpk3sp35_matches_oracle(ob, dtype, with_mb):
             ens.set_A_scalar(k, a)
         if with_mb:
             ens.set_mass_balance(mb_idx, pars)
+        ens.set_cluster_mode(cluster)
+        l0 = ens.launch_count
         steps, rej = ens.solve_forward_adaptive(t, reltol=rtol, abstol=rtol, method="rdpk3sp35")
+        if cluster != 0:   # one launch per range between mass-balance callbacks (+ the callbacks)
+            assert ens.launch_count - l0 == (2 * len(mb_idx) if with_mb else 1)
         assert np.all(steps > 0) and np.all(rej >= 0)
         for k, g in enumerate(gl):
             g2 = o.Glacier(B=_r(g.B, dtype), dx=g.dx, dy=g.dy, H0=_r(g.H0, dtype))

@@ -5,7 +5,6 @@ import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.pop("NCCL_DEBUG", None)
 import torch
 import odinn_b200 as ob
 from odinn_b200 import parallel
@@ -68,6 +67,7 @@ for k, gid in enumerate(pred.my_ids):
 nn = ob.NeuralNetwork(widths=(1, 16, 16, 1), acts=("softplus", "softplus", "sigmoid"), seed=3)
 inv = ob.Inversion(ob.Model(ob.SIA2Dmodel(A=ob.LawA(nn))), gl, params, H_ref, temperatures=temps)
 θ = np.array(inv.model.θ)
+θ[-1] = -3.0   # A_g within 2e-18 .. 7e-18: the monthly reverse Euler step of the discrete adjoint is stable there (gradient.jl:19-24)
 g = np.zeros_like(θ)
 s = timed(lambda: ob.SIA2D_grad_(g, θ, inv), reps=2)
 if rank == 0:

@@ -52,6 +52,15 @@ def run_bs3():
     ens.synchronize()
 s = timed(run_bs3)
 report("1: 128x128 forward 2010-2015, adaptive BS3 rtol 1e-4", seconds=s, steps=int(st[0][0]), rejected=int(st[1][0]))
+# the reference's default integrator at the tolerance its tests construct it with (test/params_construction.jl:7; fp32: the error estimate bottoms out near 1e-4)
+rt = 1e-8 if dtype == "f64" else 1e-4
+def run_rdpk():
+    global st
+    st = ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35")
+    ens.synchronize()
+s = timed(run_rdpk)
+report(f"1: 128x128 forward 2010-2015, adaptive RDPK3Sp35 + PID rtol {rt:g} (the reference's default solver)", seconds=s, steps=int(st[0][0]),
+       rejected=int(st[1][0]), us_per_trial_step=1e6 * s / max(int(st[0][0]), 1))
 ens.close()
 
 # config 3: 64 glaciers, sizes U{100..400}, forward Prediction run
