@@ -40,22 +40,35 @@ cudaError_t configure(K kernel, size_t smem, int cs) {
     return st;
 }
 
-// Dispatch on (element type, n == 3 && C == 0, eta0 == 1):  F<T, CUBIC, ETA1>::run(args...)
-template <template <typename, bool, bool> class F, typename... Args>
-int dispatch(odinn_ensemble* e, Args&&... args) {
+// Cells per thread and sweep item: 4 unless the band of the largest glacier holds fewer than 256 quads, then 2.  ODINN_CLUSTER_V forces
+// it (tuning).  The generic-exponent kernels exist for V = 4 only.
+int choose_v(const odinn_ensemble* e, int cs) {
+    static const int env = []() { const char* v = getenv("ODINN_CLUSTER_V"); return v ? atoi(v) : 0; }();
+    if (!e->cubic) return 4;
+    if (env == 2 || env == 4) return env;
+    long long cells = 0;
+    for (const GlacierHost& g : e->gl) cells = std::max(cells, (long long)cl_band_rows(g.ny, cs) * g.nx);
+    return cells >= 2LL * CL_NT ? 4 : 2;
+}
+
+// Dispatch on (element type, n == 3 && C == 0, eta0 == 1, V):  F<T, CUBIC, ETA1, V>::run(args...)
+template <template <typename, bool, bool, int> class F, typename... Args>
+int dispatch(odinn_ensemble* e, int v, Args&&... args) {
     const bool eta1 = (e->phys.eta0 == 1.0);
-#define DC(T, CUB, E1) return F<T, CUB, E1>::run(e, args...)
+#define DC(T, CUB, E1, VV) return F<T, CUB, E1, VV>::run(e, args...)
+#define DV(T, E1) do { if (v == 2) DC(T, true, E1, 2); else DC(T, true, E1, 4); } while (0)
     if (e->dtype == ODINN_F32) {
-        if (e->cubic) { if (eta1) DC(float, true, true); else DC(float, true, false); }
-        else { if (eta1) DC(float, false, true); else DC(float, false, false); }
+        if (e->cubic) { if (eta1) DV(float, true); else DV(float, false); }
+        else { if (eta1) DC(float, false, true, 4); else DC(float, false, false, 4); }
     } else {
-        if (e->cubic) { if (eta1) DC(double, true, true); else DC(double, true, false); }
-        else { if (eta1) DC(double, false, true); else DC(double, false, false); }
+        if (e->cubic) { if (eta1) DV(double, true); else DV(double, false); }
+        else { if (eta1) DC(double, false, true, 4); else DC(double, false, false, 4); }
     }
+#undef DV
 #undef DC
 }
 
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 struct MaxClusters {
     static int run(odinn_ensemble* e, int kind, size_t smem, int cs, int* n) {
         cudaLaunchConfig_t cfg;
@@ -63,22 +76,22 @@ struct MaxClusters {
         fill_config(e, cfg, at, smem, cs);
         cudaError_t st;
         if (kind == 0) {
-            st = configure(sia2d_interval_cluster<T, CUBIC, ETA1>, smem, cs);
-            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_interval_cluster<T, CUBIC, ETA1>, &cfg);
+            st = configure(sia2d_interval_cluster<T, CUBIC, ETA1, V>, smem, cs);
+            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_interval_cluster<T, CUBIC, ETA1, V>, &cfg);
         } else {
-            st = configure(sia2d_rdpk_cluster<T, CUBIC, ETA1>, smem, cs);
-            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_rdpk_cluster<T, CUBIC, ETA1>, &cfg);
+            st = configure(sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, smem, cs);
+            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, &cfg);
         }
         if (st != cudaSuccess) { cudaGetLastError(); *n = 0; }
         return ODINN_OK;
     }
 };
 
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 struct LaunchFixed {
     static int run(odinn_ensemble* e, int cs, size_t smem, int method, int nsub, int j0, int j1, const void* Hin, void* Hout, void* snap,
                    const double* d_t) {
-        auto k = sia2d_interval_cluster<T, CUBIC, ETA1>;
+        auto k = sia2d_interval_cluster<T, CUBIC, ETA1, V>;
         ODINN_CUDA(e, configure(k, smem, cs));   // (per device: cheap next to a launch that runs whole intervals)
         cudaLaunchConfig_t cfg;
         cudaLaunchAttribute at[1];
@@ -91,11 +104,11 @@ struct LaunchFixed {
     }
 };
 
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 struct LaunchRdpk {
     static int run(odinn_ensemble* e, int cs, size_t smem, int j0, int j1, const void* Hin, void* Hout, void* snap, const double* d_t,
                    ClRkState* states, double reltol, double abstol, double dtmax, double dt0, int max_steps, const RdpkCoef& cf) {
-        auto k = sia2d_rdpk_cluster<T, CUBIC, ETA1>;
+        auto k = sia2d_rdpk_cluster<T, CUBIC, ETA1, V>;
         ODINN_CUDA(e, configure(k, smem, cs));
         cudaLaunchConfig_t cfg;
         cudaLaunchAttribute at[1];
@@ -125,7 +138,7 @@ int cluster_plan(odinn_ensemble* e, int kind) {
         const size_t smem = smem_for(e, cs, n_planes);
         if (smem > CL_SMEM_MAX) continue;
         int n = 0;
-        dispatch<MaxClusters>(e, kind, smem, cs, &n);
+        dispatch<MaxClusters>(e, choose_v(e, cs), kind, smem, cs, &n);
         if (n <= 0) continue;
         if (n >= e->G || forced > 0) return cs;
     }
@@ -134,7 +147,7 @@ int cluster_plan(odinn_ensemble* e, int kind) {
 
 int launch_interval_cluster(odinn_ensemble* e, int cs, int method, int nsub, int j0, int j1, const void* Hin, void* Hout, void* snap,
                             const double* d_t) {
-    return dispatch<LaunchFixed>(e, cs, smem_for(e, cs, CL_PLANES_FIXED), method, nsub, j0, j1, Hin, Hout, snap, d_t);
+    return dispatch<LaunchFixed>(e, choose_v(e, cs), cs, smem_for(e, cs, CL_PLANES_FIXED), method, nsub, j0, j1, Hin, Hout, snap, d_t);
 }
 
 int upload_time_grid(odinn_ensemble* e, const double* t, int n_snap, const double** d_t) {
@@ -175,7 +188,7 @@ int solve_forward_rdpk_cluster(odinn_ensemble* e, int cs, int n_snap, const doub
     while (j0 < n_snap - 1) {
         int j1 = n_snap - 1;
         for (int m : e->mb_snap) if (m > j0 && m < j1) j1 = m;
-        if ((rc = dispatch<LaunchRdpk>(e, cs, smem, j0, j1, Hin, Hs, snapshot_ptr(e, 0), d_t, states, reltol, abstol, dtmax, dt0, max_steps, cf)))
+        if ((rc = dispatch<LaunchRdpk>(e, choose_v(e, cs), cs, smem, j0, j1, Hin, Hs, snapshot_ptr(e, 0), d_t, states, reltol, abstol, dtmax, dt0, max_steps, cf)))
             return rc;
         int applied = 0;
         if ((rc = mb_apply_step(e, j1, Hs, &applied))) return rc;   // mass-balance callback at the end of its window (inversion_utils.jl:498-517)

@@ -29,7 +29,10 @@ namespace odinn {
 
 namespace cg = cooperative_groups;
 
-constexpr int CL_NT = 512;         // threads per CTA
+#ifndef ODINN_CL_NT
+#define ODINN_CL_NT 512
+#endif
+constexpr int CL_NT = ODINN_CL_NT;         // threads per CTA
 constexpr int CL_PAD = 4;          // zero columns left of column 0 (the row pitch also leaves >= 4 right of column nx-1)
 constexpr int CL_PLANES_FIXED = 5; // B, D, three rotating H planes
 constexpr int CL_PLANES_RDPK = 8;  // B, D, three rotating planes (u, S1, S1'), S2, est, k1
@@ -42,28 +45,55 @@ inline size_t cl_smem_bytes(int nx, int ny, int cs, size_t esize, int n_planes) 
     return (size_t)n_planes * (size_t)(cl_band_rows(ny, cs) + 2) * (size_t)cl_pitch(nx) * esize;
 }
 
-template <typename T> struct Quad { T v[4]; };
-__device__ __forceinline__ Quad<float> ld4(const float* p) {
-    float4 q = *reinterpret_cast<const float4*>(p);
-    return {{q.x, q.y, q.z, q.w}};
+// V consecutive cells of one row: the unit of work of a thread.  V = 4 (16-byte accesses in fp32); bands with fewer than 256 such
+// items run with V = 2 so that more warps share the sweep (64 x 64 on 16 CTAs: 0.90 -> 0.76 us per stage).
+template <typename T, int V> struct Vec { T v[V]; };
+template <int V> __device__ __forceinline__ Vec<float, V> ldv(const float* p) {
+    Vec<float, V> r;
+    if constexpr (V == 4) { float4 q = *reinterpret_cast<const float4*>(p); r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; }
+    else if constexpr (V == 2) { float2 q = *reinterpret_cast<const float2*>(p); r.v[0] = q.x; r.v[1] = q.y; }
+    else r.v[0] = *p;
+    return r;
 }
-__device__ __forceinline__ Quad<double> ld4(const double* p) {
-    double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
-    return {{a.x, a.y, b.x, b.y}};
+template <int V> __device__ __forceinline__ Vec<double, V> ldv(const double* p) {
+    Vec<double, V> r;
+    if constexpr (V == 4) {
+        double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    } else if constexpr (V == 2) { double2 a = *reinterpret_cast<const double2*>(p); r.v[0] = a.x; r.v[1] = a.y; }
+    else r.v[0] = *p;
+    return r;
 }
-__device__ __forceinline__ void st4(float* p, const Quad<float>& q) {
-    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+template <int V> __device__ __forceinline__ void stv(float* p, const Vec<float, V>& q) {
+    if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+    else if constexpr (V == 2) *reinterpret_cast<float2*>(p) = make_float2(q.v[0], q.v[1]);
+    else *p = q.v[0];
 }
-__device__ __forceinline__ void st4(double* p, const Quad<double>& q) {
-    *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
-    *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+template <int V> __device__ __forceinline__ void stv(double* p, const Vec<double, V>& q) {
+    if constexpr (V == 4) {
+        *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+    } else if constexpr (V == 2) *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+    else *p = q.v[0];
 }
 
+// sweep over (row, first column of an item) pairs of `nrows` rows, CL_NT items at a time, without a division per iteration
+#define CL_SWEEP(ROW, COL0, NROWS)                                                                         \
+    for (int ROW = t_row, cq_ = t_col, COL0 = t_col * V; ROW < (NROWS);                                    \
+         cq_ += d_col, ROW += d_row, ROW += (cq_ >= Q), cq_ -= (cq_ >= Q) ? Q : 0, COL0 = cq_ * V)
+
+// Synchronisation between the bands is ONE hardware cluster barrier per pass (barrier.cluster arrive.release / wait.acquire).  Two
+// alternatives were measured and dropped (profiles/r02_cluster_sweep.txt, 128 x 128 on 16 CTAs, us per stage): a neighbour-only
+// hand-shake through four mbarriers per CTA (remote mbarrier.arrive.release.cluster after a CTA barrier, try_wait.acquire.cluster)
+// 1.21 vs 1.12; arriving early and evaluating the dual nodes that touch own rows only before the wait 1.17 vs 1.12 (0.90 vs 0.74 at
+// 64 x 64).  A stage costs ~0.75 us even for a 64 x 64 grid: two dependent shared-memory sweeps, the release of the remote stores
+// and the barrier -- not instruction issue (one, two or four cells per thread time the same there).
 // One CTA's band of one glacier.  Plane k of the carve-up is sm + k * plane; plane 0 is B, plane 1 is D (node row m of the band
 // in local row m), the others belong to the scheme.  Local row l <-> grid row row0 - 1 + l (l = 0 and l = Rown + 1: halo rows).
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 struct ClBand {
     int nx, ny, P, R, Q, row0, Rown, CS, rank, tid;
+    int t_row, t_col, d_row, d_col;   // this thread's first (row, item) of a sweep and its stride
     size_t plane;
     T *sm, *sB, *sD, *sm_lo, *sm_hi;
     T eta0, hdx, hdy, kx, ky, A;
@@ -76,7 +106,7 @@ struct ClBand {
         rank = (int)cluster.block_rank();
         tid = threadIdx.x;
         nx = d.nx; ny = d.ny;
-        P = cl_pitch(nx); R = cl_band_rows(ny, CS); Q = (nx + 3) >> 2;
+        P = cl_pitch(nx); R = cl_band_rows(ny, CS); Q = (nx + V - 1) / V;
         row0 = min(rank * R, ny);
         Rown = min(row0 + R, ny) - row0;
         plane = (size_t)(R + 2) * P;
@@ -92,63 +122,65 @@ struct ClBand {
         kx = hdx * d.inv_dx; ky = hdy * d.inv_dy;   // ½/Δx², ½/Δy²
         A = d.A;
         goff = d.off; gld = d.ld;
+        t_row = tid / Q; t_col = tid - t_row * Q; d_row = CL_NT / Q; d_col = CL_NT - d_row * Q;
         for (size_t k = tid; k < (size_t)n_planes * plane; k += CL_NT) sm[k] = T(0);
         __syncthreads();
     }
     __device__ __forceinline__ T* pl(int k) const { return sm + (size_t)k * plane; }
 
-    // band rows row0-1 .. row1 (clipped to the grid) of a global plane into shared plane k
+    // band rows row0-1 .. row1 (clipped to the grid) of a global plane into shared plane k (16-byte accesses: the rows of the
+    // global planes are padded to 32 elements with zeros, a full quad is always readable)
     __device__ __forceinline__ void load(int k, const T* __restrict__ g) {
         T* dst = pl(k);
-        for (int q = tid; q < (Rown + 2) * Q; q += CL_NT) {
-            const int l = q / Q, i0 = (q - l * Q) << 2, j = row0 - 1 + l;
+        const int Q4 = (nx + 3) >> 2;
+        for (int q = tid; q < (Rown + 2) * Q4; q += CL_NT) {
+            const int l = q / Q4, i0 = (q - l * Q4) << 2, j = row0 - 1 + l;
             if (Rown == 0 || j < 0 || j >= ny) continue;
-            // (rows of the global planes are padded to 32 elements with zeros: a full quad is readable)
-            st4(dst + (size_t)l * P + CL_PAD + i0, ld4(g + goff + (long long)j * gld + i0));
+            stv<4>(dst + (size_t)l * P + CL_PAD + i0, ldv<4>(g + goff + (long long)j * gld + i0));
         }
     }
-    // own rows of shared plane k to one or two global planes (16-byte stores; the row padding receives zeros)
+    // own rows of shared plane k to one or two global planes (the row padding receives zeros)
     __device__ __forceinline__ void store(int k, T* __restrict__ g0, T* __restrict__ g1) {
         const T* src = pl(k);
-        for (int q = tid; q < Rown * Q; q += CL_NT) {
-            const int lr = q / Q, i0 = (q - lr * Q) << 2;
-            const Quad<T> v = ld4(src + (size_t)(lr + 1) * P + CL_PAD + i0);
+        const int Q4 = (nx + 3) >> 2;
+        for (int q = tid; q < Rown * Q4; q += CL_NT) {
+            const int lr = q / Q4, i0 = (q - lr * Q4) << 2;
+            const Vec<T, 4> v = ldv<4>(src + (size_t)(lr + 1) * P + CL_PAD + i0);
             const long long go = goff + (long long)(row0 + lr) * gld + i0;
-            if (g0) st4(g0 + go, v);
-            if (g1) st4(g1 + go, v);
+            if (g0) stv<4>(g0 + go, v);
+            if (g1) stv<4>(g1 + go, v);
         }
     }
-    // a quad of local row l of plane k; the first / last own row also goes to the neighbour's halo row
-    __device__ __forceinline__ void put(int k, int l, size_t o, const Quad<T>& v) {
-        st4(pl(k) + o, v);
-        if (l == 1 && sm_lo) st4(sm_lo + (size_t)k * plane + o + (size_t)R * P, v);        // its local row R + 1
-        if (l == Rown && sm_hi) st4(sm_hi + (size_t)k * plane + o - (size_t)Rown * P, v);  // its local row 0
+    // an item of local row l of plane k; the first / last own row also goes to the neighbour's halo row
+    __device__ __forceinline__ void put(int k, int l, size_t o, const Vec<T, V>& v) {
+        stv<V>(pl(k) + o, v);
+        if (l == 1 && sm_lo) stv<V>(sm_lo + (size_t)k * plane + o + (size_t)R * P, v);        // its local row R + 1
+        if (l == Rown && sm_hi) stv<V>(sm_hi + (size_t)k * plane + o - (size_t)Rown * P, v);  // its local row 0
     }
-
     // ---- nodes: local node row m <-> grid node row row0 - 1 + m, between cell rows m and m + 1 ----
     __device__ __forceinline__ void nodes(const T* __restrict__ cur) {
-        for (int q = tid; q < (Rown + 1) * Q; q += CL_NT) {
-            const int m = q / Q, a0 = (q - m * Q) << 2, b = row0 - 1 + m;
+        CL_SWEEP(m, a0, Rown + 1) {
+            const int b = row0 - 1 + m;
             if (Rown == 0 || b < 0 || b > ny - 2) continue;
             const T* c0 = cur + (size_t)m * P + CL_PAD + a0;
             const T* c1 = c0 + P;
             const T* b0 = sB + (size_t)m * P + CL_PAD + a0;
             const T* b1 = b0 + P;
-            Quad<T> h0 = ld4(c0), h1 = ld4(c1), z0 = ld4(b0), z1 = ld4(b1);
-            T h0e[5], h1e[5], s0e[5], s1e[5];
+            const Vec<T, V> h0 = ldv<V>(c0), h1 = ldv<V>(c1), z0 = ldv<V>(b0), z1 = ldv<V>(b1);
+            T h0e[V + 1], h1e[V + 1], s0e[V + 1], s1e[V + 1];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { h0e[k] = h0.v[k]; h1e[k] = h1.v[k]; s0e[k] = z0.v[k]; s1e[k] = z1.v[k]; }
-            h0e[4] = c0[4]; h1e[4] = c1[4]; s0e[4] = b0[4]; s1e[4] = b1[4];
+            for (int k = 0; k < V; ++k) { h0e[k] = h0.v[k]; h1e[k] = h1.v[k]; s0e[k] = z0.v[k]; s1e[k] = z1.v[k]; }
+            h0e[V] = c0[V]; h1e[V] = c1[V]; s0e[V] = b0[V]; s1e[V] = b1[V];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
+            for (int k = 0; k < V + 1; ++k) {
                 h0e[k] = fmx(h0e[k], T(0));                     // adjoint.jl:52
                 h1e[k] = fmx(h1e[k], T(0));
                 s0e[k] = surf_store<T>(s0e[k], h0e[k]);        // fp64: S = B + H rounded first (adjoint.jl:54); fp32: B kept
                 s1e[k] = surf_store<T>(s1e[k], h1e[k]);
             }
-            Quad<T> Dq;
+            Vec<T, V> Dq;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < V; ++k) {
                 const T ex0 = sdiff<T>(s0e[k + 1], s0e[k], h0e[k + 1], h0e[k]);
                 const T ex1 = sdiff<T>(s1e[k + 1], s1e[k], h1e[k + 1], h1e[k]);
                 const T ey0 = sdiff<T>(s1e[k], s0e[k], h1e[k], h0e[k]);
@@ -159,48 +191,48 @@ struct ClBand {
                 node_raw<T, CUBIC, false>(ph, A, (h0e[k] + h0e[k + 1]) + (h1e[k] + h1e[k + 1]), g2, Dn, al, be, gA);
                 Dq.v[k] = (a0 + k <= nx - 2) ? Dn : T(0);
             }
-            st4(sD + (size_t)m * P + CL_PAD + a0, Dq);
+            stv<V>(sD + (size_t)m * P + CL_PAD + a0, Dq);
         }
         __syncthreads();
     }
 
-    // ---- cells of the band: ep(l, o, hc, f) with hc the quad of `cur` and f = SIA2D(cur) on it (0 on the border) ----
+    // ---- cells of the band: ep(l, o, hc, f) with hc the item of `cur` and f = SIA2D(cur) on it (0 on the border) ----
     template <class Ep>
     __device__ __forceinline__ void cells(const T* __restrict__ cur, Ep&& ep) {
-        for (int q = tid; q < Rown * Q; q += CL_NT) {
-            const int lr = q / Q, i0 = (q - lr * Q) << 2, l = lr + 1, j = row0 + lr;
+        CL_SWEEP(lr, i0, Rown) {
+            const int l = lr + 1, j = row0 + lr;
             const size_t o = (size_t)l * P + CL_PAD + i0;
-            const Quad<T> hc = ld4(cur + o);
-            Quad<T> f;
+            const Vec<T, V> hc = ldv<V>(cur + o);
+            Vec<T, V> f;
             if (j >= 1 && j <= ny - 2) {
-                const Quad<T> hs = ld4(cur + o - P), hn = ld4(cur + o + P);
-                const Quad<T> zc = ld4(sB + o), zs = ld4(sB + o - P), zn = ld4(sB + o + P);
-                const Quad<T> Ds = ld4(sD + o - P), Dc = ld4(sD + o);   // node rows j-1 and j, nodes i0 .. i0+3
-                const T DsW = sD[o - P - 1], DcW = sD[o - 1];           // node i0-1
-                T he[6], se[6];
+                const Vec<T, V> hs = ldv<V>(cur + o - P), hn = ldv<V>(cur + o + P);
+                const Vec<T, V> zc = ldv<V>(sB + o), zs = ldv<V>(sB + o - P), zn = ldv<V>(sB + o + P);
+                const Vec<T, V> Ds = ldv<V>(sD + o - P), Dc = ldv<V>(sD + o);   // node rows j-1 and j, nodes i0 .. i0+V-1
+                const T DsW = sD[o - P - 1], DcW = sD[o - 1];                   // node i0-1
+                T he[V + 2], se[V + 2];
                 he[0] = fmx(cur[o - 1], T(0));
-                he[5] = fmx(cur[o + 4], T(0));
+                he[V + 1] = fmx(cur[o + V], T(0));
                 se[0] = surf_store<T>(sB[o - 1], he[0]);
-                se[5] = surf_store<T>(sB[o + 4], he[5]);
+                se[V + 1] = surf_store<T>(sB[o + V], he[V + 1]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { he[k + 1] = fmx(hc.v[k], T(0)); se[k + 1] = surf_store<T>(zc.v[k], he[k + 1]); }
+                for (int k = 0; k < V; ++k) { he[k + 1] = fmx(hc.v[k], T(0)); se[k + 1] = surf_store<T>(zc.v[k], he[k + 1]); }
                 // x-edge fluxes (raw): edge e joins cells i0-1+e and i0+e                      (adjoint.jl:93-97)
-                T Fx[5];
+                T Fx[V + 1];
 #pragma unroll
-                for (int e = 0; e < 5; ++e) {
+                for (int e = 0; e < V + 1; ++e) {
                     const T ex = sdiff<T>(se[e + 1], se[e], he[e + 1], he[e]);
                     const T up = ETA1 ? he[e + 1] : eta0 * he[e + 1], lo = ETA1 ? he[e] : eta0 * he[e];
-                    const T Dsum = (e == 0) ? (DsW + DcW) : (Ds.v[e - 1] + Dc.v[e - 1]);
+                    const T Dsum = (e == 0) ? (DsW + DcW) : (Ds.v[e > 0 ? e - 1 : 0] + Dc.v[e > 0 ? e - 1 : 0]);
                     Fx[e] = Dsum * fmx(fmn(ex, up), -lo);
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < V; ++k) {
                     const T h = he[k + 1], s = se[k + 1];
                     const T hS = fmx(hs.v[k], T(0)), hN = fmx(hn.v[k], T(0));
                     const T sS = surf_store<T>(zs.v[k], hS), sN = surf_store<T>(zn.v[k], hN);
                     const T eyN = sdiff<T>(sN, s, hN, h), eyS = sdiff<T>(s, sS, h, hS);
                     const T eh = ETA1 ? h : eta0 * h, ehN = ETA1 ? hN : eta0 * hN, ehS = ETA1 ? hS : eta0 * hS;
-                    const T DW_c = (k == 0) ? DcW : Dc.v[k - 1], DW_s = (k == 0) ? DsW : Ds.v[k - 1];
+                    const T DW_c = (k == 0) ? DcW : Dc.v[k > 0 ? k - 1 : 0], DW_s = (k == 0) ? DsW : Ds.v[k > 0 ? k - 1 : 0];
                     const T FyN = (DW_c + Dc.v[k]) * fmx(fmn(eyN, ehN), -eh);
                     const T FyS = (DW_s + Ds.v[k]) * fmx(fmn(eyS, eh), -ehS);
                     // dH = ½/Δx² ΔFx_raw + ½/Δy² ΔFy_raw  (see RhsMarch::step)
@@ -210,7 +242,7 @@ struct ClBand {
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) f.v[k] = T(0);   // border rows: dH = 0
+                for (int k = 0; k < V; ++k) f.v[k] = T(0);   // border rows: dH = 0
             }
             ep(l, o, hc, f);
         }
@@ -218,22 +250,21 @@ struct ClBand {
     // elementwise sweep over the own cells: ep(l, o)
     template <class Ep>
     __device__ __forceinline__ void own(Ep&& ep) {
-        for (int q = tid; q < Rown * Q; q += CL_NT) {
-            const int lr = q / Q, i0 = (q - lr * Q) << 2;
+        CL_SWEEP(lr, i0, Rown) {
             ep(lr + 1, (size_t)(lr + 1) * P + CL_PAD + i0);
         }
     }
 };
 
 // method: 0 Euler, 1 SSPRK(3,3) (Shu-Osher form, as forward_interval in capi.cu).  Intervals j0+1 .. j1 of the time grid t.
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 __global__ void __launch_bounds__(CL_NT, 1)
 sia2d_interval_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
                        T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, int nsub,
                        int method, PhysDev<T> ph) {
     extern __shared__ __align__(16) unsigned char cl_smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
-    ClBand<T, CUBIC, ETA1> bd;
+    ClBand<T, CUBIC, ETA1, V> bd;
     bd.init(cluster, descs[blockIdx.x / cluster.num_blocks()], ph, cl_smem_raw, CL_PLANES_FIXED);
     bd.load(0, Bg);
     bd.load(2, Hin);
@@ -244,14 +275,14 @@ sia2d_interval_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__
         const T* pc = bd.pl(cur);
         const T* pu = bd.pl(u0);
         bd.nodes(pc);
-        bd.cells(pc, [&](int l, size_t o, const Quad<T>& hc, const Quad<T>& f) {
-            Quad<T> out;
+        bd.cells(pc, [&](int l, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
+            Vec<T, V> out;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) out.v[k] = sb * (hc.v[k] + sdt * f.v[k]);
+            for (int k = 0; k < V; ++k) out.v[k] = sb * (hc.v[k] + sdt * f.v[k]);
             if (sa != T(0)) {
-                const Quad<T> uq = ld4(pu + o);
+                const Vec<T, V> uq = ldv<V>(pu + o);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) out.v[k] = sa * uq.v[k] + out.v[k];
+                for (int k = 0; k < V; ++k) out.v[k] = sa * uq.v[k] + out.v[k];
             }
             bd.put(nxt, l, o, out);
         });
@@ -309,7 +340,7 @@ __device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double&
     slot ^= 1;
 }
 
-template <typename T, bool CUBIC, bool ETA1>
+template <typename T, bool CUBIC, bool ETA1, int V>
 __global__ void __launch_bounds__(CL_NT, 1)
 sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
                    T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, ClRkState* __restrict__ states,
@@ -320,7 +351,7 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
     __shared__ double ctl[4];   // h, accept, done, fac  (thread 0 -> CTA)
     cg::cluster_group cluster = cg::this_cluster();
     const int g = blockIdx.x / cluster.num_blocks();
-    ClBand<T, CUBIC, ETA1> bd;
+    ClBand<T, CUBIC, ETA1, V> bd;
     bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_RDPK);
     int a = 2, b = 3, c = 4;             // rotating planes with halos: a = u (state at the start of the step), b / c = stage values
     constexpr int pS2 = 5, pE = 6, pK1 = 7;
@@ -345,10 +376,10 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
             double d0 = 0.0, d1 = 0.0;
             const T* pu = bd.pl(a);
             bd.nodes(pu);
-            bd.cells(pu, [&](int, size_t o, const Quad<T>& hc, const Quad<T>& f) {
-                st4(bd.pl(pK1) + o, f);
+            bd.cells(pu, [&](int, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
+                stv<V>(bd.pl(pK1) + o, f);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < V; ++k) {
                     const double sk = abstol + fabs((double)hc.v[k]) * reltol;
                     const double r0 = (double)hc.v[k] / sk, r1 = (double)f.v[k] / sk;
                     d0 += r0 * r0; d1 += r1 * r1;
@@ -359,19 +390,19 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
             const double h0 = fmin((d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1, dtmax);
             const T h0T = (T)(1.0 * h0);
             bd.own([&](int l, size_t o) {   // Euler probe u1 = u + h0 f0
-                const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
-                Quad<T> x;
+                const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
+                Vec<T, V> x;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) x.v[k] = uq.v[k] + h0T * kq.v[k];
+                for (int k = 0; k < V; ++k) x.v[k] = uq.v[k] + h0T * kq.v[k];
                 bd.put(b, l, o, x);
             });
             cluster.sync();
             double d2 = 0.0, dz = 0.0;
             bd.nodes(bd.pl(b));
-            bd.cells(bd.pl(b), [&](int, size_t o, const Quad<T>&, const Quad<T>& f) {
-                const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
+            bd.cells(bd.pl(b), [&](int, size_t o, const Vec<T, V>&, const Vec<T, V>& f) {
+                const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < V; ++k) {
                     const double sk = abstol + fabs((double)uq.v[k]) * reltol;
                     const double r = (double)(f.v[k] - kq.v[k]) / sk;
                     d2 += r * r;
@@ -401,22 +432,22 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
                 const T bh = (T)(cf.B[0] * h), eh = (T)(cf.E[0] * h);
                 if (!k1_valid) {
                     bd.nodes(pu);
-                    bd.cells(pu, [&](int l, size_t o, const Quad<T>& hc, const Quad<T>& f) {
-                        Quad<T> x, y;
+                    bd.cells(pu, [&](int l, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
+                        Vec<T, V> x, y;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { x.v[k] = hc.v[k] + bh * f.v[k]; y.v[k] = eh * f.v[k]; }
-                        st4(bd.pl(pK1) + o, f);
-                        st4(bd.pl(pE) + o, y);
+                        for (int k = 0; k < V; ++k) { x.v[k] = hc.v[k] + bh * f.v[k]; y.v[k] = eh * f.v[k]; }
+                        stv<V>(bd.pl(pK1) + o, f);
+                        stv<V>(bd.pl(pE) + o, y);
                         bd.put(b, l, o, x);
                     });
                     k1_valid = true;
                 } else {
-                    bd.own([&](int l, size_t o) {
-                        const Quad<T> uq = ld4(pu + o), kq = ld4(bd.pl(pK1) + o);
-                        Quad<T> x, y;
+                            bd.own([&](int l, size_t o) {
+                        const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
+                        Vec<T, V> x, y;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { x.v[k] = uq.v[k] + bh * kq.v[k]; y.v[k] = eh * kq.v[k]; }
-                        st4(bd.pl(pE) + o, y);
+                        for (int k = 0; k < V; ++k) { x.v[k] = uq.v[k] + bh * kq.v[k]; y.v[k] = eh * kq.v[k]; }
+                        stv<V>(bd.pl(pE) + o, y);
                         bd.put(b, l, o, x);
                     });
                 }
@@ -432,31 +463,31 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
                 const bool use_u = (cf.G3[i] != 0.0);
                 const T* pc = bd.pl(cur);
                 bd.nodes(pc);
-                bd.cells(pc, [&](int l, size_t o, const Quad<T>& s1, const Quad<T>& f) {
-                    const Quad<T> uq = ld4(pu + o), er = ld4(bd.pl(pE) + o);
-                    const Quad<T> s2in = (i == 0) ? uq : ld4(bd.pl(pS2) + o);
-                    Quad<T> s2, x, y;
+                bd.cells(pc, [&](int l, size_t o, const Vec<T, V>& s1, const Vec<T, V>& f) {
+                    const Vec<T, V> uq = ldv<V>(pu + o), er = ldv<V>(bd.pl(pE) + o);
+                    const Vec<T, V> s2in = (i == 0) ? uq : ldv<V>(bd.pl(pS2) + o);
+                    Vec<T, V> s2, x, y;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < V; ++k) {
                         s2.v[k] = s2in.v[k] + dd * s1.v[k];
                         T v = g1 * s1.v[k] + g2 * s2.v[k];
                         if (use_u) v = v + g3 * uq.v[k];
                         x.v[k] = v + bh * f.v[k];
                         y.v[k] = er.v[k] + eh * f.v[k];
                     }
-                    if (i < 3) st4(bd.pl(pS2) + o, s2);
-                    st4(bd.pl(pE) + o, y);
+                    if (i < 3) stv<V>(bd.pl(pS2) + o, s2);
+                    stv<V>(bd.pl(pE) + o, y);
                     bd.put(nxt, l, o, x);
                     if (i == 3) {   // error norm of the step: sum (est / (abstol + reltol max(|u|, |u_new|)))^2        (rk_sumsq)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < V; ++k) {
                             const double m = fmax(fabs((double)uq.v[k]), fabs((double)x.v[k]));
                             const double r = (double)y.v[k] / (abstol + reltol * m);
                             acc += r * r;
                         }
                     }
                 });
-                if (i < 3) cluster.sync();
+                cluster.sync();
                 const int tmp = cur; cur = nxt; nxt = tmp;
             }
             cluster_sum2(cluster, acc, accz, red, sRed, slot);
