@@ -343,10 +343,15 @@ class ResidentArm:
         else:
             self.ens.vjp_resident(True, True, read_S=False, want_dH=True)
 
-    def loss_grad_local(self):
-        """[loss; d(theta)] of this rank from the step's per-glacier S: S is read back (G doubles), pulled through the law
-        (d(theta) = sum_g dA_g/d(theta) S_g, Model.jl:208-224) -- the buffer the reference reduces over its workers."""
-        S = self.ens.vjp_resident(False, True, read_S=True)
+    def step_loss_grad_local(self, no_fuse=False):
+        """The step at an optimiser-iteration boundary: the same launches, then [loss; d(theta)] of this rank from the step's
+        per-glacier S: S is read back (G doubles) and pulled through the law (d(theta) = sum_g dA_g/d(theta) S_g,
+        Model.jl:208-224) -- the buffer the reference reduces over its workers."""
+        if no_fuse:
+            self.ens.rhs_resident()
+            S = self.ens.vjp_resident(True, True, read_S=True)
+        else:
+            S = self.ens.vjp_resident(True, True, read_S=True, want_dH=True)
         return float(np.abs(S).sum()), self.ens.law_A_nn_pullback(N_THETA, S)
 
     def close(self):
@@ -414,10 +419,11 @@ def run_b200(args, rank, local_rank, world):
     ar_ms = []
 
     def step(i):
-        arm.step(args.no_fuse)
-        if (i + 1) % every == 0:
+        if (i + 1) % every != 0:
+            arm.step(args.no_fuse)
+        else:
             # the optimiser-iteration boundary: the REAL [loss; d(theta)] of this rank, then ONE all-reduce over the ranks
-            loss, dth = arm.loss_grad_local()
+            loss, dth = arm.step_loss_grad_local(args.no_fuse)
             ta = time.perf_counter()
             parallel.allreduce_loss_grad(loss, dth)
             ar_ms.append(1e3 * (time.perf_counter() - ta))

@@ -63,9 +63,10 @@ def allreduce_loss_grad(loss: float, dθ: np.ndarray):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return loss, dθ
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    buf = torch.empty(1 + dθ.size, dtype=torch.float64, device=dev)
-    buf[0] = float(loss)
-    buf[1:] = torch.from_numpy(np.ascontiguousarray(dθ, dtype=np.float64)).to(dev)
+    host = np.empty(1 + dθ.size, dtype=np.float64)
+    host[0] = float(loss)
+    host[1:] = np.asarray(dθ, dtype=np.float64).ravel()
+    buf = torch.from_numpy(host).to(dev)   # one copy in, one collective, one copy out
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     out = buf.cpu().numpy()
     return float(out[0]), out[1:].copy()
