@@ -1030,6 +1030,40 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
     ODINN_CUDA(e, cudaMemsetAsync(lam, 0, pbytes, e->stream));  // λ_k = 0 (gradient.jl:140)
     ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
     ODINN_CUDA(e, cudaMemsetAsync(e->d_Ssum, 0, sizeof(double) * e->G, e->stream));
+    // Small ensembles, LossH only: the WHOLE reverse loop runs cluster-resident (sia2d_cluster.cuh: lambda in shared memory, H_j / H_ref /
+    // W streamed from the snapshot planes, loss and S accumulated on the device) -- one launch per range of steps between two
+    // mass-balance tstops instead of ~4 launches per saved step.
+    bool only_H = true;
+    for (int j = 0; j < n_t; ++j) only_H = only_H && loss_weight_V(e, n_t, j) == 0.0;
+    if (const int cs = only_H ? cluster_plan(e, 2) : 0) {
+        if ((rc = sync_descs(e))) return rc;
+        std::vector<double> tw(2 * (size_t)n_t);
+        for (int j = 0; j < n_t; ++j) { tw[j] = t[j]; tw[n_t + j] = loss_weight_H(e, t, n_t, j); }
+        const double* d_tw = nullptr;
+        if ((rc = upload_time_grid(e, tw.data(), 2 * n_t, &d_tw))) return rc;
+        const void* lam_in = nullptr;   // lambda_k = 0 (gradient.jl:140)
+        int jhi = n_t - 1;
+        while (jhi >= 1) {
+            int jlo = 0;
+            for (int m : e->mb_snap) if (m < jhi && m > jlo) jlo = m;   // the next mass-balance tstop below jhi ends the range
+            if ((rc = launch_reverse_cluster(e, cs, jhi, jlo, lam_in, lam, d_tw, d_tw + n_t))) return rc;
+            // lambda_jlo += VJP_lambda_dMB/dH(lambda_jlo, H_jlo - MB) before step jlo is taken                      (gradient.jl:201-207)
+            if (jlo >= 1 && (rc = mb_adjoint_step(e, jlo, lam, plane_ptr(e, e->snap, jlo)))) return rc;
+            lam_in = lam;
+            jhi = jlo;
+        }
+        const double wH0 = loss_weight_H(e, t, n_t, 0);
+        void* H0s = plane_ptr(e, e->snap, 0);
+        if (wH0 != 0.0 && (rc = launch_loss_seed(e, H0s, plane_ptr(e, e->href, 0), plane_ptr(e, e->wmask, 0), nullptr, nullptr, nullptr, 0.0,
+                                                 0.0, e->d_loss, wH0, 1)))
+            return rc;
+        ODINN_CUDA(e, cudaMemcpyAsync(e->h_S, e->d_loss, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+        ODINN_CUDA(e, cudaMemcpyAsync(e->h_S + e->G, e->d_Ssum, sizeof(double) * e->G, cudaMemcpyDeviceToHost, e->stream));
+        ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (loss_out) memcpy(loss_out, e->h_S, sizeof(double) * e->G);
+        if (Ssum_out) memcpy(Ssum_out, e->h_S + e->G, sizeof(double) * e->G);
+        return ODINN_OK;
+    }
     // fp32 two-column kernels, glacier-wide A: the reverse time step is folded into the A1 pass (SEED variant of sia2d_vjp_march2:
     // lambda_{j-1} = lambda_j + dt VJP_H + dl_j/dH written to the other lambda plane, loss term reduced per strip): 9 words/cell per
     // saved step (A1+seed 6, A2 3) instead of 13 (A1 4, loss / seed 6, A2 3).  ODINN_NO_FUSE=1 keeps the three-pass form.

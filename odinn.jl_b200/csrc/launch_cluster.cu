@@ -78,9 +78,12 @@ struct MaxClusters {
         if (kind == 0) {
             st = configure(sia2d_interval_cluster<T, CUBIC, ETA1, V>, smem, cs);
             if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_interval_cluster<T, CUBIC, ETA1, V>, &cfg);
-        } else {
+        } else if (kind == 1) {
             st = configure(sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, smem, cs);
             if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, &cfg);
+        } else {
+            st = configure(sia2d_reverse_cluster<T, CUBIC, ETA1, V>, smem, cs);
+            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_reverse_cluster<T, CUBIC, ETA1, V>, &cfg);
         }
         if (st != cudaSuccess) { cudaGetLastError(); *n = 0; }
         return ODINN_OK;
@@ -121,6 +124,23 @@ struct LaunchRdpk {
     }
 };
 
+template <typename T, bool CUBIC, bool ETA1, int V>
+struct LaunchReverse {
+    static int run(odinn_ensemble* e, int cs, size_t smem, int jhi, int jlo, const void* lam_in, void* lam_out, const double* d_t,
+                   const double* d_wH) {
+        auto k = sia2d_reverse_cluster<T, CUBIC, ETA1, V>;
+        ODINN_CUDA(e, configure(k, smem, cs));
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[1];
+        fill_config(e, cfg, at, smem, cs);
+        ODINN_CUDA(e, cudaLaunchKernelEx(&cfg, k, (const GDesc<T>*)e->d_descs, (const T*)e->plane[ODINN_FIELD_B], (const T*)lam_in, (T*)lam_out,
+                                         (const T*)e->snap, (const T*)e->href, (const T*)e->wmask, (long long)e->total, d_t, d_wH, jhi, jlo,
+                                         e->d_loss, e->d_Ssum, make_phys<T>(e->phys)));
+        e->launches++;
+        return ODINN_OK;
+    }
+};
+
 }  // namespace
 
 // Cluster size the ensemble runs with, 0 when the cluster path does not apply: a glacier too large for the shared memory of a
@@ -131,7 +151,7 @@ int cluster_plan(odinn_ensemble* e, int kind) {
     static const int env = []() { const char* v = getenv("ODINN_CLUSTER"); return v ? atoi(v) : -1; }();   // 0: off; 1..16: this size
     const int forced = e->cluster_mode >= 0 ? e->cluster_mode : env;
     if (forced == 0 || e->law_kind != 0 || e->a_gridded) return 0;
-    const int n_planes = kind == 0 ? CL_PLANES_FIXED : CL_PLANES_RDPK;
+    const int n_planes = kind == 0 ? CL_PLANES_FIXED : (kind == 1 ? CL_PLANES_RDPK : CL_PLANES_REV);
     const int sizes[5] = {16, 8, 4, 2, 1};
     for (int cs : sizes) {
         if (forced > 0 && cs != forced) continue;
@@ -148,6 +168,14 @@ int cluster_plan(odinn_ensemble* e, int kind) {
 int launch_interval_cluster(odinn_ensemble* e, int cs, int method, int nsub, int j0, int j1, const void* Hin, void* Hout, void* snap,
                             const double* d_t) {
     return dispatch<LaunchFixed>(e, choose_v(e, cs), cs, smem_for(e, cs, CL_PLANES_FIXED), method, nsub, j0, j1, Hin, Hout, snap, d_t);
+}
+
+// Steps jhi .. jlo+1 of the discrete-adjoint reverse loop in one launch (lam_in == nullptr: lambda = 0); the loss and S terms are ADDED to
+// the handle's d_loss / d_Ssum.  d_t: device time grid, d_wH: device LossH weight per snapshot.
+int launch_reverse_cluster(odinn_ensemble* e, int cs, int jhi, int jlo, const void* lam_in, void* lam_out, const double* d_t, const double* d_wH) {
+    // (fp64: two cells per item -- the adjoint cell sweep holds ~100 values per item and spills at four)
+    const int v = e->dtype == ODINN_F64 ? 2 : choose_v(e, cs);
+    return dispatch<LaunchReverse>(e, v, cs, smem_for(e, cs, CL_PLANES_REV), jhi, jlo, lam_in, lam_out, d_t, d_wH);
 }
 
 int upload_time_grid(odinn_ensemble* e, const double* t, int n_snap, const double** d_t) {

@@ -36,6 +36,7 @@ constexpr int CL_NT = ODINN_CL_NT;         // threads per CTA
 constexpr int CL_PAD = 4;          // zero columns left of column 0 (the row pitch also leaves >= 4 right of column nx-1)
 constexpr int CL_PLANES_FIXED = 5; // B, D, three rotating H planes
 constexpr int CL_PLANES_RDPK = 8;  // B, D, three rotating planes (u, S1, S1'), S2, est, k1
+constexpr int CL_PLANES_REV = 8;   // B, D, two rotating lambda planes, H_j, and the node planes alpha D+, beta dSx D+, beta dSy D+
 constexpr int CL_MAX_CS = 16;
 
 __host__ __device__ inline int cl_pitch(int nx) { return ((nx + 3) & ~3) + 2 * CL_PAD; }
@@ -88,6 +89,22 @@ template <int V> __device__ __forceinline__ void stv(double* p, const Vec<double
 // 1.21 vs 1.12; arriving early and evaluating the dual nodes that touch own rows only before the wait 1.17 vs 1.12 (0.90 vs 0.74 at
 // 64 x 64).  A stage costs ~0.75 us even for a 64 x 64 grid: two dependent shared-memory sweeps, the release of the remote stores
 // and the barrier -- not instruction issue (one, two or four cells per thread time the same there).
+// Sub-gradient of the flux clamp on one edge (subgrad of sia2d_march.cuh without the warp vote: the sweeps here are not
+// warp-convergent).  fp64 re-checks near-ties with true divisions to take the reference's branch (inversion_utils.jl:24-28, 38-42).
+template <typename T, bool ETA1>
+__device__ __forceinline__ void cl_subgrad(T dC, T e, T lo, T up, T delta, T eta0, T& to_lower, T& to_upper) {
+    bool gt_lo = e > lo, lt_lo = lo > e, lt_up = up > e, gt_up = e > up;
+    if (sizeof(T) == 8) {
+        const T tol = T(1e-14) * (e < T(0) ? -e : e);
+        const T d1 = e - lo, d2 = up - e;
+        if ((d1 < tol && -d1 < tol) || (d2 < tol && -d2 < tol)) {
+            const T qe = e / delta, ql = lo / delta, qu = up / delta;
+            gt_lo = qe > ql; lt_lo = ql > qe; lt_up = qu > qe; gt_up = qe > qu;
+        }
+    }
+    subgrad_cmp<T, ETA1>(dC, gt_lo, lt_lo, lt_up, gt_up, eta0, to_lower, to_upper);
+}
+
 // One CTA's band of one glacier.  Plane k of the carve-up is sm + k * plane; plane 0 is B, plane 1 is D (node row m of the band
 // in local row m), the others belong to the scheme.  Local row l <-> grid row row0 - 1 + l (l = 0 and l = Rown + 1: halo rows).
 template <typename T, bool CUBIC, bool ETA1, int V>
@@ -247,6 +264,153 @@ struct ClBand {
             ep(l, o, hc, f);
         }
     }
+    // ---- discrete adjoint (A1 / A2), adjoint.jl:99-148, 235-250; oracle VJP_dSIA_dH_discrete / node_reduction_S ----
+    // lambda is used zero-extended outside the interior cells (lambda_inn, adjoint.jl:99): with it every edge / node term that does
+    // not exist on the border evaluates to zero by itself, so the sweeps carry no existence tests.
+    __device__ __forceinline__ bool col_in(int i) const { return i >= 1 && i <= nx - 2; }
+    __device__ __forceinline__ bool row_in(int j) const { return j >= 1 && j <= ny - 2; }
+
+    // Node sweep.  MODE 0 (A1): planes 1, 5, 6, 7 <- D, alpha D+, beta dSx D+, beta dSy D+ for every node row of the band.
+    // MODE 1 (A2): acc += scale * sum over the node rows this CTA OWNS (local rows 1 .. Rown) of  gA D+  (target_A.jl:71-72).
+    template <int MODE>
+    __device__ __forceinline__ void adj_nodes(const T* __restrict__ lam, const T* __restrict__ Hp, double& acc, double scale) {
+        const T inv_dx = T(2) * hdx, inv_dy = T(2) * hdy;
+        T* sP = pl(5); T* sQx = pl(6); T* sQy = pl(7);
+        CL_SWEEP(r, a0, MODE == 0 ? Rown + 1 : Rown) {
+            const int m = MODE == 0 ? r : r + 1;
+            const int b = row0 - 1 + m;
+            if (Rown == 0 || b < 0 || b > ny - 2) continue;
+            const size_t o0 = (size_t)m * P + CL_PAD + a0, o1 = o0 + P;
+            const Vec<T, V> h0 = ldv<V>(Hp + o0), h1 = ldv<V>(Hp + o1), z0 = ldv<V>(sB + o0), z1 = ldv<V>(sB + o1);
+            const Vec<T, V> q0 = ldv<V>(lam + o0), q1 = ldv<V>(lam + o1);
+            T h0e[V + 1], h1e[V + 1], s0e[V + 1], s1e[V + 1], l0e[V + 1], l1e[V + 1];
+#pragma unroll
+            for (int k = 0; k < V; ++k) { h0e[k] = h0.v[k]; h1e[k] = h1.v[k]; s0e[k] = z0.v[k]; s1e[k] = z1.v[k]; l0e[k] = q0.v[k]; l1e[k] = q1.v[k]; }
+            h0e[V] = Hp[o0 + V]; h1e[V] = Hp[o1 + V]; s0e[V] = sB[o0 + V]; s1e[V] = sB[o1 + V]; l0e[V] = lam[o0 + V]; l1e[V] = lam[o1 + V];
+            const bool rb0 = row_in(b), rb1 = row_in(b + 1);
+#pragma unroll
+            for (int k = 0; k < V + 1; ++k) {
+                h0e[k] = fmx(h0e[k], T(0));
+                h1e[k] = fmx(h1e[k], T(0));
+                s0e[k] = surf_store<T>(s0e[k], h0e[k]);
+                s1e[k] = surf_store<T>(s1e[k], h1e[k]);
+                const bool ci = col_in(a0 + k);
+                l0e[k] = (rb0 && ci) ? l0e[k] : T(0);
+                l1e[k] = (rb1 && ci) ? l1e[k] : T(0);
+            }
+            Vec<T, V> Dq, Pq, Qxq, Qyq;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const T ex0 = sdiff<T>(s0e[k + 1], s0e[k], h0e[k + 1], h0e[k]);
+                const T ex1 = sdiff<T>(s1e[k + 1], s1e[k], h1e[k + 1], h1e[k]);
+                const T ey0 = sdiff<T>(s1e[k], s0e[k], h1e[k], h0e[k]);
+                const T ey1 = sdiff<T>(s1e[k + 1], s0e[k + 1], h1e[k + 1], h0e[k + 1]);
+                const T u = (ex0 + ex1) * hdx, v = (ey0 + ey1) * hdy;
+                const T g2 = u * u + v * v;
+                T Dn, al, be, gA;
+                node_raw<T, CUBIC, true>(ph, A, (h0e[k] + h0e[k + 1]) + (h1e[k] + h1e[k + 1]), g2, Dn, al, be, gA);
+                // D+ = avg_y+(-Fx+ cx) + avg_x+(-Fy+ cy),  Fx+ = diff_x+(-lambda_inn)                       (adjoint.jl:99-104)
+                const T X0 = -((l0e[k + 1] - l0e[k]) * inv_dx) * (clamp_raw<T>(ex0, eta0, h0e[k], h0e[k + 1]) * inv_dx);
+                const T X1 = -((l1e[k + 1] - l1e[k]) * inv_dx) * (clamp_raw<T>(ex1, eta0, h1e[k], h1e[k + 1]) * inv_dx);
+                const T Y0 = -((l1e[k] - l0e[k]) * inv_dy) * (clamp_raw<T>(ey0, eta0, h0e[k], h1e[k]) * inv_dy);
+                const T Y1 = -((l1e[k + 1] - l0e[k + 1]) * inv_dy) * (clamp_raw<T>(ey1, eta0, h0e[k + 1], h1e[k + 1]) * inv_dy);
+                const T Dd = T(0.5) * (X0 + X1) + T(0.5) * (Y0 + Y1);
+                const bool ok = (a0 + k <= nx - 2);
+                if (MODE == 0) {
+                    Dq.v[k] = ok ? Dn : T(0);
+                    Pq.v[k] = ok ? al * Dd : T(0);
+                    Qxq.v[k] = ok ? be * u * Dd : T(0);
+                    Qyq.v[k] = ok ? be * v * Dd : T(0);
+                } else if (ok) {
+                    acc += scale * (double)(gA * Dd);
+                }
+            }
+            if (MODE == 0) {
+                stv<V>(sD + o0, Dq);
+                stv<V>(sP + o0, Pq);
+                stv<V>(sQx + o0, Qxq);
+                stv<V>(sQy + o0, Qyq);
+            }
+        }
+        __syncthreads();
+    }
+
+    // Cell sweep of A1: ep(l, o, i0, lam_item (raw), H_item (raw), v) with v = (dSIA/dH)^T lambda on the item      (adjoint.jl:106-148)
+    template <class Ep>
+    __device__ __forceinline__ void adj_cells(const T* __restrict__ lam, const T* __restrict__ Hp, Ep&& ep) {
+        const T inv_dx = T(2) * hdx, inv_dy = T(2) * hdy;
+        const T* sP = pl(5); const T* sQx = pl(6); const T* sQy = pl(7);
+        CL_SWEEP(lr, i0, Rown) {
+            const int l = lr + 1, j = row0 + lr;
+            const size_t o = (size_t)l * P + CL_PAD + i0;
+            const Vec<T, V> hc = ldv<V>(Hp + o), hs = ldv<V>(Hp + o - P), hn = ldv<V>(Hp + o + P);
+            const Vec<T, V> zc = ldv<V>(sB + o), zs = ldv<V>(sB + o - P), zn = ldv<V>(sB + o + P);
+            const Vec<T, V> lc = ldv<V>(lam + o), ls = ldv<V>(lam + o - P), ln = ldv<V>(lam + o + P);
+            // node rows j-1 (S) and j (C), nodes i0-1 .. i0+V-1: index q <-> node column i0 - 1 + q
+            T DS[V + 1], DC[V + 1], PS[V + 1], PC[V + 1], XS[V + 1], XC[V + 1], YS[V + 1], YC[V + 1];
+            {
+                const Vec<T, V> a = ldv<V>(sD + o - P), b = ldv<V>(sD + o), c = ldv<V>(sP + o - P), d = ldv<V>(sP + o);
+                const Vec<T, V> e = ldv<V>(sQx + o - P), f = ldv<V>(sQx + o), g = ldv<V>(sQy + o - P), h = ldv<V>(sQy + o);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    DS[k + 1] = a.v[k]; DC[k + 1] = b.v[k]; PS[k + 1] = c.v[k]; PC[k + 1] = d.v[k];
+                    XS[k + 1] = e.v[k]; XC[k + 1] = f.v[k]; YS[k + 1] = g.v[k]; YC[k + 1] = h.v[k];
+                }
+                DS[0] = sD[o - P - 1]; DC[0] = sD[o - 1]; PS[0] = sP[o - P - 1]; PC[0] = sP[o - 1];
+                XS[0] = sQx[o - P - 1]; XC[0] = sQx[o - 1]; YS[0] = sQy[o - P - 1]; YC[0] = sQy[o - 1];
+            }
+            // cell row j, columns i0-1 .. i0+V: index q <-> column i0 - 1 + q
+            T he[V + 2], se[V + 2], lt[V + 2];
+            const bool rj = row_in(j), rs = row_in(j - 1), rn = row_in(j + 1);
+            he[0] = fmx(Hp[o - 1], T(0)); he[V + 1] = fmx(Hp[o + V], T(0));
+            se[0] = surf_store<T>(sB[o - 1], he[0]); se[V + 1] = surf_store<T>(sB[o + V], he[V + 1]);
+            lt[0] = (rj && col_in(i0 - 1)) ? lam[o - 1] : T(0);
+            lt[V + 1] = (rj && col_in(i0 + V)) ? lam[o + V] : T(0);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                he[k + 1] = fmx(hc.v[k], T(0));
+                se[k + 1] = surf_store<T>(zc.v[k], he[k + 1]);
+                lt[k + 1] = (rj && col_in(i0 + k)) ? lc.v[k] : T(0);
+            }
+            Vec<T, V> out;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const bool ci = col_in(i0 + k);
+                const T hS = fmx(hs.v[k], T(0)), hN = fmx(hn.v[k], T(0));
+                const T sS = surf_store<T>(zs.v[k], hS), sN = surf_store<T>(zn.v[k], hN);
+                const T lS = (rs && ci) ? ls.v[k] : T(0), lN = (rn && ci) ? ln.v[k] : T(0);
+                // first term: avg+(alpha D+) + diff_x+(avg_y+(beta dSx D+)) + diff_y+(avg_x+(beta dSy D+))           (adjoint.jl:106-127)
+                T acc = T(0.25) * ((PS[k] + PS[k + 1]) + (PC[k] + PC[k + 1]));
+                acc += (T(0.5) * (XS[k] + XC[k]) - T(0.5) * (XS[k + 1] + XC[k + 1])) * inv_dx;
+                acc += (T(0.5) * (YS[k] + YS[k + 1]) - T(0.5) * (YC[k] + YC[k + 1])) * inv_dy;
+                // second term: the four edges of the cell through the clamp sub-gradient                            (adjoint.jl:129-144)
+                T lo_, up_;
+                {   // east edge: this cell is the lower one
+                    const T dC = -((lt[k + 2] - lt[k + 1]) * inv_dx) * (T(0.5) * (DS[k + 1] + DC[k + 1])) * inv_dx;
+                    cl_subgrad<T, ETA1>(dC, sdiff<T>(se[k + 2], se[k + 1], he[k + 2], he[k + 1]), -(eta0 * he[k + 1]), eta0 * he[k + 2], T(1) / inv_dx, eta0, lo_, up_);
+                    acc += lo_;
+                }
+                {   // west edge: this cell is the upper one
+                    const T dC = -((lt[k + 1] - lt[k]) * inv_dx) * (T(0.5) * (DS[k] + DC[k])) * inv_dx;
+                    cl_subgrad<T, ETA1>(dC, sdiff<T>(se[k + 1], se[k], he[k + 1], he[k]), -(eta0 * he[k]), eta0 * he[k + 1], T(1) / inv_dx, eta0, lo_, up_);
+                    acc += up_;
+                }
+                {   // north edge (row j -> j+1): lower
+                    const T dC = -((lN - lt[k + 1]) * inv_dy) * (T(0.5) * (DC[k] + DC[k + 1])) * inv_dy;
+                    cl_subgrad<T, ETA1>(dC, sdiff<T>(sN, se[k + 1], hN, he[k + 1]), -(eta0 * he[k + 1]), eta0 * hN, T(1) / inv_dy, eta0, lo_, up_);
+                    acc += lo_;
+                }
+                {   // south edge (row j-1 -> j): upper
+                    const T dC = -((lt[k + 1] - lS) * inv_dy) * (T(0.5) * (DS[k] + DS[k + 1])) * inv_dy;
+                    cl_subgrad<T, ETA1>(dC, sdiff<T>(se[k + 1], sS, he[k + 1], hS), -(eta0 * hS), eta0 * he[k + 1], T(1) / inv_dy, eta0, lo_, up_);
+                    acc += up_;
+                }
+                out.v[k] = (hc.v[k] > T(0)) ? acc : T(0);   // adjoint.jl:148
+            }
+            ep(l, o, i0, lc, hc, out);
+        }
+    }
+
     // elementwise sweep over the own cells: ep(l, o)
     template <class Ep>
     __device__ __forceinline__ void own(Ep&& ep) {
@@ -526,6 +690,68 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
     }
     if (total > max_steps) s.started = -1;   // maxiters: reported by the launcher
     if (cluster.block_rank() == 0 && threadIdx.x == 0) states[g] = s;
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+// Discrete-adjoint reverse loop (gradient.jl:191-253 with LossH, Losses.jl:270-291), one cluster per glacier: steps jhi .. jlo+1 in
+// ONE launch.  Per step j: H_j from the snapshot plane;  v = (dSIA/dH)^T lambda_j;  loss += w_j sum W (H_j - H_ref,j)^2;
+// lambda_{j-1} = lambda_j + dt v + 2 w_j W (H_j - H_ref,j)  (halo rows to the neighbours, cluster barrier);
+// S += dt * sum gA D+(lambda_{j-1}, H_j).  The loss and S accumulate per thread over all steps and are reduced once at the end.
+// -------------------------------------------------------------------------------------------------------------------------
+template <typename T, bool CUBIC, bool ETA1, int V>
+__global__ void __launch_bounds__(CL_NT, 1)
+sia2d_reverse_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Bg, const T* __restrict__ lam_in, T* __restrict__ lam_out,
+                      const T* __restrict__ snap, const T* __restrict__ href, const T* __restrict__ wmask, long long plane_stride,
+                      const double* __restrict__ t, const double* __restrict__ wH, int jhi, int jlo, double* __restrict__ loss_acc,
+                      double* __restrict__ S_acc, PhysDev<T> ph) {
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    __shared__ double red[2][2][CL_MAX_CS];
+    __shared__ double sRed[2 * CL_NT / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x / cluster.num_blocks();
+    ClBand<T, CUBIC, ETA1, V> bd;
+    bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_REV);
+    int la = 2, lb = 3;
+    constexpr int pH = 4;
+    bd.load(0, Bg);
+    if (lam_in) bd.load(la, lam_in);   // (else lambda_k = 0, gradient.jl:140: the planes are zero-initialised)
+    cluster.sync();
+
+    double acc_loss = 0.0, acc_S = 0.0, dummy = 0.0;
+    for (int j = jhi; j > jlo; --j) {
+        const double dt = t[j] - t[j - 1], w = wH[j];
+        const T dtT = (T)dt, cseed = (T)(2.0 * w);
+        const long long pj = (long long)j * plane_stride;
+        __syncthreads();                       // the A2 sweep of the previous step has finished reading the H plane
+        bd.load(pH, snap + pj);
+        __syncthreads();
+        const T* lam = bd.pl(la);
+        const T* Hp = bd.pl(pH);
+        bd.template adj_nodes<0>(lam, Hp, dummy, 0.0);
+        bd.adj_cells(lam, Hp, [&](int l, size_t o, int i0, const Vec<T, V>& lc, const Vec<T, V>& hc, const Vec<T, V>& v) {
+            // H_ref and W of the item straight from the global planes (read once per cell and step)
+            const long long go = bd.goff + (long long)(bd.row0 + l - 1) * bd.gld + i0;
+            const Vec<T, V> hr = ldv<V>(href + pj + go), wm = ldv<V>(wmask + pj + go);
+            Vec<T, V> x;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const T d = hc.v[k] - hr.v[k], wd = wm.v[k] * d;
+                acc_loss += w * ((double)wd * (double)d);
+                x.v[k] = lc.v[k] + dtT * v.v[k] + cseed * wd;
+            }
+            bd.put(lb, l, o, x);
+        });
+        cluster.sync();
+        bd.template adj_nodes<1>(bd.pl(lb), Hp, acc_S, dt);   // dL/dtheta += dt VJP_theta(lambda_{j-1}, H_j)   (gradient.jl:245-249)
+        const int tmp = la; la = lb; lb = tmp;
+    }
+    bd.store(la, lam_out, nullptr);
+    int slot = 0;
+    cluster_sum2(cluster, acc_loss, acc_S, red, sRed, slot);
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+        loss_acc[g] += acc_loss;
+        S_acc[g] += acc_S;
+    }
 }
 
 }  // namespace odinn

@@ -174,6 +174,70 @@ def test_cluster_rdpk3sp35_matches_oracle_and_engine(ob, dtype, cs):
         ens.close()
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("cs", [1, 2, 8, 16])
+def test_cluster_reverse_loop_matches_marching_and_oracle(ob, dtype, cs):
+    """R1 / L1 cluster-resident (the whole discrete-adjoint reverse loop in one launch): loss, S = dL/dA-scalar and lambda(t0) equal the
+    per-step kernel sequence (cluster mode 0) and the oracle's loss_and_grad_discrete; sparse H_ref data; mass-balance tstops split the
+    launch ranges."""
+    from odinn_b200 import _capi
+
+    gl = _glaciers()
+    t = np.array([2010.0, 2010.0 + 1 / 12, 2010.0 + 2.5 / 12, 2010.0 + 3 / 12, 2010.0 + 5 / 12, 2010.0 + 6 / 12])
+    ph = o.Phys(**PH)
+    for with_mb in (False, True):
+        ens = _ens(ob, gl, dtype)
+        try:
+            mb_idx = [2, 4]
+            pars = np.array([[(3.0, -0.0065, 2100.0, 0.9, 0.4, 1.2, 1.0)] * len(gl) for _ in mb_idx])
+            if with_mb:
+                ens.set_mass_balance(mb_idx, pars)
+            for k, a in enumerate(AS):
+                ens.set_A_scalar(k, a)
+            ens.set_cluster_mode(0)
+            ens.solve_forward(t, method="ssprk3", nsub=12)
+            refs = []
+            for k, g in enumerate(gl):
+                g2 = o.Glacier(B=_r(g.B, dtype), dx=g.dx, dy=g.dy, H0=_r(g.H0, dtype))
+                mb = {j: tuple(pars[m, k]) for m, j in enumerate(mb_idx)} if with_mb else None
+                Href = [_r(h, dtype) for h in o.solve_forward(g2.H0, g2, o.TargetA(ph, "const", A=2e-17), None, t, method="ssprk3", nsub=12, mb=mb)]
+                for j in range(len(t)):
+                    if j != 3:   # sparse thickness data: no H_ref at tstop 3 (gradient.jl:79-80, 144-149)
+                        ens.set_reference(k, j, len(t), Href[j], o.is_in_glacier(Href[j], 3))
+                refs.append(Href)
+            loss0, S0 = ens.grad_discrete(t)
+            lam0 = [ens.download(k, _capi.FIELD_LAMBDA) for k in range(len(gl))]
+            ens.set_cluster_mode(cs)
+            l0 = ens.launch_count
+            loss1, S1 = ens.grad_discrete(t)
+            assert ens.launch_count - l0 == (1 + 2 * len(mb_idx) if with_mb else 1), ens.launch_count - l0
+            rt = 1e-10 if dtype == "f64" else 2e-4
+            for k in range(len(gl)):
+                assert loss1[k] == pytest.approx(loss0[k], rel=rt), (k, loss1[k], loss0[k])
+                assert S1[k] == pytest.approx(S0[k], rel=1e-8 if dtype == "f64" else 5e-3, abs=1e-30), (k, S1[k], S0[k])
+                lam1 = ens.download(k, _capi.FIELD_LAMBDA)
+                assert rel_l2(lam1, lam0[k]) <= (1e-10 if dtype == "f64" else 1e-4), (k, rel_l2(lam1, lam0[k]))
+            loss2, S2 = ens.grad_discrete(t)
+            assert np.array_equal(loss1, loss2) and np.array_equal(S1, S2)   # bit-stable run to run
+            if not with_mb and dtype == "f64":   # and against the oracle on the device snapshots
+                for k, g in enumerate(gl[:3]):
+                    g2 = o.Glacier(B=g.B, dx=g.dx, dy=g.dy, H0=g.H0)
+                    Hs_d = [ens.get_snapshot(k, j).astype(np.float64) for j in range(len(t))]
+                    tgs = o.TargetA(ph, "scalar")
+                    theta = np.array([np.arctanh(2 * (AS[k] - ph.minA) / (ph.maxA - ph.minA) - 1)])
+                    Href = list(refs[k])
+                    wH = np.zeros(len(t)); last = 0
+                    for j in range(1, len(t)):
+                        if j != 3:
+                            wH[j] = t[j] - t[last]; last = j
+                    Href[3] = Hs_d[3]
+                    ell, dth = o.loss_and_grad_discrete_HV(theta, g2, tgs, t, Hs_d, Href, [None] * len(t), wH, np.zeros(len(t)))
+                    assert loss1[k] == pytest.approx(ell, rel=1e-10), k
+                    assert S1[k] * tgs.vjp_theta[0] == pytest.approx(dth[0], rel=1e-8), (k, S1[k] * tgs.vjp_theta[0], dth[0])
+        finally:
+            ens.close()
+
+
 def test_cluster_mode_automatic_choice_and_fallback(ob):
     """Automatic mode: a small ensemble runs cluster-resident (one launch), an ensemble holding a glacier too large for the shared
     memory of a cluster falls back to the marching kernels; results agree."""

@@ -61,6 +61,23 @@ def run_rdpk():
 s = timed(run_rdpk)
 report(f"1: 128x128 forward 2010-2015, adaptive RDPK3Sp35 + PID rtol {rt:g} (the reference's default solver)", seconds=s, steps=int(st[0][0]),
        rejected=int(st[1][0]), us_per_trial_step=1e6 * s / max(int(st[0][0]), 1))
+# config 1 as an inversion: one optimiser iteration = forward solve + DiscreteAdjoint reverse loop (61 monthly snapshots), the twin
+# experiment of test/inversion_test.jl on one small glacier
+ens.solve_forward(t5, method="ssprk3", nsub=8)
+for j in range(len(t5)):
+    Hj = ens.get_snapshot(0, j)
+    ens.set_reference(0, j, len(t5), 0.97 * Hj, (Hj > 0))
+ens.set_A_scalar(0, 7e-18)
+def it_ssprk3():
+    ens.solve_forward(t5, method="ssprk3", nsub=8); return ens.grad_discrete(t5)
+def it_rdpk():
+    ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35"); return ens.grad_discrete(t5)
+def it_adj():
+    return ens.grad_discrete(t5)
+l0 = ens.launch_count; it_ssprk3(); n_launch = ens.launch_count - l0
+report("1: 128x128 inversion iteration, SSPRK3 forward + discrete adjoint", seconds=timed(it_ssprk3), launches=int(n_launch))
+report("1: 128x128 inversion iteration, RDPK3Sp35 forward + discrete adjoint", seconds=timed(it_rdpk))
+report("1: 128x128 discrete-adjoint reverse loop alone (60 saved steps)", seconds=timed(it_adj), us_per_saved_step=1e6 * timed(it_adj) / 60)
 ens.close()
 
 # config 3: 64 glaciers, sizes U{100..400}, forward Prediction run
