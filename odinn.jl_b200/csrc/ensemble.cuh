@@ -134,7 +134,7 @@ enum {  // ext_dev slots
     EXT_RK_STATE = 19,                                                                              // RDPK3Sp35 per-glacier controller state (rdpk.cu)
     EXT_VQ_WORK = 20,                                                                               // 4 planes: velocity references interpolated at a quadrature node
     EXT_VQ_RED = 21,                                                                                // [2 G] mask count and sum of squares of those references
-    EXT_CL_TIMES = 24, EXT_CL_RKSTATE = 25,                                                                              // cluster-resident forward solve: time grid on the device (ext_int[4] = its length)
+    EXT_CL_TIMES = 24, EXT_CL_RKSTATE = 25, EXT_CL_STEPS = 26,                                                                              // cluster-resident forward solve: time grid on the device (ext_int[4] = its length)
     EXT_LAT_KNOTS = 22, EXT_LAT_W = 23                                                              // law pullback with interpolation = :Linear: knots, knot weights (ext_int[2], [3] = n0, n1)
 };
 
@@ -195,7 +195,7 @@ int mb_adjoint_step(odinn_ensemble* e, int j, void* lam, const void* Hj);
 // S_dst[g] += scale * dl_V/dtheta-scalar evaluated on the plane H against the velocity references interpolated linearly at time tq
 // (one datum: constant; flat outside the data range) -- the quadrature-node term of the continuous adjoint (gradient.jl:289-301, 474-507)
 int velocity_theta_term_interp(odinn_ensemble* e, double tq, const double* t, int n_t, const void* H, double scale, double* S_dst);
-// cluster-resident solves of small glaciers (launch_cluster.cu).  kind: 0 fixed-step forward (Euler / SSPRK3), 1 RDPK3Sp35, 2 discrete-adjoint reverse loop.
+// cluster-resident solves of small glaciers (launch_cluster.cu).  kind: 0 fixed-step forward (Euler / SSPRK3), 1 RDPK3Sp35, 2 discrete-adjoint reverse loop, 3 continuous adjoint.
 // cluster_plan: the cluster size the ensemble would run with (0: not eligible).  launch_interval_cluster: intervals j0+1 .. j1 of the
 // time grid in one launch (snapshots j0+1 .. j1 and the final state written by the kernel).
 int cluster_plan(odinn_ensemble* e, int kind);
@@ -204,7 +204,9 @@ int launch_interval_cluster(odinn_ensemble* e, int cs, int method, int nsub, int
 int solve_forward_rdpk_cluster(odinn_ensemble* e, int cs, int n_snap, const double* t, double reltol, double abstol, double dt0,
                                int max_steps, int* steps_out, int* rejected_out);
 int launch_reverse_cluster(odinn_ensemble* e, int cs, int jhi, int jlo, const void* lam_in, void* lam_out, const double* d_t, const double* d_wH);
-void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5]);
+int grad_continuous_adaptive_cluster(odinn_ensemble* e, int cs, const double* t, int n_t, int n_q, const double* qn, const double* qw,
+                                     double reltol, double abstol, double dtmax, int max_steps, int* steps_out);
+void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5], double C[6]);
 int upload_time_grid(odinn_ensemble* e, const double* t, int n_snap, const double** d_t);   // device copy of the tstops (EXT_CL_TIMES)
 // adaptive forward solve with the reference's default integrator (rdpk.cu)
 int solve_forward_rdpk(odinn_ensemble* e, int n_snap, const double* t, double reltol, double abstol, double dt0, int max_steps,

@@ -1,5 +1,6 @@
 // Launchers of the cluster-resident forward solves (sia2d_cluster.cuh): eligibility, cluster size, launch attributes, and the
 // host loop of the adaptive solve (launch ranges between mass-balance callbacks).
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -81,9 +82,12 @@ struct MaxClusters {
         } else if (kind == 1) {
             st = configure(sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, smem, cs);
             if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_rdpk_cluster<T, CUBIC, ETA1, V>, &cfg);
-        } else {
+        } else if (kind == 2) {
             st = configure(sia2d_reverse_cluster<T, CUBIC, ETA1, V>, smem, cs);
             if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_reverse_cluster<T, CUBIC, ETA1, V>, &cfg);
+        } else {
+            st = configure(sia2d_contadj_cluster<T, CUBIC, ETA1, V>, smem, cs);
+            if (st == cudaSuccess) st = cudaOccupancyMaxActiveClusters(n, sia2d_contadj_cluster<T, CUBIC, ETA1, V>, &cfg);
         }
         if (st != cudaSuccess) { cudaGetLastError(); *n = 0; }
         return ODINN_OK;
@@ -141,6 +145,23 @@ struct LaunchReverse {
     }
 };
 
+template <typename T, bool CUBIC, bool ETA1, int V>
+struct LaunchContAdj {
+    static int run(odinn_ensemble* e, int cs, size_t smem, void* lam_out, const double* d_tab, int n_t, int n_ev, int n_q, double reltol,
+                   double abstol, double dtmax, int max_steps, int* d_steps, const RdpkCoef& cf) {
+        auto k = sia2d_contadj_cluster<T, CUBIC, ETA1, V>;
+        ODINN_CUDA(e, configure(k, smem, cs));
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[1];
+        fill_config(e, cfg, at, smem, cs);
+        ODINN_CUDA(e, cudaLaunchKernelEx(&cfg, k, (const GDesc<T>*)e->d_descs, (const T*)e->plane[ODINN_FIELD_B], (T*)lam_out, (const T*)e->snap,
+                                         (const T*)e->href, (const T*)e->wmask, (long long)e->total, d_tab, n_t, n_ev, n_q, reltol, abstol, dtmax,
+                                         max_steps, e->d_loss, e->d_Ssum, d_steps, cf, make_phys<T>(e->phys)));
+        e->launches++;
+        return ODINN_OK;
+    }
+};
+
 }  // namespace
 
 // Cluster size the ensemble runs with, 0 when the cluster path does not apply: a glacier too large for the shared memory of a
@@ -151,7 +172,7 @@ int cluster_plan(odinn_ensemble* e, int kind) {
     static const int env = []() { const char* v = getenv("ODINN_CLUSTER"); return v ? atoi(v) : -1; }();   // 0: off; 1..16: this size
     const int forced = e->cluster_mode >= 0 ? e->cluster_mode : env;
     if (forced == 0 || e->law_kind != 0 || e->a_gridded) return 0;
-    const int n_planes = kind == 0 ? CL_PLANES_FIXED : (kind == 1 ? CL_PLANES_RDPK : CL_PLANES_REV);
+    const int n_planes = kind == 0 ? CL_PLANES_FIXED : (kind == 1 ? CL_PLANES_RDPK : (kind == 2 ? CL_PLANES_REV : CL_PLANES_CA));
     const int sizes[5] = {16, 8, 4, 2, 1};
     for (int cs : sizes) {
         if (forced > 0 && cs != forced) continue;
@@ -176,6 +197,51 @@ int launch_reverse_cluster(odinn_ensemble* e, int cs, int jhi, int jlo, const vo
     // (fp64: two cells per item -- the adjoint cell sweep holds ~100 values per item and spills at four)
     const int v = e->dtype == ODINN_F64 ? 2 : choose_v(e, cs);
     return dispatch<LaunchReverse>(e, v, cs, smem_for(e, cs, CL_PLANES_REV), jhi, jlo, lam_in, lam_out, d_t, d_wH);
+}
+
+// ContinuousAdjoint gradient, cluster-resident (sia2d_contadj_cluster): the event list is built here exactly as in
+// grad_continuous_adaptive_t (rdpk.cu) -- stops in tau = -t: sort(unique(vcat(-reverse(tstops), -t_nodes))), gradient.jl:456.
+// d_loss / d_Ssum must be zeroed by the caller; lambda(t_0) is left in FIELD_LAMBDA.
+int grad_continuous_adaptive_cluster(odinn_ensemble* e, int cs, const double* t, int n_t, int n_q, const double* qn, const double* qw,
+                                     double reltol, double abstol, double dtmax, int max_steps, int* steps_out) {
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_LAMBDA)) || (rc = ensure_plane(e, ODINN_FIELD_B))) return rc;
+    struct Ev { double tau; int is_q; int idx; };
+    std::vector<Ev> ev;
+    for (int j = 0; j < n_t; ++j) ev.push_back({-t[j], 0, j});
+    for (int m = 0; m < n_q; ++m) {
+        bool dup = false;
+        for (int j = 0; j < n_t; ++j) dup |= (qn[m] == t[j]);
+        if (!dup) ev.push_back({-qn[m], 1, m});
+    }
+    std::stable_sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.tau < b.tau; });
+    const int n_ev = (int)ev.size();
+    std::vector<double> tab;
+    tab.reserve(2 * (size_t)n_t + 2 * (size_t)n_ev + 2 * (size_t)n_q);
+    for (int j = 0; j < n_t; ++j) tab.push_back(t[j]);
+    for (int j = 0; j < n_t; ++j) tab.push_back(loss_weight_H(e, t, n_t, j));
+    for (const Ev& s : ev) tab.push_back(s.tau);
+    for (const Ev& s : ev) tab.push_back((double)(s.idx + (s.is_q ? (1 << 20) : 0)));
+    for (int m = 0; m < n_q; ++m) tab.push_back(qn[m]);
+    for (int m = 0; m < n_q; ++m) tab.push_back(qw[m]);
+    const double* d_tab = nullptr;
+    if ((rc = upload_time_grid(e, tab.data(), (int)tab.size(), &d_tab))) return rc;
+    if (!e->ext_dev[EXT_CL_STEPS]) ODINN_CUDA(e, cudaMalloc(&e->ext_dev[EXT_CL_STEPS], sizeof(int) * e->G));
+    int* d_steps = (int*)e->ext_dev[EXT_CL_STEPS];
+    RdpkCoef cf;
+    rdpk_host_coefficients(cf.G1, cf.G2, cf.G3, cf.D, cf.B, cf.E, cf.C);
+    const int v = e->dtype == ODINN_F64 ? 2 : choose_v(e, cs);
+    if ((rc = dispatch<LaunchContAdj>(e, v, cs, smem_for(e, cs, CL_PLANES_CA), e->plane[ODINN_FIELD_LAMBDA], d_tab, n_t, n_ev, n_q, reltol, abstol,
+                                      dtmax, max_steps, d_steps, cf)))
+        return rc;
+    std::vector<int> hs(e->G);
+    ODINN_CUDA(e, cudaMemcpyAsync(hs.data(), d_steps, sizeof(int) * e->G, cudaMemcpyDeviceToHost, e->stream));
+    ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int g = 0; g < e->G; ++g) {
+        if (hs[g] < 0) return fail(e, ODINN_ESTATE, "rdpk3sp35: too many steps (maxiters)");
+        if (steps_out) steps_out[g] = hs[g];
+    }
+    return ODINN_OK;
 }
 
 int upload_time_grid(odinn_ensemble* e, const double* t, int n_snap, const double** d_t) {
@@ -205,7 +271,7 @@ int solve_forward_rdpk_cluster(odinn_ensemble* e, int cs, int n_snap, const doub
     ClRkState* states = (ClRkState*)e->ext_dev[EXT_CL_RKSTATE];
     ODINN_CUDA(e, cudaMemsetAsync(states, 0, sizeof(ClRkState) * e->G, e->stream));
     RdpkCoef cf;
-    rdpk_host_coefficients(cf.G1, cf.G2, cf.G3, cf.D, cf.B, cf.E);
+    rdpk_host_coefficients(cf.G1, cf.G2, cf.G3, cf.D, cf.B, cf.E, cf.C);
     void* Hs = e->plane[ODINN_FIELD_H];
     ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, 0), e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));
     if (n_snap == 1) ODINN_CUDA(e, cudaMemcpyAsync(Hs, e->plane[ODINN_FIELD_H0], pbytes, cudaMemcpyDeviceToDevice, e->stream));

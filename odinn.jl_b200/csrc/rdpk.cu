@@ -62,9 +62,10 @@ static void rdpk_error_weights(double E[5]) {
 }
 
 // the same tables for the cluster-resident solver (launch_cluster.cu passes them as a kernel argument)
-void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5]) {
+void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4], double B[5], double E[5], double C[6]) {
     for (int i = 0; i < 4; ++i) { G1[i] = h_G1[i]; G2[i] = h_G2[i]; G3[i] = h_G3[i]; D[i] = h_D[i]; }
     for (int i = 0; i < 5; ++i) B[i] = h_B[i];
+    for (int i = 0; i < 6; ++i) C[i] = h_C[i];
     rdpk_error_weights(E);
 }
 
@@ -641,6 +642,15 @@ extern "C" int odinn_grad_continuous_adaptive(odinn_ensemble* e, const double* t
     if (continuous_vjp && e->law_kind != 0) return fail(e, ODINN_ESTATE, "the continuous VJP flavour is provided for glacier-wide A laws");
     int rc;
     if ((rc = sync_descs(e))) return rc;
+    // Small ensembles, LossH, glacier-wide A, discrete VJP flavour, no mass-balance callback: the whole reverse solve (adaptive steps,
+    // loss jumps at the tstops, quadrature of dL/dtheta) runs inside one thread-block cluster per glacier, ONE launch (sia2d_cluster.cuh).
+    bool plain = !continuous_vjp && e->law_kind == 0 && e->mb_snap.empty() && e->lossV_theta_scale == 0.0;
+    for (int j = 0; j < n_t && plain; ++j) plain = loss_weight_V(e, n_t, j) == 0.0;
+    if (const int cs = plain ? cluster_plan(e, 3) : 0) {
+        ODINN_CUDA(e, cudaMemsetAsync(e->d_loss, 0, sizeof(double) * e->G, e->stream));
+        ODINN_CUDA(e, cudaMemsetAsync(e->d_Ssum, 0, sizeof(double) * e->G, e->stream));
+        rc = grad_continuous_adaptive_cluster(e, cs, t, n_t, n_quadrature, q_nodes, q_weights, reltol, abstol, dtmax, max_steps, steps_out);
+    } else
     rc = e->dtype == ODINN_F32
              ? grad_continuous_adaptive_t<float>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, reltol, abstol, dtmax, max_steps, steps_out)
              : grad_continuous_adaptive_t<double>(e, t, n_t, n_quadrature, q_nodes, q_weights, continuous_vjp != 0, reltol, abstol, dtmax, max_steps, steps_out);

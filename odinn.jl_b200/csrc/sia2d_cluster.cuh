@@ -36,6 +36,7 @@ constexpr int CL_NT = ODINN_CL_NT;         // threads per CTA
 constexpr int CL_PAD = 4;          // zero columns left of column 0 (the row pitch also leaves >= 4 right of column nx-1)
 constexpr int CL_PLANES_FIXED = 5; // B, D, three rotating H planes
 constexpr int CL_PLANES_RDPK = 8;  // B, D, three rotating planes (u, S1, S1'), S2, est, k1
+constexpr int CL_PLANES_CA = 14;   // B, D, RDPK planes 2-7 (lambda), adjoint node planes 8-10, snapshots H_a, H_b and their interpolant H_t
 constexpr int CL_PLANES_REV = 8;   // B, D, two rotating lambda planes, H_j, and the node planes alpha D+, beta dSx D+, beta dSy D+
 constexpr int CL_MAX_CS = 16;
 
@@ -117,6 +118,7 @@ struct ClBand {
     PhysDev<T> ph;
     long long goff;
     int gld;
+    int pAdj;   // first of the three node planes of the adjoint sweeps (alpha D+, beta dSx D+, beta dSy D+)
 
     __device__ __forceinline__ void init(cg::cluster_group& cluster, const GDesc<T>& d, const PhysDev<T>& phys, unsigned char* raw, int n_planes) {
         CS = (int)cluster.num_blocks();
@@ -139,6 +141,7 @@ struct ClBand {
         kx = hdx * d.inv_dx; ky = hdy * d.inv_dy;   // ½/Δx², ½/Δy²
         A = d.A;
         goff = d.off; gld = d.ld;
+        pAdj = 5;
         t_row = tid / Q; t_col = tid - t_row * Q; d_row = CL_NT / Q; d_col = CL_NT - d_row * Q;
         for (size_t k = tid; k < (size_t)n_planes * plane; k += CL_NT) sm[k] = T(0);
         __syncthreads();
@@ -275,7 +278,7 @@ struct ClBand {
     template <int MODE>
     __device__ __forceinline__ void adj_nodes(const T* __restrict__ lam, const T* __restrict__ Hp, double& acc, double scale) {
         const T inv_dx = T(2) * hdx, inv_dy = T(2) * hdy;
-        T* sP = pl(5); T* sQx = pl(6); T* sQy = pl(7);
+        T* sP = pl(pAdj); T* sQx = pl(pAdj + 1); T* sQy = pl(pAdj + 2);
         CL_SWEEP(r, a0, MODE == 0 ? Rown + 1 : Rown) {
             const int m = MODE == 0 ? r : r + 1;
             const int b = row0 - 1 + m;
@@ -339,7 +342,7 @@ struct ClBand {
     template <class Ep>
     __device__ __forceinline__ void adj_cells(const T* __restrict__ lam, const T* __restrict__ Hp, Ep&& ep) {
         const T inv_dx = T(2) * hdx, inv_dy = T(2) * hdy;
-        const T* sP = pl(5); const T* sQx = pl(6); const T* sQy = pl(7);
+        const T* sP = pl(pAdj); const T* sQx = pl(pAdj + 1); const T* sQy = pl(pAdj + 2);
         CL_SWEEP(lr, i0, Rown) {
             const int l = lr + 1, j = row0 + lr;
             const size_t o = (size_t)l * P + CL_PAD + i0;
@@ -474,7 +477,7 @@ sia2d_interval_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__
 // -------------------------------------------------------------------------------------------------------------------------
 // RDPK3Sp35 + PID controller (the scheme of rdpk.cu / oracle integrate_rdpk3sp35, step for step), one cluster per glacier.
 // -------------------------------------------------------------------------------------------------------------------------
-struct RdpkCoef { double G1[4], G2[4], G3[4], D[4], B[5], E[5]; };
+struct RdpkCoef { double G1[4], G2[4], G3[4], D[4], B[5], E[5], C[6]; };
 
 // per-glacier controller state carried between launches (a launch range ends at a mass-balance callback)
 struct ClRkState {
@@ -504,87 +507,85 @@ __device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double&
     slot ^= 1;
 }
 
+// The RDPK3Sp35 machinery of one cluster, shared by the forward solve and the reverse ODE of the continuous adjoint.
+// rhs(plane, time, ep): evaluate f(time, plane k) on the band and call ep(l, o, item of the plane, item of f) for every own item.
+// Planes 2, 3, 4 rotate (a = state at the start of the step, b / c = stage values, all with halo rows); 5, 6, 7 = S2, est, k1.
 template <typename T, bool CUBIC, bool ETA1, int V>
-__global__ void __launch_bounds__(CL_NT, 1)
-sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
-                   T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, ClRkState* __restrict__ states,
-                   double reltol, double abstol, double dtmax, double dt0, int max_steps, RdpkCoef cf, PhysDev<T> ph) {
-    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
-    __shared__ double red[2][2][CL_MAX_CS];
-    __shared__ double sRed[2 * CL_NT / 32];
-    __shared__ double ctl[4];   // h, accept, done, fac  (thread 0 -> CTA)
-    cg::cluster_group cluster = cg::this_cluster();
-    const int g = blockIdx.x / cluster.num_blocks();
-    ClBand<T, CUBIC, ETA1, V> bd;
-    bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_RDPK);
-    int a = 2, b = 3, c = 4;             // rotating planes with halos: a = u (state at the start of the step), b / c = stage values
-    constexpr int pS2 = 5, pE = 6, pK1 = 7;
-    bd.load(0, Bg);
-    bd.load(a, Hin);
-    cluster.sync();
-
-    ClRkState s = states[g];
-    const double ncell = (double)bd.nx * (double)bd.ny;
-    int slot = 0;
+struct ClRdpk {
+    static constexpr int pS2 = 5, pE = 6, pK1 = 7;
+    ClBand<T, CUBIC, ETA1, V>& bd;
+    cg::cluster_group& cluster;
+    const RdpkCoef& cf;
+    double (*red)[2][CL_MAX_CS];
+    double* sRed;
+    double* ctl;
+    double reltol, abstol, dtmax, ncell;
+    int max_steps;
+    int a = 2, b = 3, c = 4;
     bool k1_valid = false;
+    ClRkState s;
+    int slot = 0, total = 0;
 
-    if (!s.started) {
+    __device__ __forceinline__ ClRdpk(ClBand<T, CUBIC, ETA1, V>& bd_, cg::cluster_group& cl_, const RdpkCoef& cf_, double (*red_)[2][CL_MAX_CS],
+                                      double* sRed_, double* ctl_, double reltol_, double abstol_, double dtmax_, int max_steps_)
+        : bd(bd_), cluster(cl_), cf(cf_), red(red_), sRed(sRed_), ctl(ctl_), reltol(reltol_), abstol(abstol_), dtmax(dtmax_),
+          ncell((double)bd_.nx * (double)bd_.ny), max_steps(max_steps_) {}
+
+    // first step size: dt0 > 0 as given, else OrdinaryDiffEq's ode_determine_initdt (Hairer-Wanner); sk = abstol + |u| reltol
+    template <class Rhs>
+    __device__ __forceinline__ void start(double t0, double dt0, Rhs&& rhs) {
         s.started = 1;
-        s.t = t[j0];
+        s.t = t0;
         s.err2 = s.err3 = 1.0;
         s.steps = s.rejected = 0;
         if (dt0 > 0.0) {
             s.dt = fmin(dt0, dtmax);
-        } else {
-            // OrdinaryDiffEq's ode_determine_initdt (Hairer-Wanner); sk = abstol + |u| reltol
-            double d0 = 0.0, d1 = 0.0;
-            const T* pu = bd.pl(a);
-            bd.nodes(pu);
-            bd.cells(pu, [&](int, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
-                stv<V>(bd.pl(pK1) + o, f);
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const double sk = abstol + fabs((double)hc.v[k]) * reltol;
-                    const double r0 = (double)hc.v[k] / sk, r1 = (double)f.v[k] / sk;
-                    d0 += r0 * r0; d1 += r1 * r1;
-                }
-            });
-            cluster_sum2(cluster, d0, d1, red, sRed, slot);
-            d0 = sqrt(d0 / ncell); d1 = sqrt(d1 / ncell);
-            const double h0 = fmin((d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1, dtmax);
-            const T h0T = (T)(1.0 * h0);
-            bd.own([&](int l, size_t o) {   // Euler probe u1 = u + h0 f0
-                const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
-                Vec<T, V> x;
-#pragma unroll
-                for (int k = 0; k < V; ++k) x.v[k] = uq.v[k] + h0T * kq.v[k];
-                bd.put(b, l, o, x);
-            });
-            cluster.sync();
-            double d2 = 0.0, dz = 0.0;
-            bd.nodes(bd.pl(b));
-            bd.cells(bd.pl(b), [&](int, size_t o, const Vec<T, V>&, const Vec<T, V>& f) {
-                const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const double sk = abstol + fabs((double)uq.v[k]) * reltol;
-                    const double r = (double)(f.v[k] - kq.v[k]) / sk;
-                    d2 += r * r;
-                }
-            });
-            cluster_sum2(cluster, d2, dz, red, sRed, slot);
-            d2 = sqrt(d2 / ncell) / h0;
-            const double md = fmax(d1, d2);
-            const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 3.0);
-            s.dt = fmin(fmin(100.0 * h0, h1), dtmax);
-            k1_valid = true;
+            return;
         }
+        double d0 = 0.0, d1 = 0.0;
+        const T* pu = bd.pl(a);
+        rhs(a, t0, [&](int, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
+            stv<V>(bd.pl(pK1) + o, f);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const double sk = abstol + fabs((double)hc.v[k]) * reltol;
+                const double r0 = (double)hc.v[k] / sk, r1 = (double)f.v[k] / sk;
+                d0 += r0 * r0; d1 += r1 * r1;
+            }
+        });
+        cluster_sum2(cluster, d0, d1, red, sRed, slot);
+        d0 = sqrt(d0 / ncell); d1 = sqrt(d1 / ncell);
+        const double h0 = fmin((d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1, dtmax);
+        const T h0T = (T)(1.0 * h0);
+        bd.own([&](int l, size_t o) {   // Euler probe u1 = u + h0 f0
+            const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
+            Vec<T, V> x;
+#pragma unroll
+            for (int k = 0; k < V; ++k) x.v[k] = uq.v[k] + h0T * kq.v[k];
+            bd.put(b, l, o, x);
+        });
+        cluster.sync();
+        double d2 = 0.0, dz = 0.0;
+        rhs(b, t0 + h0, [&](int, size_t o, const Vec<T, V>&, const Vec<T, V>& f) {
+            const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const double sk = abstol + fabs((double)uq.v[k]) * reltol;
+                const double r = (double)(f.v[k] - kq.v[k]) / sk;
+                d2 += r * r;
+            }
+        });
+        cluster_sum2(cluster, d2, dz, red, sRed, slot);
+        d2 = sqrt(d2 / ncell) / h0;
+        const double md = fmax(d1, d2);
+        const double h1 = (md <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 3.0);
+        s.dt = fmin(fmin(100.0 * h0, h1), dtmax);
+        k1_valid = true;
     }
 
-    int total = 0;
-    for (int j = j0 + 1; j <= j1; ++j) {
-        s.t = t[j - 1];
-        const double tstop = t[j];
+    // the `while t < tstop` loop of integrate_rdpk3sp35: trial steps until the state (plane a) has landed on tstop
+    template <class Rhs>
+    __device__ __forceinline__ void advance(double tstop, Rhs&& rhs) {
         while (s.t < tstop) {
             if (++total > max_steps) break;
             // plan the step (rk_plan_step)
@@ -592,11 +593,10 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
             const bool last = (s.t + h >= tstop) || (tstop - (s.t + h) < 1e-14 * fmax(1.0, fabs(tstop)));
             if (last) h = tstop - s.t;
             const T* pu = bd.pl(a);
-            {   // S1 = u + (B1 h) k1 ;  est = (E1 h) k1      with k1 = f(u) (re-evaluated after an accepted step: FSAL)
+            {   // S1 = u + (B1 h) k1 ;  est = (E1 h) k1      with k1 = f(t, u) (re-evaluated after an accepted step: FSAL)
                 const T bh = (T)(cf.B[0] * h), eh = (T)(cf.E[0] * h);
                 if (!k1_valid) {
-                    bd.nodes(pu);
-                    bd.cells(pu, [&](int l, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
+                    rhs(a, s.t, [&](int l, size_t o, const Vec<T, V>& hc, const Vec<T, V>& f) {
                         Vec<T, V> x, y;
 #pragma unroll
                         for (int k = 0; k < V; ++k) { x.v[k] = hc.v[k] + bh * f.v[k]; y.v[k] = eh * f.v[k]; }
@@ -606,7 +606,7 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
                     });
                     k1_valid = true;
                 } else {
-                            bd.own([&](int l, size_t o) {
+                    bd.own([&](int l, size_t o) {
                         const Vec<T, V> uq = ldv<V>(pu + o), kq = ldv<V>(bd.pl(pK1) + o);
                         Vec<T, V> x, y;
 #pragma unroll
@@ -621,13 +621,11 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
             double acc = 0.0, accz = 0.0;
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
-                // k = f(S1);  S2 = S2in + d S1;  S1 = g1 S1 + g2 S2 + g3 u + (b h) k;  est += (e h) k       (rk_stage)
+                // k = f(t + c h, S1);  S2 = S2in + d S1;  S1 = g1 S1 + g2 S2 + g3 u + (b h) k;  est += (e h) k       (rk_stage)
                 const T g1 = (T)cf.G1[i], g2 = (T)cf.G2[i], g3 = (T)cf.G3[i], dd = (T)cf.D[i];
                 const T bh = (T)(cf.B[i + 1] * h), eh = (T)(cf.E[i + 1] * h);
                 const bool use_u = (cf.G3[i] != 0.0);
-                const T* pc = bd.pl(cur);
-                bd.nodes(pc);
-                bd.cells(pc, [&](int l, size_t o, const Vec<T, V>& s1, const Vec<T, V>& f) {
+                rhs(cur, s.t + cf.C[i + 1] * h, [&](int l, size_t o, const Vec<T, V>& s1, const Vec<T, V>& f) {
                     const Vec<T, V> uq = ldv<V>(pu + o), er = ldv<V>(bd.pl(pE) + o);
                     const Vec<T, V> s2in = (i == 0) ? uq : ldv<V>(bd.pl(pS2) + o);
                     Vec<T, V> s2, x, y;
@@ -655,7 +653,7 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
                 const int tmp = cur; cur = nxt; nxt = tmp;
             }
             cluster_sum2(cluster, acc, accz, red, sRed, slot);
-            // PID controller (rk_control): every thread of every CTA evaluates the same expression on the same bits
+            // PID controller (rk_control): thread 0 of every CTA evaluates the same expression on the same bits
             if (threadIdx.x == 0) {
                 const double EEst = sqrt(acc / ncell);
                 const double e1 = 1.0 / fmax(EEst, 1e-300);
@@ -686,10 +684,42 @@ sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin
                 if (b == a || c == a) { b = (a == 2) ? 3 : 2; c = 9 - a - b; }
             }
         }
-        bd.store(a, snap ? snap + (long long)j * plane_stride : nullptr, j == j1 ? Hout : nullptr);
     }
-    if (total > max_steps) s.started = -1;   // maxiters: reported by the launcher
-    if (cluster.block_rank() == 0 && threadIdx.x == 0) states[g] = s;
+};
+
+template <typename T, bool CUBIC, bool ETA1, int V>
+__global__ void __launch_bounds__(CL_NT, 1)
+sia2d_rdpk_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Hin, const T* __restrict__ Bg, T* __restrict__ Hout,
+                   T* __restrict__ snap, long long plane_stride, const double* __restrict__ t, int j0, int j1, ClRkState* __restrict__ states,
+                   double reltol, double abstol, double dtmax, double dt0, int max_steps, RdpkCoef cf, PhysDev<T> ph) {
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    __shared__ double red[2][2][CL_MAX_CS];
+    __shared__ double sRed[2 * CL_NT / 32];
+    __shared__ double ctl[4];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x / cluster.num_blocks();
+    ClBand<T, CUBIC, ETA1, V> bd;
+    bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_RDPK);
+    ClRdpk<T, CUBIC, ETA1, V> rk(bd, cluster, cf, red, sRed, ctl, reltol, abstol, dtmax, max_steps);
+    bd.load(0, Bg);
+    bd.load(rk.a, Hin);
+    cluster.sync();
+
+    // dH/dt = SIA2D(H): autonomous
+    auto rhs = [&](int plane, double, auto&& ep) {
+        const T* pc = bd.pl(plane);
+        bd.nodes(pc);
+        bd.cells(pc, ep);
+    };
+    rk.s = states[g];
+    if (!rk.s.started) rk.start(t[j0], dt0, rhs);
+    for (int j = j0 + 1; j <= j1; ++j) {
+        rk.s.t = t[j - 1];
+        rk.advance(t[j], rhs);
+        bd.store(rk.a, snap ? snap + (long long)j * plane_stride : nullptr, j == j1 ? Hout : nullptr);
+    }
+    if (rk.total > max_steps) rk.s.started = -1;   // maxiters: reported by the launcher
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) states[g] = rk.s;
 }
 
 // -------------------------------------------------------------------------------------------------------------------------
@@ -751,6 +781,123 @@ sia2d_reverse_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ 
     if (cluster.block_rank() == 0 && threadIdx.x == 0) {
         loss_acc[g] += acc_loss;
         S_acc[g] += acc_S;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+// ContinuousAdjoint gradient with the reference's default reverse solve (gradient.jl:276-538, AdjointTypes.jl:53-66), one
+// cluster per glacier, ONE launch: the reverse ODE  d(lambda)/d(tau) = (dSIA/dH)^T lambda  at  H_itp(-tau)  (linear interpolant of
+// the forward snapshots) integrated with adaptive RDPK3Sp35 in tau = -t over the sorted union of the tstops and the Gauss-Legendre
+// nodes; at a tstop the loss jump  lambda += dl_j/dH, loss += w_j l_j  (Losses.jl:270-291); at a quadrature node
+// dL/dtheta-scalar += w_m sum gA D+(lambda, H_itp(t_m))  (gradient.jl:495-507).  LossH, glacier-wide A, discrete VJP flavour, no
+// mass-balance callback (the host-driven engine of rdpk.cu covers the rest).  tab = t[n_t] | wH[n_t] | ev_tau[n_ev] | ev_code[n_ev]
+// | qn[n_q] | qw[n_q];  ev_code = idx (+ 2^20 for a quadrature node).
+// -------------------------------------------------------------------------------------------------------------------------
+template <typename T, bool CUBIC, bool ETA1, int V>
+__global__ void __launch_bounds__(CL_NT, 1)
+sia2d_contadj_cluster(const GDesc<T>* __restrict__ descs, const T* __restrict__ Bg, T* __restrict__ lam_out, const T* __restrict__ snap,
+                      const T* __restrict__ href, const T* __restrict__ wmask, long long plane_stride, const double* __restrict__ tab,
+                      int n_t, int n_ev, int n_q, double reltol, double abstol, double dtmax, int max_steps, double* __restrict__ loss_acc,
+                      double* __restrict__ S_acc, int* __restrict__ steps_out, RdpkCoef cf, PhysDev<T> ph) {
+    extern __shared__ __align__(16) unsigned char cl_smem_raw[];
+    __shared__ double red[2][2][CL_MAX_CS];
+    __shared__ double sRed[2 * CL_NT / 32];
+    __shared__ double ctl[4];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g = blockIdx.x / cluster.num_blocks();
+    ClBand<T, CUBIC, ETA1, V> bd;
+    bd.init(cluster, descs[g], ph, cl_smem_raw, CL_PLANES_CA);
+    bd.pAdj = 8;
+    ClRdpk<T, CUBIC, ETA1, V> rk(bd, cluster, cf, red, sRed, ctl, reltol, abstol, dtmax, max_steps);
+    const double* t = tab;
+    const double* wH = tab + n_t;
+    const double* ev_tau = wH + n_t;
+    const double* ev_code = ev_tau + n_ev;
+    const double* qn = ev_code + n_ev;
+    const double* qw = qn + n_q;
+    int pHa = 11, pHb = 12;
+    constexpr int pHt = 13;
+    int jint = n_t - 2;   // the reverse solve is inside [t_jint, t_jint+1]: planes H_a = H(t_jint), H_b = H(t_jint+1)
+    bd.load(0, Bg);
+    bd.load(pHa, snap + (long long)jint * plane_stride);
+    bd.load(pHb, snap + (long long)(jint + 1) * plane_stride);
+    cluster.sync();
+
+    double acc_loss = 0.0, acc_S = 0.0, dummy = 0.0;
+    // H_t = (1 - a) H_a + a H_b on the band and its halo rows (rk_lerp)
+    auto lerp_to = [&](double tt) {
+        const T a1 = (T)((tt - t[jint]) / (t[jint + 1] - t[jint])), a0 = T(1) - a1;
+        const T* Ha = bd.pl(pHa);
+        const T* Hb = bd.pl(pHb);
+        T* Ht = bd.pl(pHt);
+        const int nq = (int)(((size_t)(bd.Rown + 2) * bd.P) >> 2);
+        for (int q = threadIdx.x; q < nq; q += CL_NT) {
+            const Vec<T, 4> x = ldv<4>(Ha + 4 * (size_t)q), y = ldv<4>(Hb + 4 * (size_t)q);
+            Vec<T, 4> z;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z.v[k] = a0 * x.v[k] + a1 * y.v[k];
+            stv<4>(Ht + 4 * (size_t)q, z);
+        }
+        __syncthreads();
+    };
+    auto rhs = [&](int plane, double tau, auto&& ep) {
+        lerp_to(-tau);
+        const T* pc = bd.pl(plane);
+        const T* Ht = bd.pl(pHt);
+        bd.template adj_nodes<0>(pc, Ht, dummy, 0.0);
+        bd.adj_cells(pc, Ht, [&](int l, size_t o, int, const Vec<T, V>& lc, const Vec<T, V>&, const Vec<T, V>& v) { ep(l, o, lc, v); });
+    };
+    // effect_loss! at tstop j on the state plane (thickness term): lambda += 2 w_j W (H_j - H_ref,j), loss += w_j sum W (H_j - H_ref,j)^2
+    auto loss_jump = [&](int j, int pHj) {
+        const double w = wH[j];
+        if (w == 0.0) return;
+        const T cseed = (T)(2.0 * w);
+        const long long pj = (long long)j * plane_stride;
+        const T* Hj = bd.pl(pHj);
+        const T* lam = bd.pl(rk.a);
+        bd.own([&](int l, size_t o) {
+            const int i0 = (int)(o - (size_t)l * bd.P) - CL_PAD;
+            const long long go = bd.goff + (long long)(bd.row0 + l - 1) * bd.gld + i0;
+            const Vec<T, V> hr = ldv<V>(href + pj + go), wm = ldv<V>(wmask + pj + go), hq = ldv<V>(Hj + o), lq = ldv<V>(lam + o);
+            Vec<T, V> x;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const T d = hq.v[k] - hr.v[k], wd = wm.v[k] * d;
+                acc_loss += w * ((double)wd * (double)d);
+                x.v[k] = lq.v[k] + cseed * wd;
+            }
+            bd.put(rk.a, l, o, x);
+        });
+        cluster.sync();
+        rk.k1_valid = false;
+    };
+
+    loss_jump(n_t - 1, pHb);                 // lambda(t_end) = dl/dH(t_end)   (gradient.jl:407-446)
+    rk.start(ev_tau[0], 0.0, rhs);
+    for (int i = 1; i < n_ev; ++i) {
+        rk.s.t = ev_tau[i - 1];
+        rk.advance(ev_tau[i], rhs);
+        const int code = (int)ev_code[i], idx = code & ((1 << 20) - 1);
+        if (code < (1 << 20)) {              // tstop idx: the loss jump; the solve continues in [t_{idx-1}, t_idx]
+            loss_jump(idx, pHa);
+            if (idx >= 1) {
+                jint = idx - 1;
+                const int tmp = pHa; pHa = pHb; pHb = tmp;   // H(t_idx) becomes the upper snapshot
+                __syncthreads();
+                bd.load(pHa, snap + (long long)jint * plane_stride);
+                __syncthreads();
+            }
+        } else {                             // quadrature node idx
+            lerp_to(qn[idx]);
+            bd.template adj_nodes<1>(bd.pl(rk.a), bd.pl(pHt), acc_S, qw[idx]);
+        }
+    }
+    bd.store(rk.a, lam_out, nullptr);
+    cluster_sum2(cluster, acc_loss, acc_S, red, sRed, rk.slot);
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+        loss_acc[g] += acc_loss;
+        S_acc[g] += acc_S;
+        steps_out[g] = rk.total > max_steps ? -1 : rk.s.steps;
     }
 }
 

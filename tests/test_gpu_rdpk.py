@@ -87,7 +87,8 @@ def test_forward_rdpk3sp35_matches_oracle(ob, dtype, with_mb, cluster):
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("vjp", ["discrete", "continuous"])
-def test_adaptive_continuous_adjoint_matches_oracle(ob, dtype, vjp):
+@pytest.mark.parametrize("cluster", [0, -1, 4])   # 0: host-driven engine; -1 / 4: the cluster-resident reverse solve (discrete flavour only)
+def test_adaptive_continuous_adjoint_matches_oracle(ob, dtype, vjp, cluster):
     """ContinuousAdjoint with the reference's default reverse solve (adaptive RDPK3Sp35, reltol = abstol = 1e-8, dtmax = 1/12)."""
     gl = [o.rough_bed_glacier(30, 31), o.rough_bed_glacier(21, 26)]
     for g in gl:
@@ -112,7 +113,11 @@ def test_adaptive_continuous_adjoint_matches_oracle(ob, dtype, vjp):
             st = {}
             ell, dth = o.loss_and_grad_continuous_adaptive(theta, g2, tgs, t, Hs, Href, n_quadrature=9, reltol=tol, abstol=tol, vjp=vjp, stats=st)
             refs.append((ell, dth[0], tgs.vjp_theta[0], st))
+        ens.set_cluster_mode(cluster)
+        l0 = ens.launch_count
         loss, Ssum, steps = ens.grad_continuous_adaptive(t, n_quadrature=9, vjp=vjp, reltol=tol, abstol=tol)
+        if cluster != 0 and vjp == "discrete":
+            assert ens.launch_count - l0 == 1   # the whole reverse solve in one launch
         rt_l, rt_g = (1e-10, 1e-7) if dtype == "f64" else (2e-4, 5e-3)
         for k in range(len(gl)):
             assert loss[k] == pytest.approx(refs[k][0], rel=rt_l), k

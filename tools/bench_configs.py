@@ -78,6 +78,19 @@ l0 = ens.launch_count; it_ssprk3(); n_launch = ens.launch_count - l0
 report("1: 128x128 inversion iteration, SSPRK3 forward + discrete adjoint", seconds=timed(it_ssprk3), launches=int(n_launch))
 report("1: 128x128 inversion iteration, RDPK3Sp35 forward + discrete adjoint", seconds=timed(it_rdpk))
 report("1: 128x128 discrete-adjoint reverse loop alone (60 saved steps)", seconds=timed(it_adj), us_per_saved_step=1e6 * timed(it_adj) / 60)
+# the reference's DEFAULT gradient: ContinuousAdjoint, adaptive RDPK3Sp35 reverse solve, dtmax 1/12, 200 quadrature nodes (AdjointTypes.jl:53-66)
+rta = 1e-8 if dtype == "f64" else 1e-5
+res = None
+def it_cont():
+    global res
+    res = ens.grad_continuous_adaptive(t5, n_quadrature=200, reltol=rta, abstol=rta)
+s = timed(it_cont)
+report(f"1: 128x128 continuous adjoint (adaptive reverse RDPK3Sp35 rtol {rta:g}, dtmax 1/12, 200 quadrature nodes) alone", seconds=s,
+       trial_steps=int(res[2][0]), us_per_trial_step=1e6 * s / max(int(res[2][0]), 1))
+def it_default():
+    ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35"); return ens.grad_continuous_adaptive(t5, n_quadrature=200, reltol=rta, abstol=rta)
+l0 = ens.launch_count; it_default(); n_launch = ens.launch_count - l0
+report("1: 128x128 inversion iteration in the reference's DEFAULT configuration (RDPK3Sp35 forward + ContinuousAdjoint)", seconds=timed(it_default), launches=int(n_launch))
 ens.close()
 
 # config 3: 64 glaciers, sizes U{100..400}, forward Prediction run
