@@ -481,7 +481,8 @@ struct RdpkCoef { double G1[4], G2[4], G3[4], D[4], B[5], E[5], C[6]; };
 
 // per-glacier controller state carried between launches (a launch range ends at a mass-balance callback)
 struct ClRkState {
-    double t, dt, err2, err3;
+    double t, dt;
+    double lerr2, lerr3;   // PID history as LOGARITHMS of 1 / EEst of the last two accepted steps (one log + one exp per step instead of three pow)
     int steps, rejected, started, pad;
 };
 
@@ -510,6 +511,19 @@ __device__ __forceinline__ void cluster_sum2(cg::cluster_group& cluster, double&
 // The RDPK3Sp35 machinery of one cluster, shared by the forward solve and the reverse ODE of the continuous adjoint.
 // rhs(plane, time, ep): evaluate f(time, plane k) on the band and call ep(l, o, item of the plane, item of f) for every own item.
 // Planes 2, 3, 4 rotate (a = state at the start of the step, b / c = stage values, all with halo rows); 5, 6, 7 = S2, est, k1.
+// one value (the error norm of a trial step)
+__device__ __forceinline__ void cluster_sum1(cg::cluster_group& cluster, double& v0, double (*red)[2][CL_MAX_CS], double* sRed, int& slot) {
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const double s0 = block_sum(v0, sRed);
+    if (threadIdx.x == 0)
+        for (int r = 0; r < CS; ++r) cluster.map_shared_rank(red, r)[slot][0][rank] = s0;
+    cluster.sync();
+    double a0 = 0.0;
+    for (int r = 0; r < CS; ++r) a0 += red[slot][0][r];
+    v0 = a0;
+    slot ^= 1;
+}
+
 template <typename T, bool CUBIC, bool ETA1, int V>
 struct ClRdpk {
     static constexpr int pS2 = 5, pE = 6, pK1 = 7;
@@ -536,7 +550,7 @@ struct ClRdpk {
     __device__ __forceinline__ void start(double t0, double dt0, Rhs&& rhs) {
         s.started = 1;
         s.t = t0;
-        s.err2 = s.err3 = 1.0;
+        s.lerr2 = s.lerr3 = 0.0;
         s.steps = s.rejected = 0;
         if (dt0 > 0.0) {
             s.dt = fmin(dt0, dtmax);
@@ -618,7 +632,7 @@ struct ClRdpk {
                 cluster.sync();
             }
             int cur = b, nxt = c;
-            double acc = 0.0, accz = 0.0;
+            double acc = 0.0;
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {
                 // k = f(t + c h, S1);  S2 = S2in + d S1;  S1 = g1 S1 + g2 S2 + g3 u + (b h) k;  est += (e h) k       (rk_stage)
@@ -652,24 +666,25 @@ struct ClRdpk {
                 cluster.sync();
                 const int tmp = cur; cur = nxt; nxt = tmp;
             }
-            cluster_sum2(cluster, acc, accz, red, sRed, slot);
-            // PID controller (rk_control): thread 0 of every CTA evaluates the same expression on the same bits
+            cluster_sum1(cluster, acc, red, sRed, slot);
+            // PID controller (rk_control): factor = e1^(b1/3) e2^(b2/3) e3^(b3/3) with e = 1 / EEst, evaluated through the logarithms by
+            // thread 0 of every CTA on the same bits
             if (threadIdx.x == 0) {
                 const double EEst = sqrt(acc / ncell);
-                const double e1 = 1.0 / fmax(EEst, 1e-300);
-                double fac = pow(e1, 0.64 / 3.0) * pow(s.err2, -0.31 / 3.0) * pow(s.err3, 0.04 / 3.0);
+                const double l1 = -log(fmax(EEst, 1e-300));
+                double fac = exp((0.64 / 3.0) * l1 + (-0.31 / 3.0) * s.lerr2 + (0.04 / 3.0) * s.lerr3);
                 fac = 1.0 + atan(fac - 1.0);
                 ctl[0] = fac;
-                ctl[1] = e1;
+                ctl[1] = l1;
             }
             __syncthreads();
-            const double fac = ctl[0], e1 = ctl[1];
+            const double fac = ctl[0], l1 = ctl[1];
             __syncthreads();
             s.steps++;
             if (fac >= 0.81) {
                 s.t = last ? tstop : s.t + h;
-                s.err3 = s.err2;
-                s.err2 = e1;
+                s.lerr3 = s.lerr2;
+                s.lerr2 = l1;
                 s.dt = h * fac;
                 // u <- S1 (plane `cur` after the last swap); the old u plane becomes a stage plane
                 const int old_a = a;
