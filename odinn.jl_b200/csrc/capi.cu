@@ -270,6 +270,17 @@ int loss_seed_planes(odinn_ensemble* e, const void* H, const void* Href, const v
     return launch_loss_seed(e, H, Href, W, lam_in, v, lam_out, dt, cseed, loss_dst, wloss, accumulate);
 }
 int rhs_planes(odinn_ensemble* e, const void* Hin, void* out) { return launch_rhs(e, -1, Hin, out); }
+bool rhs_rk_fusable(const odinn_ensemble* e) { return e->law_kind == LAW_NONE; }
+int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm) {
+    Stage st{};
+    st.rk = rkfuse;
+    int rc = launch_rhs_range(e, -1, 0, S1in, S1out, &st, false);
+    if (rc || !norm) return rc;
+    const bool two = (e->dtype == ODINN_F32 && e->march >= 2);
+    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(two ? e->d_item2_start : e->d_item_start, e->d_partial, e->d_S, 1.0, 0);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
 int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale, int accumulate) {
     reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_tile_start, tile_partial, dst, scale, accumulate);
     ODINN_CHECK_LAUNCH(e);

@@ -31,6 +31,43 @@ struct PhysDev {
     T eta0;  // η₀
 };
 
+
+// Per-glacier controller state of the RDPK3Sp35 engine (rdpk.cu).  The fused stage epilogue of the F1 kernels reads the step h.
+struct RkState {
+    double t, tstop, dt, h, EEst;
+    double err2, err3;      // PID history: 1 / EEst of the last two accepted steps
+    double sk0, sk1;        // scratch of the initial-step algorithm (d0, d1)
+    int last, accept, done;
+    int steps, rejected;
+};
+
+// One RDPK3Sp35 (3S*+) stage fused into the epilogue of the F1 kernels (rdpk.cu): with k = SIA2D(S1) at the cell
+//   S2 = S2in + d S1 ;   S1new = g1 S1 + g2 S2 + g3 u + (b h_g) k ;   est = est + (e h_g) k
+// (RKF_FIRST: S1new = S1 + (b h_g) k, est = (e h_g) k -- the stage that starts a trial step from S1 = u), h_g the glacier's own step.
+// S1new goes to a second plane (the neighbours still read S1); S2 and est are updated in place.  RKF_NORM (last stage): the pass also
+// reduces  sum (est / (abstol + reltol max(|u|, |S1new|)))^2  per work item, so that neither the error plane nor a norm pass is needed.
+enum { RKF_FIRST = 1, RKF_U = 2, RKF_WS2 = 4, RKF_WEST = 8, RKF_NORM = 16 };
+// The combinations the scheme uses, as compile-time modes of the F1 kernels: first stage; stages without / with the g3 u term (both update
+// S2 and est in place); last stage (g3 u term, error norm, neither S2 nor est written).
+enum { RKM_NONE = 0, RKM_FIRST = 1, RKM_MID = 2, RKM_MID_U = 3, RKM_LAST = 4 };
+inline int rk_mode_of_flags(int flags) {
+    if (flags & RKF_FIRST) return RKM_FIRST;
+    if (flags & RKF_NORM) return RKM_LAST;
+    return (flags & RKF_U) ? RKM_MID_U : RKM_MID;
+}
+template <typename T>
+struct RkFuse {
+    const RkState* st;
+    const T* S2in;
+    T* S2out;
+    T* est;
+    const T* u;
+    T g1, g2, g3, d;
+    double b, e;        // multiplied by the glacier's h in double, as the elementwise stage kernels do
+    T reltol, abstol;
+    int flags;
+};
+
 __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 template <typename T>

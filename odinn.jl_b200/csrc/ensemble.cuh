@@ -180,6 +180,10 @@ int sync_descs(odinn_ensemble* e);
 // shared with the other translation units of the library (adaptive.cu, ...)
 int alloc_work_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);      // zero-filled, no-op when *p is set
 int rhs_planes(odinn_ensemble* e, const void* Hin, void* out);              // out <- SIA2D(Hin), whole ensemble, one launch
+// One RDPK3Sp35 stage fused into F1 (rdpk.cu): S1out <- stage(S1in, k = SIA2D(S1in)) with the coefficients / planes of *rkfuse (RkFuse<T>);
+// norm: the stage carries RKF_NORM -- the per-glacier sums of squares of the scaled error land in d_S.  Not for per-cell laws.
+bool rhs_rk_fusable(const odinn_ensemble* e);
+int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm);
 int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale = 1.0, int accumulate = 0);  // dst[g] = Σ tiles of g
 int prepare_snapshots(odinn_ensemble* e, int n_snap);
 // A1 (wH: out <- (dSIA/dH)^T lam) and / or A2 (wS: S_dst[g] (+)= scale * S_g; nullptr -> the handle's d_S), discrete or continuous flavour

@@ -39,6 +39,8 @@ struct Stage {
     double sa, sb, sdt;
     const double* tab = nullptr;   // graph replay: device table of stage coefficients (offset to this stage) + interval counter
     const int* interval = nullptr;
+    const void* rk = nullptr;      // RkFuse<T>*: an RDPK3Sp35 stage as the epilogue instead (U0, sa, sb, sdt unused; whole ensemble only).
+                                   // With RKF_NORM the per-item partial sums of the error norm land in d_partial (two-column items in fp32).
 };
 
 int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);

@@ -23,11 +23,26 @@ int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* 
     const int* sint = st ? st->interval : nullptr;
 #define L(CUB, AF, E1, STG) \
     sia2d_rhs_march<T, CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, T(0), 0, stab, sint)
-#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
+#define LRKM(CUB, AF, E1, M)                                                                                                          \
+    sia2d_rhs_march<T, CUB, AF, E1, false, false, M><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, nullptr, T(0),    \
+                                                                                    T(0), T(0), T(0), 0, nullptr, nullptr,                     \
+                                                                                    *(const RkFuse<T>*)st->rk, e->d_partial + i0)
+#define LRK(CUB, AF, E1)                                                  \
+    do {                                                                  \
+        switch (rk_mode_of_flags(((const RkFuse<T>*)st->rk)->flags)) {    \
+            case RKM_FIRST: LRKM(CUB, AF, E1, RKM_FIRST); break;          \
+            case RKM_MID: LRKM(CUB, AF, E1, RKM_MID); break;              \
+            case RKM_MID_U: LRKM(CUB, AF, E1, RKM_MID_U); break;          \
+            default: LRKM(CUB, AF, E1, RKM_LAST); break;                  \
+        }                                                                 \
+    } while (0)
+#define L3(CUB, AF, E1) do { if (st && st->rk) LRK(CUB, AF, E1); else if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
 #define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
     ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
+#undef LRK
+#undef LRKM
 #undef L
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;

@@ -156,11 +156,25 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
     dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
 #define L(CUB, AF, E1, STG) \
     sia2d_rhs_march2<CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, stab, sint)
-#define L3(CUB, AF, E1) do { if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
+#define LRKM(CUB, AF, E1, M)                                                                                                   \
+    sia2d_rhs_march2<CUB, AF, E1, false, M><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, nullptr, 0.f, 0.f, 0.f, \
+                                                                           nullptr, nullptr, *(const RkFuse<float>*)st->rk, e->d_partial)
+#define LRK(CUB, AF, E1)                                                      \
+    do {                                                                      \
+        switch (rk_mode_of_flags(((const RkFuse<float>*)st->rk)->flags)) {    \
+            case RKM_FIRST: LRKM(CUB, AF, E1, RKM_FIRST); break;              \
+            case RKM_MID: LRKM(CUB, AF, E1, RKM_MID); break;                  \
+            case RKM_MID_U: LRKM(CUB, AF, E1, RKM_MID_U); break;              \
+            default: LRKM(CUB, AF, E1, RKM_LAST); break;                      \
+        }                                                                     \
+    } while (0)
+#define L3(CUB, AF, E1) do { if (st && st->rk) LRK(CUB, AF, E1); else if (st) L(CUB, AF, E1, true); else L(CUB, AF, E1, false); } while (0)
 #define L2(CUB, AF) ODINN_ETA(L3, CUB, AF)
     ODINN_DISPATCH(L2);
 #undef L2
 #undef L3
+#undef LRK
+#undef LRKM
 #undef L
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;

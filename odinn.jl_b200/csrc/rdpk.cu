@@ -15,6 +15,7 @@
 // elementwise kernels read their glacier's step, one controller thread per glacier accepts / rejects and plans the next step, and the
 // host reads back two integers per trial step.  Low-storage registers: S1 (stage value), S2, the step's start state u, the error
 // accumulator -- plus the stage slope k and the FSAL pair (k1, k_new): 6 work planes besides the state.
+#include <cstdlib>
 #include <vector>
 
 #include "ensemble.cuh"
@@ -69,13 +70,7 @@ void rdpk_host_coefficients(double G1[4], double G2[4], double G3[4], double D[4
     rdpk_error_weights(E);
 }
 
-struct RkState {
-    double t, tstop, dt, h, EEst;
-    double err2, err3;      // PID history: 1 / EEst of the last two accepted steps
-    double sk0, sk1;        // scratch of the initial-step algorithm (d0, d1)
-    int last, accept, done;
-    int steps, rejected;
-};
+// (RkState: common.cuh)
 
 __device__ __forceinline__ void rk_plan_step(RkState& s, double dtmax) {
     double h = fmin(fmin(s.dt, dtmax), s.tstop - s.t);
@@ -295,7 +290,7 @@ __global__ void rk_control(RkState* st, const double* __restrict__ sumsq, const 
     st[g] = s;
 }
 
-// accepted glaciers: u <- S1, k1 <- knew
+// accepted glaciers: u <- S1, k1 <- knew   (k1 == nullptr: the fused engine keeps no FSAL slope)
 template <typename T>
 __global__ void __launch_bounds__(RK_NT)
 rk_commit(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, T* __restrict__ u, const T* __restrict__ S1,
@@ -307,7 +302,7 @@ rk_commit(const GDesc<T>* __restrict__ descs, const RkState* __restrict__ st, T*
         const long long q = v0 + (long long)w * RK_NT;
         if (q < nvec) {
             reinterpret_cast<V*>(u)[base + q] = RK_LD(S1, q);
-            reinterpret_cast<V*>(k1)[base + q] = RK_LD(knew, q);
+            if (k1) reinterpret_cast<V*>(k1)[base + q] = RK_LD(knew, q);
         }
     }
 }
@@ -427,15 +422,22 @@ static int rk_norm(RkCtx<T>& c, const T* a, const T* b, const T* u, const T* v, 
     return ODINN_OK;
 }
 
+// fused (autonomous forward solve, rhs_rk_fusable): every stage update -- and the error norm in the last one -- is the epilogue of the F1
+// launch that evaluates the stage slope (rhs_planes_rk).  S1 ping-pongs between the planes c.S1 and c.k (the stencil's
+// neighbours still read the old stage value); S2 and est are updated in place; no slope plane is ever written, so there is no FSAL
+// slope either: the step starts with F1(u), which costs what the k_new evaluation of the unfused form costs.  Per trial step
+// 5 launches of 4, 7, 7, 8, 7 words per cell instead of 5 x 3 + 4 + 4 x 7.5 + 3 = 52.
 template <typename T, typename Rhs, typename OnStop>
 static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, double reltol, double abstol, double dtmax, double dt0,
-                        int max_steps, Rhs rhs, OnStop on_stop) {
+                        int max_steps, Rhs rhs, OnStop on_stop, bool fused = false) {
     odinn_ensemble* e = c.e;
     int rc;
     const int G = e->G;
+    double Ew[5];
+    rdpk_error_weights(Ew);
     rk_reset<<<c.gb, 128, 0, e->stream>>>(c.st, G, stops[0]);
     ODINN_CHECK_LAUNCH(e);
-    if ((rc = rhs(u, c.k1, 0.0))) return rc;  // FSAL seed f(t0, u0)
+    if (!(fused && dt0 > 0.0) && (rc = rhs(u, c.k1, 0.0))) return rc;  // FSAL seed f(t0, u0) (fused: only the initial-step algorithm needs it)
     if (dt0 > 0.0) {
         rk_set_dt<<<c.gb, 128, 0, e->stream>>>(c.st, G, std::min(dt0, dtmax));
         ODINN_CHECK_LAUNCH(e);
@@ -459,6 +461,28 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
         ODINN_CHECK_LAUNCH(e);
         for (;;) {
             if (++total > max_steps) return fail(e, ODINN_ESTATE, "rdpk3sp35: too many steps (maxiters)");
+            if (fused) {
+                RkFuse<T> f{};
+                f.st = c.st;
+                f.est = c.est;
+                f.u = u;
+                f.reltol = (T)reltol;
+                f.abstol = (T)abstol;
+                f.b = h_B[0];
+                f.e = Ew[0];
+                f.flags = RKF_FIRST | RKF_WEST;
+                if ((rc = rhs_planes_rk(e, u, c.S1, &f, false))) return rc;
+                for (int s = 0; s < 4; ++s) {
+                    f.S2in = s == 0 ? u : c.S2;
+                    f.S2out = c.S2;
+                    f.g1 = (T)h_G1[s]; f.g2 = (T)h_G2[s]; f.g3 = (T)h_G3[s]; f.d = (T)h_D[s];
+                    f.b = h_B[s + 1];
+                    f.e = Ew[s + 1];
+                    f.flags = (h_G3[s] != 0.0 ? RKF_U : 0) | (s < 3 ? (RKF_WS2 | RKF_WEST) : RKF_NORM);
+                    if ((rc = rhs_planes_rk(e, c.S1, c.k, &f, s == 3))) return rc;
+                    std::swap(c.S1, c.k);   // (four swaps: the new state ends in the plane the step started with as c.S1)
+                }
+            } else {
             rk_stage1_main<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.k1, c.S1, c.est);
             ODINN_CHECK_LAUNCH(e);
             for (int s = 0; s < 4; ++s) {
@@ -469,6 +493,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
             }
             if ((rc = rhs(c.S1, c.knew, 1.0))) return rc;
             if ((rc = rk_norm<T>(c, c.est, nullptr, u, c.S1, reltol, abstol))) return rc;
+            }
             ODINN_CUDA(e, cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(int), e->stream));
             rk_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, c.d_counters, dtmax);
             ODINN_CHECK_LAUNCH(e);
@@ -478,14 +503,14 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
                 std::swap(u, c.S1);
                 std::swap(c.k1, c.knew);
             } else {
-                rk_commit<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.S1, c.k1, c.knew);
+                rk_commit<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.S1, fused ? (T*)nullptr : c.k1, c.knew);
                 ODINN_CHECK_LAUNCH(e);
             }
             if (e->h_ad_active[0] == 0) break;
         }
         bool modified = false;
         if ((rc = on_stop((int)i, u, &modified))) return rc;
-        if (modified && (rc = rhs(u, c.k1, 0.0))) return rc;  // u_modified: the FSAL slope is re-evaluated (h = 0 at a stop)
+        if (modified && !fused && (rc = rhs(u, c.k1, 0.0))) return rc;  // u_modified: the FSAL slope is re-evaluated (h = 0 at a stop)
     }
     return ODINN_OK;
 }
@@ -512,7 +537,9 @@ static int solve_rdpk_t(odinn_ensemble* e, int n_snap, const double* t, double r
         ODINN_CUDA(e, cudaMemcpyAsync(snapshot_ptr(e, j), state, pbytes, cudaMemcpyDeviceToDevice, e->stream));
         return ODINN_OK;
     };
-    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop))) return rc;
+    static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
+    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop, rhs_rk_fusable(e) && !no_fuse)))
+        return rc;
     if ((void*)u != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H (the planes rotate through pointer swaps)
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], u, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     if (steps_out || rejected_out) {

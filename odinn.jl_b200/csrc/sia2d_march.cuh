@@ -139,12 +139,52 @@ __device__ __forceinline__ void subgrad(double dC, double e, double lo, double u
 // STAGE fuses a low-storage Runge-Kutta stage into the epilogue:  out = sa·U0 + sb·(H + sdt·SIA2D(H))
 // (removes the separate axpy passes of the time loop: 4 words/cell instead of 3 + 4).
 // DFIELD (with AFIELD): the node plane holds the diffusivity D itself (per-cell laws, sia2d_law.cuh) instead of A.
-template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false>
+// RK > 0: an RDPK3Sp35 stage as the epilogue (RkFuse, common.cuh; compile-time mode RKM_*) instead of the two-register stage of STAGE.
+// Straight-line: every lane loads and computes (clamped column index), only the stores and the norm accumulation are predicated.
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false, int RK = 0>
 struct RhsMarch {
     static constexpr int PF = ODINN_PF_RHS;
+    static constexpr bool RK_FIRST = RK == RKM_FIRST, RK_U = RK == RKM_MID_U || RK == RKM_LAST, RK_WR = RK == RKM_MID || RK == RKM_MID_U,
+                          RK_NORM = RK == RKM_LAST;
     // per-warp / per-lane constants
     const T *hp, *bp, *ap, *up;
     T* op;
+    // RK: the stage's planes (one element offset `oo` of the output row serves them all), the glacier's (b h, e h), the operands of
+    // the output row and of the next one (loaded one step ahead), the error-norm accumulator
+    RkFuse<T> rk;
+    long long oo;
+    T rbh, reh, r_s2, r_e, r_u, n_s2, n_e, n_u;
+    double nacc;
+
+    // operation order of rk_stage / rk_stage1_main in rdpk.cu; k = SIA2D(S1) at the cell
+    __device__ __forceinline__ void rk_epilogue(T k) {
+        const T s1 = hraw;
+        T s1n, er;
+        if (RK_FIRST) {
+            s1n = s1 + rbh * k;
+            er = reh * k;
+        } else {
+            const T s2 = r_s2 + rk.d * s1;
+            T v = rk.g1 * s1 + rk.g2 * s2;
+            if (RK_U) v = v + rk.g3 * r_u;
+            s1n = v + rbh * k;
+            er = r_e + reh * k;
+            if (RK_WR) { if (store_lane) rk.S2out[oo] = s2; }
+        }
+        if (store_lane) *op = s1n;
+        if (RK_FIRST || RK_WR) { if (store_lane) rk.est[oo] = er; }
+        if (RK_NORM) {
+            // er / den through a float-seeded reciprocal + two Newton steps (relative error ~1e-16; a true DDIV with its slow path made
+            // this launch 1.03 ms against 0.67 ms for the other stages at the bench workload); den >= abstol > 0 is far inside the float range
+            const double m = fmax(fabs((double)r_u), fabs((double)s1n));
+            const double den = (double)rk.abstol + (double)rk.reltol * m;
+            double x = (double)__frcp_rn((float)den);
+            x = fma(x, fma(-den, x, 1.0), x);
+            x = fma(x, fma(-den, x, 1.0), x);
+            const double r = (double)er * x;
+            nacc += store_lane ? r * r : 0.0;
+        }
+    }
     int ld, nym1, ny2;
     T eta0, hdx, hdy, kx, ky, A;  // kx, ky are zeroed on border columns
     T sa, sb, sdt, hraw;
@@ -174,10 +214,20 @@ struct RhsMarch {
                 prefetch_l2_row(hp + (long long)ODINN_L2PF_ROWS1 * ld);
                 prefetch_l2_row(bp + (long long)ODINN_L2PF_ROWS1 * ld);
                 if (STAGE) prefetch_l2_row(up + (long long)ODINN_L2PF_ROWS1 * ld);  // U0 has no register queue (see sia2d_rhs_march2)
+                if (RK) {   // (rows ahead of the OUTPUT row here: the epilogue planes are read PF + 1 rows behind the input rows)
+                    const long long oa = oo + (long long)(ODINN_L2PF_ROWS1 + PF + 1) * ld;
+                    if (!RK_FIRST) { prefetch_l2_row(rk.S2in + oa); prefetch_l2_row(rk.est + oa); }
+                    if (RK_U && rk.u != rk.S2in) prefetch_l2_row(rk.u + oa);
+                }
             }
         }
         T u0 = T(0);
         if (STAGE && OUT) { if (store_lane) u0 = __ldg(up); }
+        if (RK) {   // operands of the NEXT output row (plain loads: S2 and est are rewritten in place by their owner)
+            const long long on = oo + (MASKED ? ((row + 1 <= nym1) ? ld : 0) : ld);
+            if (!RK_FIRST) { r_s2 = n_s2; r_e = n_e; n_s2 = rk.S2in[on]; n_e = rk.est[on]; }
+            if (RK_U) { r_u = n_u; n_u = rk.u[on]; }
+        }
         const T hraw1 = h1;
         h1 = fmx(h1, T(0));                // adjoint.jl:52
         b1 = surf_store<T>(b1, h1);
@@ -209,20 +259,23 @@ struct RhsMarch {
             T outv = kx * (Fx - FxW) + ky * (Fy1 - Fy);
             if (MASKED) { if (row < 1 || row >= nym1) outv = T(0); }
             if (STAGE) outv = sa * u0 + sb * (hraw + sdt * outv);
-            if (store_lane) *op = outv;
+            if (RK) rk_epilogue(outv);
+            else if (store_lane) *op = outv;
         }
         op += ld;
         if (STAGE) { up += ld; hraw = hraw1; }
+        if (RK) { oo += ld; hraw = hraw1; }
         h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; Dp = D1; Fy = Fy1;
     }
 };
 
-template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false>
+template <typename T, bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, bool DFIELD = false, int RK = 0>
 __global__ void __launch_bounds__(MARCH_WARPS * 32)
 sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af, T* dH,
                 PhysDev<T> ph, const T* U0, T sa, T sb, T sdt, T A_ovr = T(0), int use_A_ovr = 0,
-                const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr) {
+                const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr,
+                RkFuse<T> rkf = RkFuse<T>(), double* __restrict__ partial = nullptr) {
     // Replayed from a CUDA graph (odinn_solve_forward): the stage coefficients of interval *interval come from a device table
     // (9 doubles per interval, stage_tab already offset to this launch's stage), so one captured graph serves every interval.
     if (STAGE && stage_tab != nullptr) {
@@ -237,7 +290,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    RhsMarch<T, CUBIC, AFIELD, ETA1, STAGE, DFIELD> m;
+    RhsMarch<T, CUBIC, AFIELD, ETA1, STAGE, DFIELD, RK> m;
     constexpr int PF = ODINN_PF_RHS;
     m.ph = ph;
     m.ld = d.ld;
@@ -260,6 +313,15 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.sb = sb;
     m.sdt = sdt;
     m.hraw = T(0);
+    if (RK) {
+        m.rk = rkf;
+        const double hh = rkf.st[it.x].h;
+        m.rbh = (T)(rkf.b * hh);
+        m.reh = (T)(rkf.e * hh);
+        m.oo = d.off + ic + (long long)(r0 - 1) * d.ld;
+        m.r_s2 = m.r_e = m.r_u = m.n_s2 = m.n_e = m.n_u = T(0);
+        m.nacc = 0.0;
+    }
 
     // ---- cell row r0-1 (rows outside the grid are clamped: they only feed masked quantities) ----
     m.h = fmx(__ldg(m.hp), T(0));
@@ -288,6 +350,14 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 #pragma unroll 4
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
+    if (RK) {
+        if (RK == RKM_LAST) {   // (only storing lanes accumulated)
+            double a = m.nacc;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+            if (lane == 0) partial[item] = a;
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------

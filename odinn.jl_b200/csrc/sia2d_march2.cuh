@@ -44,6 +44,7 @@ __device__ __forceinline__ const float* prefetch_lane_ptr(int lane, int col0, in
     const int pl = lane / 9, sec = lane - 9 * pl;
     if (pl >= NPLANES) return nullptr;
     const float* base = pl == 0 ? p0 : (pl == 1 ? p1 : p2);
+    if (base == nullptr) return nullptr;
     return base + off + min(max(col0 + 8 * sec, 0), cmax);
 }
 
@@ -113,12 +114,28 @@ __device__ __forceinline__ void ring_steps(M& m, int row) {
 // --------------------------------------------------------------------------------------------
 // F1 (see RhsMarch for the step structure; every quantity is a pair of adjacent columns)
 // --------------------------------------------------------------------------------------------
-template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
+// RK > 0: an RDPK3Sp35 stage as the epilogue (RkFuse, common.cuh) instead of the two-register stage of STAGE; the stage's shape is a
+// compile-time mode (RKM_*, common.cuh) so that the epilogue is straight-line code: every lane loads and computes (the clamped pair
+// index keeps the addresses inside the grid), only the stores and the norm accumulation are predicated.
+template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, int RK = 0>
 struct RhsMarch2 {
+    static constexpr bool RK_FIRST = RK == RKM_FIRST, RK_U = RK == RKM_MID_U || RK == RKM_LAST, RK_WR = RK == RKM_MID || RK == RKM_MID_U,
+                          RK_NORM = RK == RKM_LAST;
     static constexpr int PF = ODINN_PF2_RHS;
     const float *hp, *bp, *ap, *up;
     const float* pfp;  // this lane's L2-prefetch sector (prefetch_lane_ptr), ODINN_L2PF_ROWS rows ahead of hp
     float* op;
+    // RK: plane bases (warp-uniform; every plane shares the layout, so one element offset `oo` of the output row serves them all),
+    // the glacier's (b h, e h), the operands of the output row (loaded at the top of the step) and the error-norm accumulator
+    RkFuse<float> rk;
+    const float* outb;
+    const float* pfp2;  // second L2-prefetch sector pointer: est and u planes
+    int oo;
+    float rbh, reh;
+    f2 r_s2, r_e, r_u, nacc;       // operands of the output row
+    f2 nw;                         // 1 on the columns this lane owns (error-norm weights)
+    f2 n_s2, n_e, n_u;             // ... of the next output row (loaded one step ahead: they have no deeper register queue)
+    bool pf2_lane;
     int ld, nym1, ny2;
     float eta0;
     f2 hdx, hdy, kx, ky, A;  // kx, ky are zeroed on border / out-of-grid columns
@@ -163,6 +180,27 @@ struct RhsMarch2 {
             if (store_pair) u0 = ldg2(up);
             if (store_x) u0.x = __ldg(up);
         }
+        if (RK) {
+            if (ODINN_L2PF_ROWS > 0) {
+                if (MASKED) {
+                    pfp2 += (row + 1 + PF <= nym1) ? ld : 0;
+                } else {
+                    pfp2 += ld;
+                    if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1 && pf2_lane) prefetch_l2(pfp2);
+                }
+            }
+            // operands of the NEXT output row (plain loads: S2 and est are rewritten in place by their owner; a row past the chunk
+            // belongs to another warp and is never used; odd nx: the straddling pair reads the zero padding element)
+            {
+                const int on = oo + (MASKED ? ((row + 1 <= nym1) ? ld : 0) : ld);
+                if (!RK_FIRST) {
+                    r_s2 = n_s2; r_e = n_e;
+                    n_s2 = *reinterpret_cast<const float2*>(rk.S2in + on);
+                    n_e = *reinterpret_cast<const float2*>(rk.est + on);
+                }
+                if (RK_U) { r_u = n_u; n_u = *reinterpret_cast<const float2*>(rk.u + on); }
+            }
+        }
         f2 Anode = A;
         if (AFIELD) {
             Anode = ldg2(ap);
@@ -170,6 +208,39 @@ struct RhsMarch2 {
         }
         compute<OUT, MASKED>(row, h1, b1, u0, Anode);
         if (STAGE) up += ld;
+        if (RK) oo += ld;
+    }
+
+    // RDPK3Sp35 stage on the output row (operation order of rk_stage / rk_stage1_main in rdpk.cu); k = SIA2D(S1) of the pair.
+    __device__ __forceinline__ void rk_epilogue(f2 k) {
+        const f2 s1 = hraw;
+        f2 s1n, er;
+        if (RK_FIRST) {
+            s1n = mk2(fmaf(rbh, k.x, s1.x), fmaf(rbh, k.y, s1.y));
+            er = mk2(reh * k.x, reh * k.y);
+        } else {
+            const f2 s2 = mk2(fmaf(rk.d, s1.x, r_s2.x), fmaf(rk.d, s1.y, r_s2.y));
+            f2 v = mk2(fmaf(rk.g2, s2.x, rk.g1 * s1.x), fmaf(rk.g2, s2.y, rk.g1 * s1.y));
+            if (RK_U) v = mk2(fmaf(rk.g3, r_u.x, v.x), fmaf(rk.g3, r_u.y, v.y));
+            s1n = mk2(fmaf(rbh, k.x, v.x), fmaf(rbh, k.y, v.y));
+            er = mk2(fmaf(reh, k.x, r_e.x), fmaf(reh, k.y, r_e.y));
+            if (RK_WR) {
+                if (store_pair) *reinterpret_cast<float2*>(rk.S2out + oo) = s2;
+                if (store_x) rk.S2out[oo] = s2.x;
+            }
+        }
+        if (store_pair) *reinterpret_cast<float2*>(op) = s1n;
+        if (store_x) *op = s1n.x;
+        if (RK_FIRST || RK_WR) {
+            if (store_pair) *reinterpret_cast<float2*>(rk.est + oo) = er;
+            if (store_x) rk.est[oo] = er.x;
+        }
+        if (RK_NORM) {
+            const float rx = __fdividef(er.x, fmaf(rk.reltol, fmaxf(fabsf(r_u.x), fabsf(s1n.x)), rk.abstol));
+            const float ry = __fdividef(er.y, fmaf(rk.reltol, fmaxf(fabsf(r_u.y), fabsf(s1n.y)), rk.abstol));
+            nacc.x = fmaf(nw.x * rx, rx, nacc.x);
+            nacc.y = fmaf(nw.y * ry, ry, nacc.y);
+        }
     }
 
     // One marching step given the cell row `row+1` (h1, b1), the stage operand u0 and the node coefficient A of node
@@ -197,21 +268,26 @@ struct RhsMarch2 {
             f2 outv = fma2(ky, sub2(Fy1, Fy), mul2(kx, sub2(Fx, FxW)));
             if (MASKED) { if (row < 1 || row >= nym1) outv = bc2(0.0f); }
             if (STAGE) outv = fma2(sb, fma2(sdt, outv, hraw), mul2(sa, u0));
-            if (store_pair) *reinterpret_cast<float2*>(op) = outv;
-            if (store_x) *op = outv.x;  // (exclusive with store_pair: the pair straddling the last column, odd nx)
+            if (RK) {
+                rk_epilogue(outv);
+            } else {
+                if (store_pair) *reinterpret_cast<float2*>(op) = outv;
+                if (store_x) *op = outv.x;  // (exclusive with store_pair: the pair straddling the last column, odd nx)
+            }
         }
         op += ld;
-        if (STAGE) hraw = hraw1;
+        if (STAGE || RK) hraw = hraw1;
         h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; Dp = D1; Fy = Fy1;
     }
 };
 
-template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE>
-__global__ void __launch_bounds__(MARCH2_WARPS * 32)
+template <bool CUBIC, bool AFIELD, bool ETA1, bool STAGE, int RK = 0>
+__global__ void __launch_bounds__(MARCH2_WARPS * 32, RK == RKM_LAST ? 4 : 0)   // (the last RDPK stage would take 148 registers: 3 CTAs / SM)
 sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                  const float* __restrict__ H, const float* __restrict__ B, const float* __restrict__ Af, float* dH,
                  PhysDev<float> ph, const float* U0, float sa, float sb, float sdt,
-                 const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr) {
+                 const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr,
+                 RkFuse<float> rkf = RkFuse<float>(), double* __restrict__ partial = nullptr) {
     if (STAGE && stage_tab != nullptr) {  // graph replay: stage coefficients from the device table (see sia2d_rhs_march)
         const double* sp = stage_tab + (long long)(*interval) * 9;
         sa = (float)sp[0]; sb = (float)sp[1]; sdt = (float)sp[2];
@@ -225,7 +301,7 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     // pair index clamped into the grid (pairs start at even columns; the last pair may straddle nx when nx is odd)
     const int cmax = (d.nx - 1) & ~1;
     const int ic = min(max(c0, 0), cmax);
-    RhsMarch2<CUBIC, AFIELD, ETA1, STAGE> m;
+    RhsMarch2<CUBIC, AFIELD, ETA1, STAGE, RK> m;
     constexpr int PF = ODINN_PF2_RHS;
     m.ph = ph;
     m.ld = d.ld;
@@ -250,9 +326,26 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
         // queue (it is read at the output row), so the L2 prefetch is what hides its DRAM latency: SSPRK3 stage 0.226 -> 0.197 ms.
         // (Skipping the U0 read in stages with sa == 0 was measured SLOWER -- 0.35 ms: the branch serialises the load in every stage.)
         const float* q = STAGE ? prefetch_lane_ptr<3>(lane, it.y, cmax, d.off, H, B, U0)
+                         : RK  ? prefetch_lane_ptr<3>(lane, it.y, cmax, d.off, H, B, RK == RKM_FIRST ? nullptr : rkf.S2in)
                                : prefetch_lane_ptr<2>(lane, it.y, cmax, d.off, H, B, nullptr);
         m.pf_lane = q != nullptr;
         m.pfp = (m.pf_lane ? q : H + d.off) + (long long)rc * d.ld;  // advanced with hp below, then ODINN_L2PF_ROWS rows further
+    }
+    if (RK) {
+        // the planes of the stage epilogue that are not prefetched above: est, and u when it is not the S2 input (stage 0 reads S2in = u)
+        constexpr bool use_u = RK == RKM_MID_U || RK == RKM_LAST;
+        const float* pu = (use_u && rkf.u != rkf.S2in) ? rkf.u : nullptr;
+        const float* q2 = prefetch_lane_ptr<2>(lane, it.y, cmax, d.off, RK == RKM_FIRST ? nullptr : rkf.est, pu, nullptr);
+        m.pf2_lane = q2 != nullptr;
+        m.pfp2 = (m.pf2_lane ? q2 : H + d.off) + (long long)rc * d.ld;
+        m.rk = rkf;
+        const double hh = rkf.st[it.x].h;
+        m.rbh = (float)(rkf.b * hh);
+        m.reh = (float)(rkf.e * hh);
+        m.oo = (int)d.off + ic + (r0 - 1) * d.ld;   // (fp32 planes stay below 2^31 elements: odinn_ensemble_create)
+        m.nw = mk2((m.store_pair || m.store_x) ? 1.0f : 0.0f, m.store_pair ? 1.0f : 0.0f);
+        m.n_s2 = m.n_e = m.n_u = bc2(0.0f);
+        m.r_s2 = m.r_e = m.r_u = m.nacc = bc2(0.0f);
     }
     m.ap = AFIELD ? Af + d.off + ic + (long long)min(rc, d.ny - 2) * d.ld : nullptr;
     m.op = dH + d.off + ic + (long long)(r0 - 1) * d.ld;  // dereferenced for rows >= r0 only
@@ -282,8 +375,10 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
         if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.pfp += d.ld; }
         m.hq[k] = ldg2(m.hp);
         m.bq[k] = ldg2(m.bp);
+        if (RK) { if (r0 + k >= 1 && r0 + k <= m.nym1) m.pfp2 += d.ld; }
     }
     m.pfp += (long long)ODINN_L2PF_ROWS * d.ld;
+    if (RK) m.pfp2 += (long long)ODINN_L2PF_ROWS * d.ld;
 
     int row = r0 - 1;
     m.template step<false, true>(row);
@@ -293,6 +388,14 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     for (; row + PF <= main_end; row += PF) ring_steps<PF>(m, row);
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
+    if (RK) {
+        if (RK == RKM_LAST) {   // (weights: only the lanes that own columns accumulated)
+            double a = (double)m.nacc.x + (double)m.nacc.y;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+            if (lane == 0) partial[item] = a;
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------

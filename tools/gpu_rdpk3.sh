@@ -1,0 +1,10 @@
+#!/bin/bash
+out=gpurun_out/${1:-rdpk}
+mkdir -p $out
+python -m pytest tests -m gpu -x -q > $out/test.log 2>&1; echo "pytest rc=$?" >> $out/test.log
+tail -4 $out/test.log
+for d in f32 f64; do
+  python tools/bench_rdpk.py $d | tee -a $out/rdpk.jsonl
+  ODINN_RK_NO_FUSE=1 python tools/bench_rdpk.py $d | tee -a $out/rdpk.jsonl
+done
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file $out/launches_fused_f64.csv python tools/bench_rdpk.py f64 > $out/l1.log 2>&1
