@@ -270,6 +270,10 @@ int loss_seed_planes(odinn_ensemble* e, const void* H, const void* Href, const v
     return launch_loss_seed(e, H, Href, W, lam_in, v, lam_out, dt, cseed, loss_dst, wloss, accumulate);
 }
 int rhs_planes(odinn_ensemble* e, const void* Hin, void* out) { return launch_rhs(e, -1, Hin, out); }
+bool pdl_enabled() {
+    static const bool on = []() { const char* v = getenv("ODINN_PDL"); return v && v[0] == '1'; }();
+    return on;
+}
 bool rhs_rk_fusable(const odinn_ensemble* e) { return e->law_kind == LAW_NONE; }
 int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm) {
     Stage st{};

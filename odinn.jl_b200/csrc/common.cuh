@@ -68,6 +68,11 @@ struct RkFuse {
     int flags;
 };
 
+// Programmatic dependent launch (see launch_pdl, launch.cuh): pdl_trigger lets the next kernel of the stream start its prologue,
+// pdl_wait blocks until the previous kernel has completed and its writes are visible (no-ops in a plain launch).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 template <typename T>

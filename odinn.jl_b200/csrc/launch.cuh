@@ -45,6 +45,28 @@ struct Stage {
 
 int alloc_plane(odinn_ensemble* e, void** p, size_t n_planes = 1);
 
+// Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while the previous kernel of the stream is
+// still draining, and runs its prologue (work-item and descriptor loads, index arithmetic: everything that does not depend on the
+// previous kernel's output) until its `griddepcontrol.wait`, which returns when the previous kernel has completed and flushed.  ONLY
+// for kernels that execute pdl_wait() before their first access to data a preceding kernel may have written (the F1 marching kernels).
+// Measured on the mid-size ensembles (configs 3 / 4, forward SSPRK3 replayed from the CUDA graph) and at the bench workload
+// (profiles/r02_pdl_ab.txt): 0 - 1 % -- the launches are not bound by their start-up chain -- so it is OFF unless ODINN_PDL=1.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // fp32, two columns per lane.  g0 < 0: whole ensemble.  `packed`: packed descriptor table / packed B of the host-batch path.
 int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, const Stage* st, bool packed);
 // *starts_used: the per-glacier start table (device) that indexes the partial sums this launch wrote

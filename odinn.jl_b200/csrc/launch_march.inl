@@ -21,12 +21,14 @@ int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* 
     dim3 grid(div_up(n_items, MARCH_WARPS)), block(MARCH_WARPS * 32);
     const double* stab = st ? st->tab : nullptr;
     const int* sint = st ? st->interval : nullptr;
-#define L(CUB, AF, E1, STG) \
-    sia2d_rhs_march<T, CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, T(0), 0, stab, sint)
-#define LRKM(CUB, AF, E1, M)                                                                                                          \
-    sia2d_rhs_march<T, CUB, AF, E1, false, false, M><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, nullptr, T(0),    \
-                                                                                    T(0), T(0), T(0), 0, nullptr, nullptr,                     \
-                                                                                    *(const RkFuse<T>*)st->rk, e->d_partial + i0)
+    cudaError_t lerr = cudaSuccess;
+#define L(CUB, AF, E1, STG)                                                                                                               \
+    lerr = launch_pdl(sia2d_rhs_march<T, CUB, AF, E1, STG, false, 0>, grid, block, e->stream, descs, items, n_items, H, B, Af, dH, ph, U0, \
+                      sa, sb, sdt, T(0), 0, stab, sint, RkFuse<T>(), (double*)nullptr)
+#define LRKM(CUB, AF, E1, M)                                                                                                              \
+    lerr = launch_pdl(sia2d_rhs_march<T, CUB, AF, E1, false, false, M>, grid, block, e->stream, descs, items, n_items, H, B, Af, dH, ph,   \
+                      (const T*)nullptr, T(0), T(0), T(0), T(0), 0, (const double*)nullptr, (const int*)nullptr, *(const RkFuse<T>*)st->rk, \
+                      e->d_partial + i0)
 #define LRK(CUB, AF, E1)                                                  \
     do {                                                                  \
         switch (rk_mode_of_flags(((const RkFuse<T>*)st->rk)->flags)) {    \
@@ -44,6 +46,7 @@ int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* 
 #undef LRK
 #undef LRKM
 #undef L
+    if (lerr != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }

@@ -154,11 +154,13 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
     const double* stab = st ? st->tab : nullptr;
     const int* sint = st ? st->interval : nullptr;
     dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
-#define L(CUB, AF, E1, STG) \
-    sia2d_rhs_march2<CUB, AF, E1, STG><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, stab, sint)
-#define LRKM(CUB, AF, E1, M)                                                                                                   \
-    sia2d_rhs_march2<CUB, AF, E1, false, M><<<grid, block, 0, e->stream>>>(descs, items, n_items, H, B, Af, dH, ph, nullptr, 0.f, 0.f, 0.f, \
-                                                                           nullptr, nullptr, *(const RkFuse<float>*)st->rk, e->d_partial)
+    cudaError_t lerr = cudaSuccess;
+#define L(CUB, AF, E1, STG)                                                                                                           \
+    lerr = launch_pdl(sia2d_rhs_march2<CUB, AF, E1, STG, 0>, grid, block, e->stream, descs, items, n_items, H, B, Af, dH, ph, U0, sa, sb, sdt, \
+                      stab, sint, RkFuse<float>(), (double*)nullptr)
+#define LRKM(CUB, AF, E1, M)                                                                                                          \
+    lerr = launch_pdl(sia2d_rhs_march2<CUB, AF, E1, false, M>, grid, block, e->stream, descs, items, n_items, H, B, Af, dH, ph,       \
+                      (const float*)nullptr, 0.f, 0.f, 0.f, (const double*)nullptr, (const int*)nullptr, *(const RkFuse<float>*)st->rk, e->d_partial)
 #define LRK(CUB, AF, E1)                                                      \
     do {                                                                      \
         switch (rk_mode_of_flags(((const RkFuse<float>*)st->rk)->flags)) {    \
@@ -176,6 +178,7 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
 #undef LRK
 #undef LRKM
 #undef L
+    if (lerr != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }

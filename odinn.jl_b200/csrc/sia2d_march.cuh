@@ -52,9 +52,11 @@ template <typename T>
 __device__ __forceinline__ T shfl_up(T v) { return __shfl_up_sync(FULL, v, 1); }
 
 __device__ __forceinline__ float fmx(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double fmx(double a, double b) { return fmax(a, b); }
+// fp64: compare + select (DSETP, 2 x SEL) instead of fmax / fmin, whose NaN handling costs DSETP.MAX + 2 MOV + FSEL + SEL + LOP3 per call
+// on sm_100 (nine calls per row of the A1 step); the operands are finite, where both forms return the same value.
+__device__ __forceinline__ double fmx(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ float fmn(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double fmn(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double fmn(double a, double b) { return a < b ? a : b; }
 
 // Node diffusivity from RAW sums: Hs = Σ of the 4 thicknesses (H̄ = Hs/4), g2 = |∇S|².
 // Returns D and, when PARTIALS, α = ∂D/∂H̄, β = (1/∇S)∂D/∂∇S, gA = Γ H̄^{n+2} ∇S^{n-1} (target_A.jl:16-92).
@@ -129,6 +131,43 @@ __device__ __forceinline__ void subgrad(double dC, double e, double lo, double u
         }
     }
     subgrad_cmp<double, ETA1>(dC, gt_lo, lt_lo, lt_up, gt_up, eta0, to_lower, to_upper);
+}
+
+#ifndef ODINN_SUBGRAD_XY
+#define ODINN_SUBGRAD_XY 1
+#endif
+// Both edges of a marching step at once (cubic-form steps).  fp64: ONE warp vote covers the near-tie slow paths of the y- and the
+// x-edge, and the near-tie test itself -- |d| < 2^-46 |e| (1.4e-14 |e|; any threshold far above the 2^-52 at which a quotient can
+// round onto its neighbour serves) -- compares the high words on the integer pipe instead of a DMUL, a DSETP.MIN chain and a DSETP on
+// the FP64 pipe, which this kernel saturates.  d == 0 with e != 0 (an exact tie) is `near` as before; e == 0 never is.
+template <typename T, bool ETA1>
+__device__ __forceinline__ void subgrad_xy(float dCy, float ey, float loy, float upy, float dly, float dCx, float ex, float lox, float upx,
+                                           float dlx, float eta0, float& yl, float& yu, float& xl, float& xu) {
+    subgrad<T, ETA1>(dCy, ey, loy, upy, dly, eta0, yl, yu);
+    subgrad<T, ETA1>(dCx, ex, lox, upx, dlx, eta0, xl, xu);
+}
+__device__ __forceinline__ int hi_abs(double v) { return __double2hiint(v) & 0x7fffffff; }
+template <typename T, bool ETA1>
+__device__ __forceinline__ void subgrad_xy(double dCy, double ey, double loy, double upy, double dly, double dCx, double ex, double lox,
+                                           double upx, double dlx, double eta0, double& yl, double& yu, double& xl, double& xu) {
+    const double y1 = ey - loy, y2 = upy - ey, x1 = ex - lox, x2 = upx - ex;
+    bool y_gl = y1 > 0.0, y_ll = y1 < 0.0, y_lu = y2 > 0.0, y_gu = y2 < 0.0;
+    bool x_gl = x1 > 0.0, x_ll = x1 < 0.0, x_lu = x2 > 0.0, x_gu = x2 < 0.0;
+    const int ty = hi_abs(ey) - (46 << 20), tx = hi_abs(ex) - (46 << 20);
+    const bool near_y = hi_abs(y1) < ty || hi_abs(y2) < ty;
+    const bool near_x = hi_abs(x1) < tx || hi_abs(x2) < tx;
+    if (__any_sync(FULL, near_y || near_x)) {   // warp-uniform: keeps the divisions out of the common path
+        if (near_y) {
+            const double qe = ey / dly, ql = loy / dly, qu = upy / dly;
+            y_gl = qe > ql; y_ll = ql > qe; y_lu = qu > qe; y_gu = qe > qu;
+        }
+        if (near_x) {
+            const double qe = ex / dlx, ql = lox / dlx, qu = upx / dlx;
+            x_gl = qe > ql; x_ll = ql > qe; x_lu = qu > qe; x_gu = qe > qu;
+        }
+    }
+    subgrad_cmp<double, ETA1>(dCy, y_gl, y_ll, y_lu, y_gu, eta0, yl, yu);
+    subgrad_cmp<double, ETA1>(dCx, x_gl, x_ll, x_lu, x_gu, eta0, xl, xu);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -278,10 +317,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
                 RkFuse<T> rkf = RkFuse<T>(), double* __restrict__ partial = nullptr) {
     // Replayed from a CUDA graph (odinn_solve_forward): the stage coefficients of interval *interval come from a device table
     // (9 doubles per interval, stage_tab already offset to this launch's stage), so one captured graph serves every interval.
-    if (STAGE && stage_tab != nullptr) {
-        const double* sp = stage_tab + (long long)(*interval) * 9;
-        sa = (T)sp[0]; sb = (T)sp[1]; sdt = (T)sp[2];
-    }
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -292,6 +328,13 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
     RhsMarch<T, CUBIC, AFIELD, ETA1, STAGE, DFIELD, RK> m;
     constexpr int PF = ODINN_PF_RHS;
+    // Everything above reads tables that no F1 kernel writes (a kernel that does write them -- set_A_kernel -- never triggers early, so
+    // it has completed before this prologue starts); from here on the launch depends on the previous kernel of the stream.
+    pdl_wait();
+    if (STAGE && stage_tab != nullptr) {
+        const double* sp = stage_tab + (long long)(*interval) * 9;
+        sa = (T)sp[0]; sb = (T)sp[1]; sdt = (T)sp[2];
+    }
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
@@ -479,14 +522,13 @@ struct VjpMarch {
         }
         if (WRITE_H) {
             T yl, yu1, xl, xu;
-            {
-                T dC = fy * (D1W + D1);                      // ∂Cy/Δy = -Fy†·Dy/Δy
-                subgrad<T, ETA1>(dC, ey, -eh, eh1, dy, eta0, yl, yu1);
-            }
-            {
-                T dC = fx * (Dp + D1);
-                subgrad<T, ETA1>(dC, ex, -eh, ehE, dx, eta0, xl, xu);
-            }
+#if ODINN_SUBGRAD_XY
+            subgrad_xy<T, ETA1>(fy * (D1W + D1), ey, -eh, eh1, dy,     // ∂Cy/Δy = -Fy†·Dy/Δy
+                                fx * (Dp + D1), ex, -eh, ehE, dx, eta0, yl, yu1, xl, xu);
+#else
+            subgrad<T, ETA1>(fy * (D1W + D1), ey, -eh, eh1, dy, eta0, yl, yu1);
+            subgrad<T, ETA1>(fx * (Dp + D1), ex, -eh, ehE, dx, eta0, xl, xu);
+#endif
             T SAW = (Qp - Q1) * qy2 + (aDp + aD1) * T(5);
             T SP = (Pp + P1) * qx2;
             T ZW = shfl_up(SAW + SP + xu);                   // everything column i-1 sends to cell (i, row)

@@ -288,10 +288,7 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
                  PhysDev<float> ph, const float* U0, float sa, float sb, float sdt,
                  const double* __restrict__ stage_tab = nullptr, const int* __restrict__ interval = nullptr,
                  RkFuse<float> rkf = RkFuse<float>(), double* __restrict__ partial = nullptr) {
-    if (STAGE && stage_tab != nullptr) {  // graph replay: stage coefficients from the device table (see sia2d_rhs_march)
-        const double* sp = stage_tab + (long long)(*interval) * 9;
-        sa = (float)sp[0]; sb = (float)sp[1]; sdt = (float)sp[2];
-    }
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -303,6 +300,13 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const int ic = min(max(c0, 0), cmax);
     RhsMarch2<CUBIC, AFIELD, ETA1, STAGE, RK> m;
     constexpr int PF = ODINN_PF2_RHS;
+    // Everything above reads tables that no F1 kernel writes (a kernel that does write them -- set_A_kernel -- never triggers early, so
+    // it has completed before this prologue starts); from here on the launch depends on the previous kernel of the stream.
+    pdl_wait();
+    if (STAGE && stage_tab != nullptr) {  // graph replay: stage coefficients from the device table (see sia2d_rhs_march)
+        const double* sp = stage_tab + (long long)(*interval) * 9;
+        sa = (float)sp[0]; sb = (float)sp[1]; sdt = (float)sp[2];
+    }
     m.ph = ph;
     m.ld = d.ld;
     m.nym1 = d.ny - 1;
