@@ -275,6 +275,20 @@ bool pdl_enabled() {
     return on;
 }
 bool rhs_rk_fusable(const odinn_ensemble* e) { return e->law_kind == LAW_NONE; }
+bool vjp_rk_fusable(const odinn_ensemble* e) {
+    return e->law_kind == LAW_NONE && !e->a_gridded && ((e->dtype == ODINN_F32 && e->march >= 2) || (e->dtype == ODINN_F64 && e->cubic));
+}
+int vjp_planes_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
+                  double ta, double tb, bool norm) {
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = sync_descs(e))) return rc;
+    const bool two = (e->dtype == ODINN_F32);
+    rc = two ? launch_vjp2_rk(e, S1in, Ha, Hb, S1out, rkfuse, c, sign, ta, tb) : launch_vjp_rk_t<double>(e, S1in, Ha, Hb, S1out, rkfuse, c, sign, ta, tb);
+    if (rc || !norm) return rc;
+    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(two ? e->d_item2_start : e->d_item_start, e->d_partial, e->d_S, 1.0, 0);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
 int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm) {
     Stage st{};
     st.rk = rkfuse;

@@ -184,6 +184,11 @@ int rhs_planes(odinn_ensemble* e, const void* Hin, void* out);              // o
 // norm: the stage carries RKF_NORM -- the per-glacier sums of squares of the scaled error land in d_S.  Not for per-cell laws.
 bool rhs_rk_fusable(const odinn_ensemble* e);
 int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm);
+// The same for one stage of the continuous adjoint's reverse ODE: k = (dSIA/dH)^T S1in at H_itp = lerp(Ha, Hb) with the glacier's own
+// weight a = (sign (t_g + c h_g) - ta) / (tb - ta); discrete VJP flavour, glacier-wide A (fp64: n = 3, C = 0).
+bool vjp_rk_fusable(const odinn_ensemble* e);
+int vjp_planes_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
+                  double ta, double tb, bool norm);
 int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale = 1.0, int accumulate = 0);  // dst[g] = Σ tiles of g
 int prepare_snapshots(odinn_ensemble* e, int n_snap);
 // A1 (wH: out <- (dSIA/dH)^T lam) and / or A2 (wS: S_dst[g] (+)= scale * S_g; nullptr -> the handle's d_S), discrete or continuous flavour

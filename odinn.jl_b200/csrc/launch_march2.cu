@@ -240,6 +240,27 @@ int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void*
 }
 
 
+// One RDPK3Sp35 stage of the continuous adjoint's reverse ODE in one pass (RKA variant): S1out <- stage(S1in, k = (dSIA/dH)^T S1in at
+// H_itp = lerp(Ha, Hb)); whole ensemble, glacier-wide A.  With RKF_NORM the per-item partial sums of the error norm land in d_partial.
+int launch_vjp2_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
+                   double ta, double tb) {
+    PhysDev<float> ph = make_phys<float>(e->phys);
+    const GDesc<float>* descs = (const GDesc<float>*)e->d_descs;
+    const int n_items = e->n_items2;
+    const float* B = (const float*)e->plane[ODINN_FIELD_B];
+    const bool eta1 = (e->phys.eta0 == 1.0);
+    dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
+#define LR(CUB, E1)                                                                                                                       \
+    sia2d_vjp_march2<CUB, false, true, false, E1, false, false, true><<<grid, block, 0, e->stream>>>(                                      \
+        descs, e->d_items2, n_items, (const float*)S1in, (const float*)Ha, B, nullptr, (float*)S1out, nullptr, e->d_partial, ph, nullptr, \
+        nullptr, nullptr, 0.f, 0.f, *(const RkFuse<float>*)rkfuse, (const float*)Hb, c, sign, ta, tb)
+    if (e->cubic) { if (eta1) LR(true, true); else LR(true, false); }
+    else { if (eta1) LR(false, true); else LR(false, false); }
+#undef LR
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
+
 int launch_vjp2_seed(odinn_ensemble* e, const void* lam_, const void* H_, const void* Href_, const void* W_, void* lam_new, double dt,
                      double cseed) {
     PhysDev<float> ph = make_phys<float>(e->phys);

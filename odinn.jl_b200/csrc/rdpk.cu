@@ -427,9 +427,13 @@ static int rk_norm(RkCtx<T>& c, const T* a, const T* b, const T* u, const T* v, 
 // neighbours still read the old stage value); S2 and est are updated in place; no slope plane is ever written, so there is no FSAL
 // slope either: the step starts with F1(u), which costs what the k_new evaluation of the unfused form costs.  Per trial step
 // 5 launches of 4, 7, 7, 8, 7 words per cell instead of 5 x 3 + 4 + 4 x 7.5 + 3 = 52.
-template <typename T, typename Rhs, typename OnStop>
+// fused_rhs(S1in, S1out, f, c, norm): one launch  S1out <- stage f of (S1in, k = rhs(t_g + c h_g, S1in))  (rhs_planes_rk / vjp_planes_rk).
+struct NoFusedRhs {
+    template <typename T> int operator()(const T*, T*, const RkFuse<T>&, double, bool) const { return ODINN_ESTATE; }
+};
+template <typename T, typename Rhs, typename OnStop, typename FusedRhs = NoFusedRhs>
 static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, double reltol, double abstol, double dtmax, double dt0,
-                        int max_steps, Rhs rhs, OnStop on_stop, bool fused = false) {
+                        int max_steps, Rhs rhs, OnStop on_stop, bool fused = false, FusedRhs fused_rhs = FusedRhs()) {
     odinn_ensemble* e = c.e;
     int rc;
     const int G = e->G;
@@ -471,7 +475,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
                 f.b = h_B[0];
                 f.e = Ew[0];
                 f.flags = RKF_FIRST | RKF_WEST;
-                if ((rc = rhs_planes_rk(e, u, c.S1, &f, false))) return rc;
+                if ((rc = fused_rhs((const T*)u, c.S1, f, 0.0, false))) return rc;
                 for (int s = 0; s < 4; ++s) {
                     f.S2in = s == 0 ? u : c.S2;
                     f.S2out = c.S2;
@@ -479,7 +483,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
                     f.b = h_B[s + 1];
                     f.e = Ew[s + 1];
                     f.flags = (h_G3[s] != 0.0 ? RKF_U : 0) | (s < 3 ? (RKF_WS2 | RKF_WEST) : RKF_NORM);
-                    if ((rc = rhs_planes_rk(e, c.S1, c.k, &f, s == 3))) return rc;
+                    if ((rc = fused_rhs((const T*)c.S1, c.k, f, h_C[s + 1], s == 3))) return rc;
                     std::swap(c.S1, c.k);   // (four swaps: the new state ends in the plane the step started with as c.S1)
                 }
             } else {
@@ -538,7 +542,8 @@ static int solve_rdpk_t(odinn_ensemble* e, int n_snap, const double* t, double r
         return ODINN_OK;
     };
     static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
-    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop, rhs_rk_fusable(e) && !no_fuse)))
+    auto fused_rhs = [&](const T* in, T* out, const RkFuse<T>& f, double, bool norm) -> int { return rhs_planes_rk(e, in, out, &f, norm); };
+    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop, rhs_rk_fusable(e) && !no_fuse, fused_rhs)))
         return rc;
     if ((void*)u != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H (the planes rotate through pointer swaps)
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], u, pbytes, cudaMemcpyDeviceToDevice, e->stream));
@@ -633,7 +638,13 @@ static int grad_continuous_adaptive_t(odinn_ensemble* e, const double* t, int n_
         if (cV != 0.0 && (r = velocity_theta_term_interp(e, qn[s.idx], t, n_t, Ht, cV * qw[s.idx], e->d_Ssum))) return r;
         return ODINN_OK;
     };
-    if ((rc = rk_integrate<T>(c, lam, stops, reltol, abstol, dtmax, 0.0, max_steps, rhs, on_stop))) return rc;
+    // discrete VJP flavour, glacier-wide A: interpolation, A1 and the stage update in ONE launch per stage (RKA variants of the A1 kernels)
+    static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
+    auto fused_rhs = [&](const T* in, T* out, const RkFuse<T>& f, double cc, bool norm) -> int {
+        return vjp_planes_rk(e, in, snapshot_ptr(e, jint), snapshot_ptr(e, jint + 1), out, &f, cc, -1.0, t[jint], t[jint + 1], norm);
+    };
+    if ((rc = rk_integrate<T>(c, lam, stops, reltol, abstol, dtmax, 0.0, max_steps, rhs, on_stop, !cont_vjp && vjp_rk_fusable(e) && !no_fuse, fused_rhs)))
+        return rc;
     if ((void*)lam != e->plane[ODINN_FIELD_LAMBDA])
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_LAMBDA], lam, pbytes, cudaMemcpyDeviceToDevice, e->stream));
     if (steps_out) {

@@ -409,10 +409,52 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
 // DFIELD (with AFIELD): the node planes hold D, α = ∂D/∂H̄ and β (as the target's ∂Diffusivity∂∇H returns it) of a
 // per-cell law; the θ-integrand plane then receives D† itself (gA ≡ 1) for the law's own pullback (sia2d_law.cuh).
 // WRITE_F (cubic form only): the same pass also writes dH = SIA2D(H) -- see VjpMarch2 in sia2d_march2.cuh.
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false>
+// RKA (cubic form, WRITE_H only): one RDPK3Sp35 stage of the continuous adjoint's reverse ODE in one pass -- H is the interpolant
+// la0 Ha + la1 Hb of two forward snapshots formed when a row leaves the prefetch queues, the stage update of RkFuse (common.cuh) is the
+// epilogue (see VjpMarch2 in sia2d_march2.cuh).
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false, bool RKA = false>
 struct VjpMarch {
     static constexpr int PF = PfVjp<T>::value;
     static constexpr bool CUBIC_FORM = CUBIC && !DFIELD;  // n = 3, C = 0: step_cubic()
+    // RKA state: second snapshot row pointer + queue, interpolation weights, the stage, the glacier's (b h, e h), the offset of the
+    // output row in the stage's planes, its operands (raw S1, S2, est, u), the error-norm accumulator, two more L2-prefetch pointers
+    const T* h2p;
+    T hq2[PfVjp<T>::value];
+    T la0, la1;
+    RkFuse<T> rk;
+    const T* s1b;
+    long long oo;
+    T rbh, reh, r_s1, r_s2, r_e, r_u;
+    double nacc;
+    const T *pf2p, *pf3p;
+
+    // res = k = (dSIA/dH)^T S1 at H_itp: the stage update of rk_stage / rk_stage1_main (rdpk.cu), straight-line
+    __device__ __forceinline__ void rk_emit(T k) {
+        const T s1 = r_s1;
+        T s1n, er;
+        if (rk.flags & RKF_FIRST) {
+            s1n = s1 + rbh * k;
+            er = reh * k;
+        } else {
+            const T s2 = r_s2 + rk.d * s1;
+            T v = rk.g1 * s1 + rk.g2 * s2;
+            if (rk.flags & RKF_U) v = v + rk.g3 * r_u;
+            s1n = v + rbh * k;
+            er = r_e + reh * k;
+            if (rk.flags & RKF_WS2) { if (store_lane) rk.S2out[oo] = s2; }
+        }
+        if (store_lane) *op = s1n;
+        if (rk.flags & RKF_WEST) { if (store_lane) rk.est[oo] = er; }
+        if (rk.flags & RKF_NORM) {
+            const double m = fmax(fabs((double)r_u), fabs((double)s1n));
+            const double den = (double)rk.abstol + (double)rk.reltol * m;
+            double x = (double)__frcp_rn((float)den);   // float-seeded reciprocal + two Newton steps (see RhsMarch::rk_epilogue)
+            x = fma(x, fma(-den, x, 1.0), x);
+            x = fma(x, fma(-den, x, 1.0), x);
+            const double r = (double)er * x;
+            nacc += store_lane ? r * r : 0.0;
+        }
+    }
     const T *hp, *bp, *lp, *ap, *alp, *bep;
     const T* pfp;  // CUBIC_FORM: this lane's L2-prefetch sector (10 lanes per input plane), ODINN_L2PF_ROWS1 rows ahead
     T *op, *vp;  // output row pointer; gridded-A integrand pointer (or null)
@@ -434,8 +476,9 @@ struct VjpMarch {
     template <bool OUT, bool MASKED>
     __device__ __forceinline__ void step_cubic(int row) {
         T h1 = hq[0], b1 = bq[0], l1 = lq[0];
+        if (RKA) h1 = la0 * h1 + la1 * hq2[0];               // H_itp = (1 - a) Ha + a Hb   (rk_lerp of rdpk.cu)
 #pragma unroll
-        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
+        for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; if (RKA) hq2[k] = hq2[k + 1]; }
         T l1x = l1 * lmx, l1y = l1 * lmy;
         if (MASKED) {
             int stp = (row + 1 + PF <= nym1) ? ld : 0;
@@ -443,18 +486,29 @@ struct VjpMarch {
             bp += stp;
             lp += stp;
             pfp += stp;
+            if (RKA) { h2p += stp; pf2p += stp; if (pf3p) pf3p += stp; }
             if (!(row >= 0 && row + 1 < nym1)) l1x = l1y = T(0);  // λ_inn zero-extended on border rows
         } else {
             hp += ld;
             bp += ld;
             lp += ld;
             pfp += ld;
+            if (RKA) { h2p += ld; pf2p += ld; if (pf3p) pf3p += ld; }
         }
         hq[PF - 1] = __ldg(hp);
+        if (RKA) hq2[PF - 1] = __ldg(h2p);
         bq[PF - 1] = __ldg(bp);
         lq[PF - 1] = __ldg(lp);
         if (ODINN_L2PF_ROWS1 > 0 && !MASKED) {
-            if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) prefetch_l2_row(pfp);
+            if (row + 1 + PF + ODINN_L2PF_ROWS1 <= nym1) {
+                prefetch_l2_row(pfp);
+                if (RKA) { prefetch_l2_row(pf2p); if (pf3p) prefetch_l2_row(pf3p); }
+            }
+        }
+        if (RKA && OUT) {   // operands of the row this step emits (plain loads: S2 and est are rewritten in place by this thread)
+            r_s1 = s1b[oo];
+            if (!(rk.flags & RKF_FIRST)) { r_s2 = rk.S2in[oo]; r_e = rk.est[oo]; }
+            if (rk.flags & (RKF_U | RKF_NORM)) r_u = rk.u[oo];
         }
         h1 = fmx(h1, T(0));
         b1 = surf_store<T>(b1, h1);
@@ -535,9 +589,11 @@ struct VjpMarch {
             if (OUT) {
                 T res = ZW + (SAW - SP + xl) + (yl + yu_p);
                 if (!(h > T(0))) res = T(0);                 // adjoint.jl:148
-                if (store_lane) *op = res;
+                if (RKA) rk_emit(res);
+                else if (store_lane) *op = res;
             }
             op += ld;
+            if (RKA) oo += ld;
             yu_p = yu1;
         }
         h = h1; b = b1; eh = eh1; ex = ex1; hx = hx1; ehE = ehE1; cx = cx1;
@@ -649,12 +705,15 @@ struct VjpMarch {
     }
 };
 
-template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, ODINN_VJP1_MIN_CTAS)
+// RKA: H2 is the upper snapshot; the glacier's interpolation weight is a = (sign (t_g + lc h_g) - lta) / (ltb - lta) from its controller state.
+template <typename T, bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool DFIELD = false, bool WRITE_F = false, bool RKA = false>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, RKA ? 3 : ODINN_VJP1_MIN_CTAS)   // (RKA in fp64: 152 bytes of spills at 128 registers)
 sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                 const T* __restrict__ lam, const T* __restrict__ H, const T* __restrict__ B, const T* __restrict__ Af,
                 T* __restrict__ out, T* __restrict__ vjpA, double* __restrict__ partial, PhysDev<T> ph,
-                const T* __restrict__ alF = nullptr, const T* __restrict__ beF = nullptr, T* __restrict__ dH = nullptr) {
+                const T* __restrict__ alF = nullptr, const T* __restrict__ beF = nullptr, T* __restrict__ dH = nullptr,
+                RkFuse<T> rkf = RkFuse<T>(), const T* __restrict__ H2 = nullptr, double lc = 0.0, double lsign = 1.0, double lta = 0.0,
+                double ltb = 1.0) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -663,7 +722,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     const int i = it.y + lane, r0 = it.z, r1 = it.w;
     const int ic = min(max(i, 0), d.nx - 1);
     const bool col_inner = (i >= 1 && i <= d.nx - 2);
-    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, DFIELD, WRITE_F> m;
+    VjpMarch<T, CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, DFIELD, WRITE_F, RKA> m;
     constexpr int PF = PfVjp<T>::value;
     m.ph = ph;
     m.ld = d.ld;
@@ -703,8 +762,33 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
         m.pfp = pb + d.off + min(max(it.y + per * sec, 0), d.nx - 1) + (long long)rc * d.ld;
     }
 
+    m.h2p = nullptr; m.pf2p = m.pf3p = nullptr;
+    if (RKA) {
+        const RkState st = rkf.st[it.x];
+        const double tt = lsign * (st.t + lc * st.h);
+        m.la1 = (T)((tt - lta) / (ltb - lta));
+        m.la0 = T(1) - m.la1;
+        m.rk = rkf;
+        m.rbh = (T)(rkf.b * st.h);
+        m.reh = (T)(rkf.e * st.h);
+        m.s1b = lam;
+        m.oo = d.off + ic + (long long)(r0 - 1) * d.ld;
+        m.r_s1 = m.r_s2 = m.r_e = m.r_u = T(0);
+        m.nacc = 0.0;
+        m.h2p = H2 + d.off + ic + (long long)rc * d.ld;
+        {   // H2, S2in, est (10 lanes each); u on a third instruction when it is read and is not the S2 input
+            const int pl = min(lane / 10, 2), sec = lane - 10 * pl;
+            const bool first = (rkf.flags & RKF_FIRST) != 0;
+            const T* pb = pl == 0 ? H2 : (first ? H2 : (pl == 1 ? rkf.S2in : (const T*)rkf.est));
+            constexpr int per = 32 / (int)sizeof(T);
+            const long long po = d.off + min(max(it.y + per * sec, 0), d.nx - 1) + (long long)rc * d.ld;
+            m.pf2p = pb + po;
+            if ((rkf.flags & (RKF_U | RKF_NORM)) && rkf.u != rkf.S2in && lane < 10) m.pf3p = rkf.u + po;
+        }
+    }
+
     // ---- cell row r0-1 ----
-    m.h = fmx(__ldg(m.hp), T(0));
+    m.h = fmx(RKA ? m.la0 * __ldg(m.hp) + m.la1 * __ldg(m.h2p) : __ldg(m.hp), T(0));
     m.b = surf_store<T>(__ldg(m.bp), m.h);
     m.l = __ldg(m.lp) * m.lmask;
     if (!(r0 >= 2 && r0 <= m.nym1)) m.l = T(0);  // row r0-1 must be an inner row
@@ -737,12 +821,17 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.Dp = m.aDp = m.Pp = m.Qrow_p = m.yu_p = m.acc = m.Fyp = T(0);
 #pragma unroll
     for (int k = 0; k < PF; ++k) {  // rows r0 .. r0+PF-1 (clamped)
-        if (r0 + k >= 1 && r0 + k <= m.nym1) { m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; m.pfp += d.ld; }
+        if (r0 + k >= 1 && r0 + k <= m.nym1) {
+            m.hp += d.ld; m.bp += d.ld; m.lp += d.ld; m.pfp += d.ld;
+            if (RKA) { m.h2p += d.ld; m.pf2p += d.ld; if (m.pf3p) m.pf3p += d.ld; }
+        }
         m.hq[k] = __ldg(m.hp);
+        if (RKA) m.hq2[k] = __ldg(m.h2p);
         m.bq[k] = __ldg(m.bp);
         m.lq[k] = __ldg(m.lp);
     }
     m.pfp += (long long)ODINN_L2PF_ROWS1 * d.ld;
+    if (RKA) { m.pf2p += (long long)ODINN_L2PF_ROWS1 * d.ld; if (m.pf3p) m.pf3p += (long long)ODINN_L2PF_ROWS1 * d.ld; }
 
     int row = r0 - 1;
     m.template step<false, true>(row);  // warm-up
@@ -753,6 +842,14 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
 
+    if (RKA) {
+        if (rkf.flags & RKF_NORM) {   // (only storing lanes accumulated)
+            double a = m.nacc;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+            if (lane == 0) partial[item] = a;
+        }
+    }
     if (WRITE_S) {
         double a = m.own_lane ? (double)m.acc : 0.0;  // (the cubic form accumulates in the halo lanes too)
 #pragma unroll

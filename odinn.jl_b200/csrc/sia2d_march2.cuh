@@ -474,7 +474,11 @@ __device__ __forceinline__ void subgrad2(f2 dC, f2 e, f2 lo, f2 up, float eta0, 
 // v = (dSIA/dH)^T lambda the pass writes  lambda_new = lambda + dt v + cseed W (H - H_ref)  (gradient.jl:242 with the LossH seed of
 // Losses.jl:270-291) to a SECOND lambda plane (the neighbours still read the old one) and accumulates the loss term sum W (H - H_ref)^2
 // per strip: 5 reads + 1 write per cell instead of the 4 + 6 words of an A1 pass followed by a loss / seed pass.
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false>
+// RKA (with WRITE_H): one RDPK3Sp35 stage of the continuous adjoint's reverse ODE  d(lambda)/d(tau) = (dSIA/dH)^T lambda  at H_itp(-tau)
+// (gradient.jl:316-324) in ONE pass: H is the linear interpolant  la0 Ha + la1 Hb  of two forward snapshots formed when a row leaves the
+// prefetch queues (no interpolated plane is ever written), and the stage update of RkFuse (common.cuh) is the epilogue -- instead of an
+// interpolation pass (3 words), the A1 pass (4) and an elementwise stage pass (7-8): 9-10 words per cell and stage.
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false, bool RKA = false>
 struct VjpMarch2 {
     static constexpr int PF = ODINN_PF2_VJP;
     // Every plane shares one (offset, pitch) layout, so the kernel keeps 32-bit ELEMENT offsets and adds them to the
@@ -484,6 +488,15 @@ struct VjpMarch2 {
     float *Ob, *Vb, *Fb;
     const float *Rb, *Wb;   // SEED: H_ref and W planes
     f2 sdt, scs, lossacc;   // SEED: dt, cseed (broadcast), loss accumulator
+    // RKA: second snapshot plane + its queue, interpolation weights, the stage (planes, coefficients, flags), the glacier's (b h, e h),
+    // the operands of the output row (raw S1, S2, est, u), error-norm accumulator and weights, two more L2-prefetch bases
+    const float* H2b;
+    f2 hq2[ODINN_PF2_VJP];
+    f2 la0, la1;
+    RkFuse<float> rk;
+    float rbh, reh;
+    f2 r_s1, r_s2, r_e, r_u, nacc, nw;
+    const float *pf2, *pf3;
     const float* pfb;  // per lane: base of the plane this lane prefetches + its sector's column delta + ODINN_L2PF_ROWS rows
     int oin, oout, oa;  // offsets of the row being loaded / the row being written / the A-field node row
     int ld, nym1, ny2;
@@ -519,6 +532,37 @@ struct VjpMarch2 {
         if (ODINN_L2PF_ROWS > 0 && !MASKED && pfs != nullptr && row + ODINN_L2PF_ROWS <= nym1) prefetch_l2(pfs + oout);
     }
     __device__ __forceinline__ void emit(f2 res) {
+        if (RKA) {   // res = k = (dSIA/dH)^T S1 at H_itp: the stage update of rk_stage / rk_stage1_main (rdpk.cu), straight-line
+            const f2 k = res, s1 = r_s1;
+            f2 s1n, er;
+            if (rk.flags & RKF_FIRST) {
+                s1n = mk2(fmaf(rbh, k.x, s1.x), fmaf(rbh, k.y, s1.y));
+                er = mk2(reh * k.x, reh * k.y);
+            } else {
+                const f2 s2 = mk2(fmaf(rk.d, s1.x, r_s2.x), fmaf(rk.d, s1.y, r_s2.y));
+                f2 v = mk2(fmaf(rk.g2, s2.x, rk.g1 * s1.x), fmaf(rk.g2, s2.y, rk.g1 * s1.y));
+                if (rk.flags & RKF_U) v = mk2(fmaf(rk.g3, r_u.x, v.x), fmaf(rk.g3, r_u.y, v.y));
+                s1n = mk2(fmaf(rbh, k.x, v.x), fmaf(rbh, k.y, v.y));
+                er = mk2(fmaf(reh, k.x, r_e.x), fmaf(reh, k.y, r_e.y));
+                if (rk.flags & RKF_WS2) {
+                    if (store_pair) *reinterpret_cast<float2*>(rk.S2out + oout) = s2;
+                    if (store_x) rk.S2out[oout] = s2.x;
+                }
+            }
+            if (store_pair) *reinterpret_cast<float2*>(Ob + oout) = s1n;
+            if (store_x) Ob[oout] = s1n.x;
+            if (rk.flags & RKF_WEST) {
+                if (store_pair) *reinterpret_cast<float2*>(rk.est + oout) = er;
+                if (store_x) rk.est[oout] = er.x;
+            }
+            if (rk.flags & RKF_NORM) {
+                const float rx = __fdividef(er.x, fmaf(rk.reltol, fmaxf(fabsf(r_u.x), fabsf(s1n.x)), rk.abstol));
+                const float ry = __fdividef(er.y, fmaf(rk.reltol, fmaxf(fabsf(r_u.y), fabsf(s1n.y)), rk.abstol));
+                nacc.x = fmaf(nw.x * rx, rx, nacc.x);
+                nacc.y = fmaf(nw.y * ry, ry, nacc.y);
+            }
+            return;
+        }
         if (SEED) {
             if (!seed_lane) return;
             const f2 df = sub2(s_h, s_r), wd = mul2(s_w, df);
@@ -534,17 +578,35 @@ struct VjpMarch2 {
         constexpr int RS = SLOT < 0 ? 0 : SLOT;
         constexpr int WS = SLOT < 0 ? PF - 1 : SLOT;
         f2 h1 = hq[RS], b1 = bq[RS], l1 = lq[RS];
+        if (RKA) h1 = fma2(la1, hq2[RS], mul2(la0, h1));   // H_itp = (1 - a) Ha + a Hb   (rk_lerp of rdpk.cu)
         if (SLOT < 0) {
 #pragma unroll
-            for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; }
+            for (int k = 0; k + 1 < PF; ++k) { hq[k] = hq[k + 1]; bq[k] = bq[k + 1]; lq[k] = lq[k + 1]; if (RKA) hq2[k] = hq2[k + 1]; }
         }
         if (MASKED) oin += (row + 1 + PF <= nym1) ? ld : 0;
         else oin += ld;
         hq[WS] = ldg2(Hb + oin);
+        if (RKA) hq2[WS] = ldg2(H2b + oin);
         bq[WS] = ldg2(Bb + oin);
         lq[WS] = ldg2(Lb + oin);
         if (ODINN_L2PF_ROWS > 0 && !MASKED) {
-            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) prefetch_l2(pfb + oin);
+            if (row + 1 + PF + ODINN_L2PF_ROWS <= nym1) {
+                prefetch_l2(pfb + oin);
+                if (RKA) {
+                    prefetch_l2(pf2 + oin);
+                    if (pf3 != nullptr) prefetch_l2(pf3 + oin);
+                }
+            }
+        }
+        if (RKA && OUT) {
+            // operands of the row this step emits: every lane loads (the clamped pair index keeps the address inside the grid; plain loads:
+            // S2 and est are rewritten in place by this thread)
+            r_s1 = *reinterpret_cast<const float2*>(Lb + oout);
+            if (!(rk.flags & RKF_FIRST)) {
+                r_s2 = *reinterpret_cast<const float2*>(rk.S2in + oout);
+                r_e = *reinterpret_cast<const float2*>(rk.est + oout);
+            }
+            if (rk.flags & (RKF_U | RKF_NORM)) r_u = *reinterpret_cast<const float2*>(rk.u + oout);
         }
         f2 Anode = A;
         if (AFIELD) {
@@ -748,13 +810,16 @@ struct VjpMarch2 {
     }
 };
 
-template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false>
+// RKA: H2 is the upper snapshot; the glacier's interpolation weight is a = (sign (t_g + lc h_g) - lta) / (ltb - lta) from its controller state.
+template <bool CUBIC, bool AFIELD, bool WRITE_H, bool WRITE_S, bool ETA1, bool WRITE_F = false, bool SEED = false, bool RKA = false>
 __global__ void __launch_bounds__(MARCH2_WARPS * 32, ODINN_VJP2_MIN_CTAS)
 sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict__ items, int n_items,
                  const float* __restrict__ lam, const float* __restrict__ H, const float* __restrict__ B,
                  const float* __restrict__ Af, float* __restrict__ out, float* __restrict__ vjpA,
                  double* __restrict__ partial, PhysDev<float> ph, float* __restrict__ dH = nullptr,
-                 const float* __restrict__ Href = nullptr, const float* __restrict__ Wm = nullptr, float sdt = 0.0f, float scs = 0.0f) {
+                 const float* __restrict__ Href = nullptr, const float* __restrict__ Wm = nullptr, float sdt = 0.0f, float scs = 0.0f,
+                 RkFuse<float> rkf = RkFuse<float>(), const float* __restrict__ H2 = nullptr, double lc = 0.0, double lsign = 1.0,
+                 double lta = 0.0, double ltb = 1.0) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * MARCH2_WARPS + (threadIdx.x >> 5);
     if (item >= n_items) return;
@@ -763,8 +828,21 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     const int c0 = it.y + 2 * lane, r0 = it.z, r1 = it.w;
     const int cmax = (d.nx - 1) & ~1;
     const int ic = min(max(c0, 0), cmax);
-    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, WRITE_F, SEED> m;
+    VjpMarch2<CUBIC, AFIELD, WRITE_H, WRITE_S, ETA1, WRITE_F, SEED, RKA> m;
     constexpr int PF = ODINN_PF2_VJP;
+    m.H2b = H2;
+    m.pf2 = m.pf3 = nullptr;
+    if (RKA) {
+        const RkState st = rkf.st[it.x];
+        const double tt = lsign * (st.t + lc * st.h);
+        const float a1 = (float)((tt - lta) / (ltb - lta));
+        m.la1 = bc2(a1);
+        m.la0 = bc2(1.0f - a1);
+        m.rk = rkf;
+        m.rbh = (float)(rkf.b * st.h);
+        m.reh = (float)(rkf.e * st.h);
+        m.r_s1 = m.r_s2 = m.r_e = m.r_u = m.nacc = bc2(0.0f);
+    }
     m.Rb = Href; m.Wb = Wm;
     m.sdt = bc2(sdt); m.scs = bc2(scs); m.lossacc = bc2(0.0f);
     m.s_l = m.s_h = m.s_r = m.s_w = bc2(0.0f);
@@ -791,6 +869,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.store_x = out_lane && (c1 == d.nx);
     m.own_lane = (lane >= 1 && lane <= 30);
     m.seed_lane = m.store_pair || m.store_x;
+    m.nw = mk2(m.seed_lane ? 1.0f : 0.0f, m.store_pair ? 1.0f : 0.0f);
     m.vstore_pair = out_lane && (c1 <= d.nx - 2);
     m.vstore_x = out_lane && (c1 == d.nx - 1);
     const int rc = max(r0 - 1, 0);
@@ -806,6 +885,12 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
         const int pl = min(lane / 10, 2), sec = lane - 10 * pl;
         const float* pb = pl == 0 ? H : (pl == 1 ? B : lam);
         m.pfb = pb + (min(max(it.y + 8 * sec, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
+        if (RKA) {   // H2, and the epilogue planes S2in, est (10 lanes each); u (when it is read and is not the S2 input) on a third instruction
+            const float* pb2 = pl == 0 ? H2 : (pl == 1 ? ((rkf.flags & RKF_FIRST) ? nullptr : rkf.S2in) : ((rkf.flags & RKF_FIRST) ? nullptr : rkf.est));
+            const long long dl = (min(max(it.y + 8 * sec, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
+            if (pb2 != nullptr) m.pf2 = pb2 + dl; else m.pf2 = H2 + dl;
+            if ((rkf.flags & (RKF_U | RKF_NORM)) && rkf.u != rkf.S2in && lane < 10) m.pf3 = rkf.u + dl;
+        }
         if (SEED && lane < 18) {
             const int sp = lane / 9, ss = lane - 9 * sp;
             m.pfs = (sp == 0 ? Href : Wm) + (min(max(it.y + 8 * ss, 0), cmax) - ic) + (long long)ODINN_L2PF_ROWS * d.ld;
@@ -815,6 +900,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     // ---- cell row r0-1 ----
     {
         f2 hv = ldg2(m.Hb + m.oin), bv = ldg2(m.Bb + m.oin), lv = ldg2(m.Lb + m.oin);
+        if (RKA) hv = fma2(m.la1, ldg2(m.H2b + m.oin), mul2(m.la0, hv));
         m.h = max2(hv, bc2(0.0f));
         m.b = bv;
         m.l = mul2(lv, m.lmask);
@@ -849,6 +935,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     for (int k = 0; k < PF; ++k) {
         if (r0 + k >= 1 && r0 + k <= m.nym1) m.oin += d.ld;
         m.hq[k] = ldg2(m.Hb + m.oin);
+        if (RKA) m.hq2[k] = ldg2(m.H2b + m.oin);
         m.bq[k] = ldg2(m.Bb + m.oin);
         m.lq[k] = ldg2(m.Lb + m.oin);
     }
@@ -863,6 +950,14 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     for (; row < main_end; ++row) m.template step<true, false>(row);
     for (; row < r1; ++row) m.template step<true, true>(row);
 
+    if (RKA) {
+        if (rkf.flags & RKF_NORM) {   // (weights: only the lanes that own columns accumulated)
+            double a = (double)m.nacc.x + (double)m.nacc.y;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) a += __shfl_down_sync(FULL, a, s);
+            if (lane == 0) partial[item] = a;
+        }
+    }
     if (SEED) {   // (exclusive with WRITE_S: the strip's loss term goes where S would)
         double a = (double)m.lossacc.x + (double)m.lossacc.y;   // (only storing lanes accumulated)
 #pragma unroll
