@@ -463,6 +463,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
     for (size_t i = 1; i < stops.size(); ++i) {
         rk_begin_interval<<<c.gb, 128, 0, e->stream>>>(c.st, G, stops[i - 1], stops[i], dtmax);
         ODINN_CHECK_LAUNCH(e);
+        int n_active = G;   // glaciers that take part in the next trial step (the others have landed on the stop)
         for (;;) {
             if (++total > max_steps) return fail(e, ODINN_ESTATE, "rdpk3sp35: too many steps (maxiters)");
             if (fused) {
@@ -503,14 +504,18 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
             ODINN_CHECK_LAUNCH(e);
             ODINN_CUDA(e, cudaMemcpyAsync(e->h_ad_active, c.d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
-            if (e->h_ad_active[1] == 0) {  // every glacier accepted (idle ones took h = 0: S1 == u, knew == k1 bit for bit): swap
+            // Every glacier accepted: the commit is a pointer swap.  Unfused: idle glaciers took h = 0 (S1 == u up to rounding, knew == k1).
+            // Fused: the stage launches SKIP the glaciers that have landed on the stop (heterogeneous ensembles: the slowest glacier sets the
+            // number of ensemble-wide trial steps), so their rows of the stage planes are stale and the swap needs everybody on board.
+            if (e->h_ad_active[1] == 0 && (!fused || n_active == G)) {
                 std::swap(u, c.S1);
                 std::swap(c.k1, c.knew);
             } else {
                 rk_commit<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.S1, fused ? (T*)nullptr : c.k1, c.knew);
                 ODINN_CHECK_LAUNCH(e);
             }
-            if (e->h_ad_active[0] == 0) break;
+            n_active = e->h_ad_active[0];
+            if (n_active == 0) break;
         }
         bool modified = false;
         if ((rc = on_stop((int)i, u, &modified))) return rc;

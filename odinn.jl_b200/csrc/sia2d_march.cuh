@@ -331,6 +331,7 @@ sia2d_rhs_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     // Everything above reads tables that no F1 kernel writes (a kernel that does write them -- set_A_kernel -- never triggers early, so
     // it has completed before this prologue starts); from here on the launch depends on the previous kernel of the stream.
     pdl_wait();
+    if (RK) { if (rkf.st[it.x].done) return; }   // the glacier has landed on the tstop: nothing to integrate (rk_integrate commits by copy then)
     if (STAGE && stage_tab != nullptr) {
         const double* sp = stage_tab + (long long)(*interval) * 9;
         sa = (T)sp[0]; sb = (T)sp[1]; sdt = (T)sp[2];
@@ -765,6 +766,7 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.h2p = nullptr; m.pf2p = m.pf3p = nullptr;
     if (RKA) {
         const RkState st = rkf.st[it.x];
+        if (st.done) return;   // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then)
         const double tt = lsign * (st.t + lc * st.h);
         m.la1 = (T)((tt - lta) / (ltb - lta));
         m.la0 = T(1) - m.la1;

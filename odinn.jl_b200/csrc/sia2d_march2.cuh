@@ -303,6 +303,7 @@ sia2d_rhs_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     // Everything above reads tables that no F1 kernel writes (a kernel that does write them -- set_A_kernel -- never triggers early, so
     // it has completed before this prologue starts); from here on the launch depends on the previous kernel of the stream.
     pdl_wait();
+    if (RK) { if (rkf.st[it.x].done) return; }   // the glacier has landed on the tstop: nothing to integrate (rk_integrate commits by copy then)
     if (STAGE && stage_tab != nullptr) {  // graph replay: stage coefficients from the device table (see sia2d_rhs_march)
         const double* sp = stage_tab + (long long)(*interval) * 9;
         sa = (float)sp[0]; sb = (float)sp[1]; sdt = (float)sp[2];
@@ -834,6 +835,7 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.pf2 = m.pf3 = nullptr;
     if (RKA) {
         const RkState st = rkf.st[it.x];
+        if (st.done) return;   // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then)
         const double tt = lsign * (st.t + lc * st.h);
         const float a1 = (float)((tt - lta) / (ltb - lta));
         m.la1 = bc2(a1);

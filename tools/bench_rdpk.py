@@ -28,9 +28,5 @@ H = ens.get_snapshot(3, len(t) - 1).astype(np.float64)
 print(json.dumps(dict(what="RDPK3Sp35 + PID, 4 monthly intervals, rtol %g, %d x %dx%d" % (rt, G, n, n), dtype=dtype, fused=os.environ.get("ODINN_RK_NO_FUSE", "0") in ("", "0"),
                       seconds=s, trial_steps_max=int(steps.max()), trial_steps_min=int(steps.min()), rejected_max=int(rej.max()),
                       launches=int(ens.launch_count - l0),
-                      # ensemble-wide trial steps (every glacier inside the interval steps; the interval ends when the last one lands on the
-                      # tstop) from the launch count: 17 launches of set-up, then 7 (fused) / 13 (unfused) per trial step without rejections
-                      ensemble_trial_steps=(int(ens.launch_count - l0) - 17) / (7 if os.environ.get("ODINN_RK_NO_FUSE", "0") in ("", "0") else 13),
-                      ms_per_ensemble_trial_step=1e3 * s / ((int(ens.launch_count - l0) - 17) / (7 if os.environ.get("ODINN_RK_NO_FUSE", "0") in ("", "0") else 13)),
                       checksum=float(H.sum()), hmax=float(H.max()))), flush=True)
 ens.close()
