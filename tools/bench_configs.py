@@ -103,6 +103,15 @@ s = timed(lambda: (ens.solve_forward(t5, method="ssprk3", nsub=nsub), ens.synchr
 rhs = 60 * nsub * 3
 report("3: 64 glaciers 100-400 px, forward 2010-2015, SSPRK3 nsub 8", seconds=s, cells=cells, rhs_evals=rhs, cell_steps_per_s=cells * rhs / s,
        frac_of_hbm_peak=cells * rhs * 4 * (4 if dtype == "f32" else 8) / s / 6550.1e9)
+# the same run with the reference's default solver (host-driven engine: stage updates fused into F1, landed glaciers skipped)
+st3 = None
+def run3_rdpk():
+    global st3
+    st3 = ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35")
+    ens.synchronize()
+s = timed(run3_rdpk)
+report(f"3: 64 glaciers 100-400 px, forward 2010-2015, adaptive RDPK3Sp35 + PID rtol {rt:g} (the reference's default solver)", seconds=s, cells=cells,
+       trial_steps_min=int(st3[0].min()), trial_steps_max=int(st3[0].max()), rejected_max=int(st3[1].max()))
 ens.close()
 
 # config 4: 32 glaciers, LawA(nn 1-16-16-1), one optimiser iteration = law + forward solve + adjoint + pullback
@@ -135,6 +144,21 @@ for mode in ("discrete", "continuous"):
     s = timed(lambda: iteration(mode), reps=2)
     report(f"4: 32 glaciers, LawA(1-16-16-1), one iteration: law + forward (SSPRK3 nsub 8) + {mode} adjoint + pullback", seconds=s, cells=cells,
            n_theta=nth)
+def iteration_default():   # the reference's default configuration: RDPK3Sp35 forward + ContinuousAdjoint (adaptive reverse solve, 200 nodes)
+    ens.law_A_nn_apply(widths, acts, theta)
+    ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35")
+    ens.grad_continuous_adaptive(t5, n_quadrature=200, reltol=rta, abstol=rta)
+    return ens.law_A_nn_pullback(nth)
+def iteration_rdpk_discrete():
+    ens.law_A_nn_apply(widths, acts, theta)
+    ens.solve_forward_adaptive(t5, reltol=rt, abstol=rt, method="rdpk3sp35")
+    ens.grad_discrete(t5)
+    return ens.law_A_nn_pullback(nth)
+s = timed(iteration_rdpk_discrete, reps=2)
+report("4: 32 glaciers, LawA(1-16-16-1), one iteration: law + forward (RDPK3Sp35) + discrete adjoint + pullback", seconds=s, cells=cells, n_theta=nth)
+s = timed(iteration_default, reps=2)
+report("4: 32 glaciers, LawA(1-16-16-1), one iteration in the reference's DEFAULT configuration (RDPK3Sp35 forward + ContinuousAdjoint, 200 nodes)",
+       seconds=s, cells=cells, n_theta=nth)
 s_f = timed(lambda: (ens.solve_forward(t5, method="ssprk3", nsub=nsub), ens.synchronize()), reps=2)
 s_g = timed(lambda: ens.grad_discrete(t5), reps=2)
 report("4: split", forward_seconds=s_f, discrete_adjoint_seconds=s_g, adjoint_cell_steps_per_s=cells * 60 / s_g)
