@@ -433,12 +433,26 @@ struct NoFusedRhs {
 };
 template <typename T, typename Rhs, typename OnStop, typename FusedRhs = NoFusedRhs>
 static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, double reltol, double abstol, double dtmax, double dt0,
-                        int max_steps, Rhs rhs, OnStop on_stop, bool fused = false, FusedRhs fused_rhs = FusedRhs()) {
+                        int max_steps, Rhs rhs, OnStop on_stop, bool fused = false, FusedRhs fused_rhs = FusedRhs(), bool static_args = false) {
     odinn_ensemble* e = c.e;
     int rc;
     const int G = e->G;
     double Ew[5];
     rdpk_error_weights(Ew);
+    if ((rc = sync_descs(e))) return rc;
+    // Small and mid-size ensembles (BASELINE configs 3 / 4): a trial step is ~75 us of kernels behind ~10 API calls and a host round trip.
+    // When the launch arguments do not change from step to step (static_args) the whole trial step -- five fused stage launches, the
+    // norm reduction, the controller, the commit of the accepted glaciers (always by copy, so that no plane pointer ever swaps) and the
+    // read-back of the two counters -- is captured ONCE into a CUDA graph and replayed: one cudaGraphLaunch + one synchronize per step.
+    // Large ensembles keep the direct launches: there the pointer-swap commit saves 2 words per cell and step.
+    static const int graph_env = []() { const char* v = getenv("ODINN_RK_GRAPH"); return v ? atoi(v) : -1; }();
+    const bool use_graph = fused && static_args && (graph_env >= 0 ? graph_env != 0 : e->cells <= (8LL << 20));
+    cudaGraphExec_t step_exec = nullptr;
+    int step_launches = 0;
+    struct ExecGuard {
+        cudaGraphExec_t& x;
+        ~ExecGuard() { if (x) cudaGraphExecDestroy(x); }
+    } exec_guard{step_exec};
     rk_reset<<<c.gb, 128, 0, e->stream>>>(c.st, G, stops[0]);
     ODINN_CHECK_LAUNCH(e);
     if (!(fused && dt0 > 0.0) && (rc = rhs(u, c.k1, 0.0))) return rc;  // FSAL seed f(t0, u0) (fused: only the initial-step algorithm needs it)
@@ -466,6 +480,21 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
         int n_active = G;   // glaciers that take part in the next trial step (the others have landed on the stop)
         for (;;) {
             if (++total > max_steps) return fail(e, ODINN_ESTATE, "rdpk3sp35: too many steps (maxiters)");
+            if (use_graph && step_exec) {
+                ODINN_CUDA(e, cudaGraphLaunch(step_exec, e->stream));
+                e->launches += step_launches;
+                ODINN_CUDA(e, cudaStreamSynchronize(e->stream));
+                n_active = e->h_ad_active[0];
+                if (n_active == 0) break;
+                continue;
+            }
+            const long long cap_l0 = e->launches;
+            if (use_graph) ODINN_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            // (a failure inside a capture leaves through capture_fail, which ends the capture first)
+            auto capture_fail = [&](int code) -> int {
+                if (use_graph) { cudaGraph_t g = nullptr; cudaStreamEndCapture(e->stream, &g); if (g) cudaGraphDestroy(g); }
+                return code;
+            };
             if (fused) {
                 RkFuse<T> f{};
                 f.st = c.st;
@@ -476,7 +505,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
                 f.b = h_B[0];
                 f.e = Ew[0];
                 f.flags = RKF_FIRST | RKF_WEST;
-                if ((rc = fused_rhs((const T*)u, c.S1, f, 0.0, false))) return rc;
+                if ((rc = fused_rhs((const T*)u, c.S1, f, 0.0, false))) return capture_fail(rc);
                 for (int s = 0; s < 4; ++s) {
                     f.S2in = s == 0 ? u : c.S2;
                     f.S2out = c.S2;
@@ -484,7 +513,7 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
                     f.b = h_B[s + 1];
                     f.e = Ew[s + 1];
                     f.flags = (h_G3[s] != 0.0 ? RKF_U : 0) | (s < 3 ? (RKF_WS2 | RKF_WEST) : RKF_NORM);
-                    if ((rc = fused_rhs((const T*)c.S1, c.k, f, h_C[s + 1], s == 3))) return rc;
+                    if ((rc = fused_rhs((const T*)c.S1, c.k, f, h_C[s + 1], s == 3))) return capture_fail(rc);
                     std::swap(c.S1, c.k);   // (four swaps: the new state ends in the plane the step started with as c.S1)
                 }
             } else {
@@ -498,6 +527,22 @@ static int rk_integrate(RkCtx<T>& c, T*& u, const std::vector<double>& stops, do
             }
             if ((rc = rhs(c.S1, c.knew, 1.0))) return rc;
             if ((rc = rk_norm<T>(c, c.est, nullptr, u, c.S1, reltol, abstol))) return rc;
+            }
+            if (use_graph) {   // the rest of the captured trial step; then instantiate and run it
+                cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(int), e->stream);
+                rk_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, c.d_counters, dtmax);
+                rk_commit<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, u, c.S1, (T*)nullptr, c.knew);
+                cudaMemcpyAsync(e->h_ad_active, c.d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+                cudaGraph_t graph = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+                if (ce != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("cudaStreamEndCapture (rdpk trial step): ") + cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&step_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return fail(e, ODINN_ECUDA, std::string("cudaGraphInstantiate (rdpk trial step): ") + cudaGetErrorString(ce));
+                step_launches = (int)(e->launches - cap_l0) + 2;
+                e->launches = cap_l0;
+                --total;     // (nothing has run yet: the step is replayed from the graph)
+                continue;
             }
             ODINN_CUDA(e, cudaMemsetAsync(c.d_counters, 0, 2 * sizeof(int), e->stream));
             rk_control<<<c.gb, 128, 0, e->stream>>>(c.st, e->d_S, c.d_nx, c.d_ny, G, c.d_counters, dtmax);
@@ -548,7 +593,8 @@ static int solve_rdpk_t(odinn_ensemble* e, int n_snap, const double* t, double r
     };
     static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
     auto fused_rhs = [&](const T* in, T* out, const RkFuse<T>& f, double, bool norm) -> int { return rhs_planes_rk(e, in, out, &f, norm); };
-    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop, rhs_rk_fusable(e) && !no_fuse, fused_rhs)))
+    if (n_snap > 1 && (rc = rk_integrate<T>(c, u, stops, reltol, abstol, dtmax, dt0, max_steps, rhs, on_stop, rhs_rk_fusable(e) && !no_fuse, fused_rhs,
+                                            /*static_args=*/true)))
         return rc;
     if ((void*)u != e->plane[ODINN_FIELD_H])  // leave the final state in FIELD_H (the planes rotate through pointer swaps)
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_H], u, pbytes, cudaMemcpyDeviceToDevice, e->stream));
