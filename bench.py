@@ -587,12 +587,48 @@ def grad_iteration_arm(ob, parallel, args, dtype, rank, local_rank, world, dist)
         tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         sec = float(tt.item())
+
+    # The same iteration with the reference's DEFAULT integrator for the forward solve (RDPK3Sp35 + PID, AdjointTypes.jl:60; every stage
+    # update fused into the F1 launch, glaciers that have landed on the tstop skipped): our arm only -- the C restatement of the CPU arm
+    # has the fixed-step loops.
+    rt = 1e-4 if dtype == "f32" else 1e-6
+    stat = {}
+
+    def iteration_rdpk():
+        for k in range(G):
+            ens.upload(k, _capi.FIELD_H0, hH0[k].numpy().T)
+        ens.law_A_nn_apply(LAW_WIDTHS, LAW_ACTS, th)
+        stat["steps"], stat["rejected"] = ens.solve_forward_adaptive(t, reltol=rt, abstol=rt, method="rdpk3sp35")
+        losses, _ = ens.grad_discrete(t)
+        dth = ens.law_A_nn_pullback(N_THETA)
+        return parallel.allreduce_loss_grad(float(losses.sum()), dth)
+
+    loss_r, _ = iteration_rdpk()
+    ens.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l1 = ens.launch_count
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        loss_r, _ = iteration_rdpk()
+    ens.synchronize()
+    sec_r = (time.perf_counter() - t0) / reps
+    launches_r = (ens.launch_count - l1) // reps
+    if dist is not None:
+        tt = torch.tensor([sec_r], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec_r = float(tt.item())
+    rdpk = {"what": f"the same iteration with the forward solve by adaptive RDPK3Sp35 + PID (the reference's default integrator), rtol = atol = {rt:g}",
+            "seconds_per_iteration": sec_r, "value": world * G * n * n * 60 / sec_r, "trial_steps_per_glacier_min": int(stat["steps"].min()),
+            "trial_steps_per_glacier_max": int(stat["steps"].max()), "rejected_max": int(stat["rejected"].max()),
+            "gpu_launches_per_iteration": int(launches_r), "loss": float(loss_r)}
     ens.close()
     esz = n * n * (4 if dtype == "f32" else 8)
     return {"value": world * G * n * n * 60 / sec, "unit": "cell-steps/s (one cell through one saved step of a gradient iteration)",
             "seconds_per_iteration": sec, "saved_steps": 60, "rhs_evals_per_saved_step": 24, "glaciers_per_gpu": G,
             "h2d_bytes_per_iteration": int(G * esz + 8 * N_THETA), "d2h_bytes_per_iteration": int(8 * (G + N_THETA)),
             "gpu_launches_per_iteration": int(launches), "loss": float(loss), "norm_dtheta": float(np.linalg.norm(dth)),
+            "forward_rdpk3sp35": rdpk,
             "api": "Ensemble.upload(H0) + law_A_nn_apply(theta) + solve_forward + grad_discrete + law_A_nn_pullback + allreduce_loss_grad "
                    "(= odinn_b200.SIA2D_grad_), wall clock, max over ranks"}
 
