@@ -193,3 +193,99 @@ def test_continuous_adjoint_with_mass_balance_and_velocity_loss(ob, dtype, rever
         assert np.all(np.abs(S0 - Ssum) > 1e-6 * np.abs(Ssum)) or reverse != "adaptive"
     finally:
         ens.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("variant", ["gridded_A", "eta0", "generic_exponents"])
+def test_forward_rdpk3sp35_fused_stage_other_kernel_variants(ob, dtype, variant):
+    """The RDPK stage epilogue of the F1 kernels (csrc/rdpk.cu: every stage update is fused into the launch that evaluates its slope)
+    exists for every template variant of the F1 dispatch: gridded A (LawA(scalar = false), Laws.jl:430-454), eta0 != 1 and generic
+    exponents / sliding (n != 3, C != 0).  Host-driven engine (cluster mode 0), ragged ensemble incl. an odd-nx grid, against the oracle."""
+    gl = [o.rough_bed_glacier(41, 35), o.rough_bed_glacier(23, 50), o.dome_glacier(33, 33, H0=150.0)]
+    for g in gl[:2]:
+        g.H0 = 0.6 * g.H0
+    kw = dict(PH)
+    if variant == "eta0":
+        kw.update(eta0=0.6)
+    if variant == "generic_exponents":
+        kw.update(n=3.3, C=1e-14)   # (a sliding term that matters -- 47 instead of 22 steps -- without making the run stiff)
+    ph = o.Phys(**kw)
+    rng = np.random.default_rng(5)
+    As = []
+    for g in gl:
+        a = 2e-17 if variant != "generic_exponents" else 2e-18
+        As.append(a * np.exp(0.5 * rng.standard_normal((g.B.shape[0] - 1, g.B.shape[1] - 1))) if variant == "gridded_A" else a)
+    t = o.define_callback_steps((2010.0, 2010.25), 1.0 / 12.0)
+    rtol = 1e-6 if dtype == "f64" else 1e-4
+    ens = ob.Ensemble([g.B.shape[0] for g in gl], [g.B.shape[1] for g in gl], [g.dx for g in gl], [g.dy for g in gl], ob.Phys(**kw), dtype)
+    try:
+        from odinn_b200 import _capi
+
+        for k, g in enumerate(gl):
+            ens.upload(k, _capi.FIELD_B, g.B)
+            ens.upload(k, _capi.FIELD_H0, g.H0)
+            if variant == "gridded_A":
+                ens.set_A_field(k, As[k])
+            else:
+                ens.set_A_scalar(k, As[k])
+        ens.set_cluster_mode(0)
+        steps, rej = ens.solve_forward_adaptive(t, reltol=rtol, abstol=rtol, method="rdpk3sp35")
+        for k, g in enumerate(gl):
+            g2 = o.Glacier(B=_r(g.B, dtype), dx=g.dx, dy=g.dy, H0=_r(g.H0, dtype))
+            st = {}
+            Ak = _r(As[k], dtype) if variant == "gridded_A" else As[k]
+            Hs = o.solve_forward(g2.H0, g2, o.TargetA(ph, "const", A=Ak), None, t, method="rdpk3sp35", reltol=rtol, abstol=rtol, stats=st)
+            if dtype == "f64":
+                assert steps[k] == st["steps"] and rej[k] == st["rejected"], (k, steps[k], rej[k], st)
+            for j in (1, len(t) - 1):
+                err = rel_l2(ens.get_snapshot(k, j), Hs[j])
+                assert err <= (1e-9 if dtype == "f64" else 2e-3), (variant, k, j, err)
+    finally:
+        ens.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("phys_kw", [dict(eta0=0.6), dict(n=3.3, C=1e-14)])
+def test_adaptive_continuous_adjoint_other_kernel_variants(ob, dtype, phys_kw):
+    """The one-launch reverse-ODE stage (interpolation + A1 + RDPK stage update, RKA variants of the A1 kernels) for eta0 != 1 and for
+    generic exponents / sliding (fp32: RKA variants of the generic two-column kernel; fp64: the engine falls back to the separate
+    passes when n != 3 or C != 0) -- host-driven engine, against the oracle."""
+    gl = [o.rough_bed_glacier(31, 30), o.rough_bed_glacier(21, 26)]
+    for g in gl:
+        g.H0 = 0.6 * g.H0
+    t = o.define_callback_steps((2010.0, 2010.25), 1.0 / 12.0)
+    kw = dict(PH)
+    kw.update(phys_kw)
+    ph = o.Phys(**kw)
+    As = [3e-17, 1.2e-17] if "n" not in phys_kw else [3e-18, 1.2e-18]
+    tol = 1e-8 if dtype == "f64" else 1e-4
+    from odinn_b200 import _capi
+
+    ens = ob.Ensemble([g.B.shape[0] for g in gl], [g.B.shape[1] for g in gl], [g.dx for g in gl], [g.dy for g in gl], ob.Phys(**kw), dtype)
+    try:
+        refs = []
+        for k, g in enumerate(gl):
+            ens.upload(k, _capi.FIELD_B, g.B)
+            ens.upload(k, _capi.FIELD_H0, g.H0)
+            g2 = o.Glacier(B=_r(g.B, dtype), dx=g.dx, dy=g.dy, H0=g.H0)
+            Href = [_r(h, dtype) for h in o.solve_forward(g.H0, g, o.TargetA(ph, "const", A=1.7 * As[k]), None, t, method="ssprk3", nsub=8)]
+            Hs = [_r(h, dtype) for h in o.solve_forward(g.H0, g, o.TargetA(ph, "const", A=As[k]), None, t, method="ssprk3", nsub=8)]
+            for j in range(len(t)):
+                ens.set_snapshot(k, j, len(t), Hs[j])
+                ens.set_reference(k, j, len(t), Href[j], o.is_in_glacier(Href[j], 3))
+            ens.set_A_scalar(k, As[k])
+            tgs = o.TargetA(ph, "scalar")
+            theta = np.array([np.arctanh(2 * (As[k] - ph.minA) / (ph.maxA - ph.minA) - 1)])
+            st = {}
+            ell, dth = o.loss_and_grad_continuous_adaptive(theta, g2, tgs, t, Hs, Href, n_quadrature=7, reltol=tol, abstol=tol, vjp="discrete", stats=st)
+            refs.append((ell, dth[0], tgs.vjp_theta[0], st))
+        ens.set_cluster_mode(0)
+        loss, Ssum, steps = ens.grad_continuous_adaptive(t, n_quadrature=7, vjp="discrete", reltol=tol, abstol=tol)
+        rt_l, rt_g = (1e-10, 1e-7) if dtype == "f64" else (2e-4, 5e-3)
+        for k in range(len(gl)):
+            assert loss[k] == pytest.approx(refs[k][0], rel=rt_l), k
+            assert Ssum[k] * refs[k][2] == pytest.approx(refs[k][1], rel=rt_g), (k, Ssum[k] * refs[k][2], refs[k][1])
+            if dtype == "f64":
+                assert steps[k] == refs[k][3]["steps"], (k, steps[k], refs[k][3])
+    finally:
+        ens.close()
