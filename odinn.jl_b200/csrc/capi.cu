@@ -289,6 +289,29 @@ int vjp_planes_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const voi
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
 }
+// S_dst[g] (+)= scale * sum gA D+(lam, H_itp) with H_itp = lerp(Ha, Hb) formed on load (the quadrature-node term of the continuous
+// adjoint, gradient.jl:495-507); rkstate: the controller table the kernel takes each glacier's time from (every glacier sits on the node).
+int vjp_planes_lerp_S(odinn_ensemble* e, const void* lam, const void* Ha, const void* Hb, const void* rkstate, double sign, double ta, double tb,
+                      double* S_dst, double scale, int accumulate) {
+    int rc;
+    if ((rc = ensure_plane(e, ODINN_FIELD_B)) || (rc = sync_descs(e))) return rc;
+    const bool two = (e->dtype == ODINN_F32);
+    if (two) {
+        RkFuse<float> f{};
+        f.st = (const RkState*)rkstate;
+        f.flags = RKF_FIRST | RKF_LERP_ONLY;
+        rc = launch_vjp2_rk(e, lam, Ha, Hb, nullptr, &f, 0.0, sign, ta, tb, true);
+    } else {
+        RkFuse<double> f{};
+        f.st = (const RkState*)rkstate;
+        f.flags = RKF_FIRST | RKF_LERP_ONLY;
+        rc = launch_vjp_rk_t<double>(e, lam, Ha, Hb, nullptr, &f, 0.0, sign, ta, tb, true);
+    }
+    if (rc) return rc;
+    reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(two ? e->d_item2_start : e->d_item_start, e->d_partial, S_dst, scale, accumulate);
+    ODINN_CHECK_LAUNCH(e);
+    return ODINN_OK;
+}
 int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* rkfuse, bool norm) {
     Stage st{};
     st.rk = rkfuse;

@@ -46,7 +46,7 @@ struct RkState {
 // (RKF_FIRST: S1new = S1 + (b h_g) k, est = (e h_g) k -- the stage that starts a trial step from S1 = u), h_g the glacier's own step.
 // S1new goes to a second plane (the neighbours still read S1); S2 and est are updated in place.  RKF_NORM (last stage): the pass also
 // reduces  sum (est / (abstol + reltol max(|u|, |S1new|)))^2  per work item, so that neither the error plane nor a norm pass is needed.
-enum { RKF_FIRST = 1, RKF_U = 2, RKF_WS2 = 4, RKF_WEST = 8, RKF_NORM = 16 };
+enum { RKF_FIRST = 1, RKF_U = 2, RKF_WS2 = 4, RKF_WEST = 8, RKF_NORM = 16, RKF_LERP_ONLY = 32 };
 // The combinations the scheme uses, as compile-time modes of the F1 kernels: first stage; stages without / with the g3 u term (both update
 // S2 and est in place); last stage (g3 u term, error norm, neither S2 nor est written).
 enum { RKM_NONE = 0, RKM_FIRST = 1, RKM_MID = 2, RKM_MID_U = 3, RKM_LAST = 4 };

@@ -189,6 +189,8 @@ int rhs_planes_rk(odinn_ensemble* e, const void* S1in, void* S1out, const void* 
 bool vjp_rk_fusable(const odinn_ensemble* e);
 int vjp_planes_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
                   double ta, double tb, bool norm);
+int vjp_planes_lerp_S(odinn_ensemble* e, const void* lam, const void* Ha, const void* Hb, const void* rkstate, double sign, double ta, double tb,
+                      double* S_dst, double scale, int accumulate);
 int reduce_tiles(odinn_ensemble* e, const double* tile_partial, double* dst, double scale = 1.0, int accumulate = 0);  // dst[g] = Σ tiles of g
 int prepare_snapshots(odinn_ensemble* e, int n_snap);
 // A1 (wH: out <- (dSIA/dH)^T lam) and / or A2 (wS: S_dst[g] (+)= scale * S_g; nullptr -> the handle's d_S), discrete or continuous flavour

@@ -78,10 +78,11 @@ void tma_cache_free(odinn_ensemble* e);
 int launch_vjp2_seed(odinn_ensemble* e, const void* lam, const void* H, const void* Href, const void* W, void* lam_new, double dt, double cseed);
 
 // one RDPK3Sp35 stage of the continuous adjoint's reverse ODE in one pass: lerp(Ha, Hb) on load, A1, stage update as the epilogue
+// (s_only: the A2 pass at a quadrature node with the same interpolation on load; per-item partial sums of S -> d_partial)
 int launch_vjp2_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
-                   double ta, double tb);
+                   double ta, double tb, bool s_only = false);
 template <typename T> int launch_vjp_rk_t(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse,
-                                          double c, double sign, double ta, double tb);
+                                          double c, double sign, double ta, double tb, bool s_only = false);
 
 // one column per lane (fp32 generation 1 and fp64); items [i0, i0 + n_items)
 template <typename T> int launch_rhs_t(odinn_ensemble* e, int i0, int n_items, const void* Hin, void* out, const Stage* st, bool packed);

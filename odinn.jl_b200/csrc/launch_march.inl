@@ -133,7 +133,7 @@ int launch_vjp_t(odinn_ensemble* e, int i0, int n_items, const void* lam_, const
 // glacier-wide A); whole ensemble.  With RKF_NORM the per-item partial sums of the error norm land in d_partial.
 template <typename T>
 int launch_vjp_rk_t(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
-                    double ta, double tb) {
+                    double ta, double tb, bool s_only) {
     PhysDev<T> ph = make_phys<T>(e->phys);
     const GDesc<T>* descs = (const GDesc<T>*)e->d_descs;
     const T* B = (const T*)e->plane[ODINN_FIELD_B];
@@ -144,7 +144,13 @@ int launch_vjp_rk_t(odinn_ensemble* e, const void* S1in, const void* Ha, const v
     sia2d_vjp_march<T, true, false, true, false, E1, false, false, true><<<grid, block, 0, e->stream>>>(                                 \
         descs, e->d_items, n_items, (const T*)S1in, (const T*)Ha, B, nullptr, (T*)S1out, nullptr, e->d_partial, ph, nullptr, nullptr,   \
         nullptr, *(const RkFuse<T>*)rkfuse, (const T*)Hb, c, sign, ta, tb)
-    if (eta1) LR(true); else LR(false);
+#define LQ(E1)                                                                                                                          \
+    sia2d_vjp_march<T, true, false, false, true, E1, false, false, true><<<grid, block, 0, e->stream>>>(                                 \
+        descs, e->d_items, n_items, (const T*)S1in, (const T*)Ha, B, nullptr, nullptr, nullptr, e->d_partial, ph, nullptr, nullptr,     \
+        nullptr, *(const RkFuse<T>*)rkfuse, (const T*)Hb, c, sign, ta, tb)
+    if (s_only) { if (eta1) LQ(true); else LQ(false); }
+    else { if (eta1) LR(true); else LR(false); }
+#undef LQ
 #undef LR
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;
@@ -201,7 +207,7 @@ int launch_unitA_dot_t(odinn_ensemble* e, int g, const void* lam, const void* H,
     template int launch_vjp_law_t<T>(odinn_ensemble*, int, int, const void*, const void*, void*, bool, bool);                        \
     template int launch_vjp_t<T>(odinn_ensemble*, int, int, const void*, const void*, void*, bool, bool, bool, void*);               \
     template int launch_vjpc_t<T>(odinn_ensemble*, int, int, const void*, const void*, void*);                                       \
-    template int launch_vjp_rk_t<T>(odinn_ensemble*, const void*, const void*, const void*, void*, const void*, double, double, double, double); \
+    template int launch_vjp_rk_t<T>(odinn_ensemble*, const void*, const void*, const void*, void*, const void*, double, double, double, double, bool); \
     template int launch_unitA_dot_t<T>(odinn_ensemble*, int, const void*, const void*, double*, double, int);
 
 }  // namespace odinn

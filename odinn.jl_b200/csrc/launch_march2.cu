@@ -242,8 +242,9 @@ int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void*
 
 // One RDPK3Sp35 stage of the continuous adjoint's reverse ODE in one pass (RKA variant): S1out <- stage(S1in, k = (dSIA/dH)^T S1in at
 // H_itp = lerp(Ha, Hb)); whole ensemble, glacier-wide A.  With RKF_NORM the per-item partial sums of the error norm land in d_partial.
+// s_only: the A2 pass at a quadrature node instead (per-item partial sums of S at H_itp -> d_partial; rkfuse carries RKF_LERP_ONLY).
 int launch_vjp2_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const void* Hb, void* S1out, const void* rkfuse, double c, double sign,
-                   double ta, double tb) {
+                   double ta, double tb, bool s_only) {
     PhysDev<float> ph = make_phys<float>(e->phys);
     const GDesc<float>* descs = (const GDesc<float>*)e->d_descs;
     const int n_items = e->n_items2;
@@ -254,8 +255,18 @@ int launch_vjp2_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const vo
     sia2d_vjp_march2<CUB, false, true, false, E1, false, false, true><<<grid, block, 0, e->stream>>>(                                      \
         descs, e->d_items2, n_items, (const float*)S1in, (const float*)Ha, B, nullptr, (float*)S1out, nullptr, e->d_partial, ph, nullptr, \
         nullptr, nullptr, 0.f, 0.f, *(const RkFuse<float>*)rkfuse, (const float*)Hb, c, sign, ta, tb)
-    if (e->cubic) { if (eta1) LR(true, true); else LR(true, false); }
-    else { if (eta1) LR(false, true); else LR(false, false); }
+#define LQ(CUB, E1)                                                                                                                       \
+    sia2d_vjp_march2<CUB, false, false, true, E1, false, false, true><<<grid, block, 0, e->stream>>>(                                      \
+        descs, e->d_items2, n_items, (const float*)S1in, (const float*)Ha, B, nullptr, nullptr, nullptr, e->d_partial, ph, nullptr,       \
+        nullptr, nullptr, 0.f, 0.f, *(const RkFuse<float>*)rkfuse, (const float*)Hb, c, sign, ta, tb)
+    if (s_only) {
+        if (e->cubic) { if (eta1) LQ(true, true); else LQ(true, false); }
+        else { if (eta1) LQ(false, true); else LQ(false, false); }
+    } else {
+        if (e->cubic) { if (eta1) LR(true, true); else LR(true, false); }
+        else { if (eta1) LR(false, true); else LR(false, false); }
+    }
+#undef LQ
 #undef LR
     ODINN_CHECK_LAUNCH(e);
     return ODINN_OK;

@@ -669,6 +669,8 @@ static int grad_continuous_adaptive_t(odinn_ensemble* e, const double* t, int n_
         return vjp_planes(e, in, Ht, out, true, false, nullptr, 1.0, 0, cont_vjp);
     };
     const double cV = e->lossV_theta_scale;
+    static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
+    const bool fuse_stages = !cont_vjp && vjp_rk_fusable(e) && !no_fuse;
     auto on_stop = [&](int i, T* u, bool* modified) -> int {
         const Ev& s = ev[i];
         int r;
@@ -682,6 +684,8 @@ static int grad_continuous_adaptive_t(odinn_ensemble* e, const double* t, int n_
             return ODINN_OK;
         }
         // quadrature node:  dL/dtheta += w_m (VJP_theta(lambda(t_m), H_itp(t_m)) + dl/dtheta(t_m))   (gradient.jl:495-507)
+        if (fuse_stages && cV == 0.0)   // the A2 pass reads the two snapshots itself (the velocity term below needs the interpolated plane)
+            return vjp_planes_lerp_S(e, u, snapshot_ptr(e, jint), snapshot_ptr(e, jint + 1), c.st, -1.0, t[jint], t[jint + 1], e->d_Ssum, qw[s.idx], 1);
         rk_lerp<T><<<c.egrid, RK_NT, 0, e->stream>>>(c.descs, c.st, (const T*)snapshot_ptr(e, jint), (const T*)snapshot_ptr(e, jint + 1), Ht, 0.0,
                                                      -1.0, t[jint], t[jint + 1]);
         ODINN_CHECK_LAUNCH(e);
@@ -690,11 +694,10 @@ static int grad_continuous_adaptive_t(odinn_ensemble* e, const double* t, int n_
         return ODINN_OK;
     };
     // discrete VJP flavour, glacier-wide A: interpolation, A1 and the stage update in ONE launch per stage (RKA variants of the A1 kernels)
-    static const bool no_fuse = []() { const char* v = getenv("ODINN_RK_NO_FUSE"); return v && atoi(v) != 0; }();   // (A/B measurements)
     auto fused_rhs = [&](const T* in, T* out, const RkFuse<T>& f, double cc, bool norm) -> int {
         return vjp_planes_rk(e, in, snapshot_ptr(e, jint), snapshot_ptr(e, jint + 1), out, &f, cc, -1.0, t[jint], t[jint + 1], norm);
     };
-    if ((rc = rk_integrate<T>(c, lam, stops, reltol, abstol, dtmax, 0.0, max_steps, rhs, on_stop, !cont_vjp && vjp_rk_fusable(e) && !no_fuse, fused_rhs)))
+    if ((rc = rk_integrate<T>(c, lam, stops, reltol, abstol, dtmax, 0.0, max_steps, rhs, on_stop, fuse_stages, fused_rhs)))
         return rc;
     if ((void*)lam != e->plane[ODINN_FIELD_LAMBDA])
         ODINN_CUDA(e, cudaMemcpyAsync(e->plane[ODINN_FIELD_LAMBDA], lam, pbytes, cudaMemcpyDeviceToDevice, e->stream));

@@ -506,7 +506,7 @@ struct VjpMarch {
                 if (RKA) { prefetch_l2_row(pf2p); if (pf3p) prefetch_l2_row(pf3p); }
             }
         }
-        if (RKA && OUT) {   // operands of the row this step emits (plain loads: S2 and est are rewritten in place by this thread)
+        if (RKA && WRITE_H && OUT) {   // operands of the row this step emits (plain loads: S2 and est are rewritten in place by this thread)
             r_s1 = s1b[oo];
             if (!(rk.flags & RKF_FIRST)) { r_s2 = rk.S2in[oo]; r_e = rk.est[oo]; }
             if (rk.flags & (RKF_U | RKF_NORM)) r_u = rk.u[oo];
@@ -766,7 +766,8 @@ sia2d_vjp_march(const GDesc<T>* __restrict__ descs, const int4* __restrict__ ite
     m.h2p = nullptr; m.pf2p = m.pf3p = nullptr;
     if (RKA) {
         const RkState st = rkf.st[it.x];
-        if (st.done) return;   // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then)
+        // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then); RKF_LERP_ONLY: see VjpMarch2
+        if (st.done && !(rkf.flags & RKF_LERP_ONLY)) return;
         const double tt = lsign * (st.t + lc * st.h);
         m.la1 = (T)((tt - lta) / (ltb - lta));
         m.la0 = T(1) - m.la1;

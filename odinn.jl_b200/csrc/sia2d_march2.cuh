@@ -599,7 +599,7 @@ struct VjpMarch2 {
                 }
             }
         }
-        if (RKA && OUT) {
+        if (RKA && WRITE_H && OUT) {
             // operands of the row this step emits: every lane loads (the clamped pair index keeps the address inside the grid; plain loads:
             // S2 and est are rewritten in place by this thread)
             r_s1 = *reinterpret_cast<const float2*>(Lb + oout);
@@ -835,7 +835,9 @@ sia2d_vjp_march2(const GDesc<float>* __restrict__ descs, const int4* __restrict_
     m.pf2 = m.pf3 = nullptr;
     if (RKA) {
         const RkState st = rkf.st[it.x];
-        if (st.done) return;   // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then)
+        // the glacier has landed on the stop: nothing to integrate (rk_integrate commits by copy then).  RKF_LERP_ONLY: the A2 pass at a
+        // quadrature node (WRITE_S only: no stage, every glacier sits on the node) uses the interpolation on load alone.
+        if (st.done && !(rkf.flags & RKF_LERP_ONLY)) return;
         const double tt = lsign * (st.t + lc * st.h);
         const float a1 = (float)((tt - lta) / (ltb - lta));
         m.la1 = bc2(a1);
