@@ -205,6 +205,11 @@ int odinn_set_cluster_mode(odinn_ensemble* e, int mode);
  * test/test_grad_loss.jl:143): 5-stage 3rd-order 3S*+ low-storage scheme of Ranocha et al. (2021), FSAL, 5 RHS per trial step, PID
  * step-size controller beta = (0.64, -0.31, 0.04) with the limiter 1 + atan(x - 1) and acceptance threshold 0.81, OrdinaryDiffEq's
  * automatic initial step when dt0 <= 0 (for BS3 dt0 <= 0 means (t[1] - t[0]) / 16).
+ * Large ensembles (and every ensemble odinn_set_cluster_mode keeps off the cluster path) run RDPK3Sp35 with ONE launch per stage: the
+ * stage update -- and the error norm in the last stage -- is the epilogue of the F1 launch that evaluates the stage's slope; glaciers that
+ * have already landed on the tstop are skipped by the launches; for ensembles of <= 8 Mi cells the whole trial step is replayed from a
+ * CUDA graph.  ODINN_RK_NO_FUSE=1 selects the separate elementwise stage passes, ODINN_RK_GRAPH=0 / 1 overrides the graph choice
+ * (developer switches for A/B measurements; same results up to rounding).
  * Snapshots are kept as by odinn_solve_forward. */
 int odinn_solve_forward_adaptive(odinn_ensemble* e, int method, int n_snap, const double* t, double reltol, double abstol,
                                  double dt0, int max_steps, int* steps_out, int* rejected_out);
@@ -279,7 +284,10 @@ int odinn_grad_continuous(odinn_ensemble* e, const double* t, int n_t, int n_qua
  * Callbacks as upstream: lambda_1 = effect_loss!(t_end); the mass-balance PeriodicCallback (initial_affect: also at t_end, not at t_0)
  * lambda += VJP_lambda_dMBdH(lambda, H - MB) BEFORE the loss jump of the same tstop (CallbackSet order, gradient.jl:407-426); the
  * loss jumps use the weights of odinn_set_loss_weights, thickness AND velocity terms (gradient.jl:326-366); the velocity term's
- * dl/dtheta is quadrature-weighted (odinn_set_velocity_quadrature).  steps_out (optional): trial steps per glacier. */
+ * dl/dtheta is quadrature-weighted (odinn_set_velocity_quadrature).  steps_out (optional): trial steps per glacier.
+ * With the discrete VJP flavour and a glacier-wide A (fp64: n = 3, C = 0) a stage of the reverse ODE is ONE launch: H_itp is formed from
+ * the two bracketing snapshots as the rows are loaded, A1 runs on it, the RDPK3Sp35 stage update and the error norm are the epilogue
+ * (likewise the A2 pass at a quadrature node); small ensembles run the whole reverse solve cluster-resident (odinn_set_cluster_mode). */
 int odinn_grad_continuous_adaptive(odinn_ensemble* e, const double* t, int n_t, int n_quadrature, const double* q_nodes,
                                    const double* q_weights, int continuous_vjp, double reltol, double abstol, double dtmax,
                                    int max_steps, double* loss_out, double* Ssum_out, int* steps_out);
