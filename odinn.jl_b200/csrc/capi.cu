@@ -472,6 +472,20 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         istart2[n_glaciers] = (int)items2.size();
         e->n_items2 = (int)items2.size();
     }
+    // Big ensembles: a second table with row chunks of ~125 rows for the launches that write no per-item partial sums (F1 and the fused
+    // SSPRK3 / Euler stage over the WHOLE ensemble).  Every chunk pays a warm-up step and re-reads its halo rows: at 500 x 500 x 256 the
+    // SSPRK3 stage goes 0.197 -> 0.184 ms with 125-row chunks (profiles/r02_chunk_rows_sweep.txt).  Only where that still leaves two
+    // waves of warps; the adaptive engines keep the short chunks (their partially active launches need the parallelism).
+    std::vector<int4> items2L;
+    if (dtype == ODINN_F32 && !getenv("ODINN_CHUNK_ROWS2")) {
+        for (int g = 0; g < n_glaciers; ++g) {
+            const GlacierHost& s = e->gl[g];
+            const int nch = std::max(1, (s.ny + 62) / 125), rows = div_up(s.ny, nch);
+            for (int r0 = 0; r0 < s.ny; r0 += rows)
+                for (int st_ = 0; st_ < div_up(s.nx, STRIP2); ++st_) items2L.push_back(make_int4(g, st_ * STRIP2 - 2, r0, std::min(r0 + rows, s.ny)));
+        }
+        if ((long long)items2L.size() < 2LL * 148 * 16 || items2L.size() >= items2.size()) items2L.clear();
+    }
 
 #define CREATE_CUDA(call)                                                                     \
     do {                                                                                      \
@@ -494,6 +508,11 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     CREATE_CUDA(cudaMalloc(&e->d_item2_start, sizeof(int) * (n_glaciers + 1)));
     CREATE_CUDA(cudaMemcpy(e->d_items2, items2.data(), sizeof(int4) * e->n_items2, cudaMemcpyHostToDevice));
     CREATE_CUDA(cudaMemcpy(e->d_item2_start, istart2.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
+    if (!items2L.empty()) {
+        CREATE_CUDA(cudaMalloc(&e->ext_dev[EXT_ITEMS2_LONG], sizeof(int4) * items2L.size()));
+        CREATE_CUDA(cudaMemcpy(e->ext_dev[EXT_ITEMS2_LONG], items2L.data(), sizeof(int4) * items2L.size(), cudaMemcpyHostToDevice));
+        e->ext_int[5] = (int)items2L.size();
+    }
     CREATE_CUDA(cudaMalloc(&e->d_items, sizeof(int4) * e->n_items));
     CREATE_CUDA(cudaMalloc(&e->d_item_start, sizeof(int) * (n_glaciers + 1)));
     CREATE_CUDA(cudaMalloc(&e->d_S, sizeof(double) * n_glaciers * 4));  // S, Ssum, loss, A

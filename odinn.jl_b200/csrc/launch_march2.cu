@@ -22,9 +22,20 @@ struct TmaCache {
     double* d_partial = nullptr;
     bool usable = false;
 };
-#ifndef ODINN_TMA_CHUNK_ROWS
-#define ODINN_TMA_CHUNK_ROWS 62   // + 2 halo rows = 16 boxes of TMA_R = 4 rows: no row is loaded that is not used
-#endif
+// Row chunks of the bands: 62 rows (+ 2 halo rows = 16 boxes of TMA_R = 4 rows), or 126 when that still leaves two waves of CTAs -- every
+// chunk pays two halo rows and a warm-up step (sweep at 500x500x256, fused step: 62 rows 0.2627 ms, 126 rows 0.2590 ms, 250 rows 0.277 ms;
+// profiles/r02_chunk_rows_sweep.txt).  ODINN_TMA_CHUNK_ROWS=<rows> overrides.
+static int tma_chunk_rows(const odinn_ensemble* e) {
+    const char* v = getenv("ODINN_TMA_CHUNK_ROWS");   // (read when the band table of an ensemble is built: the tests set it per ensemble)
+    const int forced = v ? atoi(v) : 0;
+    if (forced >= 6) return forced;
+    long long ctas = 0;
+    for (int g = 0; g < e->G; ++g) {
+        const GlacierHost& s = e->gl[g];
+        ctas += (long long)div_up(div_up(s.nx, STRIP2), TMA_NW) * std::max(1, (s.ny + 63) / 126);
+    }
+    return ctas >= 2LL * 148 * 5 ? 126 : 62;
+}
 
 void tma_cache_free(odinn_ensemble* e) {
     TmaCache* c = static_cast<TmaCache*>(e->tma_cache);
@@ -52,13 +63,14 @@ static int tma_prepare(odinn_ensemble* e, TmaCache*& c) {
     c->encode = (EncodeTiledFn)fn;
     std::vector<int4> items;
     std::vector<int> start(e->G + 1, 0);
+    const int chunk_rows = tma_chunk_rows(e);
     for (int g = 0; g < e->G; ++g) {
         const GlacierHost& s = e->gl[g];
         start[g] = (int)items.size() * TMA_NW;
         const int nstrips = div_up(s.nx, STRIP2), nbands = div_up(nstrips, TMA_NW);
         // row chunks of 4k - 2 rows (+ 2 halo rows = k boxes of TMA_R = 4 rows: no row is loaded that is not used), balanced so that
         // the last chunk of a glacier is not a sliver: 500 rows -> 7 x 66 + 38
-        const int nch = std::max(1, (s.ny + ODINN_TMA_CHUNK_ROWS / 2) / ODINN_TMA_CHUNK_ROWS);
+        const int nch = std::max(1, (s.ny + chunk_rows / 2) / chunk_rows);
         const int rows = (div_up(s.ny, nch) + 2 + TMA_R - 1) / TMA_R * TMA_R - 2;
         for (int r0 = 0; r0 < s.ny; r0 += rows)
             for (int b = 0; b < nbands; ++b)
@@ -144,6 +156,10 @@ int launch_rhs2(odinn_ensemble* e, int g0, int g1, const void* Hin, void* out, c
         n_items = e->gl[g1 - 1].item20 + e->gl[g1 - 1].n_items2 - i0;
     }
     const int4* items = e->d_items2 + i0;
+    if (g0 < 0 && !(st && st->rk) && e->ext_int[5] > 0) {   // whole ensemble, no per-item partial sums: the long-chunk table (capi.cu)
+        items = (const int4*)e->ext_dev[EXT_ITEMS2_LONG];
+        n_items = e->ext_int[5];
+    }
     const float* H = (const float*)Hin;
     const float* B = (const float*)(packed ? e->bpack : e->plane[ODINN_FIELD_B]);
     const float* Af = (const float*)e->plane[ODINN_FIELD_A];

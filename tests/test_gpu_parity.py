@@ -408,3 +408,45 @@ def test_continuous_vjp_resident_ragged(ob):
             assert abs(S[k] - refS) <= 1e-11 * abs(refS) or refS == 0.0, k
     finally:
         sim.close()
+
+
+def test_long_chunk_work_items_of_big_ensembles(ob):
+    """Big fp32 ensembles run the whole-ensemble F1 / fused-stage launches over a second work-item table with ~125-row chunks
+    (capi.cu: fewer warm-up steps and halo rows per cell).  900 glaciers of 130 x 260 (5400 long items against 13500 short ones):
+    the whole-ensemble launch must equal the per-glacier call (which walks the short table) bit for bit, and the oracle within the
+    fp32 bound; the SSPRK3 loop through the long table must match the oracle's."""
+    from odinn_b200 import _capi
+
+    G, nx, ny = 900, 130, 260
+    gl = [o.rough_bed_glacier(nx, ny), o.dome_glacier(nx, ny, H0=180.0)]
+    gl[0].H0 = 0.4 * gl[0].H0   # (thin enough for the explicit loop below)
+    ens = ob.Ensemble([nx] * G, [ny] * G, [gl[0].dx] * G, [gl[0].dy] * G, ob.Phys(), "f32")
+    try:
+        A = 2.21e-18
+        for k in range(G):
+            g = gl[k % 2]
+            ens.upload(k, _capi.FIELD_B, g.B)
+            ens.upload(k, _capi.FIELD_H, g.H0)
+            ens.upload(k, _capi.FIELD_H0, g.H0)
+            ens.set_A_scalar(k, A * (1.0 + 0.001 * (k % 7)))
+        ens.rhs_resident()
+        for k in (0, 1, 450, 899):
+            g = gl[k % 2]
+            Ak = A * (1.0 + 0.001 * (k % 7))
+            whole = ens.download(k, _capi.FIELD_DH)
+            single = ens.sia2d_rhs(k, g.H0.astype(np.float32))
+            assert np.array_equal(whole, single), k
+            g32 = o.Glacier(B=g.B.astype(np.float32).astype(np.float64), dx=g.dx, dy=g.dy)
+            ref = o.SIA2D(g.H0.astype(np.float32).astype(np.float64), g32, o.TargetA(o.Phys(), "const", A=Ak))
+            assert rel_l2(whole, ref) <= 1e-5, (k, rel_l2(whole, ref))
+        t = np.array([2010.0, 2010.0 + 1.0 / 24.0])
+        ens.solve_forward(t, method="ssprk3", nsub=8)
+        for k in (1, 898):
+            g = gl[k % 2]
+            Ak = A * (1.0 + 0.001 * (k % 7))
+            g32 = o.Glacier(B=g.B.astype(np.float32).astype(np.float64), dx=g.dx, dy=g.dy)
+            Hs = o.solve_forward(g.H0.astype(np.float32).astype(np.float64), g32, o.TargetA(o.Phys(), "const", A=Ak), None, t, method="ssprk3", nsub=8)
+            assert np.isfinite(Hs[1]).all()
+            assert rel_l2(ens.get_snapshot(k, 1), Hs[1]) <= 2e-5, (k, rel_l2(ens.get_snapshot(k, 1), Hs[1]))
+    finally:
+        ens.close()
