@@ -472,18 +472,21 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         istart2[n_glaciers] = (int)items2.size();
         e->n_items2 = (int)items2.size();
     }
-    // Big ensembles: a second table with row chunks of ~125 rows for the launches that write no per-item partial sums (F1 and the fused
-    // SSPRK3 / Euler stage over the WHOLE ensemble).  Every chunk pays a warm-up step and re-reads its halo rows: at 500 x 500 x 256 the
+    // Big ensembles: a second table with row chunks of ~125 rows for the WHOLE-ensemble launches of F1, the fused SSPRK3 / Euler stage and
+    // the A1 / A2 / reverse-step kernels (their per-item partial sums are then indexed by the long table's own start array).  Every chunk pays a warm-up step and re-reads its halo rows: at 500 x 500 x 256 the
     // SSPRK3 stage goes 0.197 -> 0.184 ms with 125-row chunks (profiles/r02_chunk_rows_sweep.txt).  Only where that still leaves two
     // waves of warps; the adaptive engines keep the short chunks (their partially active launches need the parallelism).
     std::vector<int4> items2L;
+    std::vector<int> istart2L(n_glaciers + 1, 0);
     if (dtype == ODINN_F32 && !getenv("ODINN_CHUNK_ROWS2")) {
         for (int g = 0; g < n_glaciers; ++g) {
             const GlacierHost& s = e->gl[g];
+            istart2L[g] = (int)items2L.size();
             const int nch = std::max(1, (s.ny + 62) / 125), rows = div_up(s.ny, nch);
             for (int r0 = 0; r0 < s.ny; r0 += rows)
                 for (int st_ = 0; st_ < div_up(s.nx, STRIP2); ++st_) items2L.push_back(make_int4(g, st_ * STRIP2 - 2, r0, std::min(r0 + rows, s.ny)));
         }
+        istart2L[n_glaciers] = (int)items2L.size();
         if ((long long)items2L.size() < 2LL * 148 * 16 || items2L.size() >= items2.size()) items2L.clear();
     }
 
@@ -512,6 +515,8 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
         CREATE_CUDA(cudaMalloc(&e->ext_dev[EXT_ITEMS2_LONG], sizeof(int4) * items2L.size()));
         CREATE_CUDA(cudaMemcpy(e->ext_dev[EXT_ITEMS2_LONG], items2L.data(), sizeof(int4) * items2L.size(), cudaMemcpyHostToDevice));
         e->ext_int[5] = (int)items2L.size();
+        CREATE_CUDA(cudaMalloc(&e->ext_dev[EXT_ITEMS2_LONG_START], sizeof(int) * (n_glaciers + 1)));
+        CREATE_CUDA(cudaMemcpy(e->ext_dev[EXT_ITEMS2_LONG_START], istart2L.data(), sizeof(int) * (n_glaciers + 1), cudaMemcpyHostToDevice));
     }
     CREATE_CUDA(cudaMalloc(&e->d_items, sizeof(int4) * e->n_items));
     CREATE_CUDA(cudaMalloc(&e->d_item_start, sizeof(int) * (n_glaciers + 1)));
@@ -1148,8 +1153,9 @@ int odinn_grad_discrete(odinn_ensemble* e, const double* t, int n_t, double* los
         if (fused_seed && j < n_t - 1) {
             // λ_∂f∂H = VJP_H(λ_j, H_j);  ℓ += ℓ_j;  λ_{j-1} = λ_j + Δt_{j-1} λ_∂f∂H + ∂ℓ_j/∂H   in ONE pass        (:218-242)
             if ((rc = sync_descs(e))) return rc;
-            if ((rc = launch_vjp2_seed(e, lam, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), vH, dt, 2.0 * wH))) return rc;
-            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(e->d_item2_start, e->d_partial, e->d_loss, wH, 1);
+            const int* seed_starts = e->d_item2_start;
+            if ((rc = launch_vjp2_seed(e, lam, Hj, plane_ptr(e, e->href, j), plane_ptr(e, e->wmask, j), vH, dt, 2.0 * wH, &seed_starts))) return rc;
+            reduce_scaled_kernel<<<e->G, NT, 0, e->stream>>>(seed_starts, e->d_partial, e->d_loss, wH, 1);
             ODINN_CHECK_LAUNCH(e);
             std::swap(lam, vH);
         } else {

@@ -135,6 +135,7 @@ enum {  // ext_dev slots
     EXT_VQ_WORK = 20,                                                                               // 4 planes: velocity references interpolated at a quadrature node
     EXT_VQ_RED = 21,                                                                                // [2 G] mask count and sum of squares of those references
     EXT_CL_TIMES = 24, EXT_CL_RKSTATE = 25, EXT_CL_STEPS = 26,                                                                              // cluster-resident forward solve: time grid on the device (ext_int[4] = its length)
+    EXT_ITEMS2_LONG_START = 28,                                                                     // [G + 1] first long item of every glacier (indexes the partial sums of a launch over the long table)
     EXT_ITEMS2_LONG = 27,                                                                           // long-chunk two-column work items for the F1 / stage launches of big ensembles (ext_int[5] = their number)
     EXT_LAT_KNOTS = 22, EXT_LAT_W = 23                                                              // law pullback with interpolation = :Linear: knots, knot weights (ext_int[2], [3] = n0, n1)
 };

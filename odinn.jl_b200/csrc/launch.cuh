@@ -75,7 +75,8 @@ int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam, const void* 
 void tma_cache_free(odinn_ensemble* e);
 // A1 + reverse time step in one pass (fp32 two-column kernel, whole ensemble, glacier-wide A):
 //   lam_new = lam + dt (dSIA/dH)^T lam + cseed W (H - Href);   partial sums of  sum W (H - Href)^2  per work item -> d_partial / d_item2_start
-int launch_vjp2_seed(odinn_ensemble* e, const void* lam, const void* H, const void* Href, const void* W, void* lam_new, double dt, double cseed);
+int launch_vjp2_seed(odinn_ensemble* e, const void* lam, const void* H, const void* Href, const void* W, void* lam_new, double dt, double cseed,
+                     const int** starts_used);
 
 // one RDPK3Sp35 stage of the continuous adjoint's reverse ODE in one pass: lerp(Ha, Hb) on load, A1, stage update as the epilogue
 // (s_only: the A2 pass at a quadrature node with the same interpolation on load; per-item partial sums of S -> d_partial)

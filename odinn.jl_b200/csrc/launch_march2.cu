@@ -231,6 +231,11 @@ int launch_vjp2(odinn_ensemble* e, int g0, int g1, const void* lam_, const void*
     float* vjpA = (wS && e->a_gridded) ? (float*)e->plane[ODINN_FIELD_VJP_A] : nullptr;
     double* partial = e->d_partial + i0;
     const int4* items = e->d_items2 + i0;
+    if (g0 < 0 && e->ext_int[5] > 0) {   // whole (big) ensemble: the long-chunk table and its own start array (capi.cu)
+        items = (const int4*)e->ext_dev[EXT_ITEMS2_LONG];
+        n_items = e->ext_int[5];
+        *starts_used = (const int*)e->ext_dev[EXT_ITEMS2_LONG_START];
+    }
     const bool eta1 = (e->phys.eta0 == 1.0);
     dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
 #define L(CUB, AF, WH, WS, E1) \
@@ -289,16 +294,23 @@ int launch_vjp2_rk(odinn_ensemble* e, const void* S1in, const void* Ha, const vo
 }
 
 int launch_vjp2_seed(odinn_ensemble* e, const void* lam_, const void* H_, const void* Href_, const void* W_, void* lam_new, double dt,
-                     double cseed) {
+                     double cseed, const int** starts_used) {
     PhysDev<float> ph = make_phys<float>(e->phys);
     const GDesc<float>* descs = (const GDesc<float>*)e->d_descs;
-    const int n_items = e->n_items2;
+    int n_items = e->n_items2;
+    const int4* seed_items = e->d_items2;
+    *starts_used = e->d_item2_start;
+    if (e->ext_int[5] > 0) {   // big ensemble: the long-chunk table (capi.cu)
+        seed_items = (const int4*)e->ext_dev[EXT_ITEMS2_LONG];
+        n_items = e->ext_int[5];
+        *starts_used = (const int*)e->ext_dev[EXT_ITEMS2_LONG_START];
+    }
     const float* B = (const float*)e->plane[ODINN_FIELD_B];
     const bool eta1 = (e->phys.eta0 == 1.0);
     dim3 grid(div_up(n_items, MARCH2_WARPS)), block(MARCH2_WARPS * 32);
 #define LS(CUB, E1)                                                                                                                      \
     sia2d_vjp_march2<CUB, false, true, false, E1, false, true><<<grid, block, 0, e->stream>>>(                                            \
-        descs, e->d_items2, n_items, (const float*)lam_, (const float*)H_, B, nullptr, (float*)lam_new, nullptr, e->d_partial, ph, nullptr, \
+        descs, seed_items, n_items, (const float*)lam_, (const float*)H_, B, nullptr, (float*)lam_new, nullptr, e->d_partial, ph, nullptr, \
         (const float*)Href_, (const float*)W_, (float)dt, (float)cseed)
     if (e->cubic) { if (eta1) LS(true, true); else LS(true, false); }
     else { if (eta1) LS(false, true); else LS(false, false); }

@@ -439,8 +439,45 @@ def test_long_chunk_work_items_of_big_ensembles(ob):
             g32 = o.Glacier(B=g.B.astype(np.float32).astype(np.float64), dx=g.dx, dy=g.dy)
             ref = o.SIA2D(g.H0.astype(np.float32).astype(np.float64), g32, o.TargetA(o.Phys(), "const", A=Ak))
             assert rel_l2(whole, ref) <= 1e-5, (k, rel_l2(whole, ref))
-        t = np.array([2010.0, 2010.0 + 1.0 / 24.0])
+        # A1 / A2 over the long table (vjp_resident) against the per-glacier calls (short table): A1 equal up to the last bit of a few cells
+        # of the rows next to a chunk seam (measured: 10 - 16 cells per glacier, 1 ulp, rel-L2 6e-9), S to fp32 summation order
+        rng = np.random.default_rng(3)
+        lam = [rng.standard_normal((nx, ny)).astype(np.float32) for _ in range(2)]
+        for k in range(G):
+            ens.upload(k, _capi.FIELD_LAMBDA, lam[k % 2])
+        S = ens.vjp_resident(True, True)
+        for k in (0, 1, 899):
+            g = gl[k % 2]
+            whole = ens.download(k, _capi.FIELD_VJP_H)
+            single = ens.sia2d_vjp_H(k, lam[k % 2], g.H0.astype(np.float32))
+            assert rel_l2(whole, single) <= 1e-7 and np.count_nonzero(whole != single) <= 64, (k, rel_l2(whole, single))
+            S1 = ens.sia2d_vjp_theta(k, lam[k % 2], g.H0.astype(np.float32))
+            assert S[k] == pytest.approx(S1, rel=1e-5, abs=1e-6 * abs(S).max()), (k, S[k], S1)
+        Sf = ens.vjp_resident(True, True, want_dH=True)   # the fused step (TMA bands) on the same inputs
+        assert np.allclose(Sf, S, rtol=1e-5, atol=1e-6 * abs(S).max())
+        t = np.array([2010.0, 2010.0 + 1.0 / 24.0, 2010.0 + 2.0 / 24.0])
         ens.solve_forward(t, method="ssprk3", nsub=8)
+        # discrete-adjoint reverse loop over the long table against a 2-glacier ensemble (short table) with the same data
+        small = ob.Ensemble([nx] * 2, [ny] * 2, [gl[0].dx] * 2, [gl[0].dy] * 2, ob.Phys(), "f32")
+        try:
+            snaps = [[ens.get_snapshot(k, j) for j in range(len(t))] for k in range(2)]
+            for k in range(2):
+                small.upload(k, _capi.FIELD_B, gl[k].B)
+                small.set_A_scalar(k, A * (1.0 + 0.001 * (k % 7)))
+                for j in range(len(t)):
+                    small.set_snapshot(k, j, len(t), snaps[k][j])
+                    small.set_reference(k, j, len(t), 0.95 * snaps[k][j], snaps[k][j] > 0)
+            for k in range(G):
+                for j in range(len(t)):
+                    ens.set_reference(k, j, len(t), 0.95 * snaps[k % 2][j], snaps[k % 2][j] > 0)
+            loss_b, S_b = ens.grad_discrete(t)
+            loss_s, S_s = small.grad_discrete(t)
+            for k in range(2):   # glaciers 0 and 1 of the big ensemble carry the same A as the small one's
+                assert loss_b[k] == pytest.approx(loss_s[k], rel=1e-5), (k, loss_b[k], loss_s[k])
+                assert S_b[k] == pytest.approx(S_s[k], rel=1e-4), (k, S_b[k], S_s[k])
+        finally:
+            small.close()
+        t = t[:2]
         for k in (1, 898):
             g = gl[k % 2]
             Ak = A * (1.0 + 0.001 * (k % 7))
