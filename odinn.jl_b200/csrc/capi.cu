@@ -424,11 +424,16 @@ int odinn_ensemble_create(int device, int dtype, int n_glaciers, const int* nx, 
     // ensembles so that the grid still fills 148 SMs.
     std::vector<int4> items;
     std::vector<int> istart(n_glaciers + 1);
-    for (int rows = 32; rows >= 8; rows /= 2) {
+    // (Every chunk pays a warm-up step and re-reads its halo rows.  fp64 sweep at 500 x 500 x 256, profiles/r02_chunk_rows_sweep.txt: fused
+    //  F1+A1+A2 step 0.627 ms with 32-row chunks, 0.589 with 64, 0.576 with 100, 0.591 with 167; F1 0.305 -> 0.268 ms.)
+    for (int rows : {100, 64, 32, 16, 8}) {
         long long n = 0;
         for (int g = 0; g < n_glaciers; ++g) n += (long long)div_up(e->gl[g].nx, STRIP) * div_up(e->gl[g].ny, rows);
         e->chunk_rows = rows;
         if (n >= 148LL * 48) break;
+    }
+    if (const char* envr1 = getenv("ODINN_CHUNK_ROWS1")) {   // (tuning sweeps)
+        if (atoi(envr1) >= 4) e->chunk_rows = atoi(envr1);
     }
     for (int g = 0; g < n_glaciers; ++g) {
         GlacierHost& s = e->gl[g];
