@@ -22,9 +22,9 @@ struct TmaCache {
     double* d_partial = nullptr;
     bool usable = false;
 };
-// Row chunks of the bands: 62 rows (+ 2 halo rows = 16 boxes of TMA_R = 4 rows), or 126 when that still leaves two waves of CTAs -- every
-// chunk pays two halo rows and a warm-up step (sweep at 500x500x256, fused step: 62 rows 0.2627 ms, 126 rows 0.2590 ms, 250 rows 0.277 ms;
-// profiles/r02_chunk_rows_sweep.txt).  ODINN_TMA_CHUNK_ROWS=<rows> overrides.
+// Row chunks of the bands: 62 rows (+ 2 halo rows = 16 boxes of TMA_R = 4 rows), or ~100 when that still leaves two waves of CTAs -- every
+// chunk pays two halo rows and a warm-up step (sweeps at 500x500x256, fused step: 62-row bands 0.2627 ms, 102 rows (5 chunks) 0.2570 ms,
+// 126 rows (4 chunks) 0.2590 ms, 166 rows 0.266 ms, 250 rows 0.277 ms; profiles/r02_chunk_rows_sweep.txt).  ODINN_TMA_CHUNK_ROWS=<rows> overrides.
 static int tma_chunk_rows(const odinn_ensemble* e) {
     const char* v = getenv("ODINN_TMA_CHUNK_ROWS");   // (read when the band table of an ensemble is built: the tests set it per ensemble)
     const int forced = v ? atoi(v) : 0;
@@ -32,9 +32,9 @@ static int tma_chunk_rows(const odinn_ensemble* e) {
     long long ctas = 0;
     for (int g = 0; g < e->G; ++g) {
         const GlacierHost& s = e->gl[g];
-        ctas += (long long)div_up(div_up(s.nx, STRIP2), TMA_NW) * std::max(1, (s.ny + 63) / 126);
+        ctas += (long long)div_up(div_up(s.nx, STRIP2), TMA_NW) * std::max(1, (s.ny + 50) / 100);
     }
-    return ctas >= 2LL * 148 * 5 ? 126 : 62;
+    return ctas >= 2LL * 148 * 5 ? 100 : 62;
 }
 
 void tma_cache_free(odinn_ensemble* e) {

@@ -57,11 +57,11 @@ def _S_close(S, ref, mag, dtype):
 # ------------------------------------------------------------------------------------------------------------------
 # config 2, per call
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype,tma_rows", [("f64", None), ("f32", None), ("f32", "126")])
+@pytest.mark.parametrize("dtype,tma_rows", [("f64", None), ("f32", None), ("f32", "100")])
 @pytest.mark.parametrize("maker", ["rough", "noisy"])
 def test_config2_per_call_operators_vs_oracle(ob, dtype, maker, tma_rows, monkeypatch):
     """500 x 500 = 9 strips x 8 row chunks of the marching kernels: every strip / chunk seam is compared with the oracle.
-    tma_rows: the row chunks of the fused step's TMA bands (62 for a small ensemble like this one, 126 for the bench ensemble)."""
+    tma_rows: the row chunks of the fused step's TMA bands (62 for a small ensemble like this one, ~100 for the bench ensemble)."""
     from odinn_b200 import _capi
 
     if tma_rows:
